@@ -1,0 +1,211 @@
+"""Oracle self-checks (CPU): autograd restatement vs independent closed forms, structural facts of
+SURVEY 8c(iii), and the reference's analytical known-answer tests (tests/test_analytical.py)."""
+import math
+
+import pytest
+import torch
+
+from oracle import pc_oracle as O
+
+torch.manual_seed(0)
+
+
+def _data(B, d_in, d_out, seed=1, dtype=torch.float64, onehot_out=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, d_in, generator=g, dtype=torch.float64).to(dtype)
+    if onehot_out:
+        idx = torch.randint(0, d_out, (B,), generator=g)
+        y = torch.nn.functional.one_hot(idx, d_out).to(dtype)
+    else:
+        y = torch.randn(B, d_out, generator=g, dtype=torch.float64).to(dtype)
+    return x, y
+
+
+def _perturb(acts, seed=2, scale=0.3):
+    g = torch.Generator().manual_seed(seed)
+    return [a + scale * torch.randn(a.shape, generator=g, dtype=torch.float64).to(a.dtype) for a in acts]
+
+
+@pytest.mark.parametrize("act", O.ACT_FNS)
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_autograd_matches_closed_form(act, use_bias):
+    model = O.make_mlp(0, 10, 20, 4, 5, act, use_bias=use_bias)
+    x, y = _data(4, 10, 5)
+    acts = _perturb(O.init_activities_with_ffwd(model, x))
+    _, g_ad = O.compute_pc_activity_grad(model, None, acts, y, x=x)
+    g_cf = O.closed_form_activity_grad(model, None, acts, y, x)
+    for a, b in zip(g_ad, g_cf):
+        assert O.max_rel_err(a, b) < 1e-12
+    p_ad = O.compute_pc_param_grads(model, None, acts, y, x=x)
+    p_cf = O.closed_form_param_grads(model, None, acts, y, x)
+    for a, b in zip(p_ad, p_cf):
+        assert O.max_rel_err(a["W"], b["W"]) < 1e-12
+        if use_bias:
+            assert O.max_rel_err(a["b"], b["b"]) < 1e-12
+
+
+@pytest.mark.parametrize("param_type", ["mupc", "ntp"])
+def test_closed_form_skips_scalings_gamma(param_type):
+    depth = 6
+    model = O.make_mlp(0, 12, 16, depth, 3, "relu", param_type=param_type)
+    skips = O.make_skip_model(depth)
+    x, y = _data(5, 12, 3)
+    kw = dict(param_type=param_type, gamma=0.5, output_energy_scaling=2.5)
+    acts = _perturb(O.init_activities_with_ffwd(model, x, skips=skips, param_type=param_type, gamma=0.5))
+    _, g_ad = O.compute_pc_activity_grad(model, skips, acts, y, x=x, activity_decay=0.1, **kw)
+    g_cf = O.closed_form_activity_grad(model, skips, acts, y, x, activity_decay=0.1, **kw)
+    for a, b in zip(g_ad, g_cf):
+        assert O.max_rel_err(a, b) < 1e-12
+    p_ad = O.compute_pc_param_grads(model, skips, acts, y, x=x, **kw)
+    p_cf = O.closed_form_param_grads(model, skips, acts, y, x, **kw)
+    for a, b in zip(p_ad, p_cf):
+        assert O.max_rel_err(a["W"], b["W"]) < 1e-12
+
+
+def test_structural_facts():
+    model = O.make_mlp(0, 10, 20, 3, 5, "relu")  # reference conftest shapes (tests/conftest.py:16-87)
+    x, y = _data(4, 10, 5)
+    acts = O.init_activities_with_ffwd(model, x)
+    E = O.pc_energy_fn(model, None, acts, y, x=x, record_layers=True)
+    assert len(E) == len(model) and torch.all(E >= 0) and torch.all(torch.isfinite(E))
+    # hidden errors are zero at the feed-forward init; only the output layer carries energy
+    assert float(E[1:].abs().max()) < 1e-25
+    tot = O.pc_energy_fn(model, None, acts, y, x=x)
+    assert abs(float(tot) - float(E.sum())) < 1e-12
+    # output energy at the ffwd init equals the mse loss
+    assert abs(float(E[0]) - float(O.mse_loss(acts[-1], y))) < 1e-12
+    _, g = O.compute_pc_activity_grad(model, None, acts, y, x=x)
+    assert float(g[-1].abs().max()) == 0.0  # dummy slot
+    assert float(g[0].abs().max()) == 0.0   # wavefront: only z_{L-1} moves on the first step (F7)
+    assert float(g[1].abs().max()) > 0.0
+
+
+def test_euler_equals_sgd_and_batch_sharding():
+    model = O.make_mlp(0, 10, 20, 3, 5, "tanh", use_bias=True)
+    x, y = _data(8, 10, 5)
+    acts0 = O.init_activities_with_ffwd(model, x)
+    sol, n = O.solve_inference(model, None, acts0, y, x=x, solver="euler", max_t1=5.0, dt=0.5)
+    assert n == 10
+    a = [t.clone() for t in acts0]
+    for _ in range(10):
+        _, g = O.compute_pc_activity_grad(model, None, a, y, x=x)
+        a = O.sgd_update(a, g, 0.5)
+    for p, q in zip(sol, a):
+        assert O.max_rel_err(p, q) < 1e-13
+    # closed-form vector field gives the same trajectory
+    sol_cf, _ = O.solve_inference(model, None, acts0, y, x=x, solver="euler", max_t1=5.0, dt=0.5,
+                                  use_closed_form=True)
+    for p, q in zip(sol, sol_cf):
+        assert O.max_rel_err(p, q) < 1e-12
+    # heun differs from euler but both decrease the energy
+    solh, nh = O.solve_inference(model, None, acts0, y, x=x, solver="heun", max_t1=5.0, dt=0.5)
+    assert nh == 10
+    e0 = float(O.pc_energy_fn(model, None, acts0, y, x=x))
+    assert float(O.pc_energy_fn(model, None, sol, y, x=x)) < e0
+    assert float(O.pc_energy_fn(model, None, solh, y, x=x)) < e0
+
+
+def test_n_fixed_steps():
+    assert O.n_fixed_steps(10, 0.5) == 20
+    assert O.n_fixed_steps(25, 0.5) == 50
+    assert O.n_fixed_steps(1, 0.3) == 4  # last step clipped
+
+
+# ---- reference known-answer tests (reference tests/test_analytical.py) ------------------------
+def _kat_setup():
+    input_dim, width, depth, gamma, B = 16, 128, 2, 0.01, 2
+    model = O.make_mlp(42, input_dim, width, depth, 1, "linear", param_type="mupc")
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, input_dim, generator=g, dtype=torch.float64)
+    y = torch.randn(B, 1, generator=g, dtype=torch.float64)
+    lam = gamma ** 2 * width * depth
+    return model, x, y, gamma, lam, B
+
+
+def test_kat_linear_equilib_energy_matches_inference():
+    """reference tests/test_analytical.py:162-224 (rtol=atol=1e-2 there)."""
+    model, x, y, gamma, lam, B = _kat_setup()
+    kw = dict(param_type="mupc", gamma=gamma, output_energy_scaling=lam)
+    theory = float(O.linear_equilib_energy(model, None, x, y, **kw))
+    acts = O.init_activities_with_ffwd(model, x, param_type="mupc", gamma=gamma)
+    energy = None
+    for _ in range(200):
+        energy, g = O.compute_pc_activity_grad(model, None, acts, y, x=x, **kw)
+        acts = O.sgd_update(acts, g, 0.5 * B)
+    assert math.isclose(theory, float(energy), rel_tol=1e-2, abs_tol=1e-2)
+    assert math.isclose(theory, float(energy), rel_tol=1e-6)  # far tighter in fp64
+
+
+def test_kat_linear_activity_solution_matches_inference():
+    """reference tests/test_analytical.py:293-368."""
+    model, x, y, gamma, lam, B = _kat_setup()
+    kw = dict(param_type="mupc", gamma=gamma, output_energy_scaling=lam)
+    acts = O.init_activities_with_ffwd(model, x, param_type="mupc", gamma=gamma)
+    energy = None
+    for _ in range(300):
+        energy, g = O.compute_pc_activity_grad(model, None, acts, y, x=x, **kw)
+        acts = O.sgd_update(acts, g, 0.5 * B)
+    theory_acts = O.linear_activity_solution(model, None, x, y, **kw)
+    theory_energy = float(O.pc_energy_fn(model, None, theory_acts, y, x=x, **kw))
+    assert math.isclose(theory_energy, float(energy), rel_tol=1e-2, abs_tol=1e-2)
+    assert float(torch.linalg.norm(acts[0] - theory_acts[0], dim=1).mean()) < 1e-2
+    # and the two analytical answers agree with each other
+    assert math.isclose(theory_energy, float(O.linear_equilib_energy(model, None, x, y, **kw)), rel_tol=1e-9)
+
+
+def test_kat_equilib_energy_is_loss_over_s():
+    """reference tests/test_analytical.py:227-290: scalar output => F* = loss / s."""
+    input_dim, width, depth, gamma = 16, 64, 2, 0.01
+    model = O.make_mlp(3, input_dim, width, depth, 1, "linear", param_type="mupc")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, input_dim, generator=g, dtype=torch.float64)
+    y = torch.randn(3, 1, generator=g, dtype=torch.float64)
+    lam = gamma ** 2 * width * depth
+    scal = O.get_param_scalings(model, x, None, "mupc", gamma)
+    s = float(O.linear_equilib_rescaling([l["W"] for l in model], scal, lam)[0, 0])
+    out = O.init_activities_with_ffwd(model, x, param_type="mupc", gamma=gamma)[-1]
+    loss = float(O.mse_loss(out, y))
+    F = float(O.linear_equilib_energy(model, None, x, y, param_type="mupc", gamma=gamma,
+                                      output_energy_scaling=lam))
+    assert math.isclose(F, loss / s, rel_tol=1e-5, abs_tol=1e-5)
+
+
+def test_kat_with_skips_deep_linear():
+    """Skip branch of linear_equilib_energy against a long Euler run (deep linear mupc resnet)."""
+    depth, width = 5, 24
+    model = O.make_mlp(11, 8, width, depth, 2, "linear", param_type="mupc")
+    skips = O.make_skip_model(depth)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 8, generator=g, dtype=torch.float64)
+    y = torch.randn(3, 2, generator=g, dtype=torch.float64)
+    kw = dict(param_type="mupc")
+    theory = float(O.linear_equilib_energy(model, skips, x, y, **kw))
+    sol = O.linear_activity_solution(model, skips, x, y, **kw)
+    assert math.isclose(theory, float(O.pc_energy_fn(model, skips, sol, y, x=x, **kw)), rel_tol=1e-9)
+
+
+# ---- bPC ------------------------------------------------------------------------------------
+def test_bpc_energy_and_grads():
+    H = 3
+    td = O.make_mlp(0, 5, 12, H + 1, 9, "relu")
+    bu = O.make_mlp(1, 9, 12, H + 1, 5, "tanh")[::-1]
+    x, _ = _data(4, 5, 5)
+    _, y = _data(4, 9, 9, seed=3, onehot_out=False)
+    acts = _perturb(O.init_activities_with_ffwd(td, x))  # H+1 entries; last = dummy
+    E = O.bpc_energy_fn(td, bu, acts, y, x=x, record_layers=True,
+                        forward_energy_weight=0.7, backward_energy_weight=1.3)
+    assert len(E) == 2 * (H + 1) and torch.all(E >= 0)
+    tot, g = O.compute_bpc_activity_grad(td, bu, acts, y, x=x,
+                                         forward_energy_weight=0.7, backward_energy_weight=1.3)
+    assert abs(float(tot) - float(E.sum())) < 1e-12
+    assert float(g[-1].abs().max()) == 0.0
+    gtd, gbu = O.compute_bpc_param_grads(td, bu, acts, y, x=x)
+    assert len(gtd) == H + 1 and len(gbu) == H + 1
+    assert all(float(gi["W"].abs().max()) > 0 for gi in gtd + gbu)
+
+
+def test_errors():
+    with pytest.raises(ValueError):
+        O.check_param_type("bogus")
+    with pytest.raises(ValueError):
+        O.act_fn("bogus", torch.zeros(1))
