@@ -1,0 +1,180 @@
+/* jpc_b200.h -- C-ABI of the B200-native predictive-coding (PC) train-step path.
+ *
+ * This is the drop-in boundary for the hot path of thebuckleylab/jpc (reference citations are
+ * relative to the reference repository root).  The reference has no FFI of its own (it is pure
+ * Python/JAX); each entry point below replaces the XLA program that one reference function
+ * lowers to, and is what a `jax.ffi` custom call (or the ctypes binding in jpc_b200/_lib.py)
+ * binds.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no torch / XLA types.  Every data pointer is a DEVICE pointer
+ *    unless stated otherwise; arrays of pointers (`W`, `b`, `A`, ...) are HOST arrays of device
+ *    pointers.  All tensors are dense row-major fp32: activities [batch_local, d], weights
+ *    [d_out, d_in] (equinox nn.Linear convention), biases [d_out].
+ *  - The caller owns every buffer, including the workspace (`jpcb_pc_workspace_bytes`).  The
+ *    library allocates nothing, never synchronises the device, and enqueues only on `stream`.
+ *  - Return value: 0 on success, a JPCB_E* code otherwise; `jpcb_last_error()` gives the message
+ *    (thread-local).  There is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with JPCB_ECUDA.
+ *  - Data parallelism: each rank passes its `batch_local` rows and the GLOBAL batch size used for
+ *    the 1/B normalisation (jpc/_core/_energies.py:85,153); energies, losses and parameter
+ *    gradients returned are this rank's partial sums, to be all-reduced with SUM by the caller.
+ */
+#ifndef JPC_B200_H_
+#define JPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPCB_VERSION 100
+#define JPCB_MAX_LAYERS 256
+
+/* error codes */
+#define JPCB_OK 0
+#define JPCB_EINVAL 1   /* bad descriptor / argument (ValueError in the reference) */
+#define JPCB_ENOTIMPL 2 /* valid in the reference but not on this path (NotImplementedError) */
+#define JPCB_EWORKSPACE 3
+#define JPCB_ECUDA 4
+
+/* GEMM operand arithmetic.  F32: fp32 CUDA-core FMA (1e-5 parity configs).  BF16: tcgen05 tensor
+ * cores, bf16 operands, fp32 accumulation in TMEM, fp32 master activities (2e-2 parity). */
+#define JPCB_DTYPE_F32 0
+#define JPCB_DTYPE_BF16 1
+
+/* activation ids, order of jpc/_utils.py:13-15 */
+#define JPCB_ACT_LINEAR 0
+#define JPCB_ACT_TANH 1
+#define JPCB_ACT_HARD_TANH 2
+#define JPCB_ACT_RELU 3
+#define JPCB_ACT_LEAKY_RELU 4
+#define JPCB_ACT_GELU 5
+#define JPCB_ACT_SELU 6
+#define JPCB_ACT_SILU 7
+
+#define JPCB_LOSS_MSE 0
+#define JPCB_LOSS_CE 1
+
+#define JPCB_SOLVER_EULER 0 /* diffrax.Euler  + ConstantStepSize */
+#define JPCB_SOLVER_HEUN 1  /* diffrax.Heun   + ConstantStepSize */
+
+/* Descriptor of one PC network in the reference's make_mlp layer form
+ * f_l(u) = W_l act_l(u) + b_l  (jpc/_utils.py:87-106), l = 0..n_layers-1. */
+typedef struct jpcb_pc_desc {
+  int32_t n_layers;                  /* L = len(model) >= 2 */
+  int32_t batch_local;               /* rows held by this rank */
+  int32_t batch_global;              /* B of the 1/B energy normalisation */
+  int32_t dims[JPCB_MAX_LAYERS + 1]; /* d_0 .. d_L */
+  int32_t act[JPCB_MAX_LAYERS];      /* activation applied to the INPUT of layer l */
+  int32_t has_bias;                  /* all layers carry a bias (make_mlp use_bias) */
+  uint8_t skip[JPCB_MAX_LAYERS];     /* identity skip at layer l (jpc/_utils.py:122-126) */
+  float scalings[JPCB_MAX_LAYERS];   /* a_l of _get_param_scalings (jpc/_core/_energies.py:879-933) */
+  int32_t dtype;                     /* JPCB_DTYPE_* */
+  int32_t loss;                      /* JPCB_LOSS_* (only MSE on this path so far) */
+  float output_energy_scaling;       /* lambda; 1 when the reference passes None */
+  float activity_decay;
+  int32_t solver;                    /* JPCB_SOLVER_* */
+  int32_t n_steps;                   /* T fixed steps */
+  float dt;                          /* step size of steps 0..T-2 */
+  float dt_last;                     /* step size of the last step (ConstantStepSize clips to t1) */
+} jpcb_pc_desc;
+
+int jpcb_version(void);
+const char* jpcb_last_error(void);
+
+/* Bytes of caller-provided device workspace any entry point below may use for `desc`. */
+size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc);
+
+/* init_activities_with_ffwd  (jpc/_core/_init.py:12-82).
+ * A_out[l] (l = 0..L-1) receives z_{l+1} = a_l f_l(z_l) (+ z_l where skip[l]); A_out[L-1] is the
+ * network output.  If `loss_out` and `y` are non-NULL, *loss_out (device float) receives this
+ * rank's part of mse_loss(A_out[L-1], y) = 1/(2B) sum (y - out)^2  (jpc/_utils.py:129-130,
+ * jpc/_train.py:159-162). */
+int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                      const float* x, float* const* A_out, const float* y, float* loss_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* pc_energy_fn(..., record_layers=True)  (jpc/_core/_energies.py:13-158).
+ * E_layers: device float[L], order [output layer, hidden net_l = 1..L-2, first layer], each
+ * divided by batch_global (regularisers excluded, as in the reference's record_layers branch). */
+int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                   const float* const* A, const float* x, const float* y, float* E_layers,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* compute_pc_activity_grad / neg_pc_activity_grad  (jpc/_core/_grads.py:22-167).
+ * gA[l] receives dF/dA[l] for l = 0..L-1 (gA[L-1], the dummy slot, is activity_decay*A/B).
+ * F (device float, may be NULL) receives the total energy incl. the activity-decay term. */
+int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                          const float* const* A, const float* x, const float* y, float* F,
+                          float* const* gA, void* workspace, size_t workspace_bytes, void* stream);
+
+/* solve_inference with a fixed-step solver  (jpc/_core/_infer.py:20-133): desc->n_steps steps of
+ * Euler/Heun on dA/dt = -dF/dA, in place on A.  All L layers x T steps run without returning to
+ * the host.  `sumsq_out` (device float[2], may be NULL) receives {sum A^2, numel} after the last
+ * step so the caller can evaluate the reference's steady-state Event (jpc/_core/_infer.py:136-145). */
+int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                  float* const* A, const float* x, const float* y, float* sumsq_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* compute_pc_param_grads  (jpc/_core/_grads.py:436-499).  gW[l]: [d_{l+1}, d_l]; gb[l]:
+ * [d_{l+1}] (ignored when !has_bias; gb may then be NULL).  Partial sums over local rows,
+ * already divided by batch_global.  E_layers (may be NULL) as in jpcb_pc_energy, for free. */
+int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                        const float* const* A, const float* x, const float* y, float* const* gW,
+                        float* const* gb, float* E_layers, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* make_pc_step up to (excluding) the optimiser  (jpc/_train.py:135-232): ffwd init, loss at the
+ * init, T-step inference, per-layer energies at the solution, parameter gradients. */
+int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                       const float* x, const float* y, float* const* A_out, float* loss_out,
+                       float* E_layers, float* const* gW, float* const* gb, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- bidirectional PC (jpc/_core/_energies.py:246-357) ---------------------------------------
+ * top-down model W (layers 0..H, f_l), bottom-up model V (layers 0..H, g_l); H = n_layers-1 of
+ * `td`.  Activities A[0..H-1] are z_0..z_{H-1}; A[H] is the unused dummy slot.  `bu->dims[l]` is
+ * the INPUT dim of bottom_up_model[l] and bu->dims[l+1]... see DESIGN.md for the index map. */
+typedef struct jpcb_bpc_desc {
+  jpcb_pc_desc td;                 /* top-down model: dims d_0(x) .. d_{H+1}(y); solver fields used */
+  int32_t bu_act[JPCB_MAX_LAYERS]; /* activation applied to the input of bottom_up_model[l] */
+  int32_t bu_has_bias;
+  float forward_energy_weight;     /* alpha_f */
+  float backward_energy_weight;    /* alpha_b */
+} jpcb_bpc_desc;
+
+size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc);
+
+/* bpc_energy_fn(record_layers=True): E_pairs = device float[2*(H+1)], reference order
+ * [(e_out, delta_0), (e_0, delta'_0), ...] / batch  (jpc/_core/_energies.py:322-355). */
+int jpcb_bpc_energy(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW,
+                    const float* const* V, const float* const* bV, const float* const* A,
+                    const float* x, const float* y, float* E_pairs, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* compute_bpc_activity_grad (jpc/_core/_grads.py:170-226) */
+int jpcb_bpc_activity_grad(const jpcb_bpc_desc* desc, const float* const* W,
+                           const float* const* bW, const float* const* V, const float* const* bV,
+                           const float* const* A, const float* x, const float* y, float* F,
+                           float* const* gA, void* workspace, size_t workspace_bytes, void* stream);
+
+/* td.n_steps fused Euler steps (== update_bpc_activities with optax.sgd(dt), looped;
+ * jpc/_core/_updates.py:206-281), in place on A. */
+int jpcb_bpc_infer(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW,
+                   const float* const* V, const float* const* bV, float* const* A, const float* x,
+                   const float* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* compute_bpc_param_grads (jpc/_core/_grads.py:544-612) */
+int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW,
+                         const float* const* V, const float* const* bV, const float* const* A,
+                         const float* x, const float* y, float* const* gW, float* const* gbW,
+                         float* const* gV, float* const* gbV, float* E_pairs, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPC_B200_H_ */

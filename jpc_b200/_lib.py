@@ -1,0 +1,116 @@
+"""ctypes binding of the C-ABI in include/jpc_b200.h.
+
+The CUDA library is the product: if it is missing and cannot be built, importing this module
+raises -- there is no Python/CPU fallback for any compute entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+MAX_LAYERS = 256
+
+OK, EINVAL, ENOTIMPL, EWORKSPACE, ECUDA = 0, 1, 2, 3, 4
+DTYPE_F32, DTYPE_BF16 = 0, 1
+LOSS_MSE, LOSS_CE = 0, 1
+SOLVER_EULER, SOLVER_HEUN = 0, 1
+ACT_IDS = {"linear": 0, "tanh": 1, "hard_tanh": 2, "relu": 3, "leaky_relu": 4, "gelu": 5, "selu": 6, "silu": 7}
+
+
+class PcDesc(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32),
+        ("batch_local", C.c_int32),
+        ("batch_global", C.c_int32),
+        ("dims", C.c_int32 * (MAX_LAYERS + 1)),
+        ("act", C.c_int32 * MAX_LAYERS),
+        ("has_bias", C.c_int32),
+        ("skip", C.c_uint8 * MAX_LAYERS),
+        ("scalings", C.c_float * MAX_LAYERS),
+        ("dtype", C.c_int32),
+        ("loss", C.c_int32),
+        ("output_energy_scaling", C.c_float),
+        ("activity_decay", C.c_float),
+        ("solver", C.c_int32),
+        ("n_steps", C.c_int32),
+        ("dt", C.c_float),
+        ("dt_last", C.c_float),
+    ]
+
+
+class BpcDesc(C.Structure):
+    _fields_ = [
+        ("td", PcDesc),
+        ("bu_act", C.c_int32 * MAX_LAYERS),
+        ("bu_has_bias", C.c_int32),
+        ("forward_energy_weight", C.c_float),
+        ("backward_energy_weight", C.c_float),
+    ]
+
+
+_P = C.c_void_p
+_PP = C.POINTER(C.c_void_p)
+
+# every symbol include/jpc_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "jpcb_version": (C.c_int, []),
+    "jpcb_last_error": (C.c_char_p, []),
+    "jpcb_pc_workspace_bytes": (C.c_size_t, [C.POINTER(PcDesc)]),
+    "jpcb_pc_ffwd_init": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _P, _PP, _P, _P, _P, C.c_size_t, _P]),
+    "jpcb_pc_energy": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
+    "jpcb_pc_activity_grad": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _PP, _P, C.c_size_t, _P]),
+    "jpcb_pc_infer": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
+    "jpcb_pc_param_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _PP, _PP, _P, _P, C.c_size_t, _P]),
+    "jpcb_pc_train_step": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _P, _P, _PP, _P, _P, _PP, _PP, _P, C.c_size_t, _P]),
+    "jpcb_bpc_workspace_bytes": (C.c_size_t, [C.POINTER(BpcDesc)]),
+    "jpcb_bpc_energy": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
+    "jpcb_bpc_activity_grad": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, _PP, _P, C.c_size_t, _P]),
+    "jpcb_bpc_infer": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, C.c_size_t, _P]),
+    "jpcb_bpc_param_grads": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
+}
+
+
+def _load() -> C.CDLL:
+    path = _build.LIB
+    if not os.path.exists(path):
+        # one attempt to build in-tree; failure is fatal (no fallback implementation exists)
+        _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class JpcbError(RuntimeError):
+    pass
+
+
+def check(code: int) -> None:
+    """Maps C-ABI error codes to the exceptions the reference raises for the same conditions."""
+    if code == OK:
+        return
+    msg = lib.jpcb_last_error().decode("utf-8", "replace")
+    if code == EINVAL:
+        raise ValueError(msg)
+    if code == ENOTIMPL:
+        raise NotImplementedError(msg)
+    raise JpcbError(f"jpc_b200 error {code}: {msg}")
+
+
+def ptr_array(tensors) -> "C.Array":
+    """Host array of device pointers from a list of tensors (None -> NULL)."""
+    arr = (C.c_void_p * max(1, len(tensors)))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())

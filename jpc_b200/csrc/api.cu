@@ -1,0 +1,659 @@
+// api.cu -- C-ABI (include/jpc_b200.h) of the PC train-step path: validates the descriptor,
+// carves the caller's workspace, builds the per-phase grouped GEMM task lists and enqueues the
+// kernels on the caller's stream.  No allocation, no synchronisation, no CPU arithmetic.
+//
+// Index conventions used throughout (reference: jpc/_core/_energies.py:86-126):
+//   layer l = 0..L-1 maps its input u_l (u_0 = x, u_l = A[l-1]) to a prediction of its target
+//   t_l (t_l = A[l] for l < L-1, t_{L-1} = y);  err[l] = t_l - a_l (W_l act_l(u_l) + b_l) - s_l u_l.
+//   A[l-1] (l = 1..L-1) is updated with  g = err[l-1] - act_l'(A[l-1]) (a_l err[l] W_l) - s_l err[l].
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jpc_b200.h"
+#include "elementwise.cuh"
+#include "simt_gemm.cuh"
+#include "tc_gemm.cuh"
+
+using namespace jpcb;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) return fail(JPCB_ECUDA, "%s -> %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+#define RET(call)            \
+  do {                       \
+    int _r = (call);         \
+    if (_r != JPCB_OK) return _r; \
+  } while (0)
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    return v;
+  }();
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// descriptor validation
+// ---------------------------------------------------------------------------------------------
+int validate(const jpcb_pc_desc* d) {
+  if (!d) return fail(JPCB_EINVAL, "null descriptor");
+  if (d->n_layers < 2 || d->n_layers > JPCB_MAX_LAYERS) return fail(JPCB_EINVAL, "n_layers=%d outside [2,%d]", d->n_layers, JPCB_MAX_LAYERS);
+  if (d->batch_local <= 0 || d->batch_global < d->batch_local) return fail(JPCB_EINVAL, "bad batch sizes local=%d global=%d", d->batch_local, d->batch_global);
+  for (int l = 0; l <= d->n_layers; ++l)
+    if (d->dims[l] <= 0) return fail(JPCB_EINVAL, "dims[%d]=%d", l, d->dims[l]);
+  for (int l = 0; l < d->n_layers; ++l) {
+    if (d->act[l] < 0 || d->act[l] > JPCB_ACT_SILU) return fail(JPCB_EINVAL, "Invalid activation function ID %d at layer %d", d->act[l], l);
+    if (d->skip[l] && d->dims[l] != d->dims[l + 1]) return fail(JPCB_EINVAL, "identity skip at layer %d needs equal dims (%d vs %d)", l, d->dims[l], d->dims[l + 1]);
+  }
+  if (d->loss == JPCB_LOSS_CE) return fail(JPCB_ENOTIMPL, "cross-entropy output energy is not on the B200 path yet");
+  if (d->loss != JPCB_LOSS_MSE) return fail(JPCB_EINVAL, "`mse` and `ce` are the only valid losses.");
+  if (d->dtype != JPCB_DTYPE_F32 && d->dtype != JPCB_DTYPE_BF16) return fail(JPCB_EINVAL, "bad dtype %d", d->dtype);
+  if (d->solver != JPCB_SOLVER_EULER && d->solver != JPCB_SOLVER_HEUN) return fail(JPCB_EINVAL, "bad solver %d", d->solver);
+  if (d->n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", d->n_steps);
+  if (d->dtype == JPCB_DTYPE_BF16) {
+    if (d->batch_local % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs batch_local %% 8 == 0 (got %d)", d->batch_local);
+    for (int l = 0; l <= d->n_layers; ++l)
+      if (d->dims[l] % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs every dim %% 8 == 0 (dims[%d]=%d)", l, d->dims[l]);
+  }
+  return JPCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+struct Bump {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~(size_t)1023;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+constexpr int RED_FLOATS = JPCB_MAX_LAYERS + 64;  // [0,L): layer energy sums; then misc accumulators
+constexpr int RED_LOSS = JPCB_MAX_LAYERS + 0;
+constexpr int RED_SUMSQ = JPCB_MAX_LAYERS + 1;
+
+struct Ws {
+  float* red = nullptr;
+  std::vector<float*> err;   // [L]  err[l]: [Bl, d_{l+1}] fp32 (F32 path)
+  float* P1 = nullptr;       // hoisted layer-0 prediction [Bl, d_1]
+  std::vector<float*> Zt;    // [L-1] Heun stage state of A[l]
+  std::vector<float*> G1;    // [L-1] Heun first-stage gradient of A[l]
+  // bf16 operand copies (tensor-core path)
+  std::vector<bf16*> Wb, WTb;  // [L]   W_l [d_{l+1}, d_l] and its transpose [d_l, d_{l+1}]
+  std::vector<bf16*> Hb;       // [L]   act_l(u_l)  [Bl, d_l]
+  std::vector<bf16*> Htb;      // [L]   same for the Heun stage state
+  std::vector<bf16*> Eb;       // [L]   err[l] [Bl, d_{l+1}]
+  std::vector<bf16*> EbT;      // [L]   err[l]^T [d_{l+1}, Bl]
+  std::vector<bf16*> HbT;      // [L]   act_l(u_l)^T [d_l, Bl]
+  size_t bytes = 0;
+};
+
+void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
+  const int L = d->n_layers;
+  const size_t Bl = (size_t)d->batch_local;
+  Bump b{reinterpret_cast<char*>(base)};
+  w->red = b.take<float>(RED_FLOATS);
+  w->err.resize(L);
+  w->Zt.assign(L, nullptr);
+  w->G1.assign(L, nullptr);
+  w->P1 = b.take<float>(Bl * d->dims[1]);
+  const bool tc = d->dtype == JPCB_DTYPE_BF16, heun = d->solver == JPCB_SOLVER_HEUN;
+  for (int l = 0; l < L; ++l) w->err[l] = tc ? nullptr : b.take<float>(Bl * d->dims[l + 1]);
+  if (heun)
+    for (int l = 0; l < L - 1; ++l) {
+      w->Zt[l] = b.take<float>(Bl * d->dims[l + 1]);
+      w->G1[l] = b.take<float>(Bl * d->dims[l + 1]);
+    }
+  w->Wb.assign(L, nullptr); w->WTb.assign(L, nullptr); w->Hb.assign(L, nullptr); w->Htb.assign(L, nullptr);
+  w->Eb.assign(L, nullptr); w->EbT.assign(L, nullptr); w->HbT.assign(L, nullptr);
+  if (tc) {
+    for (int l = 0; l < L; ++l) {
+      const size_t wn = (size_t)d->dims[l] * d->dims[l + 1];
+      w->Wb[l] = b.take<bf16>(wn);
+      if (l >= 1) w->WTb[l] = b.take<bf16>(wn);
+      w->Hb[l] = b.take<bf16>(Bl * d->dims[l]);
+      if (heun && l >= 1) w->Htb[l] = b.take<bf16>(Bl * d->dims[l]);
+      w->Eb[l] = b.take<bf16>(Bl * d->dims[l + 1]);
+      w->EbT[l] = b.take<bf16>(Bl * d->dims[l + 1]);
+      w->HbT[l] = b.take<bf16>(Bl * d->dims[l]);
+    }
+  }
+  w->bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic task = one GEMM + fused epilogue, lowered to either kernel family
+// ---------------------------------------------------------------------------------------------
+struct GTask {
+  Epi e;
+  int K = 0;
+  const float* a_p = nullptr; long long a_smn = 0, a_sk = 0; int a_act = ACT_LINEAR;
+  const float* b_p = nullptr; long long b_smn = 0, b_sk = 0; int b_act = ACT_LINEAR;
+  const bf16* a_b = nullptr;  // [M, K] K-major
+  const bf16* b_b = nullptr;  // [N, K] K-major
+  GTask() { memset(&e, 0, sizeof(e)); e.gscale = 1.f; e.escale = 1.f; }
+};
+
+template <int BM, int BN, int BK, int RM, int RN>
+int launch_simt_cfg(const std::vector<GTask>& tasks, cudaStream_t st) {
+  size_t i = 0;
+  while (i < tasks.size()) {
+    SimtGroup g;
+    memset(&g, 0, sizeof(int) * 2);
+    int n = 0, tiles = 0;
+    for (; i < tasks.size() && n < SIMT_MAX_TASKS; ++i, ++n) {
+      const GTask& t = tasks[i];
+      SimtTask& s = g.t[n];
+      s.A = Opnd{t.a_p, t.a_smn, t.a_sk, t.a_act, 0};
+      s.B = Opnd{t.b_p, t.b_smn, t.b_sk, t.b_act, 0};
+      s.K = t.K;
+      s.tile_begin = tiles;
+      s.tiles_n = (t.e.N + BN - 1) / BN;
+      s.pad_ = 0;
+      s.e = t.e;
+      tiles += s.tiles_n * ((t.e.M + BM - 1) / BM);
+    }
+    g.ntasks = n;
+    g.total_tiles = tiles;
+    if (tiles == 0) continue;
+    constexpr int NT = (BM / (4 * RM)) * (BN / (4 * RN));
+    simt_grouped_gemm<BM, BN, BK, RM, RN><<<tiles, NT, 0, st>>>(g);
+    CK(cudaGetLastError());
+  }
+  return JPCB_OK;
+}
+
+int launch_simt(const std::vector<GTask>& tasks, cudaStream_t st) {
+  if (tasks.empty()) return JPCB_OK;
+  // pick the tile shape from the amount of parallelism the phase offers
+  long long t128 = 0, t64 = 0;
+  for (const GTask& t : tasks) {
+    t128 += (long long)((t.e.M + 127) / 128) * ((t.e.N + 127) / 128);
+    t64 += (long long)((t.e.M + 63) / 64) * ((t.e.N + 63) / 64);
+  }
+  const int sms = num_sms();
+  if (t128 >= 2LL * sms) return launch_simt_cfg<128, 128, 16, 2, 2>(tasks, st);
+  if (t64 >= sms) return launch_simt_cfg<64, 64, 16, 1, 1>(tasks, st);
+  return launch_simt_cfg<32, 32, 16, 1, 1>(tasks, st);  // (8x8 threads) latency-bound small layers
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// bf16 [rows, cols] row-major, box = {64 cols, box_rows}, SWIZZLE_128B, OOB reads give zeros
+int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+  return JPCB_OK;
+}
+
+int launch_tc(const std::vector<GTask>& tasks, cudaStream_t st) {
+  if (tasks.empty()) return JPCB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(tc_grouped_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  size_t i = 0;
+  while (i < tasks.size()) {
+    TcGroup g;
+    memset(&g, 0, 64);
+    int n = 0, tiles = 0;
+    for (; i < tasks.size() && n < TC_MAX_TASKS; ++i, ++n) {
+      const GTask& t = tasks[i];
+      if (t.K <= 0 || !t.a_b || !t.b_b) return fail(JPCB_EINVAL, "internal: tensor-core task without bf16 operands");
+      TcTask& s = g.t[n];
+      RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
+      RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, TC_BLOCK_N));
+      s.K = t.K;
+      s.tile_begin = tiles;
+      s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;
+      s.pad_ = 0;
+      s.e = t.e;
+      tiles += s.tiles_n * ((t.e.M + TC_BLOCK_M - 1) / TC_BLOCK_M);
+    }
+    g.ntasks = n;
+    g.total_tiles = tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    tc_grouped_gemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
+    CK(cudaGetLastError());
+  }
+  return JPCB_OK;
+}
+
+int ew_grid(size_t work_items, int per_block) {
+  size_t blocks = (work_items + per_block - 1) / per_block;
+  const size_t cap = (size_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one invocation: descriptor + caller buffers + carved workspace
+// ---------------------------------------------------------------------------------------------
+struct Run {
+  const jpcb_pc_desc* d;
+  const float* const* W;
+  const float* const* b;
+  const float* x;
+  const float* y;
+  Ws ws;
+  cudaStream_t st;
+  int L, Bl;
+  float invB;
+  bool tc;
+
+  int init(const jpcb_pc_desc* desc, const float* const* W_, const float* const* b_, const float* x_, const float* y_, void* wsp,
+           size_t ws_bytes, void* stream) {
+    RET(validate(desc));
+    d = desc; W = W_; b = b_; x = x_; y = y_;
+    st = reinterpret_cast<cudaStream_t>(stream);
+    L = d->n_layers; Bl = d->batch_local; invB = 1.f / (float)d->batch_global;
+    tc = d->dtype == JPCB_DTYPE_BF16;
+    if (!W || !x) return fail(JPCB_EINVAL, "null weight list or input");
+    if (d->has_bias && !b) return fail(JPCB_EINVAL, "has_bias set but no bias list");
+    carve(d, wsp, &ws);
+    if (!wsp || ws_bytes < ws.bytes) return fail(JPCB_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, ws_bytes);
+    return JPCB_OK;
+  }
+  const float* bias(int l) const { return d->has_bias ? b[l] : nullptr; }
+  float eskip(int l) const { return (d->skip[l] && l >= 1 && l <= L - 2) ? 1.f : 0.f; }  // energy-side skip (_energies.py:111-117)
+  int launch(const std::vector<GTask>& t) { return tc ? launch_tc(t, st) : launch_simt(t, st); }
+
+  int zero_red() { CK(cudaMemsetAsync(ws.red, 0, RED_FLOATS * sizeof(float), st)); return JPCB_OK; }
+
+  // ---- bf16 operand preparation ----
+  int prep_weights() {
+    if (!tc) return JPCB_OK;
+    for (int l = 0; l < L; ++l) {
+      const size_t n = (size_t)d->dims[l] * d->dims[l + 1];
+      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR);
+      if (l >= 1) {
+        const int R = d->dims[l + 1], C = d->dims[l];
+        const int tiles = ((R + 31) / 32) * ((C + 31) / 32);
+        transpose_to_bf16_kernel<float><<<ew_grid(tiles, 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C);
+      }
+    }
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+  // Hb[0] = bf16(act_0(x)); when `S` is given also Hdst[l] = bf16(act_l(S[l-1])) for l = 1..L-1
+  int prep_inputs(const float* const* S, std::vector<bf16*>& Hdst) {
+    if (!tc) return JPCB_OK;
+    const size_t n0 = (size_t)Bl * d->dims[0];
+    cast_act_bf16_kernel<<<ew_grid(n0 / 4 + 1, 256), 256, 0, st>>>(x, ws.Hb[0], n0, d->act[0]);
+    if (S)
+      for (int l = 1; l < L; ++l) {
+        const size_t n = (size_t)Bl * d->dims[l];
+        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], Hdst[l], n, d->act[l]);
+      }
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+
+  // ---- task builders ----
+  // forward GEMM of layer l on state S (u_l = x or S[l-1]); H = bf16 operand list for that state
+  void fwd_operands(GTask& t, int l, const float* const* S, const std::vector<bf16*>& H) const {
+    t.e.M = Bl; t.e.N = d->dims[l + 1]; t.K = d->dims[l];
+    t.a_p = l == 0 ? x : S[l - 1]; t.a_smn = d->dims[l]; t.a_sk = 1; t.a_act = d->act[l];
+    t.b_p = W[l]; t.b_smn = d->dims[l]; t.b_sk = 1;
+    t.a_b = l == 0 ? ws.Hb[0] : H[l]; t.b_b = ws.Wb[l];
+    t.e.alpha = d->scalings[l];
+    t.e.bias = bias(l);
+  }
+
+  // init_activities_with_ffwd (jpc/_core/_init.py:68-80); layer 0 also leaves the hoisted P1
+  int ffwd(float* const* A_out, float* loss_acc, bool keep_p1) {
+    for (int l = 0; l < L; ++l) {
+      GTask t;
+      fwd_operands(t, l, A_out, ws.Hb);
+      t.e.mode = EPI_FFWD;
+      t.e.skip = d->skip[l] ? 1.f : 0.f;  // the init honours any non-None skip (_init.py:69-78)
+      t.e.U = l == 0 ? x : A_out[l - 1];
+      t.e.O = A_out[l];
+      if (l == 0 && keep_p1) t.e.O2 = ws.P1;
+      if (tc && l + 1 < L) { t.e.Ob = ws.Hb[l + 1]; t.e.act = d->act[l + 1]; }
+      if (l == L - 1 && loss_acc && y) { t.e.red = loss_acc; t.e.Y = y; }
+      RET(launch({t}));
+    }
+    return JPCB_OK;
+  }
+
+  // hoisted layer-0 prediction P1 = a_0 (W_0 act_0(x) + b_0)  (constant during inference)
+  int predict_p1() {
+    GTask t;
+    fwd_operands(t, 0, nullptr, ws.Hb);
+    t.e.mode = EPI_FFWD;
+    t.e.O = ws.P1;
+    return launch({t});
+  }
+
+  // prediction errors err[l] for l in [lo, L) on state S; optional per-layer energy sums
+  int errors(int lo, const float* const* S, const std::vector<bf16*>& H, bool energy) {
+    std::vector<GTask> ts;
+    for (int l = lo; l < L; ++l) {
+      GTask t;
+      fwd_operands(t, l, S, H);
+      t.e.mode = EPI_ERR;
+      t.e.skip = eskip(l);
+      t.e.U = l == 0 ? x : S[l - 1];
+      t.e.T = l == L - 1 ? y : S[l];
+      t.e.escale = l == L - 1 ? d->output_energy_scaling : 1.f;
+      t.e.O = ws.err[l];
+      t.e.Ob = ws.Eb[l];
+      if (energy) t.e.red = ws.red + l;
+      ts.push_back(t);
+    }
+    return launch(ts);
+  }
+  // err[0] = S[0] - P1 without a GEMM (K = 0 task on the CUDA-core kernel), optional energy
+  int error0_from_p1(const float* const* S, bool energy) {
+    GTask t;
+    t.e.mode = EPI_ERR;
+    t.e.M = Bl; t.e.N = d->dims[1]; t.K = 0;
+    t.e.alpha = 0.f; t.e.skip = 1.f; t.e.U = ws.P1; t.e.T = S[0];
+    t.e.O = ws.err[0]; t.e.Ob = ws.Eb[0];
+    if (energy) t.e.red = ws.red + 0;
+    t.a_p = S[0]; t.b_p = S[0];  // never dereferenced (K == 0)
+    return launch_simt({t}, st);
+  }
+
+  // gradient/update of A[l-1], l = 1..L-1.  Z: state where act' is evaluated; p1_hoisted: err[0]
+  // is formed on the fly as Z[0] - P1.
+  int grads(int sub, float c, const float* const* Z, const float* const* Z0, float* const* Out, const std::vector<bf16*>& Hout,
+            bool p1_hoisted) {
+    std::vector<GTask> ts;
+    for (int l = 1; l < L; ++l) {
+      GTask t;
+      t.e.mode = EPI_GRAD; t.e.sub = sub; t.e.act = d->act[l];
+      t.e.M = Bl; t.e.N = d->dims[l]; t.K = d->dims[l + 1];
+      t.a_p = ws.err[l]; t.a_smn = d->dims[l + 1]; t.a_sk = 1;
+      t.b_p = W[l]; t.b_smn = 1; t.b_sk = d->dims[l];  // B(n,k) = W_l[k][n]
+      t.a_b = ws.Eb[l]; t.b_b = ws.WTb[l];
+      t.e.alpha = d->scalings[l];
+      t.e.skip = eskip(l);
+      t.e.En = ws.err[l]; t.e.Enb = ws.Eb[l];
+      t.e.Z = Z[l - 1];
+      if (l == 1 && p1_hoisted) t.e.P = ws.P1;
+      else { t.e.El = ws.err[l - 1]; t.e.Elb = ws.Eb[l - 1]; }
+      t.e.c = c; t.e.ad = d->activity_decay; t.e.gscale = 1.f;
+      t.e.O = Out[l - 1];
+      if (sub == GRAD_HEUN1 || sub == GRAD_HEUN2) t.e.G1 = ws.G1[l - 1];
+      if (sub == GRAD_HEUN2) t.e.Z0 = Z0[l - 1];
+      if (tc && sub != GRAD_OUT) t.e.Ob = Hout[l];
+      ts.push_back(t);
+    }
+    return launch(ts);
+  }
+
+  int scale_inplace(float* p, size_t n, float s) {
+    scale_kernel<<<ew_grid(n, 256), 256, 0, st>>>(p, p, n, s);
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+
+  // T fixed steps of Euler / Heun, in place on A (jpc/_core/_infer.py:109-132; diffrax Euler.step /
+  // Heun tableau).  Requires P1 and, on the tensor-core path, Hb[l] = act_l(A[l-1]).
+  int infer_loop(float* const* A) {
+    const int T = d->n_steps;
+    const size_t n_dummy = (size_t)Bl * d->dims[L];
+    for (int s = 0; s < T; ++s) {
+      const float h = s == T - 1 ? d->dt_last : d->dt;
+      const float c = h * invB;
+      if (d->solver == JPCB_SOLVER_EULER) {
+        RET(errors(1, A, ws.Hb, false));
+        RET(grads(GRAD_EULER, c, A, nullptr, A, ws.Hb, true));
+        if (d->activity_decay != 0.f) RET(scale_inplace(A[L - 1], n_dummy, 1.f - c * d->activity_decay));
+      } else {
+        std::vector<float*> zt(ws.Zt.begin(), ws.Zt.begin() + (L - 1));
+        zt.push_back(A[L - 1]);  // dummy slot is never read by the error tasks
+        RET(errors(1, A, ws.Hb, false));
+        RET(grads(GRAD_HEUN1, c, A, nullptr, zt.data(), ws.Htb, true));
+        RET(errors(1, zt.data(), ws.Htb, false));
+        RET(grads(GRAD_HEUN2, c, zt.data(), A, A, ws.Hb, true));
+        if (d->activity_decay != 0.f) {
+          const float q = c * d->activity_decay;
+          RET(scale_inplace(A[L - 1], n_dummy, 1.f - q + 0.5f * q * q));
+        }
+      }
+    }
+    return JPCB_OK;
+  }
+
+  // parameter gradients from err[] (already computed on state S) -- jpc/_core/_grads.py:487-499
+  int wgrads(const float* const* S, float* const* gW, float* const* gb) {
+    if (tc) {
+      for (int l = 0; l < L; ++l) {
+        const int dn = d->dims[l + 1], dk = d->dims[l];
+        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dn + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Eb[l], ws.EbT[l], Bl, dn);
+        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dk + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Hb[l], ws.HbT[l], Bl, dk);
+      }
+      CK(cudaGetLastError());
+    }
+    std::vector<GTask> ts;
+    for (int l = 0; l < L; ++l) {
+      GTask t;
+      t.e.mode = EPI_SCALE;
+      t.e.M = d->dims[l + 1]; t.e.N = d->dims[l]; t.K = Bl;
+      t.a_p = ws.err[l]; t.a_smn = 1; t.a_sk = d->dims[l + 1];
+      t.b_p = l == 0 ? x : S[l - 1]; t.b_smn = 1; t.b_sk = d->dims[l]; t.b_act = d->act[l];
+      t.a_b = ws.EbT[l]; t.b_b = ws.HbT[l];
+      t.e.alpha = -d->scalings[l] * invB;
+      t.e.O = gW[l];
+      ts.push_back(t);
+    }
+    RET(launch(ts));
+    if (d->has_bias) {
+      if (!gb) return fail(JPCB_EINVAL, "has_bias set but no bias-gradient list");
+      for (int l = 0; l < L; ++l) {
+        const int N = d->dims[l + 1];
+        const float sc = -d->scalings[l] * invB;
+        if (tc) colsum_kernel<bf16><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.Eb[l], gb[l], Bl, N, sc);
+        else colsum_kernel<float><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.err[l], gb[l], Bl, N, sc);
+      }
+      CK(cudaGetLastError());
+    }
+    return JPCB_OK;
+  }
+
+  int finalize(float* E_layers, float* F, bool with_sumsq, float* loss_out) {
+    finalize_kernel<<<1, 32, 0, st>>>(ws.red, L, invB, E_layers, F, with_sumsq ? ws.red + RED_SUMSQ : nullptr, d->activity_decay,
+                                      ws.red + RED_LOSS, loss_out);
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+  int sumsq_all(const float* const* A, float* out) {
+    for (int l = 0; l < L; ++l) {
+      const size_t n = (size_t)Bl * d->dims[l + 1];
+      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, st>>>(A[l], n, out);
+    }
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+};
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int jpcb_version(void) { return JPCB_VERSION; }
+const char* jpcb_last_error(void) { return g_err.c_str(); }
+
+size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc) {
+  if (validate(desc) != JPCB_OK) return 0;
+  Ws w;
+  carve(desc, nullptr, &w);
+  return w.bytes;
+}
+
+int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, float* const* A_out,
+                      const float* y, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!A_out) return fail(JPCB_EINVAL, "null activity list");
+  RET(r.zero_red());
+  RET(r.prep_weights());
+  RET(r.prep_inputs(nullptr, r.ws.Hb));
+  const bool want_loss = loss_out && y;
+  RET(r.ffwd(A_out, want_loss ? r.ws.red + RED_LOSS : nullptr, false));
+  if (want_loss) RET(r.finalize(nullptr, nullptr, false, loss_out));
+  return JPCB_OK;
+}
+
+int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A, const float* x,
+                   const float* y, float* E_layers, void* workspace, size_t workspace_bytes, void* stream) {
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!A || !y || !E_layers) return fail(JPCB_EINVAL, "null activities / target / output");
+  RET(r.zero_red());
+  RET(r.prep_weights());
+  RET(r.prep_inputs(A, r.ws.Hb));
+  RET(r.errors(0, A, r.ws.Hb, true));
+  return r.finalize(E_layers, nullptr, false, nullptr);
+}
+
+int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
+                          const float* x, const float* y, float* F, float* const* gA, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!A || !y || !gA) return fail(JPCB_EINVAL, "null activities / target / output");
+  RET(r.zero_red());
+  RET(r.prep_weights());
+  RET(r.prep_inputs(A, r.ws.Hb));
+  RET(r.errors(0, A, r.ws.Hb, true));
+  RET(r.grads(GRAD_OUT, r.invB, A, nullptr, gA, r.ws.Hb, false));
+  const size_t n_dummy = (size_t)r.Bl * desc->dims[r.L];
+  scale_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[r.L - 1], gA[r.L - 1], n_dummy, desc->activity_decay * r.invB);
+  CK(cudaGetLastError());
+  if (F) {
+    const bool ad = desc->activity_decay != 0.f;
+    if (ad) RET(r.sumsq_all(A, r.ws.red + RED_SUMSQ));
+    RET(r.finalize(nullptr, F, ad, nullptr));
+  }
+  return JPCB_OK;
+}
+
+int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, float* const* A, const float* x,
+                  const float* y, float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!A || !y) return fail(JPCB_EINVAL, "null activities / target");
+  RET(r.prep_weights());
+  RET(r.prep_inputs(A, r.ws.Hb));
+  RET(r.predict_p1());
+  RET(r.infer_loop(A));
+  if (sumsq_out) {
+    CK(cudaMemsetAsync(sumsq_out, 0, 2 * sizeof(float), r.st));
+    RET(r.sumsq_all(A, sumsq_out));
+    size_t numel = 0;
+    for (int l = 0; l < r.L; ++l) numel += (size_t)r.Bl * desc->dims[l + 1];
+    const float nf = (float)numel;
+    CK(cudaMemcpyAsync(sumsq_out + 1, &nf, sizeof(float), cudaMemcpyHostToDevice, r.st));
+  }
+  return JPCB_OK;
+}
+
+int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
+                        const float* x, const float* y, float* const* gW, float* const* gb, float* E_layers, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!A || !y || !gW) return fail(JPCB_EINVAL, "null activities / target / output");
+  RET(r.zero_red());
+  RET(r.prep_weights());
+  RET(r.prep_inputs(A, r.ws.Hb));
+  RET(r.errors(0, A, r.ws.Hb, E_layers != nullptr));
+  RET(r.wgrads(A, gW, gb));
+  if (E_layers) RET(r.finalize(E_layers, nullptr, false, nullptr));
+  return JPCB_OK;
+}
+
+int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, const float* y,
+                       float* const* A_out, float* loss_out, float* E_layers, float* const* gW, float* const* gb, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!A_out || !y || !gW) return fail(JPCB_EINVAL, "null activities / target / output");
+  RET(r.zero_red());
+  RET(r.prep_weights());
+  RET(r.prep_inputs(nullptr, r.ws.Hb));
+  RET(r.ffwd(A_out, r.ws.red + RED_LOSS, true));   // init + loss at the init + hoisted P1 + bf16 operands
+  RET(r.infer_loop(A_out));
+  RET(r.errors(1, A_out, r.ws.Hb, true));           // errors + layer energies at the solution
+  RET(r.error0_from_p1(A_out, true));
+  RET(r.wgrads(A_out, gW, gb));
+  return r.finalize(E_layers, nullptr, false, loss_out);
+}
+
+// ---- bPC ----
+size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc) { (void)desc; return 0; }
+int jpcb_bpc_energy(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
+                    const float* const*, const float*, const float*, float*, void*, size_t, void*) {
+  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
+}
+int jpcb_bpc_activity_grad(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
+                           const float* const*, const float*, const float*, float*, float* const*, void*, size_t, void*) {
+  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
+}
+int jpcb_bpc_infer(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
+                   float* const*, const float*, const float*, void*, size_t, void*) {
+  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
+}
+int jpcb_bpc_param_grads(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
+                         const float* const*, const float*, const float*, float* const*, float* const*, float* const*,
+                         float* const*, float*, void*, size_t, void*) {
+  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
+}
+
+}  // extern "C"

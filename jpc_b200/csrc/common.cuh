@@ -1,0 +1,284 @@
+// common.cuh -- device-side vocabulary shared by the fp32 CUDA-core kernels (simt_gemm.cu) and the
+// tcgen05 tensor-core kernels (tc_gemm.cu): activation functions with the reference's (jax.nn)
+// conventions, the fused-epilogue descriptor, and the epilogue itself.
+//
+// Every GEMM on the PC hot path is  D[M,N] = A[M,K] * B[N,K]^T  followed by ONE of four fused
+// epilogues (reference math in jpc/_core/_energies.py:103-126 and its
+// reverse-mode derivative jpc/_core/_grads.py:79-91,487-499):
+//   FFWD  z_out = a (D + b) + s u                        (feed-forward init, _init.py:68-80)
+//   ERR   e     = lam (T - a (D + b) - s u),  E += lam/2 (..)^2   (prediction errors + layer energy)
+//   GRAD  g     = Gin + w (e_l - act'(z) (a D) - s e_next) + ad z ; then Euler/Heun update of z
+//   SCALE out   = a D                                    (weight gradients, K = batch)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jpcb {
+
+enum : int { ACT_LINEAR = 0, ACT_TANH, ACT_HARD_TANH, ACT_RELU, ACT_LEAKY_RELU, ACT_GELU, ACT_SELU, ACT_SILU };
+enum : int { EPI_FFWD = 0, EPI_ERR = 1, EPI_GRAD = 2, EPI_SCALE = 3 };
+enum : int { GRAD_OUT = 0, GRAD_EULER = 1, GRAD_HEUN1 = 2, GRAD_HEUN2 = 3 };
+
+#define JPCB_SELU_ALPHA 1.6732632423543772848170429916717f
+#define JPCB_SELU_SCALE 1.0507009873554804934193349852946f
+
+// FAST=false: accurate libm-grade fp32 (1e-5 parity path).  FAST=true: MUFU approximations
+// (tanh.approx / ex2.approx) for the bf16 tensor-core path, whose operands are rounded to 8 bits anyway.
+template <bool FAST>
+__device__ __forceinline__ float tanh_f(float x) {
+  if constexpr (FAST) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  } else {
+    return tanhf(x);
+  }
+}
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_f(float x) {
+  if constexpr (FAST) return __fdividef(1.f, 1.f + __expf(-x));
+  else return 1.f / (1.f + expf(-x));
+}
+
+// act(x) and act'(x); conventions at kinks follow jax.nn.
+template <bool FAST>
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case ACT_LINEAR: return x;
+    case ACT_TANH: return tanh_f<FAST>(x);
+    case ACT_HARD_TANH: return x > 1.f ? 1.f : (x < -1.f ? -1.f : x);
+    case ACT_RELU: return x > 0.f ? x : 0.f;
+    case ACT_LEAKY_RELU: return x >= 0.f ? x : 0.01f * x;
+    case ACT_GELU: {
+      const float c = 0.7978845608028654f;
+      float u = c * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.f + tanh_f<FAST>(u));
+    }
+    case ACT_SELU: return JPCB_SELU_SCALE * (x > 0.f ? x : JPCB_SELU_ALPHA * (FAST ? (__expf(x) - 1.f) : expm1f(x)));
+    case ACT_SILU: return x * sigmoid_f<FAST>(x);
+  }
+  return x;
+}
+template <bool FAST>
+__device__ __forceinline__ float act_bwd(int act, float x) {
+  switch (act) {
+    case ACT_LINEAR: return 1.f;
+    case ACT_TANH: { float t = tanh_f<FAST>(x); return 1.f - t * t; }
+    case ACT_HARD_TANH: return (x > 1.f || x < -1.f) ? 0.f : 1.f;
+    case ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case ACT_LEAKY_RELU: return x >= 0.f ? 1.f : 0.01f;
+    case ACT_GELU: {
+      const float c = 0.7978845608028654f;
+      float x2 = x * x;
+      float t = tanh_f<FAST>(c * (x + 0.044715f * x * x2));
+      return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * c * (1.f + 3.f * 0.044715f * x2);
+    }
+    case ACT_SELU: return JPCB_SELU_SCALE * (x > 0.f ? 1.f : JPCB_SELU_ALPHA * (FAST ? __expf(x) : expf(x)));
+    case ACT_SILU: { float s = sigmoid_f<FAST>(x); return s * (1.f + x * (1.f - s)); }
+  }
+  return 1.f;
+}
+
+// Fused-epilogue descriptor: plain data, passed to kernels by value inside the grouped-launch
+// parameter block.  All [M,N] tensors are dense row-major with row pitch N.
+struct Epi {
+  int mode;   // EPI_*
+  int sub;    // GRAD_* when mode == EPI_GRAD
+  int act;    // activation id: act'(z) in GRAD, act(out) for the bf16 operand copy `Ob`
+  int M, N;
+  int accum;  // SCALE: out += a*D instead of =
+  float alpha;   // layer scaling a_l (SCALE: -(a_l/B))
+  float skip;    // s_l (0 or 1)
+  float escale;  // ERR: lam (output_energy_scaling on the output layer, else 1)
+  float c;       // GRAD: OUT -> multiplier of g (1/B); EULER/HEUN -> dt/B
+  float ad;      // GRAD: activity_decay
+  float gscale;  // GRAD: weight w of this term (bPC alpha_f / alpha_b; 1 for PC)
+  const float* bias;           // [N] or null
+  const float* T;              // ERR: target
+  const float* U;              // FFWD/ERR: skip input
+  const float* Z;              // GRAD: state at which act' is evaluated (z, or Heun stage state)
+  const float* Z0;             // GRAD_HEUN2: state at the start of the step
+  const float* El;             // GRAD: e_l fp32, or
+  const __nv_bfloat16* Elb;    //       e_l bf16, or (both null)
+  const float* P;              //       e_l = Z - P  (hoisted layer-0 prediction, or clamped-side target)
+  const float* En;             // GRAD: e_{l+1} for the skip term (fp32) or
+  const __nv_bfloat16* Enb;    //       bf16
+  const float* Gin;            // GRAD: partial gradient to add (bPC second direction) or null
+  float* G1;                   // GRAD_HEUN1: out g1;  GRAD_HEUN2: in g1
+  float* O;                    // fp32 out (z_out / e / g / scaled D)
+  float* O2;                   // FFWD: optional second fp32 copy
+  __nv_bfloat16* Ob;           // bf16 out: act(z_out) (FFWD / GRAD updates) or e (ERR)
+  float* red;                  // ERR: energy accumulator; FFWD: loss accumulator (needs Y)
+  const float* Y;              // FFWD: loss target
+};
+
+__device__ __forceinline__ void ld4(const float* __restrict__ p, size_t idx, int nvalid, bool vec, float (&v)[4]) {
+  if (vec) {
+    float4 t = *reinterpret_cast<const float4*>(p + idx);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = j < nvalid ? p[idx + j] : 0.f;
+  }
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* __restrict__ p, size_t idx, int nvalid, bool vec, float (&v)[4]) {
+  if (vec) {
+    uint2 t = *reinterpret_cast<const uint2*>(p + idx);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = j < nvalid ? __bfloat162float(p[idx + j]) : 0.f;
+  }
+}
+__device__ __forceinline__ void st4(float* __restrict__ p, size_t idx, int nvalid, bool vec, const float (&v)[4]) {
+  if (vec) {
+    *reinterpret_cast<float4*>(p + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j < nvalid) p[idx + j] = v[j];
+  }
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, size_t idx, int nvalid, bool vec, const float (&v)[4]) {
+  if (vec) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p + idx) = t;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j < nvalid) p[idx + j] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+// Applies the fused epilogue to 4 horizontally adjacent accumulator values D[row, col..col+3].
+// `nvalid` (1..4) columns are inside the matrix; `vec` says 16-byte vector access is legal
+// (N % 4 == 0 and nvalid == 4).  Returns this thread's contribution to the reduction (`red`).
+template <bool FAST>
+__device__ __forceinline__ float epi_apply4(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec) {
+  const size_t idx = (size_t)row * (size_t)e.N + (size_t)col;
+  float r = 0.f;
+  float out[4];
+  if (e.mode == EPI_SCALE) {
+    if (e.accum) {
+      float o[4];
+      ld4(e.O, idx, nvalid, vec, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[j] = o[j] + e.alpha * acc[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[j] = e.alpha * acc[j];
+    }
+    st4(e.O, idx, nvalid, vec, out);
+    return 0.f;
+  }
+  if (e.mode == EPI_FFWD || e.mode == EPI_ERR) {
+    float pred[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float bj = (e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f;
+      pred[j] = e.alpha * (acc[j] + bj);
+    }
+    if (e.skip != 0.f) {
+      float u[4];
+      ld4(e.U, idx, nvalid, vec, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pred[j] += e.skip * u[j];
+    }
+    if (e.mode == EPI_FFWD) {
+      st4(e.O, idx, nvalid, vec, pred);
+      if (e.O2) st4(e.O2, idx, nvalid, vec, pred);
+      if (e.Ob) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = act_fwd<FAST>(e.act, pred[j]);
+        st4(e.Ob, idx, nvalid, vec, out);
+      }
+      if (e.red) {
+        float y[4];
+        ld4(e.Y, idx, nvalid, vec, y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nvalid) { float d = y[j] - pred[j]; r += 0.5f * d * d; }
+      }
+      return r;
+    }
+    float t[4];
+    ld4(e.T, idx, nvalid, vec, t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d = j < nvalid ? t[j] - pred[j] : 0.f;
+      r += 0.5f * e.escale * d * d;
+      out[j] = e.escale * d;
+    }
+    if (e.O) st4(e.O, idx, nvalid, vec, out);
+    if (e.Ob) st4(e.Ob, idx, nvalid, vec, out);
+    return e.red ? r : 0.f;
+  }
+  // ---- EPI_GRAD ----
+  float z[4], el[4], g[4];
+  ld4(e.Z, idx, nvalid, vec, z);
+  if (e.El) ld4(e.El, idx, nvalid, vec, el);
+  else if (e.Elb) ld4(e.Elb, idx, nvalid, vec, el);
+  else {
+    float p[4];
+    ld4(e.P, idx, nvalid, vec, p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) el[j] = z[j] - p[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) g[j] = el[j] - act_bwd<FAST>(e.act, z[j]) * (e.alpha * acc[j]);
+  if (e.skip != 0.f) {
+    float en[4];
+    if (e.En) ld4(e.En, idx, nvalid, vec, en);
+    else ld4(e.Enb, idx, nvalid, vec, en);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] -= e.skip * en[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) g[j] = e.gscale * g[j] + e.ad * z[j];
+  if (e.Gin) {
+    float gi[4];
+    ld4(e.Gin, idx, nvalid, vec, gi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] += gi[j];
+  }
+  if (e.sub == GRAD_OUT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = e.c * g[j];
+    st4(e.O, idx, nvalid, vec, out);
+    return 0.f;
+  }
+  if (e.sub == GRAD_EULER) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = z[j] - e.c * g[j];
+  } else if (e.sub == GRAD_HEUN1) {
+    st4(e.G1, idx, nvalid, vec, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = z[j] - e.c * g[j];
+  } else {  // GRAD_HEUN2
+    float z0[4], g1[4];
+    ld4(e.Z0, idx, nvalid, vec, z0);
+    ld4(e.G1, idx, nvalid, vec, g1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = z0[j] - 0.5f * e.c * (g1[j] + g[j]);
+  }
+  st4(e.O, idx, nvalid, vec, out);
+  if (e.Ob) {
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = act_fwd<FAST>(e.act, out[j]);
+    st4(e.Ob, idx, nvalid, vec, h);
+  }
+  return 0.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace jpcb

@@ -1,0 +1,117 @@
+// elementwise.cuh -- the small HBM-bound kernels around the GEMMs: bf16 operand casts (with the
+// activation fused), bf16 transposes for the weight-gradient GEMMs, bias-gradient column sums,
+// sum-of-squares reductions, and the energy finaliser.  All are grid-stride, 16-byte vectorised
+// where the layout allows, and sized as a multiple of the SM count by the host.
+#pragma once
+#include "common.cuh"
+
+namespace jpcb {
+
+// dst[i] = bf16(act(src[i]))
+__global__ void cast_act_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n, int act) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    float v[4];
+    const int nv = (int)min((size_t)4, n - i);
+    ld4(src, i, nv, nv == 4, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = act_fwd<true>(act, v[j]);
+    st4(dst, i, nv, nv == 4, v);
+  }
+}
+
+// dst[c][r] = bf16(src[r][c]); src is [R, C] row-major (fp32 or bf16), dst [C, R] row-major.
+template <typename TIn>
+__global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {
+  __shared__ float tile[32][33];
+  const int tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      float v = 0.f;
+      if (r < R && c < C) {
+        if constexpr (sizeof(TIn) == 2) v = __bfloat162float(src[(size_t)r * C + c]);
+        else v = src[(size_t)r * C + c];
+      }
+      tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) dst[(size_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+    __syncthreads();
+  }
+}
+
+// out[n] = scale * sum_m E[m, n]   (bias gradients, jpc/_core/_grads.py:487-499 closed form)
+template <typename TIn>
+__global__ void colsum_kernel(const TIn* __restrict__ E, float* __restrict__ out, int M, int N, float scale) {
+  // block (32, 8): 32 adjacent columns, 8 row-lanes
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < N) {
+    for (int m = threadIdx.y; m < M; m += 8) {
+      if constexpr (sizeof(TIn) == 2) s += __bfloat162float(E[(size_t)m * N + c]);
+      else s += E[(size_t)m * N + c];
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i][threadIdx.x];
+    out[c] = scale * tot;
+  }
+}
+
+// *out += sum p[i]^2
+__global__ void sumsq_kernel(const float* __restrict__ p, size_t n, float* __restrict__ out) {
+  __shared__ float red_s[32];
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = p[i];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red_s[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// dst[i] = s * src[i]  (dst may alias src)
+__global__ void scale_kernel(const float* src, float* dst, size_t n, float s) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = s * src[i];
+}
+
+// Turns raw per-layer sums acc[l] = lam/2 * sum err_l^2 into the reference's outputs:
+//   E_layers (order [output, hidden 1..L-2, first], each / B)   jpc/_core/_energies.py:155-156
+//   F = sum(acc)/B + ad/(2B) * sumsq                             jpc/_core/_energies.py:145-153
+//   loss = acc_loss / B                                          jpc/_utils.py:129-130
+__global__ void finalize_kernel(const float* __restrict__ acc, int L, float inv_b, float* E_layers, float* F,
+                                const float* sumsq, float ad, const float* loss_acc, float* loss_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (E_layers) {
+      E_layers[0] = acc[L - 1] * inv_b;
+      for (int k = 1; k <= L - 2; ++k) E_layers[k] = acc[k] * inv_b;
+      E_layers[L - 1] = acc[0] * inv_b;
+    }
+    if (F) {
+      float tot = 0.f;
+      for (int l = 0; l < L; ++l) tot += acc[l];
+      tot *= inv_b;
+      if (sumsq) tot += 0.5f * ad * inv_b * sumsq[0];
+      *F = tot;
+    }
+    if (loss_out) *loss_out = loss_acc[0] * inv_b;
+  }
+}
+
+}  // namespace jpcb

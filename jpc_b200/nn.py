@@ -1,0 +1,223 @@
+"""Minimal model containers with the duck-typed protocol the reference relies on
+(`len(model)`, `model[l]`, `model[l].layers[1].weight`, `model[0][1].weight`;
+jpc/_core/_energies.py:915-923) plus `make_mlp` / `make_skip_model` / `get_act_fn`
+(jpc/_utils.py:13-126).  Weights are torch tensors on the CUDA device; the containers only HOLD
+parameters -- all hot-path arithmetic happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from ._errors import _check_param_type
+
+_ACT_FNS = ["linear", "tanh", "hard_tanh", "relu", "leaky_relu", "gelu", "selu", "silu"]
+
+
+class Identity:
+    """equinox.nn.Identity stand-in."""
+    name = "linear"
+
+    def __call__(self, x, *, key=None):
+        return x
+
+    def __repr__(self):
+        return "Identity()"
+
+
+class Activation:
+    """A named activation (one of the 8 ids of jpc/_utils.py:13-15).  Calling it evaluates the
+    function with torch ops (for user-side evaluation code); the CUDA kernels use the id."""
+
+    def __init__(self, name: str):
+        if name not in _ACT_FNS:
+            raise ValueError(f"""
+                Invalid activation function ID. Options are {_ACT_FNS}.
+        """)
+        self.name = name
+
+    def __call__(self, x, *, key=None):
+        n = self.name
+        if n == "linear":
+            return x
+        if n == "tanh":
+            return torch.tanh(x)
+        if n == "hard_tanh":
+            return torch.clamp(x, -1.0, 1.0)
+        if n == "relu":
+            return torch.relu(x)
+        if n == "leaky_relu":
+            return torch.where(x >= 0, x, 0.01 * x)
+        if n == "gelu":
+            return torch.nn.functional.gelu(x, approximate="tanh")
+        if n == "selu":
+            return torch.selu(x)
+        return x * torch.sigmoid(x)
+
+    def __repr__(self):
+        return f"Activation({self.name!r})"
+
+
+def get_act_fn(name: str) -> Callable:
+    """jpc/_utils.py:18-38."""
+    if name == "linear":
+        return Identity()
+    return Activation(name)
+
+
+class Lambda:
+    """equinox.nn.Lambda stand-in: wraps a callable, no parameters."""
+
+    def __init__(self, fn: Callable):
+        self.fn = fn
+
+    def __call__(self, x, *, key=None):
+        return self.fn(x)
+
+    def __repr__(self):
+        return f"Lambda({self.fn!r})"
+
+
+class Linear:
+    """equinox.nn.Linear stand-in: weight [out, in], optional bias [out]; y = W x + b.
+    Default init U(-1/sqrt(in), 1/sqrt(in)) for both, as equinox does."""
+
+    def __init__(self, in_features: int, out_features: int, use_bias: bool = True, *, key=None,
+                 device=None, dtype=torch.float32):
+        gen = _as_generator(key)
+        lim = 1.0 / math.sqrt(in_features)
+        w = (torch.rand(out_features, in_features, generator=gen, dtype=torch.float64) * 2 - 1) * lim
+        self.weight = w.to(dtype).to(device or _default_device())
+        self.bias = None
+        if use_bias:
+            b = (torch.rand(out_features, generator=gen, dtype=torch.float64) * 2 - 1) * lim
+            self.bias = b.to(dtype).to(device or _default_device())
+        self.in_features, self.out_features, self.use_bias = in_features, out_features, use_bias
+
+    def __call__(self, x, *, key=None):
+        y = x @ self.weight.T
+        return y if self.bias is None else y + self.bias
+
+    def __repr__(self):
+        return f"Linear({self.in_features}, {self.out_features}, use_bias={self.use_bias})"
+
+
+class Sequential:
+    """equinox.nn.Sequential stand-in."""
+
+    def __init__(self, layers: Sequence):
+        self.layers = tuple(layers)
+
+    def __getitem__(self, i):
+        return self.layers[i]
+
+    def __len__(self):
+        return len(self.layers)
+
+    def __iter__(self):
+        return iter(self.layers)
+
+    def __call__(self, x, *, key=None):
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+    def __repr__(self):
+        return f"Sequential({list(self.layers)!r})"
+
+
+def _default_device():
+    return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+
+
+def _as_generator(key) -> Optional[torch.Generator]:
+    """`key` plays the role of a jax PRNGKey: an int seed, a torch.Generator, or None."""
+    if key is None:
+        return None
+    if isinstance(key, torch.Generator):
+        return key
+    return torch.Generator().manual_seed(int(key))
+
+
+def make_mlp(key, input_dim: int, width: int, depth: int, output_dim: int, act_fn: str,
+             use_bias: bool = False, param_type: str = "sp", *, device=None) -> List[Sequential]:
+    """jpc/_utils.py:41-108: layer i = Sequential([Lambda(act_i), Linear]), act_0 = Identity,
+    i.e. f_l(z) = W_l act(z) + b_l.  `mupc` re-draws the weights from N(0,1)."""
+    _check_param_type(param_type)
+    gen = _as_generator(key)
+    layers = []
+    for i in range(depth):
+        act_fn_l = Identity() if i == 0 else get_act_fn(act_fn)
+        _in = input_dim if i == 0 else width
+        _out = output_dim if (i + 1) == depth else width
+        linear = Linear(_in, _out, use_bias=use_bias, key=gen, device=device)
+        if param_type == "mupc":
+            W = torch.randn(_out, _in, generator=gen, dtype=torch.float64)
+            linear.weight = W.to(linear.weight.dtype).to(linear.weight.device)
+        layers.append(Sequential([Lambda(act_fn_l), linear]))
+    return layers
+
+
+def make_skip_model(depth: int) -> list:
+    """jpc/_utils.py:111-126: identity skips at layers 1..depth-2, None elsewhere."""
+    skips = [None] * depth
+    for l in range(1, depth - 1):
+        skips[l] = Lambda(Identity())
+    return skips
+
+
+# ---------------------------------------------------------------------------------------------
+# tiny pytree utilities (equinox/jax.tree_util stand-ins for the structures above)
+# ---------------------------------------------------------------------------------------------
+def tree_leaves(tree) -> list:
+    """Array leaves (torch tensors) in a deterministic order."""
+    out = []
+    if tree is None:
+        return out
+    if torch.is_tensor(tree):
+        return [tree]
+    if isinstance(tree, (list, tuple)):
+        for t in tree:
+            out.extend(tree_leaves(t))
+    elif isinstance(tree, Sequential):
+        for t in tree.layers:
+            out.extend(tree_leaves(t))
+    elif isinstance(tree, Linear):
+        out.append(tree.weight)
+        if tree.bias is not None:
+            out.append(tree.bias)
+    elif isinstance(tree, dict):
+        for k in sorted(tree):
+            out.extend(tree_leaves(tree[k]))
+    return out
+
+
+def tree_unflatten_like(tree, leaves: list):
+    """Rebuilds `tree`'s structure around new leaves (consumed front to back)."""
+    if tree is None:
+        return None
+    if torch.is_tensor(tree):
+        return leaves.pop(0)
+    if isinstance(tree, list):
+        return [tree_unflatten_like(t, leaves) for t in tree]
+    if isinstance(tree, tuple):
+        return tuple(tree_unflatten_like(t, leaves) for t in tree)
+    if isinstance(tree, Sequential):
+        return Sequential([tree_unflatten_like(t, leaves) for t in tree.layers])
+    if isinstance(tree, Linear):
+        new = Linear.__new__(Linear)
+        new.__dict__.update(tree.__dict__)
+        new.weight = leaves.pop(0)
+        new.bias = leaves.pop(0) if tree.bias is not None else None
+        return new
+    if isinstance(tree, dict):
+        return {k: tree_unflatten_like(tree[k], leaves) for k in sorted(tree)}
+    return tree  # Lambda / Identity / Activation: no leaves
+
+
+def tree_map(fn, tree, *rest):
+    cols = [tree_leaves(tree)] + [tree_leaves(r) for r in rest]
+    new = [fn(*xs) for xs in zip(*cols)]
+    return tree_unflatten_like(tree, new)
