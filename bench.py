@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- PC train samples/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+A "step" is one predictive-coding train step of the workload: feed-forward init, loss at the init,
+T fixed-step inference iterations, per-layer energies at the solution, parameter gradients (and,
+at N > 1, ONE NCCL all-reduce of the flat gradient/energy/loss buffer).  The optimiser update is
+host-framework work outside the kernels, as in the reference (jpc/_train.py:234-242); it is
+included in the `e2e` number, which goes through the public `jpc_b200.make_pc_step` API from
+pinned HOST buffers.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c1|c2|c3] [--impl reference]
+
+Launched under torchrun for N > 1 (one rank per GPU, NCCL).  Weak scaling: every rank holds the
+workload's full batch; the energy normalisation uses the GLOBAL batch.
+`--impl reference` times the CPU restatement of the reference (oracle/, torch-CPU autograd of the
+restated energy -- JAX is not installable in this image) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name -> (d_in, width, depth, d_out, act, use_bias, param_type, skips, B, solver, max_t1, dt, dtype)
+WORKLOADS = {
+    "c1": dict(d_in=784, width=300, depth=3, d_out=10, act="tanh", bias=False, ptype="sp", skips=False, B=64,
+               solver="euler", max_t1=10.0, dt=0.5, dtype="f32",
+               desc="discriminative MLP 784-300-300-10 tanh, batch 64, 20 Euler steps, fp32"),
+    "c2": dict(d_in=10, width=256, depth=3, d_out=784, act="relu", bias=True, ptype="sp", skips=False, B=256,
+               solver="heun", max_t1=25.0, dt=0.5, dtype="f32",
+               desc="supervised generative PC MLP 10-256-256-784, batch 256, 50 Heun steps, fp32"),
+    "c3": dict(d_in=784, width=128, depth=128, d_out=10, act="relu", bias=False, ptype="mupc", skips=True, B=128,
+               solver="euler", max_t1=10.0, dt=0.5, dtype="f32",
+               desc="muPC deep residual MLP width 128 depth 128, batch 128, 20 Euler steps, fp32"),
+    "c4": dict(d_in=2048, width=2048, depth=8, d_out=2048, act="tanh", bias=False, ptype="sp", skips=False, B=4096,
+               solver="euler", max_t1=10.0, dt=0.5, dtype="bf16",
+               desc="wide MLP width 2048 depth 8 (2048-in, 2048-out), batch 4096 per GPU, bf16 operands / fp32 "
+                    "accumulate+master, 20 Euler steps"),
+}
+METRIC = "PC train samples/sec (T inference iters)"
+UNIT = "samples/s"
+
+
+def n_steps(w):
+    import math
+    return max(1, int(math.ceil(w["max_t1"] / w["dt"] - 1e-6)))
+
+
+def flops_per_step(w):
+    """SURVEY Appendix D closed-form schedule (layer-0 prediction hoisted): g_l = 2 B d_l d_{l+1}."""
+    dims = [w["d_in"]] + [w["width"]] * (w["depth"] - 1) + [w["d_out"]]
+    g = [2.0 * w["B"] * dims[l] * dims[l + 1] for l in range(w["depth"])]
+    evals = n_steps(w) * (2 if w["solver"] == "heun" else 1)
+    per_eval = 2 * sum(g[1:])
+    return {"init": sum(g), "per_eval": per_eval, "inference": evals * per_eval, "energy": sum(g[1:]),
+            "wgrad": sum(g), "total": 2 * sum(g) + evals * per_eval + sum(g[1:]), "evals": evals}
+
+
+def make_inputs(w, seed_w=0, seed_d=1):
+    """SURVEY 8d synthetic inputs: weights seed 0 (U(+-1/sqrt(in)); N(0,1) for mupc), data seed 1 (input side
+    N(0,1), target side one-hot).  Plain dicts {"W","b","act"} in fp32 on the host; no oracle code involved."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed_w)
+    layers = []
+    for i in range(w["depth"]):
+        _in = w["d_in"] if i == 0 else w["width"]
+        _out = w["d_out"] if i + 1 == w["depth"] else w["width"]
+        lim = 1.0 / math.sqrt(_in)
+        W = (torch.rand(_out, _in, generator=g, dtype=torch.float32) * 2 - 1) * lim
+        b = (torch.rand(_out, generator=g, dtype=torch.float32) * 2 - 1) * lim if w["bias"] else None
+        if w["ptype"] == "mupc":
+            W = torch.randn(_out, _in, generator=g, dtype=torch.float32)
+        layers.append({"W": W, "b": b, "act": "linear" if i == 0 else w["act"]})
+    g = torch.Generator().manual_seed(seed_d)
+    x = torch.randn(w["B"], w["d_in"], generator=g, dtype=torch.float32)
+    idx = torch.randint(0, w["d_out"], (w["B"],), generator=g)
+    y = torch.nn.functional.one_hot(idx, w["d_out"]).to(torch.float32)
+    return layers, x, y
+
+
+def to_device_model(layers, device):
+    """host layer dicts -> jpc_b200.nn model (Sequential([Lambda(act), Linear]) per layer) on `device`."""
+    from jpc_b200 import nn
+    out = []
+    for layer in layers:
+        lin = nn.Linear.__new__(nn.Linear)
+        lin.weight = layer["W"].contiguous().to(device)
+        lin.bias = None if layer["b"] is None else layer["b"].contiguous().to(device)
+        lin.out_features, lin.in_features = layer["W"].shape
+        lin.use_bias = layer["b"] is not None
+        out.append(nn.Sequential([nn.Lambda(nn.get_act_fn(layer["act"])), lin]))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step_fn(w, sample_rows):
+    """The reference's own algorithm on the host cores: restated energy + reverse-mode AD + fixed-step
+    loop (oracle.pc_train_step), fp32, on `sample_rows` rows of the workload."""
+    import torch
+    from oracle import pc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    om, x, y = make_inputs(w)
+    x, y = x[:sample_rows].contiguous(), y[:sample_rows].contiguous()
+    skips = O.make_skip_model(w["depth"]) if w["skips"] else None
+
+    def step():
+        return O.pc_train_step(om, skips, x, y, solver=w["solver"], max_t1=w["max_t1"], dt=w["dt"], param_type=w["ptype"])
+    return step
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    rows = min(w["B"], args.cpu_rows)
+    step = cpu_reference_step_fn(w, rows)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = rows * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{rows} of {w['B']} rows of the workload per step, fp32, torch-CPU autograd restatement of jpc.make_pc_step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "rows_per_step": rows},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-rows", type=int, default=256, help="rows per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: jpc_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import jpc_b200 as J
+    from jpc_b200 import _lib
+    from jpc_b200._core import _Net, _solver_id, _time_grid
+    from jpc_b200._train import _Arena
+
+    J.set_compute_dtype(w["dtype"])
+    om, x_h, y_h = make_inputs(w, seed_d=1 + rank)
+    gm = to_device_model(om, dev)
+    gsk = J.make_skip_model(w["depth"]) if w["skips"] else None
+    x_pin, y_pin = x_h.pin_memory(), y_h.pin_memory()
+    x, y = x_pin.to(dev), y_pin.to(dev)
+    solver = J.Euler() if w["solver"] == "euler" else J.Heun()
+    T, h, hl = _time_grid(w["max_t1"], w["dt"])
+    B_global = w["B"] * world
+
+    def mknet(n_steps_):
+        return _Net(gm, gsk, x, y, param_type=w["ptype"], loss_id="mse", gamma=None, output_energy_scaling=None,
+                    activity_decay=0.0, weight_decay=0.0, spectral_penalty=0.0, solver=_solver_id(solver),
+                    n_steps=n_steps_, dt=h, dt_last=hl, batch_global=B_global)
+    net = mknet(T)
+    arena = _Arena(net)
+    acts = net.new_acts()
+    ws = net.workspace()
+    stream = net.stream()
+    A_ptrs, gW_ptrs = _lib.ptr_array(acts), _lib.ptr_array(arena.gW)
+    gb_ptrs = _lib.ptr_array(arena.gb) if arena.gb else None
+
+    def step():
+        _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(x), _lib.ptr(y), A_ptrs, _lib.ptr(arena.loss),
+                                               _lib.ptr(arena.E), gW_ptrs, gb_ptrs, _lib.ptr(ws), ws.numel(), stream))
+        if world > 1:
+            dist.all_reduce(arena.flat, op=dist.ReduceOp.SUM)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib.jpcb_launch_count()
+    ms = timed(step, args.steps)
+    launches = _lib.lib.jpcb_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = B_global * args.steps / (ms * 1e-3)
+    loss_val = float(arena.loss)
+
+    # ---- end to end through the public API, inputs from pinned host memory every step ----
+    opt = J.optim.sgd(1e-3 * w["B"])
+    st = opt.init((gm, gsk))
+    model, skipm = gm, gsk
+
+    def e2e_step():
+        nonlocal model, skipm, st
+        xd = x_pin.to(dev, non_blocking=True)
+        yd = y_pin.to(dev, non_blocking=True)
+        out = J.make_pc_step(model, opt, st, yd, input=xd, param_type=w["ptype"], ode_solver=solver, max_t1=w["max_t1"],
+                             dt=w["dt"], stepsize_controller=J.ConstantStepSize(), skip_model=skipm)
+        model, skipm, st = out["model"], out["skip_model"], out["opt_state"]
+        return float(out["loss"])  # device -> host read of the step's result
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+    e2e_val = B_global * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (grouped GEMM of one inference phase) ----
+    fl = flops_per_step(w)
+    roof = None
+    if rank == 0:
+        net0 = mknet(0)
+        reps = max(3, args.steps // 2)
+
+        def infer(nobj):
+            _lib.check(_lib.lib.jpcb_pc_infer(nobj.desc, nobj.W, nobj.b, A_ptrs, _lib.ptr(x), _lib.ptr(y), None,
+                                              _lib.ptr(ws), ws.numel(), stream))
+        for nobj in (net, net0):
+            infer(nobj)
+        torch.cuda.synchronize()
+
+        def ev(nobj):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                infer(nobj)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        ms_T, ms_0 = ev(net), ev(net0)
+        n_launch = 2 * fl["evals"]
+        per_launch_ms = (ms_T - ms_0) / n_launch
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if w["dtype"] == "bf16":
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            src = "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PF sustained"
+            ach = fl["per_eval"] / 2 / (per_launch_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "kernel": "tc_grouped_gemm (one inference phase = all layers' GEMMs + fused epilogue)",
+                    "launch_ms": per_launch_ms, "flops_per_launch": fl["per_eval"] / 2, "peak_source": src,
+                    "peak_burst": peaks.get("bf16_tflops"),
+                    "whole_step_tflops": fl["total"] / (ms / args.steps * 1e-3) / 1e12}
+        else:
+            # narrow fp32 configs: latency-bound; report algorithmic HBM bytes of one phase launch
+            dims = [w["d_in"]] + [w["width"]] * (w["depth"] - 1) + [w["d_out"]]
+            wbytes = 4 * sum(dims[l] * dims[l + 1] for l in range(1, w["depth"]))
+            abytes = 4 * w["B"] * sum(dims[1:]) * 2
+            peak = peaks.get("hbm_gbs", 6650.0)
+            ach = (wbytes + abytes) / (per_launch_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "kernel": "simt_grouped_gemm (one inference phase)", "launch_ms": per_launch_ms,
+                    "bytes_per_launch": wbytes + abytes,
+                    "whole_step_tflops": fl["total"] / (ms / args.steps * 1e-3) / 1e12}
+
+    # ---- CPU baseline (rank 0, N == 1 only): the oracle timed on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = min(w["B"], args.cpu_rows)
+        cstep = cpu_reference_step_fn(w, rows)
+        cstep()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            cstep()
+            reps += 1
+        cdt = time.perf_counter() - t0
+        cpu = {"value": rows * reps / cdt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{reps} steps of {rows} of {w['B']} rows, fp32 torch-CPU autograd restatement of jpc.make_pc_step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["desc"], "global_batch": B_global, "inference_steps": T, "solver": w["solver"],
+                       "parallelism": f"dp{world}", "l2": "working set (activities + operand copies > 126 MB L2) exceeds L2; no flush"
+                       if args.workload == "c4" else "working set fits L2 (latency-bound config); no flush",
+                       "algorithmic_gflop_per_step": fl["total"] / 1e9},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel() * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "loss": loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -84,6 +84,8 @@ typedef struct jpcb_pc_desc {
 
 int jpcb_version(void);
 const char* jpcb_last_error(void);
+/* Number of CUDA kernels this library has enqueued in this process (bench.py's gpu_launches). */
+unsigned long long jpcb_launch_count(void);
 
 /* Bytes of caller-provided device workspace any entry point below may use for `desc`. */
 size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc);

@@ -57,6 +57,7 @@ _PP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "jpcb_version": (C.c_int, []),
     "jpcb_last_error": (C.c_char_p, []),
+    "jpcb_launch_count": (C.c_ulonglong, []),
     "jpcb_pc_workspace_bytes": (C.c_size_t, [C.POINTER(PcDesc)]),
     "jpcb_pc_ffwd_init": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _P, _PP, _P, _P, _P, C.c_size_t, _P]),
     "jpcb_pc_energy": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
@@ -72,17 +73,26 @@ SIGNATURES = {
 }
 
 
-def _load() -> C.CDLL:
-    path = _build.LIB
-    if not os.path.exists(path):
-        # one attempt to build in-tree; failure is fatal (no fallback implementation exists)
-        _build.build()
+def _bind(path: str) -> C.CDLL:
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
         fn.restype = res
         fn.argtypes = args
     return lib
+
+
+def _load() -> C.CDLL:
+    path = _build.LIB
+    if not os.path.exists(path):
+        # one attempt to build in-tree; failure is fatal (no fallback implementation exists)
+        _build.build()
+    try:
+        return _bind(path)
+    except (AttributeError, OSError):
+        # stale binary from an older source tree: rebuild once, then fail loudly
+        _build.build(force=True)
+        return _bind(path)
 
 
 lib = _load()

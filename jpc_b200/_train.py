@@ -1,0 +1,121 @@
+"""make_pc_step (jpc/_train.py:35-267) over the fused C-ABI train step.
+
+One call = ffwd init -> loss at the init -> T-step inference -> per-layer energies at the solution
+-> parameter gradients (all inside jpcb_pc_train_step, one stream, no host round trip), then --
+when torch.distributed is initialised with world_size > 1 -- ONE all-reduce (SUM) of the flat
+fp32 buffer [gW_0, gb_0, ..., gW_{L-1}, gb_{L-1}, E_layers, loss] over NCCL, then the optax-shaped
+optimiser update, exactly where the reference leaves it to optax (jpc/_train.py:234-242).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_with_ffwd)
+from ._errors import _check_param_type
+from ._utils import compute_accuracy, compute_activity_norms, compute_param_norms
+from .optim import apply_updates
+from .solvers import ConstantStepSize, Heun, PIDController
+
+
+def _world():
+    """(world_size, process group available) of the data-parallel job, 1 when not distributed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+class _Arena:
+    """One flat fp32 buffer holding every tensor that must be summed over ranks, so a train step
+    needs a single collective: [gW_0, gb_0, ..., E_layers(L), loss(1)].  Segments start on
+    256-byte boundaries (the kernels use 16-byte vector stores)."""
+
+    def __init__(self, net: _Net):
+        sizes = []
+        for lin in net.linears:
+            sizes.append(lin.weight.numel())
+            if net.has_bias:
+                sizes.append(lin.bias.numel())
+        sizes += [net.L, 1]
+        offs, off = [], 0
+        for s in sizes:
+            offs.append(off)
+            off += (s + 63) // 64 * 64
+        self.flat = torch.empty(off, dtype=torch.float32, device=net.dev)
+        views = [self.flat[o:o + s] for o, s in zip(offs, sizes)]
+        self.gW, self.gb = [], ([] if net.has_bias else None)
+        i = 0
+        for lin in net.linears:
+            self.gW.append(views[i].view_as(lin.weight)); i += 1
+            if net.has_bias:
+                self.gb.append(views[i].view_as(lin.bias)); i += 1
+        self.E = views[i]
+        self.loss = views[i + 1].view(())
+
+
+def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", param_type="sp", ode_solver=None,
+                 max_t1=20, dt=None, stepsize_controller=None, skip_model=None, weight_decay=0.0,
+                 spectral_penalty=0.0, activity_decay=0.0, key=None, layer_sizes=None, batch_size=None,
+                 sigma=0.05, record_activities=False, record_energies=False, record_every=None,
+                 activity_norms=False, param_norms=False, grad_norms=False, calculate_accuracy=False):
+    """jpc/_train.py:35-267.  Same arguments, same 13-key result dict."""
+    _check_param_type(param_type)
+    if input is None and any(arg is None for arg in (key, layer_sizes, batch_size)):
+        raise ValueError("""
+            If there is no input (i.e. `x = None`), then unsupervised training 
+            is assumed, and `key`, `layer_sizes` and `batch_size` must be 
+            passed for random initialisation of activities.
+        """)
+    if loss_id not in ("mse", "ce"):
+        raise ValueError("`mse` and `ce` are the only valid losses.")
+    if record_activities or record_energies or record_every is not None:
+        raise NotImplementedError("record_activities / record_energies / record_every are not on the B200 path yet")
+    ode_solver = Heun() if ode_solver is None else ode_solver
+    stepsize_controller = PIDController(rtol=1e-3, atol=1e-3) if stepsize_controller is None else stepsize_controller
+    if not isinstance(stepsize_controller, ConstantStepSize):
+        raise NotImplementedError("adaptive PIDController stepping is not on the B200 path yet; pass "
+                                  "stepsize_controller=ConstantStepSize() and dt")
+    T, h, h_last = _time_grid(max_t1, dt)
+    if T > 4096:
+        raise RuntimeError("The maximum number of solver steps (4096) was reached.")
+    world = _world()
+    net = _Net(model, skip_model, input, output, param_type=param_type, loss_id=loss_id, gamma=None,
+               output_energy_scaling=None, activity_decay=activity_decay, weight_decay=weight_decay,
+               spectral_penalty=spectral_penalty, solver=_solver_id(ode_solver), n_steps=T, dt=h, dt_last=h_last,
+               batch_global=input.shape[0] * world)
+    if tuple(output.shape) != (net.B, net.dims[-1]):
+        raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.dims[-1])}")
+    arena = _Arena(net)
+    acts = net.new_acts()
+    ws = net.workspace()
+    _lib.check(_lib.lib.jpcb_pc_train_step(
+        net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr(output), _lib.ptr_array(acts), _lib.ptr(arena.loss),
+        _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
+        _lib.ptr(ws), ws.numel(), net.stream()))
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(arena.flat, op=dist.ReduceOp.SUM)  # the one exchange step of the data-parallel path
+    param_grads = _grads_pytree(net, arena.gW, arena.gb)
+    p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)
+    g_norms = compute_param_norms(param_grads) if grad_norms else (None, None)
+    a_norms = compute_activity_norms(acts) if activity_norms else None
+    updates, opt_state = optim.update(param_grads, opt_state, (model, skip_model))
+    model, skip_model = apply_updates((model, skip_model), updates)
+    acc = compute_accuracy(output, init_activities_with_ffwd(model, input, skip_model=skip_model,
+                                                             param_type=param_type)[-1]) if calculate_accuracy else None
+    return {
+        "model": model,
+        "skip_model": skip_model,
+        "opt_state": opt_state,
+        "loss": arena.loss,
+        "acc": acc,
+        "activities": [a.unsqueeze(0) for a in acts],
+        "t_max": 0,
+        "energies": arena.E,
+        "activity_norms": a_norms,
+        "model_param_norms": p_norms[0],
+        "skip_model_param_norms": p_norms[1],
+        "model_grad_norms": g_norms[0],
+        "skip_model_grad_norms": g_norms[1],
+    }

@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,7 @@ typedef __nv_bfloat16 bf16;
 namespace {
 
 thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};  // kernels enqueued by this library (jpcb_launch_count)
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -188,7 +190,7 @@ int launch_simt_cfg(const std::vector<GTask>& tasks, cudaStream_t st) {
     g.total_tiles = tiles;
     if (tiles == 0) continue;
     constexpr int NT = (BM / (4 * RM)) * (BN / (4 * RN));
-    simt_grouped_gemm<BM, BN, BK, RM, RN><<<tiles, NT, 0, st>>>(g);
+    simt_grouped_gemm<BM, BN, BK, RM, RN><<<tiles, NT, 0, st>>>(g); ++g_launches;
     CK(cudaGetLastError());
   }
   return JPCB_OK;
@@ -263,7 +265,7 @@ int launch_tc(const std::vector<GTask>& tasks, cudaStream_t st) {
     g.ntasks = n;
     g.total_tiles = tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    tc_grouped_gemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
+    tc_grouped_gemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g); ++g_launches;
     CK(cudaGetLastError());
   }
   return JPCB_OK;
@@ -316,11 +318,11 @@ struct Run {
     if (!tc) return JPCB_OK;
     for (int l = 0; l < L; ++l) {
       const size_t n = (size_t)d->dims[l] * d->dims[l + 1];
-      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR);
+      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR); ++g_launches;
       if (l >= 1) {
         const int R = d->dims[l + 1], C = d->dims[l];
         const int tiles = ((R + 31) / 32) * ((C + 31) / 32);
-        transpose_to_bf16_kernel<float><<<ew_grid(tiles, 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C);
+        transpose_to_bf16_kernel<float><<<ew_grid(tiles, 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C); ++g_launches;
       }
     }
     CK(cudaGetLastError());
@@ -330,11 +332,11 @@ struct Run {
   int prep_inputs(const float* const* S, std::vector<bf16*>& Hdst) {
     if (!tc) return JPCB_OK;
     const size_t n0 = (size_t)Bl * d->dims[0];
-    cast_act_bf16_kernel<<<ew_grid(n0 / 4 + 1, 256), 256, 0, st>>>(x, ws.Hb[0], n0, d->act[0]);
+    cast_act_bf16_kernel<<<ew_grid(n0 / 4 + 1, 256), 256, 0, st>>>(x, ws.Hb[0], n0, d->act[0]); ++g_launches;
     if (S)
       for (int l = 1; l < L; ++l) {
         const size_t n = (size_t)Bl * d->dims[l];
-        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], Hdst[l], n, d->act[l]);
+        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], Hdst[l], n, d->act[l]); ++g_launches;
       }
     CK(cudaGetLastError());
     return JPCB_OK;
@@ -436,7 +438,7 @@ struct Run {
   }
 
   int scale_inplace(float* p, size_t n, float s) {
-    scale_kernel<<<ew_grid(n, 256), 256, 0, st>>>(p, p, n, s);
+    scale_kernel<<<ew_grid(n, 256), 256, 0, st>>>(p, p, n, s); ++g_launches;
     CK(cudaGetLastError());
     return JPCB_OK;
   }
@@ -474,8 +476,8 @@ struct Run {
     if (tc) {
       for (int l = 0; l < L; ++l) {
         const int dn = d->dims[l + 1], dk = d->dims[l];
-        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dn + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Eb[l], ws.EbT[l], Bl, dn);
-        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dk + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Hb[l], ws.HbT[l], Bl, dk);
+        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dn + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Eb[l], ws.EbT[l], Bl, dn); ++g_launches;
+        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dk + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Hb[l], ws.HbT[l], Bl, dk); ++g_launches;
       }
       CK(cudaGetLastError());
     }
@@ -499,6 +501,7 @@ struct Run {
         const float sc = -d->scalings[l] * invB;
         if (tc) colsum_kernel<bf16><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.Eb[l], gb[l], Bl, N, sc);
         else colsum_kernel<float><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.err[l], gb[l], Bl, N, sc);
+        ++g_launches;
       }
       CK(cudaGetLastError());
     }
@@ -508,13 +511,14 @@ struct Run {
   int finalize(float* E_layers, float* F, bool with_sumsq, float* loss_out) {
     finalize_kernel<<<1, 32, 0, st>>>(ws.red, L, invB, E_layers, F, with_sumsq ? ws.red + RED_SUMSQ : nullptr, d->activity_decay,
                                       ws.red + RED_LOSS, loss_out);
+    ++g_launches;
     CK(cudaGetLastError());
     return JPCB_OK;
   }
   int sumsq_all(const float* const* A, float* out) {
     for (int l = 0; l < L; ++l) {
       const size_t n = (size_t)Bl * d->dims[l + 1];
-      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, st>>>(A[l], n, out);
+      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, st>>>(A[l], n, out); ++g_launches;
     }
     CK(cudaGetLastError());
     return JPCB_OK;
@@ -528,6 +532,7 @@ extern "C" {
 
 int jpcb_version(void) { return JPCB_VERSION; }
 const char* jpcb_last_error(void) { return g_err.c_str(); }
+unsigned long long jpcb_launch_count(void) { return g_launches.load(); }
 
 size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc) {
   if (validate(desc) != JPCB_OK) return 0;
@@ -574,7 +579,7 @@ int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const
   RET(r.errors(0, A, r.ws.Hb, true));
   RET(r.grads(GRAD_OUT, r.invB, A, nullptr, gA, r.ws.Hb, false));
   const size_t n_dummy = (size_t)r.Bl * desc->dims[r.L];
-  scale_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[r.L - 1], gA[r.L - 1], n_dummy, desc->activity_decay * r.invB);
+  scale_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[r.L - 1], gA[r.L - 1], n_dummy, desc->activity_decay * r.invB); ++g_launches;
   CK(cudaGetLastError());
   if (F) {
     const bool ad = desc->activity_decay != 0.f;

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the reference-shaped Python API) against
+the fp64 oracle on the same seeded inputs.  Tolerances are north_star's: 1e-5 max-norm relative
+error in fp32, 2e-2 in bf16 (SURVEY 8d 'parity gates')."""
+import math
+
+import pytest
+import torch
+
+from oracle import pc_oracle as O
+from tests.helpers import data, dev, devs, f32_model, perturb, rel, to_gpu_model
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+TOLBF = 2e-2
+
+
+@pytest.fixture(autouse=True)
+def _f32():
+    import jpc_b200 as J
+    J.set_compute_dtype("f32")
+    yield
+    J.set_compute_dtype("f32")
+
+
+def _case(d_in, width, depth, d_out, act, B, use_bias=False, param_type="sp", skips=False, seed=0, **dkw):
+    om = f32_model(O.make_mlp(seed, d_in, width, depth, d_out, act, use_bias=use_bias, param_type=param_type))
+    sk = O.make_skip_model(depth) if skips else None
+    x, y = data(B, d_in, d_out, **dkw)
+    x, y = x.float().double(), y.float().double()
+    return om, sk, x, y
+
+
+def _gpu_skip(sk):
+    import jpc_b200 as J
+    return None if sk is None else J.make_skip_model(len(sk))
+
+
+def _check_all(om, sk, x, y, tol, *, param_type="sp", gamma=None, lam=None, ad=0.0, perturbed=True):
+    import jpc_b200 as J
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    gx, gy = dev(x), dev(y)
+    kw = dict(param_type=param_type, gamma=gamma, output_energy_scaling=lam)
+    # feed-forward init
+    a0 = O.init_activities_with_ffwd(om, x, skips=sk, param_type=param_type, gamma=gamma)
+    ga0 = J.init_activities_with_ffwd(gm, gx, skip_model=gsk, param_type=param_type, gamma=gamma)
+    for p, q in zip(ga0, a0):
+        assert rel(p, q) < tol
+    acts = [a.float().double() for a in (perturb(a0) if perturbed else a0)]
+    gacts = devs(acts)
+    # energies
+    E = O.pc_energy_fn(om, sk, acts, y, x=x, record_layers=True, activity_decay=ad, **kw)
+    gE = J.pc_energy_fn((gm, gsk), gacts, gy, x=gx, record_layers=True, activity_decay=ad, **kw)
+    assert gE.shape == (len(om),)
+    assert rel(gE, E) < tol
+    F, g = O.compute_pc_activity_grad(om, sk, acts, y, x=x, activity_decay=ad, **kw)
+    gF, gg = J.compute_pc_activity_grad((gm, gsk), gacts, gy, x=gx, activity_decay=ad, **kw)
+    assert abs(float(gF) - float(F)) <= tol * abs(float(F))
+    assert abs(float(J.pc_energy_fn((gm, gsk), gacts, gy, x=gx, activity_decay=ad, **kw)) - float(F)) <= tol * abs(float(F))
+    gmax = max(float(t.abs().max()) for t in g)
+    for p, q in zip(gg, g):
+        # per-tensor max-norm; tensors that are exactly zero in the oracle must be zero
+        assert rel(p, q) < tol or float((p.double().cpu() - q).abs().max()) < tol * gmax
+    # parameter gradients
+    pg = O.compute_pc_param_grads(om, sk, acts, y, x=x, activity_decay=ad, **kw)
+    gpg, gskip = J.compute_pc_param_grads((gm, gsk), gacts, gy, x=gx, activity_decay=ad, **kw)
+    assert (gskip is None) == (gsk is None)
+    for l, q in enumerate(pg):
+        assert rel(gpg[l][1].weight, q["W"]) < tol
+        if q["b"] is not None:
+            assert rel(gpg[l][1].bias, q["b"]) < tol
+
+
+@pytest.mark.parametrize("act", O.ACT_FNS)
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_fixture_shapes_all_activations(act, use_bias):
+    """reference tests/conftest.py shapes: batch 4, 10 -> 20 -> 20 -> 5."""
+    _check_all(*_case(10, 20, 3, 5, act, 4, use_bias=use_bias), TOL32)
+
+
+@pytest.mark.parametrize("param_type", ["mupc", "ntp"])
+def test_skips_scalings_gamma_decay(param_type):
+    om, sk, x, y = _case(12, 16, 6, 3, "relu", 5, param_type=param_type, skips=True)
+    _check_all(om, sk, x, y, TOL32, param_type=param_type, gamma=0.5, lam=2.5, ad=0.1)
+
+
+def test_ragged_dims_not_multiple_of_4():
+    _check_all(*_case(7, 13, 4, 3, "tanh", 3, use_bias=True), TOL32)
+    _check_all(*_case(33, 65, 3, 1, "gelu", 129, use_bias=True), TOL32)
+
+
+def test_two_layer_minimum():
+    _check_all(*_case(6, 9, 2, 4, "silu", 2), TOL32)
+
+
+def _solve_case(om, sk, x, y, solver, max_t1, dt, tol, param_type="sp", ad=0.0, perturbed=False):
+    import jpc_b200 as J
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    gx, gy = dev(x), dev(y)
+    a0 = O.init_activities_with_ffwd(om, x, skips=sk, param_type=param_type)
+    if perturbed:
+        a0 = [a.float().double() for a in perturb(a0)]
+    sol, n = O.solve_inference(om, sk, a0, y, x=x, solver=solver, max_t1=max_t1, dt=dt, param_type=param_type,
+                               activity_decay=ad, use_closed_form=True, event_atol=0.0, event_rtol=0.0)
+    gsol = J.solve_inference((gm, gsk), devs(a0), gy, input=gx, param_type=param_type,
+                             solver=J.Euler() if solver == "euler" else J.Heun(), max_t1=max_t1, dt=dt,
+                             stepsize_controller=J.ConstantStepSize(), activity_decay=ad)
+    assert len(gsol) == len(om)
+    for p, q in zip(gsol, sol):
+        assert p.ndim == 3 and p.shape[0] == 1
+        assert rel(p[0], q) < tol
+    return n
+
+
+@pytest.mark.parametrize("solver", ["euler", "heun"])
+def test_solve_inference_small(solver):
+    om, sk, x, y = _case(10, 20, 3, 5, "tanh", 8, use_bias=True)
+    assert _solve_case(om, sk, x, y, solver, 5.0, 0.5, TOL32) == 10
+    # non-binary dt: the last step is clipped to t1
+    assert _solve_case(om, sk, x, y, solver, 1.0, 0.3, TOL32, perturbed=True) == 4
+    # stress step size ~ 0.1 * B
+    _solve_case(om, sk, x, y, solver, 8.0, 0.8, TOL32, perturbed=True, ad=0.05)
+
+
+def test_euler_equals_looped_update_pc_activities():
+    """Euler(dt) == optax.sgd(dt) applied T times (SURVEY 8c iii)."""
+    import jpc_b200 as J
+    om, sk, x, y = _case(10, 20, 4, 5, "relu", 8)
+    gm = to_gpu_model(om)
+    gx, gy = dev(x), dev(y)
+    acts = J.init_activities_with_ffwd(gm, gx)
+    sol = J.solve_inference((gm, None), acts, gy, input=gx, solver=J.Euler(), max_t1=3.0, dt=0.5,
+                            stepsize_controller=J.ConstantStepSize())
+    opt = J.optim.sgd(0.5)
+    st = opt.init(acts)
+    a = acts
+    for _ in range(6):
+        r = J.update_pc_activities((gm, None), a, opt, st, gy, input=gx)
+        assert set(r) == {"energy", "activities", "grads", "opt_state"}
+        a, st = r["activities"], r["opt_state"]
+    for p, q in zip(sol, a):
+        assert rel(p[0], q) < 1e-6
+
+
+def _train_case(om, sk, x, y, solver, max_t1, dt, tol, param_type="sp", zero_tol=1e-12):
+    import jpc_b200 as J
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    gx, gy = dev(x), dev(y)
+    ref = O.pc_train_step(om, sk, x, y, solver=solver, max_t1=max_t1, dt=dt, param_type=param_type)
+    opt = J.optim.sgd(0.0)
+    out = J.make_pc_step(gm, opt, opt.init((gm, gsk)), gy, input=gx, param_type=param_type,
+                         ode_solver=J.Euler() if solver == "euler" else J.Heun(), max_t1=max_t1, dt=dt,
+                         stepsize_controller=J.ConstantStepSize(), skip_model=gsk, grad_norms=True)
+    assert set(out) == {"model", "skip_model", "opt_state", "loss", "acc", "activities", "t_max", "energies",
+                        "activity_norms", "model_param_norms", "skip_model_param_norms", "model_grad_norms",
+                        "skip_model_grad_norms"}
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+    assert rel(out["energies"], ref["energies"]) < tol
+    amax = max(float(t.abs().max()) for t in ref["activities"])
+    for p, q in zip(out["activities"], ref["activities"]):
+        assert rel(p[0], q) < tol or float((p[0].double().cpu() - q).abs().max()) < tol * amax
+    return out, ref
+
+
+def _check_train_grads(om, sk, x, y, solver, max_t1, dt, tol, param_type="sp"):
+    """Parameter gradients of the fused train step (read back through update_pc_params-free path)."""
+    import jpc_b200 as J
+    from jpc_b200._train import _Arena  # noqa: F401
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    gx, gy = dev(x), dev(y)
+    ref = O.pc_train_step(om, sk, x, y, solver=solver, max_t1=max_t1, dt=dt, param_type=param_type)
+    # sgd(lr=1): new = old - g  =>  g = old - new
+    opt = J.optim.sgd(1.0)
+    out = J.make_pc_step(gm, opt, opt.init((gm, gsk)), gy, input=gx, param_type=param_type,
+                         ode_solver=J.Euler() if solver == "euler" else J.Heun(), max_t1=max_t1, dt=dt,
+                         stepsize_controller=J.ConstantStepSize(), skip_model=gsk)
+    gmax = max(float(g["W"].abs().max()) for g in ref["grads"])
+    for l, q in enumerate(ref["grads"]):
+        g = gm[l][1].weight.double() - out["model"][l][1].weight.double()
+        # the subtraction itself costs ~1e-7 * |W|; compare on the gradient's own scale
+        wmax = float(gm[l][1].weight.abs().max())
+        assert float((g.cpu() - q["W"]).abs().max()) < tol * max(float(q["W"].abs().max()), 1e-30) + 2e-7 * wmax or \
+            float((g.cpu() - q["W"]).abs().max()) < tol * gmax
+
+
+def test_make_pc_step_small():
+    om, sk, x, y = _case(10, 20, 3, 5, "relu", 4)
+    _train_case(om, sk, x, y, "euler", 5.0, 0.5, TOL32)
+    _train_case(om, sk, x, y, "heun", 5.0, 0.5, TOL32)
+
+
+def _fused_step_raw(om, sk, x, y, solver, max_t1, dt, param_type="sp"):
+    """jpcb_pc_train_step through the Python plumbing, returning raw gradients."""
+    import jpc_b200 as J
+    from jpc_b200 import _lib
+    from jpc_b200._core import _Net, _solver_id, _time_grid
+    from jpc_b200._train import _Arena
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    gx, gy = dev(x), dev(y)
+    T, h, hl = _time_grid(max_t1, dt)
+    net = _Net(gm, gsk, gx, gy, param_type=param_type, loss_id="mse", gamma=None, output_energy_scaling=None,
+               activity_decay=0.0, weight_decay=0.0, spectral_penalty=0.0,
+               solver=_solver_id(J.Euler() if solver == "euler" else J.Heun()), n_steps=T, dt=h, dt_last=hl)
+    arena = _Arena(net)
+    acts = net.new_acts()
+    ws = net.workspace()
+    _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(gx), _lib.ptr(gy), _lib.ptr_array(acts),
+                                           _lib.ptr(arena.loss), _lib.ptr(arena.E), _lib.ptr_array(arena.gW),
+                                           _lib.ptr_array(arena.gb) if arena.gb else None, _lib.ptr(ws), ws.numel(),
+                                           net.stream()))
+    torch.cuda.synchronize()
+    return acts, arena
+
+
+def _check_fused(om, sk, x, y, solver, max_t1, dt, tol, param_type="sp"):
+    ref = O.pc_train_step(om, sk, x, y, solver=solver, max_t1=max_t1, dt=dt, param_type=param_type)
+    acts, arena = _fused_step_raw(om, sk, x, y, solver, max_t1, dt, param_type)
+    assert abs(float(arena.loss) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+    emax = float(ref["energies"].abs().max())
+    assert float((arena.E.double().cpu() - ref["energies"]).abs().max()) < tol * emax
+    amax = max(float(t.abs().max()) for t in ref["activities"])
+    for p, q in zip(acts, ref["activities"]):
+        assert rel(p, q) < tol or float((p.double().cpu() - q).abs().max()) < tol * amax
+    gmax = max(float(g["W"].abs().max()) for g in ref["grads"])
+    for l, q in enumerate(ref["grads"]):
+        assert rel(arena.gW[l], q["W"]) < tol or float((arena.gW[l].double().cpu() - q["W"]).abs().max()) < tol * gmax
+        if q["b"] is not None:
+            assert rel(arena.gb[l], q["b"]) < tol or float((arena.gb[l].double().cpu() - q["b"]).abs().max()) < tol * gmax
+
+
+def test_config1_discriminative_full_size():
+    """BASELINE config 1: 784-300-300-10 tanh, batch 64, 20 Euler steps, fp32."""
+    om, sk, x, y = _case(784, 300, 3, 10, "tanh", 64)
+    _check_fused(om, sk, x, y, "euler", 10.0, 0.5, TOL32)
+    _check_all(om, sk, x, y, TOL32)
+
+
+def test_config2_generative_full_size():
+    """BASELINE config 2: 10-256-256-784 relu+bias, batch 256, 50 Heun steps."""
+    om, sk, x, y = _case(10, 256, 3, 784, "relu", 256, use_bias=True, onehot_in=True, onehot_out=False)
+    _check_fused(om, sk, x, y, "heun", 25.0, 0.5, TOL32)
+
+
+def test_config3_mupc_deep_residual_full_size():
+    """BASELINE config 3: muPC width 128 depth 128 + identity skips, batch 128, 20 steps."""
+    om, sk, x, y = _case(784, 128, 128, 10, "relu", 128, param_type="mupc", skips=True)
+    _check_fused(om, sk, x, y, "euler", 10.0, 0.5, TOL32, param_type="mupc")
+    _check_all(om, sk, x, y, TOL32, param_type="mupc")
+
+
+# ---- bf16 tensor-core path -------------------------------------------------------------------
+def test_bf16_path_medium():
+    import jpc_b200 as J
+    J.set_compute_dtype("bf16")
+    om, sk, x, y = _case(256, 512, 4, 128, "tanh", 384, use_bias=True, onehot_out=False)
+    _check_all(om, sk, x, y, TOLBF)
+    _check_fused(om, sk, x, y, "euler", 5.0, 0.5, TOLBF)
+    _check_fused(om, sk, x, y, "heun", 2.0, 0.5, TOLBF)
+
+
+def test_bf16_path_ragged_tiles():
+    """dims that are multiples of 8 but not of the 128x256x64 tile."""
+    import jpc_b200 as J
+    J.set_compute_dtype("bf16")
+    om, sk, x, y = _case(72, 200, 3, 40, "relu", 136, onehot_out=False)
+    _check_all(om, sk, x, y, TOLBF)
+    _check_fused(om, sk, x, y, "euler", 2.0, 0.5, TOLBF)
+
+
+def test_bf16_rejects_unaligned():
+    import jpc_b200 as J
+    J.set_compute_dtype("bf16")
+    om, sk, x, y = _case(10, 20, 3, 5, "relu", 4)
+    with pytest.raises(NotImplementedError):
+        J.init_activities_with_ffwd(to_gpu_model(om), dev(x))
+
+
+# ---- error behaviour (reference raises the same exception types) -----------------------------
+def test_error_behaviour():
+    import jpc_b200 as J
+    om, sk, x, y = _case(10, 20, 3, 5, "relu", 4)
+    gm = to_gpu_model(om)
+    gx, gy = dev(x), dev(y)
+    acts = J.init_activities_with_ffwd(gm, gx)
+    with pytest.raises(ValueError):
+        J.pc_energy_fn((gm, None), acts, gy, x=gx, param_type="bogus")
+    with pytest.raises(ValueError):
+        J.pc_energy_fn((gm, None), acts, gy, x=gx, loss="bogus")
+    opt = J.optim.sgd(0.1)
+    with pytest.raises(ValueError):
+        J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=None)
+    with pytest.raises(NotImplementedError):  # adaptive default controller: 'next' row
+        J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx)
+    with pytest.raises(RuntimeError):  # no CPU path
+        J.init_activities_with_ffwd(to_gpu_model(om, device="cpu"), x.float())
