@@ -12,22 +12,24 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "../../include/jpc_b200.h"
 #include "elementwise.cuh"
+#include "host.cuh"
 #include "simt_gemm.cuh"
-#include "tc_gemm.cuh"
 
 using namespace jpcb;
 typedef __nv_bfloat16 bf16;
 
 namespace {
-
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};  // kernels enqueued by this library (jpcb_launch_count)
+}  // namespace
+
+namespace jpcb {
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -39,16 +41,7 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define CK(call)                                                                            \
-  do {                                                                                      \
-    cudaError_t _e = (call);                                                                \
-    if (_e != cudaSuccess) return fail(JPCB_ECUDA, "%s -> %s", #call, cudaGetErrorString(_e)); \
-  } while (0)
-#define RET(call)            \
-  do {                       \
-    int _r = (call);         \
-    if (_r != JPCB_OK) return _r; \
-  } while (0)
+void count_launch(int n) { g_launches += (unsigned long long)n; }
 
 int num_sms() {
   static int n = [] {
@@ -59,6 +52,15 @@ int num_sms() {
   }();
   return n;
 }
+
+int tc_flags() {
+  static const int f = [] { const char* v = getenv("JPCB_TC_FLAGS"); return v ? atoi(v) : 0; }();
+  return f;
+}
+
+}  // namespace jpcb
+
+namespace {
 
 // ---------------------------------------------------------------------------------------------
 // descriptor validation
@@ -155,18 +157,8 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// generic task = one GEMM + fused epilogue, lowered to either kernel family
+// CUDA-core launches (the tensor-core ones live in tc_gemm.cu)
 // ---------------------------------------------------------------------------------------------
-struct GTask {
-  Epi e;
-  int K = 0;
-  const float* a_p = nullptr; long long a_smn = 0, a_sk = 0; int a_act = ACT_LINEAR;
-  const float* b_p = nullptr; long long b_smn = 0, b_sk = 0; int b_act = ACT_LINEAR;
-  const bf16* a_b = nullptr;  // [M, K] K-major
-  const bf16* b_b = nullptr;  // [N, K] K-major
-  GTask() { memset(&e, 0, sizeof(e)); e.gscale = 1.f; e.escale = 1.f; }
-};
-
 template <int BM, int BN, int BK, int RM, int RN>
 int launch_simt_cfg(const std::vector<GTask>& tasks, cudaStream_t st) {
   size_t i = 0;
@@ -190,13 +182,15 @@ int launch_simt_cfg(const std::vector<GTask>& tasks, cudaStream_t st) {
     g.total_tiles = tiles;
     if (tiles == 0) continue;
     constexpr int NT = (BM / (4 * RM)) * (BN / (4 * RN));
-    simt_grouped_gemm<BM, BN, BK, RM, RN><<<tiles, NT, 0, st>>>(g); ++g_launches;
+    simt_grouped_gemm<BM, BN, BK, RM, RN><<<tiles, NT, 0, st>>>(g); count_launch();
     CK(cudaGetLastError());
   }
   return JPCB_OK;
 }
 
-int launch_simt(const std::vector<GTask>& tasks, cudaStream_t st) {
+}  // namespace
+
+int jpcb::launch_simt(const std::vector<GTask>& tasks, cudaStream_t st) {
   if (tasks.empty()) return JPCB_OK;
   // pick the tile shape from the amount of parallelism the phase offers
   long long t128 = 0, t64 = 0;
@@ -210,66 +204,7 @@ int launch_simt(const std::vector<GTask>& tasks, cudaStream_t st) {
   return launch_simt_cfg<32, 32, 16, 1, 1>(tasks, st);  // (8x8 threads) latency-bound small layers
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
-    return (EncodeTiledFn)p;
-  }();
-  return fn;
-}
-
-// bf16 [rows, cols] row-major, box = {64 cols, box_rows}, SWIZZLE_128B, OOB reads give zeros
-int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
-  EncodeTiledFn fn = encode_tiled();
-  if (!fn) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d", (int)r, rows, cols);
-  return JPCB_OK;
-}
-
-int launch_tc(const std::vector<GTask>& tasks, cudaStream_t st) {
-  if (tasks.empty()) return JPCB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc_grouped_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
-  size_t i = 0;
-  while (i < tasks.size()) {
-    TcGroup g;
-    memset(&g, 0, 64);
-    int n = 0, tiles = 0;
-    for (; i < tasks.size() && n < TC_MAX_TASKS; ++i, ++n) {
-      const GTask& t = tasks[i];
-      if (t.K <= 0 || !t.a_b || !t.b_b) return fail(JPCB_EINVAL, "internal: tensor-core task without bf16 operands");
-      TcTask& s = g.t[n];
-      RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
-      RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, TC_BLOCK_N));
-      s.K = t.K;
-      s.tile_begin = tiles;
-      s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;
-      s.pad_ = 0;
-      s.e = t.e;
-      tiles += s.tiles_n * ((t.e.M + TC_BLOCK_M - 1) / TC_BLOCK_M);
-    }
-    g.ntasks = n;
-    g.total_tiles = tiles;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    tc_grouped_gemm<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g); ++g_launches;
-    CK(cudaGetLastError());
-  }
-  return JPCB_OK;
-}
+namespace {
 
 int ew_grid(size_t work_items, int per_block) {
   size_t blocks = (work_items + per_block - 1) / per_block;
@@ -318,11 +253,11 @@ struct Run {
     if (!tc) return JPCB_OK;
     for (int l = 0; l < L; ++l) {
       const size_t n = (size_t)d->dims[l] * d->dims[l + 1];
-      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR); ++g_launches;
+      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR); count_launch();
       if (l >= 1) {
         const int R = d->dims[l + 1], C = d->dims[l];
         const int tiles = ((R + 31) / 32) * ((C + 31) / 32);
-        transpose_to_bf16_kernel<float><<<ew_grid(tiles, 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C); ++g_launches;
+        transpose_to_bf16_kernel<float><<<ew_grid(tiles, 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C); count_launch();
       }
     }
     CK(cudaGetLastError());
@@ -332,11 +267,11 @@ struct Run {
   int prep_inputs(const float* const* S, std::vector<bf16*>& Hdst) {
     if (!tc) return JPCB_OK;
     const size_t n0 = (size_t)Bl * d->dims[0];
-    cast_act_bf16_kernel<<<ew_grid(n0 / 4 + 1, 256), 256, 0, st>>>(x, ws.Hb[0], n0, d->act[0]); ++g_launches;
+    cast_act_bf16_kernel<<<ew_grid(n0 / 4 + 1, 256), 256, 0, st>>>(x, ws.Hb[0], n0, d->act[0]); count_launch();
     if (S)
       for (int l = 1; l < L; ++l) {
         const size_t n = (size_t)Bl * d->dims[l];
-        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], Hdst[l], n, d->act[l]); ++g_launches;
+        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], Hdst[l], n, d->act[l]); count_launch();
       }
     CK(cudaGetLastError());
     return JPCB_OK;
@@ -438,7 +373,7 @@ struct Run {
   }
 
   int scale_inplace(float* p, size_t n, float s) {
-    scale_kernel<<<ew_grid(n, 256), 256, 0, st>>>(p, p, n, s); ++g_launches;
+    scale_kernel<<<ew_grid(n, 256), 256, 0, st>>>(p, p, n, s); count_launch();
     CK(cudaGetLastError());
     return JPCB_OK;
   }
@@ -476,8 +411,8 @@ struct Run {
     if (tc) {
       for (int l = 0; l < L; ++l) {
         const int dn = d->dims[l + 1], dk = d->dims[l];
-        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dn + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Eb[l], ws.EbT[l], Bl, dn); ++g_launches;
-        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dk + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Hb[l], ws.HbT[l], Bl, dk); ++g_launches;
+        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dn + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Eb[l], ws.EbT[l], Bl, dn); count_launch();
+        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dk + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Hb[l], ws.HbT[l], Bl, dk); count_launch();
       }
       CK(cudaGetLastError());
     }
@@ -501,7 +436,7 @@ struct Run {
         const float sc = -d->scalings[l] * invB;
         if (tc) colsum_kernel<bf16><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.Eb[l], gb[l], Bl, N, sc);
         else colsum_kernel<float><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.err[l], gb[l], Bl, N, sc);
-        ++g_launches;
+        count_launch();
       }
       CK(cudaGetLastError());
     }
@@ -511,14 +446,14 @@ struct Run {
   int finalize(float* E_layers, float* F, bool with_sumsq, float* loss_out) {
     finalize_kernel<<<1, 32, 0, st>>>(ws.red, L, invB, E_layers, F, with_sumsq ? ws.red + RED_SUMSQ : nullptr, d->activity_decay,
                                       ws.red + RED_LOSS, loss_out);
-    ++g_launches;
+    count_launch();
     CK(cudaGetLastError());
     return JPCB_OK;
   }
   int sumsq_all(const float* const* A, float* out) {
     for (int l = 0; l < L; ++l) {
       const size_t n = (size_t)Bl * d->dims[l + 1];
-      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, st>>>(A[l], n, out); ++g_launches;
+      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, st>>>(A[l], n, out); count_launch();
     }
     CK(cudaGetLastError());
     return JPCB_OK;
@@ -579,7 +514,7 @@ int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const
   RET(r.errors(0, A, r.ws.Hb, true));
   RET(r.grads(GRAD_OUT, r.invB, A, nullptr, gA, r.ws.Hb, false));
   const size_t n_dummy = (size_t)r.Bl * desc->dims[r.L];
-  scale_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[r.L - 1], gA[r.L - 1], n_dummy, desc->activity_decay * r.invB); ++g_launches;
+  scale_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[r.L - 1], gA[r.L - 1], n_dummy, desc->activity_decay * r.invB); count_launch();
   CK(cudaGetLastError());
   if (F) {
     const bool ad = desc->activity_decay != 0.f;

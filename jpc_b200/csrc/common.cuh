@@ -113,6 +113,20 @@ struct Epi {
   const float* Y;              // FFWD: loss target
 };
 
+// Copies a descriptor out of kernel-parameter space into registers and makes every field opaque to
+// the compiler, so later uses read registers.  Descriptors sit in a runtime-indexed array of the
+// grouped-launch parameter block; a runtime-indexed constant load is a variable-latency operation
+// that shares scoreboard slots with outstanding global loads, so re-reading a field in the middle
+// of the epilogue's load stream would wait for every load in flight.
+__device__ __forceinline__ Epi epi_pin(const Epi& src) {
+  Epi e = src;
+  asm volatile("" : "+r"(e.mode), "+r"(e.sub), "+r"(e.act), "+r"(e.M), "+r"(e.N), "+r"(e.accum));
+  asm volatile("" : "+f"(e.alpha), "+f"(e.skip), "+f"(e.escale), "+f"(e.c), "+f"(e.ad), "+f"(e.gscale));
+  asm volatile("" : "+l"(e.bias), "+l"(e.T), "+l"(e.U), "+l"(e.Z), "+l"(e.Z0), "+l"(e.El), "+l"(e.Elb), "+l"(e.P));
+  asm volatile("" : "+l"(e.En), "+l"(e.Enb), "+l"(e.Gin), "+l"(e.G1), "+l"(e.O), "+l"(e.O2), "+l"(e.Ob), "+l"(e.red), "+l"(e.Y));
+  return e;
+}
+
 __device__ __forceinline__ void ld4(const float* __restrict__ p, size_t idx, int nvalid, bool vec, float (&v)[4]) {
   if (vec) {
     float4 t = *reinterpret_cast<const float4*>(p + idx);
@@ -155,61 +169,97 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, size_t idx, i
   }
 }
 
-// Applies the fused epilogue to 4 horizontally adjacent accumulator values D[row, col..col+3].
+// The fused epilogue is split in two so that callers can put many independent global loads in
+// flight before they consume any of them (the tensor-core epilogue issues a whole 32x32 patch of
+// loads, then reads the accumulator from TMEM, then finishes):
+//   epi_preload : issues the mode's per-element input loads for D[row, col..col+3] (raw values)
+//   epi_finish  : consumes them + the 4 accumulator values, stores, returns the reduction term
+struct EpiPre {
+  float a[4];  // GRAD: z          ERR: target T    FFWD: loss target Y   SCALE(accum): old O
+  float b[4];  // GRAD: e_l (fp32) or P, or -- when Elb is the source -- the 4 packed bf16 of e_l as raw bits
+               // in b[0..1]                        FFWD/ERR: skip input U
+};
+
+__device__ __forceinline__ void unpack_bf16x4(const uint2& t, float (&v)[4]) {
+  __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+  __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+
+// MODE / SUB / ACT >= 0 fix the corresponding descriptor field at compile time (the tensor-core
+// epilogue dispatches once per tile so that its inner loop is straight-line code); -1 = read it
+// from the descriptor at run time.
+template <int MODE = -1>
+__device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int nvalid, bool vec, EpiPre& p) {
+  const size_t idx = (size_t)row * (size_t)e.N + (size_t)col;
+  const int mode = MODE >= 0 ? MODE : e.mode;
+  if (mode == EPI_GRAD) {
+    ld4(e.Z, idx, nvalid, vec, p.a);
+    if (e.El) ld4(e.El, idx, nvalid, vec, p.b);
+    else if (e.Elb) {
+      if (vec) {
+        const uint2 t = *reinterpret_cast<const uint2*>(e.Elb + idx);
+        p.b[0] = __uint_as_float(t.x);
+        p.b[1] = __uint_as_float(t.y);
+      } else ld4(e.Elb, idx, nvalid, false, p.b);
+    } else ld4(e.P, idx, nvalid, vec, p.b);
+  } else if (mode == EPI_ERR) {
+    ld4(e.T, idx, nvalid, vec, p.a);
+    if (e.skip != 0.f) ld4(e.U, idx, nvalid, vec, p.b);
+  } else if (mode == EPI_FFWD) {
+    if (e.skip != 0.f) ld4(e.U, idx, nvalid, vec, p.b);
+    if (e.red) ld4(e.Y, idx, nvalid, vec, p.a);
+  } else if (e.accum) {
+    ld4(e.O, idx, nvalid, vec, p.a);
+  }
+}
+
 // `nvalid` (1..4) columns are inside the matrix; `vec` says 16-byte vector access is legal
 // (N % 4 == 0 and nvalid == 4).  Returns this thread's contribution to the reduction (`red`).
-template <bool FAST>
-__device__ __forceinline__ float epi_apply4(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec) {
+// `have_bias4`: the caller already holds the 4 bias values of columns col..col+3 in `bias4`.
+template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1>
+__device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec,
+                                            const EpiPre& p, bool have_bias4, const float (&bias4)[4]) {
   const size_t idx = (size_t)row * (size_t)e.N + (size_t)col;
+  const int mode = MODE >= 0 ? MODE : e.mode;
+  const int sub = SUB >= 0 ? SUB : e.sub;
+  const int act = ACT >= 0 ? ACT : e.act;
   float r = 0.f;
   float out[4];
-  if (e.mode == EPI_SCALE) {
-    if (e.accum) {
-      float o[4];
-      ld4(e.O, idx, nvalid, vec, o);
+  if (mode == EPI_SCALE) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[j] = o[j] + e.alpha * acc[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out[j] = e.alpha * acc[j];
-    }
+    for (int j = 0; j < 4; ++j) out[j] = (e.accum ? p.a[j] : 0.f) + e.alpha * acc[j];
     st4(e.O, idx, nvalid, vec, out);
     return 0.f;
   }
-  if (e.mode == EPI_FFWD || e.mode == EPI_ERR) {
+  if (mode == EPI_FFWD || mode == EPI_ERR) {
     float pred[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float bj = (e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f;
+      float bj = have_bias4 ? bias4[j] : ((e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f);
       pred[j] = e.alpha * (acc[j] + bj);
     }
     if (e.skip != 0.f) {
-      float u[4];
-      ld4(e.U, idx, nvalid, vec, u);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pred[j] += e.skip * u[j];
+      for (int j = 0; j < 4; ++j) pred[j] += e.skip * p.b[j];
     }
-    if (e.mode == EPI_FFWD) {
+    if (mode == EPI_FFWD) {
       st4(e.O, idx, nvalid, vec, pred);
       if (e.O2) st4(e.O2, idx, nvalid, vec, pred);
       if (e.Ob) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) out[j] = act_fwd<FAST>(e.act, pred[j]);
+        for (int j = 0; j < 4; ++j) out[j] = act_fwd<FAST>(act, pred[j]);
         st4(e.Ob, idx, nvalid, vec, out);
       }
       if (e.red) {
-        float y[4];
-        ld4(e.Y, idx, nvalid, vec, y);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (j < nvalid) { float d = y[j] - pred[j]; r += 0.5f * d * d; }
+        for (int j = 0; j < 4; ++j) if (j < nvalid) { float d = p.a[j] - pred[j]; r += 0.5f * d * d; }
       }
       return r;
     }
-    float t[4];
-    ld4(e.T, idx, nvalid, vec, t);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float d = j < nvalid ? t[j] - pred[j] : 0.f;
+      float d = j < nvalid ? p.a[j] - pred[j] : 0.f;
       r += 0.5f * e.escale * d * d;
       out[j] = e.escale * d;
     }
@@ -218,18 +268,23 @@ __device__ __forceinline__ float epi_apply4(const Epi& e, int row, int col, cons
     return e.red ? r : 0.f;
   }
   // ---- EPI_GRAD ----
-  float z[4], el[4], g[4];
-  ld4(e.Z, idx, nvalid, vec, z);
-  if (e.El) ld4(e.El, idx, nvalid, vec, el);
-  else if (e.Elb) ld4(e.Elb, idx, nvalid, vec, el);
-  else {
-    float p[4];
-    ld4(e.P, idx, nvalid, vec, p);
+  float el[4], g[4];
+  const float (&z)[4] = p.a;
+  if (e.El) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) el[j] = z[j] - p[j];
+    for (int j = 0; j < 4; ++j) el[j] = p.b[j];
+  } else if (e.Elb) {
+    if (vec) unpack_bf16x4(make_uint2(__float_as_uint(p.b[0]), __float_as_uint(p.b[1])), el);
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) el[j] = p.b[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) el[j] = z[j] - p.b[j];
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) g[j] = el[j] - act_bwd<FAST>(e.act, z[j]) * (e.alpha * acc[j]);
+  for (int j = 0; j < 4; ++j) g[j] = el[j] - act_bwd<FAST>(act, z[j]) * (e.alpha * acc[j]);
   if (e.skip != 0.f) {
     float en[4];
     if (e.En) ld4(e.En, idx, nvalid, vec, en);
@@ -245,16 +300,16 @@ __device__ __forceinline__ float epi_apply4(const Epi& e, int row, int col, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) g[j] += gi[j];
   }
-  if (e.sub == GRAD_OUT) {
+  if (sub == GRAD_OUT) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[j] = e.c * g[j];
     st4(e.O, idx, nvalid, vec, out);
     return 0.f;
   }
-  if (e.sub == GRAD_EULER) {
+  if (sub == GRAD_EULER) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[j] = z[j] - e.c * g[j];
-  } else if (e.sub == GRAD_HEUN1) {
+  } else if (sub == GRAD_HEUN1) {
     st4(e.G1, idx, nvalid, vec, g);
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[j] = z[j] - e.c * g[j];
@@ -269,10 +324,19 @@ __device__ __forceinline__ float epi_apply4(const Epi& e, int row, int col, cons
   if (e.Ob) {
     float h[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = act_fwd<FAST>(e.act, out[j]);
+    for (int j = 0; j < 4; ++j) h[j] = act_fwd<FAST>(act, out[j]);
     st4(e.Ob, idx, nvalid, vec, h);
   }
   return 0.f;
+}
+
+// Applies the fused epilogue to 4 horizontally adjacent accumulator values D[row, col..col+3].
+template <bool FAST>
+__device__ __forceinline__ float epi_apply4(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec) {
+  EpiPre p;
+  epi_preload<-1>(e, row, col, nvalid, vec, p);
+  const float nob[4] = {0.f, 0.f, 0.f, 0.f};
+  return epi_finish<FAST>(e, row, col, acc, nvalid, vec, p, false, nob);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

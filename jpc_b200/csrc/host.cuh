@@ -1,0 +1,53 @@
+// host.cuh -- host-side vocabulary shared by the translation units of libjpc_b200.so (api.cu: C-ABI,
+// descriptor validation, phase schedule, CUDA-core launches; tc_gemm.cu: tensor-core launches;
+// bpc.cu: bidirectional-PC schedule): error reporting, the launch counter, and GTask, the
+// "one GEMM + fused epilogue" work item both kernel families are driven by.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <vector>
+
+#include "../../include/jpc_b200.h"
+#include "common.cuh"
+
+namespace jpcb {
+
+// sets the thread-local message returned by jpcb_last_error() and returns `code`
+int fail(int code, const char* fmt, ...);
+// one more kernel enqueued by this library (jpcb_launch_count)
+void count_launch(int n = 1);
+int num_sms();
+// experiment switches from the environment variable JPCB_TC_FLAGS (bit 1: 1-CTA tensor-core kernel)
+int tc_flags();
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess) return ::jpcb::fail(JPCB_ECUDA, "%s -> %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+#define RET(call)                 \
+  do {                            \
+    int _r = (call);              \
+    if (_r != JPCB_OK) return _r; \
+  } while (0)
+
+// D[M,N] = A[M,K] * B[N,K]^T followed by the fused epilogue `e`.  fp32 operands are described by
+// strides (so W, W^T, e^T, act(z)^T are read in place by the CUDA-core kernel); bf16 operands
+// (tensor-core kernel) are dense K-major copies.
+struct GTask {
+  Epi e;
+  int K = 0;
+  const float* a_p = nullptr; long long a_smn = 0, a_sk = 0; int a_act = ACT_LINEAR;
+  const float* b_p = nullptr; long long b_smn = 0, b_sk = 0; int b_act = ACT_LINEAR;
+  const __nv_bfloat16* a_b = nullptr;  // [M, K] K-major
+  const __nv_bfloat16* b_b = nullptr;  // [N, K] K-major
+  GTask() { memset(&e, 0, sizeof(e)); e.gscale = 1.f; e.escale = 1.f; }
+};
+
+// one grouped launch (per <= 16 / 64 tasks) of the tcgen05 / CUDA-core kernel over `tasks`
+int launch_tc(const std::vector<GTask>& tasks, cudaStream_t st);
+int launch_simt(const std::vector<GTask>& tasks, cudaStream_t st);
+
+}  // namespace jpcb

@@ -1,0 +1,127 @@
+// tc_gemm.cu -- host side of the tcgen05 grouped GEMM (tc_gemm.cuh): TMA tensor maps, tile counts,
+// cluster launch, and the choice of the compile-time epilogue specialisation for a launch.
+#include <cuda.h>
+
+#include "host.cuh"
+#include "tc_gemm.cuh"
+
+namespace jpcb {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// bf16 [rows, cols] row-major, box = {64 cols, box_rows}, SWIZZLE_128B, OOB reads give zeros
+int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+  return JPCB_OK;
+}
+
+template <int CG, int MODE, int SUB, int ACT>
+int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
+  using Cfg = TcCfg<CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT>, g));
+  count_launch();
+  return JPCB_OK;
+}
+
+// Epilogue specialisations compiled in: what the timed configurations run (errors, tanh / relu
+// Euler updates, scaled weight-gradient outputs).  A launch whose tasks do not all share one of
+// these takes the generic descriptor-driven kernel.
+template <int CG>
+int launch_group(const TcGroup& g, int grid, cudaStream_t st) {
+  const Epi& e0 = g.t[0].e;
+  bool same = true;
+  for (int i = 1; i < g.ntasks; ++i) {
+    const Epi& e = g.t[i].e;
+    same = same && e.mode == e0.mode && e.sub == e0.sub && e.act == e0.act;
+  }
+  if (same && !(tc_flags() & 4)) {
+    if (e0.mode == EPI_ERR) return launch_variant<CG, EPI_ERR, 0, 0>(g, grid, st);
+    if (e0.mode == EPI_SCALE) return launch_variant<CG, EPI_SCALE, 0, 0>(g, grid, st);
+    if (e0.mode == EPI_GRAD && e0.sub == GRAD_EULER && e0.act == ACT_TANH) return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH>(g, grid, st);
+    if (e0.mode == EPI_GRAD && e0.sub == GRAD_EULER && e0.act == ACT_RELU) return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU>(g, grid, st);
+  }
+  return launch_variant<CG, -1, -1, -1>(g, grid, st);
+}
+
+template <int CG>
+int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
+  using Cfg = TcCfg<CG>;
+  constexpr int BM = TC_BLOCK_M * CG;  // rows of one tile (owned by a CTA, or by a CTA pair)
+  size_t i = 0;
+  while (i < tasks.size()) {
+    TcGroup g;
+    memset(&g, 0, 64);
+    int n = 0, tiles = 0;
+    for (; i < tasks.size() && n < TC_MAX_TASKS; ++i, ++n) {
+      const GTask& t = tasks[i];
+      if (t.K <= 0 || !t.a_b || !t.b_b) return fail(JPCB_EINVAL, "internal: tensor-core task without bf16 operands");
+      TcTask& s = g.t[n];
+      RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
+      RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, Cfg::B_ROWS));
+      s.K = t.K;
+      s.tile_begin = tiles;
+      s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;
+      s.pad_ = 0;
+      s.e = t.e;
+      tiles += s.tiles_n * ((t.e.M + BM - 1) / BM);
+    }
+    g.ntasks = n;
+    g.total_tiles = tiles;
+    const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
+    const int grid = CG * (tiles < units ? tiles : units);
+    RET(launch_group<CG>(g, grid, st));
+  }
+  return JPCB_OK;
+}
+
+}  // namespace
+
+int launch_tc(const std::vector<GTask>& tasks, cudaStream_t st) {
+  if (tasks.empty()) return JPCB_OK;
+#ifdef JPCB_TC_WITH_CG1
+  if (tc_flags() & 2) return launch_tc_cg<1>(tasks, st);
+#endif
+  return launch_tc_cg<2>(tasks, st);
+}
+
+}  // namespace jpcb

@@ -2,21 +2,33 @@
 // epilogues of common.cuh.  D[M,N] = A[M,K] * B[N,K]^T, A and B bf16 K-major in HBM, fp32
 // accumulation in TMEM.
 //
-//   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 bf16 along K) into a
-//                              4-stage shared-memory ring, completion on `full` mbarriers
-//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//                              (128 x 256 x 16 per instruction), tcgen05.commit frees ring slots and
-//                              publishes the accumulator; also owns the TMEM allocation (512 columns
-//                              = two 128x256 fp32 accumulator stages, so tile i+1's MMAs overlap
-//                              tile i's epilogue)
-//   warps 2..9  epilogue     : tcgen05.ld the accumulator (lane = row), transpose 32x16 patches
-//                              through XOR-swizzled shared memory so that all global traffic of
-//                              the fused epilogue is row-contiguous 16-byte vectors, then
-//                              epi_apply4 (activation, derivative, error, Euler/Heun update,
-//                              bf16 operand copy for the next GEMM, energy reduction)
+// The kernel is a template on CG, the tcgen05 cta_group:
+//   CG = 2 (default): thread-block clusters of two CTAs (one SM pair) own a 256 x 256 output tile.
+//        Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N-rows) per
+//        64-wide K block -- 32 KB per stage instead of 48 KB, 6 stages instead of 4 -- and the
+//        leader CTA issues tcgen05.mma.cta_group::2 (256 x 256 x 16), which reads A and B from
+//        both CTAs' shared memory and writes each CTA's 128 x 256 accumulator half into that CTA's
+//        TMEM.  Per-SM shared-memory fill traffic per flop drops by a third, which is what the
+//        main loop of the 1-CTA version was bound by.
+//   CG = 1: one CTA per 128 x 256 tile (kept for A/B measurements: JPCB_TC_FLAGS bit 1).
+//
+//   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 bf16 along K) into the
+//                              shared-memory ring; completion (of BOTH CTAs' bytes when CG = 2) on
+//                              the leader's `full` mbarriers
+//   warp 1      MMA issuer   : one elected lane of the leader CTA issues tcgen05.mma; tcgen05.commit
+//                              (multicast to both CTAs) frees ring slots and publishes the
+//                              accumulator; also owns the TMEM allocation (512 columns = two
+//                              accumulator stages, so tile i+1's MMAs overlap tile i's epilogue)
+//   warps 2..9  epilogue     : per 32x16 patch: issue all global loads of the fused epilogue (one
+//                              patch ahead, so two patches of loads are in flight), tcgen05.ld the
+//                              accumulator (lane = row), transpose it through XOR-swizzled shared
+//                              memory so that all global traffic is row-contiguous 16-byte vectors,
+//                              then epi_finish (activation, derivative, error, Euler/Heun update,
+//                              bf16 operand copy for the next GEMM, energy reduction), specialised
+//                              at compile time per mode / activation.
 //
 // One launch processes every layer of a phase (grouped): tiles of all tasks are flattened and
-// CTA c handles tiles c, c+grid, c+2*grid, ...  (grid = min(#tiles, #SMs), 1 CTA/SM).
+// cluster c handles tiles c, c+#clusters, ...  (grid = min(CG * #tiles, #SMs), 1 CTA/SM).
 #pragma once
 #include <cuda.h>
 
@@ -24,23 +36,28 @@
 
 namespace jpcb {
 
-constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_M = 128;  // rows per CTA (a CG = 2 cluster tile has 256)
 constexpr int TC_BLOCK_N = 256;
 constexpr int TC_BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
-constexpr int TC_B_BYTES = TC_BLOCK_N * TC_BLOCK_K * 2;
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_XPOSE_BYTES = 32 * 16 * 4;  // one 32x16 fp32 patch per epilogue warp
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES + TC_EPI_WARPS * TC_XPOSE_BYTES + 256;
 constexpr int TC_TMEM_COLS = 512;
+
+template <int CG>
+struct TcCfg {
+  static constexpr int B_ROWS = TC_BLOCK_N / CG;           // N-rows of B staged by each CTA
+  static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + TC_EPI_WARPS * TC_XPOSE_BYTES + 256;
+};
 
 struct alignas(64) TcTask {
   CUtensorMap tmA;  // bf16 [M, K] row-major, box {64, 128}
-  CUtensorMap tmB;  // bf16 [N, K] row-major, box {64, 256}
+  CUtensorMap tmB;  // bf16 [N, K] row-major, box {64, 256 / CG}
   int K;
   int tile_begin;
   int tiles_n;
@@ -100,42 +117,114 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// TMA tile load into this CTA's shared memory.  CG = 2: completion bytes are signalled on `bar`,
+// a shared::cluster address that may belong to the peer (leader) CTA.
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      :
-      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// ---- thread-block cluster helpers (CG = 2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier given by a shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  // relaxed: the arrive only hands a TMEM stage back (its reads completed at tcgen05.wait::ld); a
+  // release here would first drain all of the epilogue's global stores
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]
+// D[tmem] (+)= A[smem desc] * B[smem desc]; CG = 2: M = 256 over the CTA pair, operands from both CTAs
+template <int CG>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
+// mbarrier arrive once all previously issued MMAs have completed; CG = 2: on the barrier at the
+// same offset in BOTH CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
 }
@@ -159,61 +248,146 @@ __device__ __forceinline__ int tc_find_task(const TcGroup& g, int tile) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Epilogue of one warp's 32-row x 128-column share of a tile: 8 patches of 32 rows x 16 columns.
+// Per patch: (1) the global loads the fused epilogue needs were issued one patch earlier (the
+// first patch's even before the accumulator is complete), in the coalesced layout (4 lanes x 16 B
+// = one 64-byte row segment, 8 rows per instruction; unconditional, on clamped coordinates), so
+// two patches of loads are in flight per thread; (2) tcgen05.ld the accumulator patch (lane =
+// row); (3) transpose it through XOR-swizzled shared memory into the same coalesced layout;
+// (4) finish + store.  MODE/SUB/ACT are compile-time so that (4) is straight-line code
+// (-1 = generic: read from the descriptor).
+template <int MODE>
+__device__ __forceinline__ void tc_epi_loads(const Epi& e, int row0, int cb, int lane, EpiPre (&pre)[4], float (&bias4)[4]) {
+  const int c4 = lane & 3, rq = lane >> 2;
+  const int colc = min(cb + 4 * c4, e.N - 4);  // N % 8 == 0 on this path
+#pragma unroll
+  for (int i = 0; i < 4; ++i) epi_preload<MODE>(e, min(row0 + rq + 8 * i, e.M - 1), colc, 4, true, pre[i]);
+  if (MODE == EPI_FFWD || MODE == EPI_ERR || MODE < 0) {
+    if (e.bias != nullptr) {
+      const float4 bv = *reinterpret_cast<const float4*>(e.bias + colc);
+      bias4[0] = bv.x; bias4[1] = bv.y; bias4[2] = bv.z; bias4[3] = bv.w;
+    }
+  }
+}
+
+template <int MODE, int SUB, int ACT>
+__device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, int lane, uint32_t taddr, float* xp,
+                                              const EpiPre (&pre)[4], const float (&bias4)[4]) {
+  const int c4 = lane & 3, rq = lane >> 2;
+  const int col = cb + 4 * c4;
+  const bool cok = col < e.N;
+  uint4* xp4 = reinterpret_cast<uint4*>(xp);
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
+  tmem_ld_wait();
+  // row `lane` of the patch -> smem; 16-byte chunk k of row r sits at r*4 + (k ^ ((r >> 1) & 3))
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    xp4[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = rq + 8 * i;
+    const float4 a = *reinterpret_cast<const float4*>(xp4 + rl * 4 + (c4 ^ ((rl >> 1) & 3)));
+    const int row = row0 + rl;
+    if (cok && row < e.M) {
+      const float a4[4] = {a.x, a.y, a.z, a.w};
+      r += epi_finish<true, MODE, SUB, ACT>(e, row, col, a4, 4, true, pre[i], true, bias4);
+    }
+  }
+  __syncwarp();
+  return r;
+}
+
+template <int MODE, int SUB, int ACT>
+__device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
+                                             uint32_t tphase) {
+  float r = 0.f;
+  EpiPre pa[4], pb[4];
+  float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+  tc_epi_loads<MODE>(e, row0, col0, lane, pa, ba);
+  mbar_wait(tfull, tphase);  // accumulator of this tile complete
+  tc_fence_after();
+#pragma unroll 1
+  for (int ch = 0; ch < 8; ch += 2) {
+    const int cb = col0 + ch * 16;  // first column of this 16-wide patch
+    if (cb >= e.N) break;           // warp-uniform
+    tc_epi_loads<MODE>(e, row0, cb + 16, lane, pb, bb);
+    r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
+    if (cb + 16 >= e.N) break;
+    if (ch + 2 < 8) tc_epi_loads<MODE>(e, row0, cb + 32, lane, pa, ba);
+    r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MODE/SUB/ACT >= 0: every task of the launch has that epilogue mode / GRAD sub-mode / activation
+// (the host checks), compiled in; -1 = generic descriptor-driven epilogue.
+template <int CG, int MODE, int SUB, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
+  using Cfg = TcCfg<CG>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t xpose_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
-  float* xpose_ptr = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t xpose_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  float* xpose_ptr = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
   const uint32_t bar_base = xpose_base + TC_EPI_WARPS * TC_XPOSE_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_EPI_WARPS * TC_XPOSE_BYTES + 8 * (2 * TC_STAGES + 4));
-  const uint32_t tmem_slot_addr = bar_base + 8u * (2 * TC_STAGES + 4);
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + TC_EPI_WARPS * TC_XPOSE_BYTES + 8 * (2 * STAGES + 4));
+  const uint32_t tmem_slot_addr = bar_base + 8u * (2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader CTA of the pair
+  const int unit = (int)blockIdx.x / CG, nunits = (int)gridDim.x / CG;  // tile-owning CTA (pair) and their number
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx (covers both CTAs' bytes)
+      mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast to both CTAs when CG = 2)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), TC_EPI_WARPS);
+      mbar_init(tempty_bar(s), TC_EPI_WARPS * CG);  // the epilogue warps of both CTAs arrive on the leader's
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot_addr, TC_TMEM_COLS);
+  if (warp == 1) tmem_alloc<CG>(tmem_slot_addr, TC_TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < g.total_tiles; tile += nunits) {
       const int ti = tc_find_task(g, tile);
       const TcTask& t = g.t[ti];
       const int local = tile - t.tile_begin;
-      const int m0 = (local / t.tiles_n) * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
+      const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M;
+      const int n0 = (local % t.tiles_n) * TC_BLOCK_N + (int)rank * Cfg::B_ROWS;
       const int nkb = (t.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
       if (lane == 0) {
         tma_prefetch_desc(&t.tmA);
         tma_prefetch_desc(&t.tmB);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-          tma_load_2d(sa, &t.tmA, full_bar(stage), kb * TC_BLOCK_K, m0);
-          tma_load_2d(sa + TC_A_BYTES, &t.tmB, full_bar(stage), kb * TC_BLOCK_K, n0);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CG);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d<CG>(sa, &t.tmA, fb, kb * TC_BLOCK_K, m0);
+          tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
       // keep the warp's lanes in lock-step with the elected lane's ring position
@@ -221,90 +395,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       phase = __shfl_sync(0xffffffffu, phase, 0);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M, TC_BLOCK_N);
-    int stage = 0;
-    uint32_t phase = 0;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-      const int ti = tc_find_task(g, tile);
-      const int nkb = (g.t[ti].K + TC_BLOCK_K - 1) / TC_BLOCK_K;
-      if (lane == 0) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BLOCK_N);
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M * CG, TC_BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = unit; tile < g.total_tiles; tile += nunits) {
+        const int ti = tc_find_task(g, tile);
+        const int nkb = (g.t[ti].K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+        if (lane == 0) {
+          mbar_wait(tempty_bar(as), aphase ^ 1u);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-          const uint64_t da = umma_desc_kmajor_sw128(sa);
-          const uint64_t db = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BLOCK_N);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint64_t da = umma_desc_kmajor_sw128(sa);
+            const uint64_t db = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-            // advancing K inside the 128-byte swizzle row: +32 B => +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+              // advancing K inside the 128-byte swizzle row: +32 B => +2 in the (addr >> 4) field
+              umma_f16<CG>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<CG>(empty_bar(stage));  // ring slot reusable once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(empty_bar(stage));  // ring slot reusable once these MMAs have read it
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          umma_commit<CG>(tfull_bar(as));  // accumulator complete
         }
-        umma_commit(tfull_bar(as));  // accumulator complete
+        stage = __shfl_sync(0xffffffffu, stage, 0);
+        phase = __shfl_sync(0xffffffffu, phase, 0);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-      stage = __shfl_sync(0xffffffffu, stage, 0);
-      phase = __shfl_sync(0xffffffffu, phase, 0);
-      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
     const int ew = warp - 2;          // 0..7
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = ew >> 2;         // which 128 columns of the 256-wide tile
     float* xp = xpose_ptr + ew * (TC_XPOSE_BYTES / 4);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < g.total_tiles; tile += nunits) {
       const int ti = tc_find_task(g, tile);
       const TcTask& t = g.t[ti];
-      const Epi& e = t.e;
+      const Epi e = epi_pin(t.e);  // registers, not runtime-indexed parameter space (see epi_pin)
       const int local = tile - t.tile_begin;
-      const int m0 = (local / t.tiles_n) * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      float r = 0.f;
+      const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + half * 128);
-#pragma unroll 1
-      for (int ch = 0; ch < 8; ++ch) {
-        const int cb = n0 + half * 128 + ch * 16;  // first column of this 16-wide patch
-        if (cb >= e.N) break;                       // warp-uniform
-        uint32_t v[16];
-        tmem_ld16(t_row + (uint32_t)(ch * 16), v);
-        tmem_ld_wait();
-        // row `lane` of the patch -> swizzled smem (16-byte chunk k of row r sits at r*4 + (k ^ ((r>>1)&3)))
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int pos = lane * 4 + (k ^ ((lane >> 1) & 3));
-          *reinterpret_cast<uint4*>(xp + pos * 4) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        }
-        __syncwarp();
-        const int c4 = lane & 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rl = (lane >> 2) + 8 * i;
-          const int pos = rl * 4 + (c4 ^ ((rl >> 1) & 3));
-          const float4 a = *reinterpret_cast<const float4*>(xp + pos * 4);
-          const int row = m0 + q * 32 + rl;
-          const int col = cb + 4 * c4;
-          if (row < e.M && col < e.N) {
-            const float a4[4] = {a.x, a.y, a.z, a.w};
-            r += epi_apply4<true>(e, row, col, a4, 4, true);
-          }
-        }
-        __syncwarp();
-      }
+      // (waits for the accumulator inside, after the first patch's loads are in flight)
+      float r = tc_epi_warp<MODE, SUB, ACT>(e, m0 + q * 32, n0 + half * 128, lane, t_row, xp, tfull_bar(as), aphase);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): release the stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));
+        else mbar_arrive(tempty_bar(as));
+      }
       if (e.red != nullptr) {
         r = warp_sum(r);
         if (lane == 0) atomicAdd(e.red, r);
@@ -314,10 +463,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, TC_TMEM_COLS);
   }
 }
 
