@@ -176,8 +176,10 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, size_t idx, i
 //   epi_finish  : consumes them + the 4 accumulator values, stores, returns the reduction term
 struct EpiPre {
   float a[4];  // GRAD: z          ERR: target T    FFWD: loss target Y   SCALE(accum): old O
-  float b[4];  // GRAD: e_l (fp32) or P, or -- when Elb is the source -- the 4 packed bf16 of e_l as raw bits
-               // in b[0..1]                        FFWD/ERR: skip input U
+  float b[4];  // GRAD: e_l (fp32) or P              FFWD/ERR: skip input U
+  uint2 h;     // GRAD: e_l as 4 packed bf16 when Elb is the source.  Deliberately NOT overlaid on b: two
+               // differently predicated loads into the same registers make the second one wait for
+               // every load that shares the first one's scoreboard slot.
 };
 
 __device__ __forceinline__ void unpack_bf16x4(const uint2& t, float (&v)[4]) {
@@ -195,14 +197,9 @@ __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int 
   const int mode = MODE >= 0 ? MODE : e.mode;
   if (mode == EPI_GRAD) {
     ld4(e.Z, idx, nvalid, vec, p.a);
-    if (e.El) ld4(e.El, idx, nvalid, vec, p.b);
-    else if (e.Elb) {
-      if (vec) {
-        const uint2 t = *reinterpret_cast<const uint2*>(e.Elb + idx);
-        p.b[0] = __uint_as_float(t.x);
-        p.b[1] = __uint_as_float(t.y);
-      } else ld4(e.Elb, idx, nvalid, false, p.b);
-    } else ld4(e.P, idx, nvalid, vec, p.b);
+    if (e.El || !e.Elb) ld4(e.El ? e.El : e.P, idx, nvalid, vec, p.b);
+    else if (vec) p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
+    else ld4(e.Elb, idx, nvalid, false, p.b);
   } else if (mode == EPI_ERR) {
     ld4(e.T, idx, nvalid, vec, p.a);
     if (e.skip != 0.f) ld4(e.U, idx, nvalid, vec, p.b);
@@ -274,7 +271,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) el[j] = p.b[j];
   } else if (e.Elb) {
-    if (vec) unpack_bf16x4(make_uint2(__float_as_uint(p.b[0]), __float_as_uint(p.b[1])), el);
+    if (vec) unpack_bf16x4(p.h, el);
     else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) el[j] = p.b[j];

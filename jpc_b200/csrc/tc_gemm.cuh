@@ -41,7 +41,15 @@ constexpr int TC_BLOCK_N = 256;
 constexpr int TC_BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
-constexpr int TC_EPI_WARPS = 8;
+#ifndef JPCB_TC_EPI_WARPS
+#define JPCB_TC_EPI_WARPS 8
+#endif
+#ifndef JPCB_TC_EPI_PIPE
+#define JPCB_TC_EPI_PIPE 1
+#endif
+constexpr int TC_EPI_WARPS = JPCB_TC_EPI_WARPS;                 // 8 or 16 (multiples of the 4 TMEM lane quarters)
+constexpr int TC_EPI_COLS = TC_BLOCK_N / (TC_EPI_WARPS / 4);   // columns of the tile one epilogue warp owns
+constexpr int TC_EPI_PATCHES = TC_EPI_COLS / 16;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_XPOSE_BYTES = 32 * 16 * 4;  // one 32x16 fp32 patch per epilogue warp
 constexpr int TC_TMEM_COLS = 512;
@@ -304,21 +312,36 @@ template <int MODE, int SUB, int ACT>
 __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
                                              uint32_t tphase) {
   float r = 0.f;
+#if JPCB_TC_EPI_PIPE
   EpiPre pa[4], pb[4];
   float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
   tc_epi_loads<MODE>(e, row0, col0, lane, pa, ba);
   mbar_wait(tfull, tphase);  // accumulator of this tile complete
   tc_fence_after();
 #pragma unroll 1
-  for (int ch = 0; ch < 8; ch += 2) {
+  for (int ch = 0; ch < TC_EPI_PATCHES; ch += 2) {
     const int cb = col0 + ch * 16;  // first column of this 16-wide patch
     if (cb >= e.N) break;           // warp-uniform
     tc_epi_loads<MODE>(e, row0, cb + 16, lane, pb, bb);
     r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
     if (cb + 16 >= e.N) break;
-    if (ch + 2 < 8) tc_epi_loads<MODE>(e, row0, cb + 32, lane, pa, ba);
+    if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE>(e, row0, cb + 32, lane, pa, ba);
     r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
   }
+#else
+  EpiPre pa[4];
+  float ba[4] = {0.f, 0.f, 0.f, 0.f};
+  tc_epi_loads<MODE>(e, row0, col0, lane, pa, ba);
+  mbar_wait(tfull, tphase);  // accumulator of this tile complete
+  tc_fence_after();
+#pragma unroll 1
+  for (int ch = 0; ch < TC_EPI_PATCHES; ++ch) {
+    const int cb = col0 + ch * 16;
+    if (cb >= e.N) break;
+    if (ch > 0) tc_epi_loads<MODE>(e, row0, cb, lane, pa, ba);
+    r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
+  }
+#endif
   return r;
 }
 
@@ -432,9 +455,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
     }
   } else {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
-    const int ew = warp - 2;          // 0..7
+    const int ew = warp - 2;          // 0..TC_EPI_WARPS-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = ew >> 2;         // which 128 columns of the 256-wide tile
+    const int part = ew >> 2;         // which TC_EPI_COLS columns of the 256-wide tile
     float* xp = xpose_ptr + ew * (TC_XPOSE_BYTES / 4);
     int as = 0;
     uint32_t aphase = 0;
@@ -444,9 +467,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       const Epi e = epi_pin(t.e);  // registers, not runtime-indexed parameter space (see epi_pin)
       const int local = tile - t.tile_begin;
       const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + half * 128);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + part * TC_EPI_COLS);
       // (waits for the accumulator inside, after the first patch's loads are in flight)
-      float r = tc_epi_warp<MODE, SUB, ACT>(e, m0 + q * 32, n0 + half * 128, lane, t_row, xp, tfull_bar(as), aphase);
+      float r = tc_epi_warp<MODE, SUB, ACT>(e, m0 + q * 32, n0 + part * TC_EPI_COLS, lane, t_row, xp, tfull_bar(as), aphase);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): release the stage
       tc_fence_before();
       __syncwarp();
