@@ -137,9 +137,14 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
                        size_t workspace_bytes, void* stream);
 
 /* ---- bidirectional PC (jpc/_core/_energies.py:246-357) ---------------------------------------
- * top-down model W (layers 0..H, f_l), bottom-up model V (layers 0..H, g_l); H = n_layers-1 of
- * `td`.  Activities A[0..H-1] are z_0..z_{H-1}; A[H] is the unused dummy slot.  `bu->dims[l]` is
- * the INPUT dim of bottom_up_model[l] and bu->dims[l+1]... see DESIGN.md for the index map. */
+ * H = td.n_layers - 1.  Top-down model W_j (j = 0..H): [td.dims[j+1], td.dims[j]], maps u_j (x for
+ * j = 0, else z_{j-1}) to a prediction of t_j (z_j, or y for j = H).  Bottom-up model V_j (j = 0..H):
+ * [td.dims[j], td.dims[j+1]], maps v_j (z_j, or y for j = H) to a prediction of tau_j (x for j = 0,
+ * else z_{j-1}).  Activities A[0..H-1] = z_0..z_{H-1} with z_k of width td.dims[k+1]; A[H] is the
+ * unused dummy slot ([batch, td.dims[H+1]]).  x: [batch, td.dims[0]], y: [batch, td.dims[H+1]].
+ * td.skip[j] (1 <= j <= H-1) applies to both directions, td.scalings is ignored (the reference
+ * validates param_type but applies no scalings, _energies.py:314).  Supervised mode (x given), Euler
+ * steps, fp32 CUDA-core path in this version (td.dtype = JPCB_DTYPE_F32). */
 typedef struct jpcb_bpc_desc {
   jpcb_pc_desc td;                 /* top-down model: dims d_0(x) .. d_{H+1}(y); solver fields used */
   int32_t bu_act[JPCB_MAX_LAYERS]; /* activation applied to the input of bottom_up_model[l] */

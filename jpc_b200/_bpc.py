@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's bidirectional-PC functions over the jpcb_bpc_* C-ABI.
+
+  bpc_energy_fn              jpc/_core/_energies.py:246-357
+  compute_bpc_activity_grad  jpc/_core/_grads.py:170-226
+  compute_bpc_param_grads    jpc/_core/_grads.py:544-612
+  update_bpc_activities      jpc/_core/_updates.py:206-281
+  update_bpc_params          jpc/_core/_updates.py:284-372
+  solve_bpc_inference        (no reference twin: the fused equivalent of the reference's Python loop
+                              `for _ in range(T): update_bpc_activities(..., optax.sgd(dt))`,
+                              examples/bidirectional_pc.ipynb cell 8 -- all T steps stay on the device)
+
+Same names, arguments, return structures and exceptions as the reference; no arithmetic here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._core import _layer_parts, _skip_flags, _WS_CACHE
+from ._errors import _check_param_type
+from .nn import tree_unflatten_like
+from .optim import apply_updates
+
+
+class _BpcNet:
+    """(top_down, bottom_up) lowered to a jpcb_bpc_desc + pointer arrays."""
+
+    def __init__(self, top_down_model, bottom_up_model, x, y, *, skip_model, param_type, backward_energy_weight,
+                 forward_energy_weight, n_steps=0, dt=0.0, batch_global=None):
+        _check_param_type(param_type)  # validated; bpc_energy_fn applies no scalings (_energies.py:314)
+        if x is None:
+            raise NotImplementedError("bPC with an unclamped input (x=None) is not on the B200 path yet")
+        if len(top_down_model) != len(bottom_up_model):
+            raise ValueError("top_down_model and bottom_up_model must have the same number of layers")
+        n = len(top_down_model)
+        H = n - 1
+        td = [_layer_parts(l) for l in top_down_model]
+        bu = [_layer_parts(l) for l in bottom_up_model]
+        self.td_lin, self.bu_lin = [p[1] for p in td], [p[1] for p in bu]
+        self.top_down_model, self.bottom_up_model = top_down_model, bottom_up_model
+        Ws, Vs = [l.weight for l in self.td_lin], [l.weight for l in self.bu_lin]
+        dev = Ws[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("jpc_b200 has no CPU path: model weights must be CUDA tensors")
+        for t in Ws + Vs + [x, y]:
+            if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
+        dims = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+        for j in range(n):
+            if Ws[j].shape[1] != dims[j]:
+                raise ValueError(f"top-down layer {j}: weight shape {tuple(Ws[j].shape)} does not chain from {dims[j]}")
+            if tuple(Vs[j].shape) != (dims[j], dims[j + 1]):
+                raise ValueError(f"bottom-up layer {j}: weight shape {tuple(Vs[j].shape)}, expected {(dims[j], dims[j + 1])}")
+        if x.shape[1] != dims[0] or y.shape[1] != dims[-1] or x.shape[0] != y.shape[0]:
+            raise ValueError("input / output shapes do not match the models")
+        td_bias = [l.bias is not None for l in self.td_lin]
+        bu_bias = [l.bias is not None for l in self.bu_lin]
+        if (any(td_bias) and not all(td_bias)) or (any(bu_bias) and not all(bu_bias)):
+            raise NotImplementedError("mixed bias / no-bias layers are not on the B200 path")
+        skips = _skip_flags(skip_model, n)
+        B = x.shape[0]
+        d = _lib.BpcDesc()
+        d.td.n_layers, d.td.batch_local = n, B
+        d.td.batch_global = B if batch_global is None else int(batch_global)
+        for i, v in enumerate(dims):
+            d.td.dims[i] = v
+        for j in range(n):
+            d.td.act[j] = _lib.ACT_IDS[td[j][0]]
+            d.bu_act[j] = _lib.ACT_IDS[bu[j][0]]
+            d.td.skip[j] = 1 if skips[j] else 0
+            d.td.scalings[j] = 1.0
+        d.td.has_bias, d.bu_has_bias = int(all(td_bias)), int(all(bu_bias))
+        d.td.dtype, d.td.loss = _lib.DTYPE_F32, _lib.LOSS_MSE
+        d.td.output_energy_scaling, d.td.activity_decay = 1.0, 0.0
+        d.td.solver, d.td.n_steps, d.td.dt, d.td.dt_last = _lib.SOLVER_EULER, int(n_steps), float(dt), float(dt)
+        d.forward_energy_weight, d.backward_energy_weight = float(forward_energy_weight), float(backward_energy_weight)
+        self.desc = d
+        self.ws_bytes = _lib.lib.jpcb_bpc_workspace_bytes(d)
+        if self.ws_bytes == 0:
+            _lib.check(_lib.lib.jpcb_bpc_energy(d, None, None, None, None, None, None, None, None, None, 0, None) or _lib.EINVAL)
+        self.H, self.B, self.dims, self.dev = H, B, dims, dev
+        self.td_bias, self.bu_bias = all(td_bias), all(bu_bias)
+        self.W, self.V = _lib.ptr_array(Ws), _lib.ptr_array(Vs)
+        self.bW = _lib.ptr_array([l.bias for l in self.td_lin]) if self.td_bias else None
+        self.bV = _lib.ptr_array([l.bias for l in self.bu_lin]) if self.bu_bias else None
+        self._keep = (Ws, Vs)
+        self.x, self.y = x, y
+
+    def workspace(self):
+        ws = _WS_CACHE.get((self.dev,))
+        if ws is None or ws.numel() < self.ws_bytes:
+            ws = torch.empty(max(self.ws_bytes, 1 << 20), dtype=torch.uint8, device=self.dev)
+            _WS_CACHE[(self.dev,)] = ws
+        return ws
+
+    def stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def check_acts(self, activities):
+        """H+1 arrays: z_0..z_{H-1} and the unused last slot (activities[-2] must be z_{H-1},
+        jpc/_core/_energies.py:331)."""
+        if len(activities) != self.H + 1:
+            raise ValueError(f"expected {self.H + 1} activity arrays (z_0..z_{self.H - 1} + the unused output slot), got {len(activities)}")
+        for k, a in enumerate(activities[:-1]):
+            if tuple(a.shape) != (self.B, self.dims[k + 1]):
+                raise ValueError(f"activities[{k}] has shape {tuple(a.shape)}, expected {(self.B, self.dims[k + 1])}")
+        for a in activities:
+            if a.device != self.dev or a.dtype != torch.float32 or not a.is_contiguous():
+                raise ValueError("activities must be contiguous fp32 CUDA tensors")
+
+    def args(self):
+        return (self.desc, self.W, self.bW, self.V, self.bV)
+
+
+def _net(top_down_model, bottom_up_model, x, y, skip_model, param_type, backward_energy_weight, forward_energy_weight, **kw):
+    return _BpcNet(top_down_model, bottom_up_model, x, y, skip_model=skip_model, param_type=param_type,
+                   backward_energy_weight=backward_energy_weight, forward_energy_weight=forward_energy_weight, **kw)
+
+
+def bpc_energy_fn(top_down_model, bottom_up_model, activities, y, *, x=None, skip_model=None, param_type="sp",
+                  record_layers=False, backward_energy_weight=1.0, forward_energy_weight=1.0):
+    """jpc/_core/_energies.py:246-357."""
+    net = _net(top_down_model, bottom_up_model, x, y, skip_model, param_type, backward_energy_weight, forward_energy_weight)
+    net.check_acts(activities)
+    ws = net.workspace()
+    E = torch.empty(2 * (net.H + 1), dtype=torch.float32, device=net.dev)
+    _lib.check(_lib.lib.jpcb_bpc_energy(*net.args(), _lib.ptr_array(activities), _lib.ptr(x), _lib.ptr(y), _lib.ptr(E),
+                                        _lib.ptr(ws), ws.numel(), net.stream()))
+    return E if record_layers else E.sum()
+
+
+def compute_bpc_activity_grad(top_down_model, bottom_up_model, activities, y, *, x=None, skip_model=None, param_type="sp",
+                              backward_energy_weight=1.0, forward_energy_weight=1.0):
+    """jpc/_core/_grads.py:170-226: (energy, dF/dactivities)."""
+    net = _net(top_down_model, bottom_up_model, x, y, skip_model, param_type, backward_energy_weight, forward_energy_weight)
+    net.check_acts(activities)
+    ws = net.workspace()
+    F = torch.empty((), dtype=torch.float32, device=net.dev)
+    g = [torch.empty_like(a) for a in activities]
+    _lib.check(_lib.lib.jpcb_bpc_activity_grad(*net.args(), _lib.ptr_array(activities), _lib.ptr(x), _lib.ptr(y), _lib.ptr(F),
+                                               _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
+    return F, g
+
+
+def _param_grads(net, activities, want_energies=False):
+    gW = [torch.empty_like(l.weight) for l in net.td_lin]
+    gV = [torch.empty_like(l.weight) for l in net.bu_lin]
+    gbW = [torch.empty_like(l.bias) for l in net.td_lin] if net.td_bias else None
+    gbV = [torch.empty_like(l.bias) for l in net.bu_lin] if net.bu_bias else None
+    E = torch.empty(2 * (net.H + 1), dtype=torch.float32, device=net.dev) if want_energies else None
+    ws = net.workspace()
+    _lib.check(_lib.lib.jpcb_bpc_param_grads(*net.args(), _lib.ptr_array(activities), _lib.ptr(net.x), _lib.ptr(net.y),
+                                             _lib.ptr_array(gW), _lib.ptr_array(gbW) if gbW else None, _lib.ptr_array(gV),
+                                             _lib.ptr_array(gbV) if gbV else None, _lib.ptr(E), _lib.ptr(ws), ws.numel(),
+                                             net.stream()))
+
+    def tree(model, gw, gb):
+        leaves = []
+        for j in range(len(gw)):
+            leaves.append(gw[j])
+            if gb is not None:
+                leaves.append(gb[j])
+        return tree_unflatten_like(model, leaves)
+    return tree(net.top_down_model, gW, gbW), tree(net.bottom_up_model, gV, gbV), E
+
+
+def compute_bpc_param_grads(top_down_model, bottom_up_model, activities, y, *, x=None, skip_model=None, param_type="sp",
+                            backward_energy_weight=1.0, forward_energy_weight=1.0):
+    """jpc/_core/_grads.py:544-612: (top_down_grads, bottom_up_grads) with the models' structure."""
+    net = _net(top_down_model, bottom_up_model, x, y, skip_model, param_type, backward_energy_weight, forward_energy_weight)
+    net.check_acts(activities)
+    td, bu, _ = _param_grads(net, activities)
+    return td, bu
+
+
+def update_bpc_activities(top_down_model, bottom_up_model, activities, optim, opt_state, output, *, input=None,
+                          skip_model=None, param_type="sp", backward_energy_weight=1.0, forward_energy_weight=1.0):
+    """jpc/_core/_updates.py:206-281."""
+    energy, grads = compute_bpc_activity_grad(top_down_model, bottom_up_model, activities, output, x=input,
+                                              skip_model=skip_model, param_type=param_type,
+                                              backward_energy_weight=backward_energy_weight,
+                                              forward_energy_weight=forward_energy_weight)
+    updates, opt_state = optim.update(grads, opt_state, activities)
+    activities = apply_updates(activities, updates)
+    return {"energy": energy, "activities": activities, "grads": grads, "opt_state": opt_state}
+
+
+def update_bpc_params(top_down_model, bottom_up_model, activities, top_down_optim, bottom_up_optim, top_down_opt_state,
+                      bottom_up_opt_state, output, *, input=None, skip_model=None, param_type="sp",
+                      backward_energy_weight=1.0, forward_energy_weight=1.0):
+    """jpc/_core/_updates.py:284-372."""
+    td_g, bu_g = compute_bpc_param_grads(top_down_model, bottom_up_model, activities, output, x=input, skip_model=skip_model,
+                                         param_type=param_type, backward_energy_weight=backward_energy_weight,
+                                         forward_energy_weight=forward_energy_weight)
+    td_u, top_down_opt_state = top_down_optim.update(td_g, top_down_opt_state, top_down_model)
+    bu_u, bottom_up_opt_state = bottom_up_optim.update(bu_g, bottom_up_opt_state, bottom_up_model)
+    top_down_model = apply_updates(top_down_model, td_u)
+    bottom_up_model = apply_updates(bottom_up_model, bu_u)
+    return {"models": (top_down_model, bottom_up_model), "grads": (td_g, bu_g),
+            "opt_states": (top_down_opt_state, bottom_up_opt_state)}
+
+
+def solve_bpc_inference(top_down_model, bottom_up_model, activities, output, *, input=None, n_steps=1, dt=0.5,
+                        skip_model=None, param_type="sp", backward_energy_weight=1.0, forward_energy_weight=1.0):
+    """n_steps fused Euler steps of size dt on the bPC energy == n_steps x update_bpc_activities with
+    optax.sgd(dt) (the reference's inference loop), without returning to the host in between."""
+    net = _net(top_down_model, bottom_up_model, input, output, skip_model, param_type, backward_energy_weight,
+               forward_energy_weight, n_steps=n_steps, dt=dt)
+    net.check_acts(activities)
+    A = [a.clone() for a in activities]
+    ws = net.workspace()
+    _lib.check(_lib.lib.jpcb_bpc_infer(*net.args(), _lib.ptr_array(A), _lib.ptr(input), _lib.ptr(output), _lib.ptr(ws),
+                                       ws.numel(), net.stream()))
+    return A

@@ -576,24 +576,4 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
   return r.finalize(E_layers, nullptr, false, loss_out);
 }
 
-// ---- bPC ----
-size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc) { (void)desc; return 0; }
-int jpcb_bpc_energy(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
-                    const float* const*, const float*, const float*, float*, void*, size_t, void*) {
-  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
-}
-int jpcb_bpc_activity_grad(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
-                           const float* const*, const float*, const float*, float*, float* const*, void*, size_t, void*) {
-  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
-}
-int jpcb_bpc_infer(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
-                   float* const*, const float*, const float*, void*, size_t, void*) {
-  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
-}
-int jpcb_bpc_param_grads(const jpcb_bpc_desc*, const float* const*, const float* const*, const float* const*, const float* const*,
-                         const float* const*, const float*, const float*, float* const*, float* const*, float* const*,
-                         float* const*, float*, void*, size_t, void*) {
-  return fail(JPCB_ENOTIMPL, "bPC is not on the B200 path yet");
-}
-
 }  // extern "C"

@@ -1,0 +1,324 @@
+// bpc.cu -- bidirectional predictive coding (reference: jpc/_core/_energies.py:246-357 `bpc_energy_fn`,
+// jpc/_core/_grads.py:170-226,544-612, jpc/_core/_updates.py:206-372) on the grouped-GEMM kernels.
+//
+// Index map (H = n_layers-1 of the top-down model; D[0..H+1] = td.dims; activities A[0..H-1] =
+// z_0..z_{H-1}, A[H] = unused dummy slot):
+//   top-down  layer j = 0..H : W_j [D[j+1], D[j]],  input u_j = x (j=0) | z_{j-1},  target t_j = z_j | y (j=H)
+//       e_j     = t_j - (W_j phi_j(u_j) + b_j) - s_j u_j              (s_j = 1 only for 1 <= j <= H-1)
+//   bottom-up layer j = 0..H : V_j [D[j], D[j+1]],  input v_j = z_j | y (j=H),      target tau_j = x (j=0) | z_{j-1}
+//       delta_j = tau_j - (V_j psi_j(v_j) + c_j) - s_j v_j            (s_j = 1 only for 1 <= j <= H-1)
+//   F = (alpha_f sum_j |e_j|^2/2 + alpha_b sum_j |delta_j|^2/2) / B     (no param_type scalings, _energies.py:314)
+//   dF/dz_k = (1/B) [ alpha_f (e_k     - phi_{k+1}'(z_k) (e_{k+1} W_{k+1}) - s_{k+1} e_{k+1})
+//                   + alpha_b (delta_{k+1} - psi_k'(z_k)   (delta_k V_k)     - s_k delta_k) ]
+//   dF/dW_j = -(alpha_f/B) e_j^T phi_j(u_j)        dF/dV_j = -(alpha_b/B) delta_j^T psi_j(v_j)
+// One evaluation = three grouped launches: all 2(H+1) errors; the forward-direction half of every
+// activity gradient (into a scratch buffer); the backward-direction half + combination + Euler
+// update.  The two constant predictions (W_0 phi_0(x) and V_H psi_H(y)) are hoisted out of the loop.
+//
+// This first version runs the fp32 CUDA-core path (1e-5 parity, BASELINE config 5 is fp32); the
+// bf16 tensor-core schedule for bPC is the next step.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "elementwise.cuh"
+#include "host.cuh"
+
+using namespace jpcb;
+
+namespace {
+
+// acc[0..H] = sum |e_j|^2/2, acc[H+1..2H+1] = sum |delta_j|^2/2  ->  reference pair order
+// [(e_H, delta_0), (e_0, delta_1), ..., (e_{H-1}, delta_H)] / B  (jpc/_core/_energies.py:322-355)
+__global__ void bpc_finalize_kernel(const float* __restrict__ acc, int H, float inv_b, float af, float ab, float* E_pairs, float* F) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float* e = acc;
+    const float* d = acc + H + 1;
+    float tot = 0.f;
+    for (int j = 0; j <= H; ++j) tot += af * e[j] + ab * d[j];
+    if (E_pairs) {
+      E_pairs[0] = af * e[H] * inv_b;
+      E_pairs[1] = ab * d[0] * inv_b;
+      for (int l = 0; l < H; ++l) {
+        E_pairs[2 + 2 * l] = af * e[l] * inv_b;
+        E_pairs[3 + 2 * l] = ab * d[l + 1] * inv_b;
+      }
+    }
+    if (F) *F = tot * inv_b;
+  }
+}
+
+int validate_bpc(const jpcb_bpc_desc* d) {
+  if (!d) return fail(JPCB_EINVAL, "null descriptor");
+  const jpcb_pc_desc& t = d->td;
+  if (t.n_layers < 2 || t.n_layers > JPCB_MAX_LAYERS) return fail(JPCB_EINVAL, "n_layers=%d outside [2,%d]", t.n_layers, JPCB_MAX_LAYERS);
+  if (t.batch_local <= 0 || t.batch_global < t.batch_local) return fail(JPCB_EINVAL, "bad batch sizes local=%d global=%d", t.batch_local, t.batch_global);
+  for (int l = 0; l <= t.n_layers; ++l)
+    if (t.dims[l] <= 0) return fail(JPCB_EINVAL, "dims[%d]=%d", l, t.dims[l]);
+  for (int l = 0; l < t.n_layers; ++l) {
+    if (t.act[l] < 0 || t.act[l] > JPCB_ACT_SILU || d->bu_act[l] < 0 || d->bu_act[l] > JPCB_ACT_SILU)
+      return fail(JPCB_EINVAL, "Invalid activation function ID at layer %d", l);
+    if (t.skip[l] && l >= 1 && l <= t.n_layers - 2 && t.dims[l] != t.dims[l + 1])
+      return fail(JPCB_EINVAL, "identity skip at layer %d needs equal dims (%d vs %d)", l, t.dims[l], t.dims[l + 1]);
+  }
+  if (t.dtype == JPCB_DTYPE_BF16) return fail(JPCB_ENOTIMPL, "bPC runs the fp32 path; the bf16 tensor-core schedule for bPC is not built yet");
+  if (t.dtype != JPCB_DTYPE_F32) return fail(JPCB_EINVAL, "bad dtype %d", t.dtype);
+  if (t.solver != JPCB_SOLVER_EULER) return fail(JPCB_ENOTIMPL, "bPC inference is Euler (update_bpc_activities with optax.sgd); Heun is not on this path");
+  if (t.n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", t.n_steps);
+  if (t.activity_decay != 0.f) return fail(JPCB_EINVAL, "bpc_energy_fn has no activity_decay");
+  return JPCB_OK;
+}
+
+struct Bump {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~(size_t)1023;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct BpcRun {
+  const jpcb_bpc_desc* d;
+  const float* const* W; const float* const* bW;
+  const float* const* V; const float* const* bV;
+  const float* x; const float* y;
+  cudaStream_t st;
+  int H, Bl;
+  const int32_t* D;
+  float invB, af, ab;
+  // workspace
+  float* red = nullptr;             // [2(H+1)] energy sums
+  std::vector<float*> e, dl, Gf;    // e_j [Bl, D[j+1]], delta_j [Bl, D[j]], forward half of dF/dz_k [Bl, D[k+1]]
+  float* P0 = nullptr;              // W_0 phi_0(x) + b_0        [Bl, D[1]]
+  float* QH = nullptr;              // V_H psi_H(y) + c_H        [Bl, D[H]]
+  size_t bytes = 0;
+
+  void carve(void* base) {
+    Bump b{reinterpret_cast<char*>(base)};
+    red = b.take<float>(2 * (H + 1) + 8);
+    e.resize(H + 1); dl.resize(H + 1); Gf.resize(H);
+    for (int j = 0; j <= H; ++j) e[j] = b.take<float>((size_t)Bl * D[j + 1]);
+    for (int j = 0; j <= H; ++j) dl[j] = b.take<float>((size_t)Bl * D[j]);
+    for (int k = 0; k < H; ++k) Gf[k] = b.take<float>((size_t)Bl * D[k + 1]);
+    P0 = b.take<float>((size_t)Bl * D[1]);
+    QH = b.take<float>((size_t)Bl * D[H]);
+    bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
+  }
+
+  int init(const jpcb_bpc_desc* desc, const float* const* W_, const float* const* bW_, const float* const* V_, const float* const* bV_,
+           const float* x_, const float* y_, void* ws, size_t ws_bytes, void* stream) {
+    RET(validate_bpc(desc));
+    d = desc; W = W_; bW = bW_; V = V_; bV = bV_; x = x_; y = y_;
+    st = reinterpret_cast<cudaStream_t>(stream);
+    H = d->td.n_layers - 1; Bl = d->td.batch_local; D = d->td.dims;
+    invB = 1.f / (float)d->td.batch_global; af = d->forward_energy_weight; ab = d->backward_energy_weight;
+    if (!W || !V || !x || !y) return fail(JPCB_EINVAL, "null weight lists / input / target");
+    if (d->td.has_bias && !bW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias list");
+    if (d->bu_has_bias && !bV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias list");
+    carve(ws);
+    if (!ws || ws_bytes < bytes) return fail(JPCB_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", bytes, ws_bytes);
+    return JPCB_OK;
+  }
+  float skip(int j) const { return (d->td.skip[j] && j >= 1 && j <= H - 1) ? 1.f : 0.f; }
+  const float* biasW(int j) const { return d->td.has_bias ? bW[j] : nullptr; }
+  const float* biasV(int j) const { return d->bu_has_bias ? bV[j] : nullptr; }
+
+  // top-down prediction GEMM of layer j on state S: phi_j(u_j) W_j^T
+  void td_operands(GTask& t, int j, const float* const* S) const {
+    t.e.M = Bl; t.e.N = D[j + 1]; t.K = D[j];
+    t.a_p = j == 0 ? x : S[j - 1]; t.a_smn = D[j]; t.a_sk = 1; t.a_act = d->td.act[j];
+    t.b_p = W[j]; t.b_smn = D[j]; t.b_sk = 1;
+    t.e.alpha = 1.f; t.e.bias = biasW(j);
+  }
+  // bottom-up prediction GEMM of layer j on state S: psi_j(v_j) V_j^T
+  void bu_operands(GTask& t, int j, const float* const* S) const {
+    t.e.M = Bl; t.e.N = D[j]; t.K = D[j + 1];
+    t.a_p = j == H ? y : S[j]; t.a_smn = D[j + 1]; t.a_sk = 1; t.a_act = d->bu_act[j];
+    t.b_p = V[j]; t.b_smn = D[j + 1]; t.b_sk = 1;
+    t.e.alpha = 1.f; t.e.bias = biasV(j);
+  }
+
+  // the two predictions whose inputs are clamped: P0 = f_0(x), QH = g_H(y)
+  int hoist() {
+    GTask a, b;
+    td_operands(a, 0, nullptr); a.e.mode = EPI_FFWD; a.e.O = P0;
+    bu_operands(b, H, nullptr); b.e.mode = EPI_FFWD; b.e.O = QH;
+    return launch_simt({a, b}, st);
+  }
+
+  // all 2(H+1) prediction errors on state S (+ energy sums when `energy`)
+  int errors(const float* const* S, bool energy, bool hoisted) {
+    std::vector<GTask> ts;
+    for (int j = 0; j <= H; ++j) {
+      GTask t;
+      t.e.mode = EPI_ERR; t.e.escale = 1.f;
+      if (j == 0 && hoisted) {  // e_0 = z_0 - P0 without a GEMM
+        t.e.M = Bl; t.e.N = D[1]; t.K = 0; t.e.alpha = 0.f; t.e.skip = 1.f; t.e.U = P0;
+        t.a_p = S[0]; t.b_p = S[0];
+      } else {
+        td_operands(t, j, S);
+        t.e.skip = skip(j); t.e.U = j == 0 ? x : S[j - 1];
+      }
+      t.e.T = j == H ? y : S[j];
+      t.e.O = e[j];
+      if (energy) t.e.red = red + j;
+      ts.push_back(t);
+    }
+    for (int j = 0; j <= H; ++j) {
+      GTask t;
+      t.e.mode = EPI_ERR; t.e.escale = 1.f;
+      if (j == H && hoisted) {  // delta_H = z_{H-1} - QH
+        t.e.M = Bl; t.e.N = D[H]; t.K = 0; t.e.alpha = 0.f; t.e.skip = 1.f; t.e.U = QH;
+        t.a_p = S[0]; t.b_p = S[0];
+      } else {
+        bu_operands(t, j, S);
+        t.e.skip = skip(j); t.e.U = j == H ? y : S[j];
+      }
+      t.e.T = j == 0 ? x : S[j - 1];
+      t.e.O = dl[j];
+      if (energy) t.e.red = red + H + 1 + j;
+      ts.push_back(t);
+    }
+    return launch_simt(ts, st);
+  }
+
+  // dF/dz_k (sub = GRAD_OUT, c = 1/B, into Out[k]) or the Euler update z_k -= c * B dF/dz_k (in place)
+  int grads(int sub, float c, const float* const* Z, float* const* Out) {
+    std::vector<GTask> f, b;
+    for (int k = 0; k < H; ++k) {
+      GTask t;  // forward-direction half: alpha_f (e_k - phi_{k+1}'(z_k) (e_{k+1} W_{k+1}) - s_{k+1} e_{k+1})
+      t.e.mode = EPI_GRAD; t.e.sub = GRAD_OUT; t.e.act = d->td.act[k + 1];
+      t.e.M = Bl; t.e.N = D[k + 1]; t.K = D[k + 2];
+      t.a_p = e[k + 1]; t.a_smn = D[k + 2]; t.a_sk = 1;
+      t.b_p = W[k + 1]; t.b_smn = 1; t.b_sk = D[k + 1];  // B(n,k') = W_{k+1}[k'][n]
+      t.e.alpha = 1.f; t.e.skip = skip(k + 1); t.e.En = e[k + 1];
+      t.e.Z = Z[k]; t.e.El = e[k];
+      t.e.gscale = af; t.e.c = 1.f; t.e.O = Gf[k];
+      f.push_back(t);
+      GTask u;  // backward-direction half + combination (+ update)
+      u.e.mode = EPI_GRAD; u.e.sub = sub; u.e.act = d->bu_act[k];
+      u.e.M = Bl; u.e.N = D[k + 1]; u.K = D[k];
+      u.a_p = dl[k]; u.a_smn = D[k]; u.a_sk = 1;
+      u.b_p = V[k]; u.b_smn = 1; u.b_sk = D[k + 1];       // B(n,k') = V_k[k'][n]
+      u.e.alpha = 1.f; u.e.skip = skip(k); u.e.En = dl[k];
+      u.e.Z = Z[k]; u.e.El = dl[k + 1];
+      u.e.gscale = ab; u.e.Gin = Gf[k]; u.e.c = c; u.e.O = Out[k];
+      b.push_back(u);
+    }
+    RET(launch_simt(f, st));
+    return launch_simt(b, st);
+  }
+
+  int finalize(float* E_pairs, float* F) {
+    bpc_finalize_kernel<<<1, 32, 0, st>>>(red, H, invB, af, ab, E_pairs, F);
+    count_launch();
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+  int zero_red() { CK(cudaMemsetAsync(red, 0, (2 * (H + 1) + 8) * sizeof(float), st)); return JPCB_OK; }
+};
+
+}  // namespace
+
+extern "C" {
+
+size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc) {
+  if (validate_bpc(desc) != JPCB_OK) return 0;
+  BpcRun r;
+  r.d = desc; r.H = desc->td.n_layers - 1; r.Bl = desc->td.batch_local; r.D = desc->td.dims;
+  r.carve(nullptr);
+  return r.bytes;
+}
+
+int jpcb_bpc_energy(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                    const float* const* bV, const float* const* A, const float* x, const float* y, float* E_pairs, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  BpcRun r;
+  RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
+  if (!A || !E_pairs) return fail(JPCB_EINVAL, "null activities / output");
+  RET(r.zero_red());
+  RET(r.errors(A, true, false));
+  return r.finalize(E_pairs, nullptr);
+}
+
+int jpcb_bpc_activity_grad(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                           const float* const* bV, const float* const* A, const float* x, const float* y, float* F, float* const* gA,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  BpcRun r;
+  RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
+  if (!A || !gA) return fail(JPCB_EINVAL, "null activities / output");
+  RET(r.zero_red());
+  RET(r.errors(A, true, false));
+  RET(r.grads(GRAD_OUT, r.invB, A, gA));
+  CK(cudaMemsetAsync(gA[r.H], 0, (size_t)r.Bl * r.D[r.H + 1] * sizeof(float), r.st));  // dummy slot: dF/dA[-1] = 0
+  if (F) RET(r.finalize(nullptr, F));
+  return JPCB_OK;
+}
+
+int jpcb_bpc_infer(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                   const float* const* bV, float* const* A, const float* x, const float* y, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  BpcRun r;
+  RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
+  if (!A) return fail(JPCB_EINVAL, "null activities");
+  RET(r.hoist());
+  const int T = desc->td.n_steps;
+  for (int s = 0; s < T; ++s) {
+    const float h = s == T - 1 ? desc->td.dt_last : desc->td.dt;
+    RET(r.errors(A, false, true));
+    RET(r.grads(GRAD_EULER, h * r.invB, A, A));
+  }
+  return JPCB_OK;
+}
+
+int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                         const float* const* bV, const float* const* A, const float* x, const float* y, float* const* gW,
+                         float* const* gbW, float* const* gV, float* const* gbV, float* E_pairs, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  BpcRun r;
+  RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
+  if (!A || !gW || !gV) return fail(JPCB_EINVAL, "null activities / outputs");
+  RET(r.zero_red());
+  RET(r.errors(A, E_pairs != nullptr, false));
+  const int H = r.H, Bl = r.Bl;
+  const int32_t* D = r.D;
+  std::vector<GTask> ts;
+  for (int j = 0; j <= H; ++j) {
+    GTask t;  // gW_j = -(alpha_f/B) e_j^T phi_j(u_j)
+    t.e.mode = EPI_SCALE; t.e.M = D[j + 1]; t.e.N = D[j]; t.K = Bl;
+    t.a_p = r.e[j]; t.a_smn = 1; t.a_sk = D[j + 1];
+    t.b_p = j == 0 ? x : A[j - 1]; t.b_smn = 1; t.b_sk = D[j]; t.b_act = desc->td.act[j];
+    t.e.alpha = -r.af * r.invB; t.e.O = gW[j];
+    ts.push_back(t);
+    GTask u;  // gV_j = -(alpha_b/B) delta_j^T psi_j(v_j)
+    u.e.mode = EPI_SCALE; u.e.M = D[j]; u.e.N = D[j + 1]; u.K = Bl;
+    u.a_p = r.dl[j]; u.a_smn = 1; u.a_sk = D[j];
+    u.b_p = j == H ? y : A[j]; u.b_smn = 1; u.b_sk = D[j + 1]; u.b_act = desc->bu_act[j];
+    u.e.alpha = -r.ab * r.invB; u.e.O = gV[j];
+    ts.push_back(u);
+  }
+  RET(launch_simt(ts, r.st));
+  if (desc->td.has_bias) {
+    if (!gbW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias-gradient list");
+    for (int j = 0; j <= H; ++j) {
+      colsum_kernel<float><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.e[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
+      count_launch();
+    }
+  }
+  if (desc->bu_has_bias) {
+    if (!gbV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias-gradient list");
+    for (int j = 0; j <= H; ++j) {
+      colsum_kernel<float><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.dl[j], gbV[j], Bl, D[j], -r.ab * r.invB);
+      count_launch();
+    }
+  }
+  CK(cudaGetLastError());
+  if (E_pairs) RET(r.finalize(E_pairs, nullptr));
+  return JPCB_OK;
+}
+
+}  // extern "C"

@@ -8,7 +8,7 @@
 namespace jpcb {
 
 // dst[i] = bf16(act(src[i]))
-__global__ void cast_act_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n, int act) {
+static __global__ void cast_act_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n, int act) {
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     float v[4];
@@ -22,7 +22,7 @@ __global__ void cast_act_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 
 // dst[c][r] = bf16(src[r][c]); src is [R, C] row-major (fp32 or bf16), dst [C, R] row-major.
 template <typename TIn>
-__global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {
+static __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {
   __shared__ float tile[32][33];
   const int tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
   for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
@@ -47,7 +47,7 @@ __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloa
 
 // out[n] = scale * sum_m E[m, n]   (bias gradients, jpc/_core/_grads.py:487-499 closed form)
 template <typename TIn>
-__global__ void colsum_kernel(const TIn* __restrict__ E, float* __restrict__ out, int M, int N, float scale) {
+static __global__ void colsum_kernel(const TIn* __restrict__ E, float* __restrict__ out, int M, int N, float scale) {
   // block (32, 8): 32 adjacent columns, 8 row-lanes
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -69,7 +69,7 @@ __global__ void colsum_kernel(const TIn* __restrict__ E, float* __restrict__ out
 }
 
 // *out += sum p[i]^2
-__global__ void sumsq_kernel(const float* __restrict__ p, size_t n, float* __restrict__ out) {
+static __global__ void sumsq_kernel(const float* __restrict__ p, size_t n, float* __restrict__ out) {
   __shared__ float red_s[32];
   float s = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -87,7 +87,7 @@ __global__ void sumsq_kernel(const float* __restrict__ p, size_t n, float* __res
 }
 
 // dst[i] = s * src[i]  (dst may alias src)
-__global__ void scale_kernel(const float* src, float* dst, size_t n, float s) {
+static __global__ void scale_kernel(const float* src, float* dst, size_t n, float s) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = s * src[i];
 }
 
@@ -95,7 +95,7 @@ __global__ void scale_kernel(const float* src, float* dst, size_t n, float s) {
 //   E_layers (order [output, hidden 1..L-2, first], each / B)   jpc/_core/_energies.py:155-156
 //   F = sum(acc)/B + ad/(2B) * sumsq                             jpc/_core/_energies.py:145-153
 //   loss = acc_loss / B                                          jpc/_utils.py:129-130
-__global__ void finalize_kernel(const float* __restrict__ acc, int L, float inv_b, float* E_layers, float* F,
+static __global__ void finalize_kernel(const float* __restrict__ acc, int L, float inv_b, float* E_layers, float* F,
                                 const float* sumsq, float ad, const float* loss_acc, float* loss_out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (E_layers) {

@@ -293,3 +293,100 @@ def test_error_behaviour():
         J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx)
     with pytest.raises(RuntimeError):  # no CPU path
         J.init_activities_with_ffwd(to_gpu_model(om, device="cpu"), x.float())
+
+
+# ---- bidirectional PC (BASELINE config 5) ------------------------------------------------------
+def _bpc_case(d_x, width, depth, d_y, act, B, use_bias=False, skips=False, seed=0):
+    """top-down make_mlp(d_x -> d_y), bottom-up make_mlp(d_y -> d_x)[::-1] (examples/bidirectional_pc.ipynb cell 8)."""
+    td = f32_model(O.make_mlp(seed, d_x, width, depth, d_y, act, use_bias=use_bias))
+    bu = f32_model(O.make_mlp(seed + 1, d_y, width, depth, d_x, act, use_bias=use_bias))[::-1]
+    sk = O.make_skip_model(depth) if skips else None
+    x, y = data(B, d_x, d_y, onehot_in=True, onehot_out=False)
+    x, y = x.float().double(), y.float().double()
+    # activities z_0..z_{H-1} + unused slot: a forward sweep of the top-down model, perturbed so every error is active
+    a0 = O.init_activities_with_ffwd(td, x)
+    acts = [a.float().double() for a in perturb(a0)]
+    return td, bu, sk, x, y, acts
+
+
+def _check_bpc(td, bu, sk, x, y, acts, tol, af=1.0, ab=1.0):
+    import jpc_b200 as J
+    gtd, gbu, gsk = to_gpu_model(td), to_gpu_model(bu), _gpu_skip(sk)
+    gx, gy, gacts = dev(x), dev(y), devs(acts)
+    kw = dict(forward_energy_weight=af, backward_energy_weight=ab)
+    E = O.bpc_energy_fn(td, bu, acts, y, x=x, skips=sk, record_layers=True, **kw)
+    gE = J.bpc_energy_fn(gtd, gbu, gacts, gy, x=gx, skip_model=gsk, record_layers=True, **kw)
+    assert gE.shape == (2 * len(td),)
+    assert rel(gE, E) < tol
+    F, g = O.compute_bpc_activity_grad(td, bu, acts, y, x=x, skips=sk, **kw)
+    gF, gg = J.compute_bpc_activity_grad(gtd, gbu, gacts, gy, x=gx, skip_model=gsk, **kw)
+    assert abs(float(gF) - float(F)) <= tol * abs(float(F))
+    assert abs(float(J.bpc_energy_fn(gtd, gbu, gacts, gy, x=gx, skip_model=gsk, **kw)) - float(F)) <= tol * abs(float(F))
+    gmax = max(float(t.abs().max()) for t in g)
+    for p, q in zip(gg, g):
+        assert rel(p, q) < tol or float((p.double().cpu() - q).abs().max()) < tol * gmax
+    tdg, bug = O.compute_bpc_param_grads(td, bu, acts, y, x=x, skips=sk, **kw)
+    gtdg, gbug = J.compute_bpc_param_grads(gtd, gbu, gacts, gy, x=gx, skip_model=gsk, **kw)
+    for got, want in ((gtdg, tdg), (gbug, bug)):
+        for l, q in enumerate(want):
+            assert rel(got[l][1].weight, q["W"]) < tol
+            if q["b"] is not None:
+                assert rel(got[l][1].bias, q["b"]) < tol
+
+
+def _check_bpc_infer(td, bu, sk, x, y, acts, tol, T, dt, af=1.0, ab=1.0):
+    """fused T Euler steps == T x (oracle gradient step with sgd(dt))."""
+    import jpc_b200 as J
+    kw = dict(forward_energy_weight=af, backward_energy_weight=ab)
+    a = [t.clone() for t in acts]
+    for _ in range(T):
+        _, g = O.compute_bpc_activity_grad(td, bu, a, y, x=x, skips=sk, **kw)
+        a = [p - dt * q for p, q in zip(a, g)]
+    gtd, gbu, gsk = to_gpu_model(td), to_gpu_model(bu), _gpu_skip(sk)
+    ga = J.solve_bpc_inference(gtd, gbu, devs(acts), dev(y), input=dev(x), n_steps=T, dt=dt, skip_model=gsk, **kw)
+    for p, q in zip(ga[:-1], a[:-1]):
+        assert rel(p, q) < tol
+    # and the reference-shaped discrete twin
+    opt = J.optim.sgd(dt)
+    b, st = devs(acts), opt.init(devs(acts))
+    for _ in range(T):
+        r = J.update_bpc_activities(gtd, gbu, b, opt, st, dev(y), input=dev(x), skip_model=gsk, **kw)
+        assert set(r) == {"energy", "activities", "grads", "opt_state"}
+        b, st = r["activities"], r["opt_state"]
+    for p, q in zip(b[:-1], ga[:-1]):
+        assert rel(p, q) < 1e-6
+
+
+@pytest.mark.parametrize("act", ["relu", "tanh", "gelu"])
+def test_bpc_small(act):
+    c = _bpc_case(6, 12, 4, 9, act, 5, use_bias=True)
+    _check_bpc(*c, TOL32)
+    _check_bpc(*c, TOL32, af=1e-3, ab=0.7)
+    _check_bpc_infer(*c, TOL32, T=6, dt=0.4 * 5, af=1e-3)
+
+
+def test_bpc_skips_ragged():
+    c = _bpc_case(7, 13, 5, 3, "tanh", 3, skips=True)
+    _check_bpc(*c, TOL32)
+    _check_bpc_infer(*c, TOL32, T=4, dt=0.9)
+
+
+def test_bpc_two_layer_minimum():
+    _check_bpc(*_bpc_case(5, 8, 2, 4, "silu", 4), TOL32)
+
+
+def test_bpc_update_params_keys():
+    import jpc_b200 as J
+    td, bu, sk, x, y, acts = _bpc_case(6, 12, 3, 9, "relu", 4)
+    gtd, gbu = to_gpu_model(td), to_gpu_model(bu)
+    o1, o2 = J.optim.adam(1e-3), J.optim.adam(1e-3)
+    r = J.update_bpc_params(gtd, gbu, devs(acts), o1, o2, o1.init(gtd), o2.init(gbu), dev(y), input=dev(x))
+    assert set(r) == {"models", "grads", "opt_states"}
+    assert len(r["models"]) == 2 and len(r["grads"]) == 2 and len(r["opt_states"]) == 2
+
+
+def test_config5_bpc_full_size():
+    """BASELINE config 5: bPC width 1024 depth 6 (10 -> 784), batch 1024, 30 Euler steps, fp32."""
+    c = _bpc_case(10, 1024, 6, 784, "relu", 1024)
+    _check_bpc(*c, TOL32)
+    _check_bpc_infer(*c, TOL32, T=30, dt=0.5)
