@@ -246,8 +246,7 @@ def main():
     def step():
         _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(x), _lib.ptr(y), A_ptrs, _lib.ptr(arena.loss),
                                                _lib.ptr(arena.E), gW_ptrs, gb_ptrs, _lib.ptr(ws), ws.numel(), stream))
-        if world > 1:
-            dist.all_reduce(arena.flat, op=dist.ReduceOp.SUM)
+        arena.all_reduce()  # ONE NCCL all-reduce (SUM) of [gW, gb, E_layers, loss]; no-op at N = 1
 
     def sync_all():
         if world > 1:
@@ -343,7 +342,12 @@ def main():
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             src = "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PF sustained"
             ach = fl["per_eval"] / 2 / (per_launch_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            traffic = None
+            try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["bytes_per_launch"]
+            except Exception:
+                pass
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                     "kernel": "tc_grouped_gemm (one inference phase = all layers' GEMMs + fused epilogue)",
                     "launch_ms": per_launch_ms, "flops_per_launch": fl["per_eval"] / 2, "peak_source": src,
                     "peak_burst": peaks.get("bf16_tflops"),

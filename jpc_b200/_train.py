@@ -31,27 +31,47 @@ class _Arena:
     needs a single collective: [gW_0, gb_0, ..., E_layers(L), loss(1)].  Segments start on
     256-byte boundaries (the kernels use 16-byte vector stores)."""
 
-    def __init__(self, net: _Net):
-        sizes = []
-        for lin in net.linears:
-            sizes.append(lin.weight.numel())
-            if net.has_bias:
-                sizes.append(lin.bias.numel())
-        sizes += [net.L, 1]
+    def __init__(self, net=None, *, weight_shapes=None, bias_shapes=None, device=None):
+        if net is not None:
+            weight_shapes = [tuple(lin.weight.shape) for lin in net.linears]
+            bias_shapes = [tuple(lin.bias.shape) for lin in net.linears] if net.has_bias else None
+            device = net.dev
+        L = len(weight_shapes)
+        shapes = []
+        for l in range(L):
+            shapes.append(weight_shapes[l])
+            if bias_shapes is not None:
+                shapes.append(bias_shapes[l])
+        shapes += [(L,), ()]
+        sizes = [int(torch.Size(sh).numel()) for sh in shapes]
         offs, off = [], 0
         for s in sizes:
             offs.append(off)
             off += (s + 63) // 64 * 64
-        self.flat = torch.empty(off, dtype=torch.float32, device=net.dev)
-        views = [self.flat[o:o + s] for o, s in zip(offs, sizes)]
-        self.gW, self.gb = [], ([] if net.has_bias else None)
+        self.flat = torch.empty(off, dtype=torch.float32, device=device)
+        views = [self.flat[o:o + s].view(sh) for o, s, sh in zip(offs, sizes, shapes)]
+        self.gW, self.gb = [], ([] if bias_shapes is not None else None)
         i = 0
-        for lin in net.linears:
-            self.gW.append(views[i].view_as(lin.weight)); i += 1
-            if net.has_bias:
-                self.gb.append(views[i].view_as(lin.bias)); i += 1
+        for l in range(L):
+            self.gW.append(views[i]); i += 1
+            if bias_shapes is not None:
+                self.gb.append(views[i]); i += 1
         self.E = views[i]
-        self.loss = views[i + 1].view(())
+        self.loss = views[i + 1]
+
+    def all_reduce(self):
+        """The one exchange step of the data-parallel path: SUM over ranks of every rank's partial
+        gradients / energies / loss (each already divided by the GLOBAL batch size)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+
+
+def shard_rows(n_rows: int, rank: int, world: int):
+    """Contiguous batch-row block [lo, hi) of `rank` (samples are the sharded unit)."""
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
 
 
 def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", param_type="sp", ode_solver=None,
@@ -93,9 +113,7 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr(output), _lib.ptr_array(acts), _lib.ptr(arena.loss),
         _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
         _lib.ptr(ws), ws.numel(), net.stream()))
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(arena.flat, op=dist.ReduceOp.SUM)  # the one exchange step of the data-parallel path
+    arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
     param_grads = _grads_pytree(net, arena.gW, arena.gb)
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)
     g_norms = compute_param_norms(param_grads) if grad_norms else (None, None)

@@ -1,0 +1,86 @@
+"""Data-parallel host logic on CPU: world_size-2 `gloo` processes, the oracle standing in for the
+CUDA kernels.  Checks what the N>1 path of jpc_b200.make_pc_step relies on: contiguous
+row shards, every rank normalising by the GLOBAL batch, ONE all-reduce (SUM) of the flat arena
+[gW, gb, E_layers, loss] reproducing the full-batch train step."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pc_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from jpc_b200._train import _Arena, shard_rows
+        B, dims = 11, (6, 12, 3, 4)  # 11 rows over 2 ranks: a ragged 6 + 5 split
+        om = O.make_mlp(0, dims[0], dims[1], dims[2], dims[3], "tanh", use_bias=True)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(B, dims[0], generator=g, dtype=torch.float64)
+        y = torch.randn(B, dims[3], generator=g, dtype=torch.float64)
+        lo, hi = shard_rows(B, rank, world)
+        scale = (hi - lo) / B  # local results are normalised by the local batch in the oracle; the kernels use B_global
+        # dt enters the dynamics as dt / B: keep the per-sample step and the step count of the full-batch run
+        r = O.pc_train_step(om, None, x[lo:hi], y[lo:hi], solver="heun", max_t1=3.0 * (hi - lo) / B, dt=0.5 * (hi - lo) / B)
+        arena = _Arena(weight_shapes=[tuple(l["W"].shape) for l in om], bias_shapes=[tuple(l["b"].shape) for l in om],
+                       device="cpu")
+        for l, gr in enumerate(r["grads"]):
+            arena.gW[l].copy_((gr["W"] * scale).float())
+            arena.gb[l].copy_((gr["b"] * scale).float())
+        arena.E.copy_((r["energies"] * scale).float())
+        arena.loss.copy_((r["loss"] * scale).float())
+        arena.all_reduce()
+        if rank == 0:
+            full = O.pc_train_step(om, None, x, y, solver="heun", max_t1=3.0, dt=0.5)
+            err = max(O.max_rel_err(arena.gW[l], full["grads"][l]["W"]) for l in range(len(om)))
+            err = max(err, max(O.max_rel_err(arena.gb[l], full["grads"][l]["b"]) for l in range(len(om))))
+            err = max(err, O.max_rel_err(arena.E, full["energies"]), abs(float(arena.loss) - float(full["loss"])) / float(full["loss"]))
+            q.put(err)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_matches_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() < 1e-5  # fp32 arena
+
+
+def test_shard_rows_cover_and_are_contiguous():
+    from jpc_b200._train import shard_rows
+    for n, w in ((10, 2), (10, 3), (4096, 8), (7, 8), (1, 1)):
+        spans = [shard_rows(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_arena_layout():
+    from jpc_b200._train import _Arena
+    a = _Arena(weight_shapes=[(5, 3), (2, 5)], bias_shapes=[(5,), (2,)], device="cpu")
+    ptrs = [t.data_ptr() for t in a.gW + a.gb + [a.E, a.loss]]
+    assert all(p % 256 == 0 for p in [q - a.flat.data_ptr() for q in ptrs])
+    assert a.E.shape == (2,) and a.loss.shape == ()
+    a.flat.zero_()
+    a.gW[1].fill_(3.0)
+    assert float(a.flat.sum()) == 30.0
