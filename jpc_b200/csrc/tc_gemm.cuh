@@ -121,6 +121,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// true in exactly one (elected) lane of a fully active warp; ptxas knows the region it guards is
+// single-threaded, so tcgen05 / TMA instructions inside it need no per-instruction election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -400,22 +411,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M;
       const int n0 = (local % t.tiles_n) * TC_BLOCK_N + (int)rank * Cfg::B_ROWS;
       const int nkb = (t.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
-      if (lane == 0) {
-        tma_prefetch_desc(&t.tmA);
-        tma_prefetch_desc(&t.tmB);
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+      // the whole warp walks the ring (warp-uniform state); one elected lane issues
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
           const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CG);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           tma_load_2d<CG>(sa, &t.tmA, fb, kb * TC_BLOCK_K, m0);
           tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      // keep the warp's lanes in lock-step with the elected lane's ring position
-      stage = __shfl_sync(0xffffffffu, stage, 0);
-      phase = __shfl_sync(0xffffffffu, phase, 0);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -428,13 +436,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       for (int tile = unit; tile < g.total_tiles; tile += nunits) {
         const int ti = tc_find_task(g, tile);
         const int nkb = (g.t[ti].K + TC_BLOCK_K - 1) / TC_BLOCK_K;
-        if (lane == 0) {
-          mbar_wait(tempty_bar(as), aphase ^ 1u);
+        mbar_wait(tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BLOCK_N);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BLOCK_N);
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
+          if (elect_one()) {
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             const uint64_t da = umma_desc_kmajor_sw128(sa);
             const uint64_t db = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
@@ -444,12 +452,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
               umma_f16<CG>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit<CG>(empty_bar(stage));  // ring slot reusable once these MMAs have read it
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (kb == nkb - 1) umma_commit<CG>(tfull_bar(as));  // accumulator complete
           }
-          umma_commit<CG>(tfull_bar(as));  // accumulator complete
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        stage = __shfl_sync(0xffffffffu, stage, 0);
-        phase = __shfl_sync(0xffffffffu, phase, 0);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
