@@ -75,6 +75,8 @@ int validate(const jpcb_pc_desc* d) {
     if (d->act[l] < 0 || d->act[l] > JPCB_ACT_SILU) return fail(JPCB_EINVAL, "Invalid activation function ID %d at layer %d", d->act[l], l);
     if (d->skip[l] && d->dims[l] != d->dims[l + 1]) return fail(JPCB_EINVAL, "identity skip at layer %d needs equal dims (%d vs %d)", l, d->dims[l], d->dims[l + 1]);
   }
+  for (int l = 0; l <= d->n_layers; ++l)
+    if ((long long)d->batch_local * d->dims[l] >= (1LL << 31)) return fail(JPCB_ENOTIMPL, "batch_local * dims[%d] must be < 2^31 (32-bit element indices)", l);
   if (d->loss == JPCB_LOSS_CE) return fail(JPCB_ENOTIMPL, "cross-entropy output energy is not on the B200 path yet");
   if (d->loss != JPCB_LOSS_MSE) return fail(JPCB_EINVAL, "`mse` and `ce` are the only valid losses.");
   if (d->dtype != JPCB_DTYPE_F32 && d->dtype != JPCB_DTYPE_BF16) return fail(JPCB_EINVAL, "bad dtype %d", d->dtype);

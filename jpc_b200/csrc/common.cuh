@@ -127,7 +127,7 @@ __device__ __forceinline__ Epi epi_pin(const Epi& src) {
   return e;
 }
 
-__device__ __forceinline__ void ld4(const float* __restrict__ p, size_t idx, int nvalid, bool vec, float (&v)[4]) {
+__device__ __forceinline__ void ld4(const float* __restrict__ p, uint32_t idx, int nvalid, bool vec, float (&v)[4]) {
   if (vec) {
     float4 t = *reinterpret_cast<const float4*>(p + idx);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void ld4(const float* __restrict__ p, size_t idx, int
     for (int j = 0; j < 4; ++j) v[j] = j < nvalid ? p[idx + j] : 0.f;
   }
 }
-__device__ __forceinline__ void ld4(const __nv_bfloat16* __restrict__ p, size_t idx, int nvalid, bool vec, float (&v)[4]) {
+__device__ __forceinline__ void ld4(const __nv_bfloat16* __restrict__ p, uint32_t idx, int nvalid, bool vec, float (&v)[4]) {
   if (vec) {
     uint2 t = *reinterpret_cast<const uint2*>(p + idx);
     __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
@@ -147,7 +147,7 @@ __device__ __forceinline__ void ld4(const __nv_bfloat16* __restrict__ p, size_t 
     for (int j = 0; j < 4; ++j) v[j] = j < nvalid ? __bfloat162float(p[idx + j]) : 0.f;
   }
 }
-__device__ __forceinline__ void st4(float* __restrict__ p, size_t idx, int nvalid, bool vec, const float (&v)[4]) {
+__device__ __forceinline__ void st4(float* __restrict__ p, uint32_t idx, int nvalid, bool vec, const float (&v)[4]) {
   if (vec) {
     *reinterpret_cast<float4*>(p + idx) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
@@ -155,7 +155,7 @@ __device__ __forceinline__ void st4(float* __restrict__ p, size_t idx, int nvali
     for (int j = 0; j < 4; ++j) if (j < nvalid) p[idx + j] = v[j];
   }
 }
-__device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, size_t idx, int nvalid, bool vec, const float (&v)[4]) {
+__device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, uint32_t idx, int nvalid, bool vec, const float (&v)[4]) {
   if (vec) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
     __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
@@ -176,7 +176,7 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, size_t idx, i
 //   epi_finish  : consumes them + the 4 accumulator values, stores, returns the reduction term
 struct EpiPre {
   float a[4];  // GRAD: z          ERR: target T    FFWD: loss target Y   SCALE(accum): old O
-  float b[4];  // GRAD: e_l (fp32) or P              FFWD/ERR: skip input U
+  float b[4];  // GRAD: e_l (fp32) or P
   uint2 h;     // GRAD: e_l as 4 packed bf16 when Elb is the source.  Deliberately NOT overlaid on b: two
                // differently predicated loads into the same registers make the second one wait for
                // every load that shares the first one's scoreboard slot.
@@ -191,20 +191,21 @@ __device__ __forceinline__ void unpack_bf16x4(const uint2& t, float (&v)[4]) {
 // MODE / SUB / ACT >= 0 fix the corresponding descriptor field at compile time (the tensor-core
 // epilogue dispatches once per tile so that its inner loop is straight-line code); -1 = read it
 // from the descriptor at run time.
-template <int MODE = -1>
+// ELSRC fixes where GRAD takes e_l from: 0 = Elb (packed bf16), 1 = z - P (hoisted prediction), -1 = run time.
+template <int MODE = -1, int ELSRC = -1>
 __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int nvalid, bool vec, EpiPre& p) {
-  const size_t idx = (size_t)row * (size_t)e.N + (size_t)col;
+  const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
   const int mode = MODE >= 0 ? MODE : e.mode;
   if (mode == EPI_GRAD) {
     ld4(e.Z, idx, nvalid, vec, p.a);
-    if (e.El || !e.Elb) ld4(e.El ? e.El : e.P, idx, nvalid, vec, p.b);
+    if (ELSRC == 0) p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
+    else if (ELSRC == 1) ld4(e.P, idx, nvalid, vec, p.b);
+    else if (e.El || !e.Elb) ld4(e.El ? e.El : e.P, idx, nvalid, vec, p.b);
     else if (vec) p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
     else ld4(e.Elb, idx, nvalid, false, p.b);
   } else if (mode == EPI_ERR) {
-    ld4(e.T, idx, nvalid, vec, p.a);
-    if (e.skip != 0.f) ld4(e.U, idx, nvalid, vec, p.b);
+    ld4(e.T, idx, nvalid, vec, p.a);  // (the skip input U, rare, is read in epi_finish)
   } else if (mode == EPI_FFWD) {
-    if (e.skip != 0.f) ld4(e.U, idx, nvalid, vec, p.b);
     if (e.red) ld4(e.Y, idx, nvalid, vec, p.a);
   } else if (e.accum) {
     ld4(e.O, idx, nvalid, vec, p.a);
@@ -214,10 +215,10 @@ __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int 
 // `nvalid` (1..4) columns are inside the matrix; `vec` says 16-byte vector access is legal
 // (N % 4 == 0 and nvalid == 4).  Returns this thread's contribution to the reduction (`red`).
 // `have_bias4`: the caller already holds the 4 bias values of columns col..col+3 in `bias4`.
-template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1>
+template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1, int ELSRC = -1>
 __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec,
                                             const EpiPre& p, bool have_bias4, const float (&bias4)[4]) {
-  const size_t idx = (size_t)row * (size_t)e.N + (size_t)col;
+  const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
   const int mode = MODE >= 0 ? MODE : e.mode;
   const int sub = SUB >= 0 ? SUB : e.sub;
   const int act = ACT >= 0 ? ACT : e.act;
@@ -237,8 +238,10 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
       pred[j] = e.alpha * (acc[j] + bj);
     }
     if (e.skip != 0.f) {
+      float u[4];
+      ld4(e.U, idx, nvalid, vec, u);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pred[j] += e.skip * p.b[j];
+      for (int j = 0; j < 4; ++j) pred[j] += e.skip * u[j];
     }
     if (mode == EPI_FFWD) {
       st4(e.O, idx, nvalid, vec, pred);
@@ -267,7 +270,12 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
   // ---- EPI_GRAD ----
   float el[4], g[4];
   const float (&z)[4] = p.a;
-  if (e.El) {
+  if (ELSRC == 0) {
+    unpack_bf16x4(p.h, el);
+  } else if (ELSRC == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) el[j] = z[j] - p.b[j];
+  } else if (e.El) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) el[j] = p.b[j];
   } else if (e.Elb) {

@@ -37,12 +37,12 @@ int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   return JPCB_OK;
 }
 
-template <int CG, int MODE, int SUB, int ACT>
+template <int CG, int MODE, int SUB, int ACT, int ELSRC>
 int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   using Cfg = TcCfg<CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -58,58 +58,75 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT>, g));
+  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC>, g));
   count_launch();
   return JPCB_OK;
 }
 
 // Epilogue specialisations compiled in: what the timed configurations run (errors, tanh / relu
-// Euler updates, scaled weight-gradient outputs).  A launch whose tasks do not all share one of
-// these takes the generic descriptor-driven kernel.
+// Euler updates with e_l from the bf16 error copy or from the hoisted layer-0 prediction, scaled
+// weight-gradient outputs).  Anything else takes the generic descriptor-driven kernel.
+int variant_key(const Epi& e) {
+  if (tc_flags() & 4) return 0;
+  if (e.mode == EPI_ERR) return 1;
+  if (e.mode == EPI_SCALE) return 2;
+  if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && (e.act == ACT_TANH || e.act == ACT_RELU) && !e.El && (e.Elb || e.P))
+    return 3 + (e.act == ACT_RELU ? 2 : 0) + (e.Elb ? 0 : 1);
+  return 0;
+}
+
 template <int CG>
-int launch_group(const TcGroup& g, int grid, cudaStream_t st) {
-  const Epi& e0 = g.t[0].e;
-  bool same = true;
-  for (int i = 1; i < g.ntasks; ++i) {
-    const Epi& e = g.t[i].e;
-    same = same && e.mode == e0.mode && e.sub == e0.sub && e.act == e0.act;
+int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
+  switch (key) {
+    case 1: return launch_variant<CG, EPI_ERR, 0, 0, -1>(g, grid, st);
+    case 2: return launch_variant<CG, EPI_SCALE, 0, 0, -1>(g, grid, st);
+    case 3: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0>(g, grid, st);
+    case 4: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 1>(g, grid, st);
+    case 5: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0>(g, grid, st);
+    case 6: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 1>(g, grid, st);
+    default: return launch_variant<CG, -1, -1, -1, -1>(g, grid, st);
   }
-  if (same && !(tc_flags() & 4)) {
-    if (e0.mode == EPI_ERR) return launch_variant<CG, EPI_ERR, 0, 0>(g, grid, st);
-    if (e0.mode == EPI_SCALE) return launch_variant<CG, EPI_SCALE, 0, 0>(g, grid, st);
-    if (e0.mode == EPI_GRAD && e0.sub == GRAD_EULER && e0.act == ACT_TANH) return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH>(g, grid, st);
-    if (e0.mode == EPI_GRAD && e0.sub == GRAD_EULER && e0.act == ACT_RELU) return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU>(g, grid, st);
-  }
-  return launch_variant<CG, -1, -1, -1>(g, grid, st);
 }
 
 template <int CG>
 int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
   using Cfg = TcCfg<CG>;
   constexpr int BM = TC_BLOCK_M * CG;  // rows of one tile (owned by a CTA, or by a CTA pair)
-  size_t i = 0;
-  while (i < tasks.size()) {
-    TcGroup g;
-    memset(&g, 0, 64);
-    int n = 0, tiles = 0;
-    for (; i < tasks.size() && n < TC_MAX_TASKS; ++i, ++n) {
-      const GTask& t = tasks[i];
-      if (t.K <= 0 || !t.a_b || !t.b_b) return fail(JPCB_EINVAL, "internal: tensor-core task without bf16 operands");
-      TcTask& s = g.t[n];
-      RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
-      RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, Cfg::B_ROWS));
-      s.K = t.K;
-      s.tile_begin = tiles;
-      s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;
-      s.pad_ = 0;
-      s.e = t.e;
-      tiles += s.tiles_n * ((t.e.M + BM - 1) / BM);
+  // tasks of one phase are independent: launch them grouped by epilogue specialisation
+  std::vector<int> keys(tasks.size());
+  std::vector<char> done(tasks.size(), 0);
+  for (size_t i = 0; i < tasks.size(); ++i) keys[i] = variant_key(tasks[i].e);
+  for (size_t first = 0; first < tasks.size(); ++first) {
+    if (done[first]) continue;
+    const int key = keys[first];
+    size_t i = first;
+    while (i < tasks.size()) {
+      TcGroup g;
+      memset(&g, 0, 64);
+      int n = 0, tiles = 0;
+      for (; i < tasks.size() && n < TC_MAX_TASKS; ++i) {
+        if (done[i] || keys[i] != key) continue;
+        done[i] = 1;
+        const GTask& t = tasks[i];
+        if (t.K <= 0 || !t.a_b || !t.b_b) return fail(JPCB_EINVAL, "internal: tensor-core task without bf16 operands");
+        TcTask& s = g.t[n];
+        RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
+        RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, Cfg::B_ROWS));
+        s.K = t.K;
+        s.tile_begin = tiles;
+        s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;
+        s.pad_ = 0;
+        s.e = t.e;
+        tiles += s.tiles_n * ((t.e.M + BM - 1) / BM);
+        ++n;
+      }
+      if (n == 0) break;
+      g.ntasks = n;
+      g.total_tiles = tiles;
+      const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
+      const int grid = CG * (tiles < units ? tiles : units);
+      RET(launch_group<CG>(g, key, grid, st));
     }
-    g.ntasks = n;
-    g.total_tiles = tiles;
-    const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
-    const int grid = CG * (tiles < units ? tiles : units);
-    RET(launch_group<CG>(g, grid, st));
   }
   return JPCB_OK;
 }

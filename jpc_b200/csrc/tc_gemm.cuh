@@ -44,12 +44,10 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
 #ifndef JPCB_TC_EPI_WARPS
 #define JPCB_TC_EPI_WARPS 8
 #endif
-#ifndef JPCB_TC_EPI_PIPE
-#define JPCB_TC_EPI_PIPE 1
-#endif
 constexpr int TC_EPI_WARPS = JPCB_TC_EPI_WARPS;                 // 8 or 16 (multiples of the 4 TMEM lane quarters)
 constexpr int TC_EPI_COLS = TC_BLOCK_N / (TC_EPI_WARPS / 4);   // columns of the tile one epilogue warp owns
 constexpr int TC_EPI_PATCHES = TC_EPI_COLS / 16;
+
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_XPOSE_BYTES = 32 * 16 * 4;  // one 32x16 fp32 patch per epilogue warp
 constexpr int TC_TMEM_COLS = 512;
@@ -275,12 +273,12 @@ __device__ __forceinline__ int tc_find_task(const TcGroup& g, int tile) {
 // row); (3) transpose it through XOR-swizzled shared memory into the same coalesced layout;
 // (4) finish + store.  MODE/SUB/ACT are compile-time so that (4) is straight-line code
 // (-1 = generic: read from the descriptor).
-template <int MODE>
+template <int MODE, int ELSRC>
 __device__ __forceinline__ void tc_epi_loads(const Epi& e, int row0, int cb, int lane, EpiPre (&pre)[4], float (&bias4)[4]) {
   const int c4 = lane & 3, rq = lane >> 2;
   const int colc = min(cb + 4 * c4, e.N - 4);  // N % 8 == 0 on this path
 #pragma unroll
-  for (int i = 0; i < 4; ++i) epi_preload<MODE>(e, min(row0 + rq + 8 * i, e.M - 1), colc, 4, true, pre[i]);
+  for (int i = 0; i < 4; ++i) epi_preload<MODE, ELSRC>(e, min(row0 + rq + 8 * i, e.M - 1), colc, 4, true, pre[i]);
   if (MODE == EPI_FFWD || MODE == EPI_ERR || MODE < 0) {
     if (e.bias != nullptr) {
       const float4 bv = *reinterpret_cast<const float4*>(e.bias + colc);
@@ -289,7 +287,7 @@ __device__ __forceinline__ void tc_epi_loads(const Epi& e, int row0, int cb, int
   }
 }
 
-template <int MODE, int SUB, int ACT>
+template <int MODE, int SUB, int ACT, int ELSRC>
 __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, int lane, uint32_t taddr, float* xp,
                                               const EpiPre (&pre)[4], const float (&bias4)[4]) {
   const int c4 = lane & 3, rq = lane >> 2;
@@ -312,54 +310,54 @@ __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, in
     const int row = row0 + rl;
     if (cok && row < e.M) {
       const float a4[4] = {a.x, a.y, a.z, a.w};
-      r += epi_finish<true, MODE, SUB, ACT>(e, row, col, a4, 4, true, pre[i], true, bias4);
+      r += epi_finish<true, MODE, SUB, ACT, ELSRC>(e, row, col, a4, 4, true, pre[i], true, bias4);
     }
   }
   __syncwarp();
   return r;
 }
 
-template <int MODE, int SUB, int ACT>
+template <int MODE, int SUB, int ACT, int ELSRC>
 __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
                                              uint32_t tphase) {
   float r = 0.f;
-#if JPCB_TC_EPI_PIPE
+#if 1
   EpiPre pa[4], pb[4];
   float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-  tc_epi_loads<MODE>(e, row0, col0, lane, pa, ba);
+  tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pa, ba);
   mbar_wait(tfull, tphase);  // accumulator of this tile complete
   tc_fence_after();
 #pragma unroll 1
   for (int ch = 0; ch < TC_EPI_PATCHES; ch += 2) {
     const int cb = col0 + ch * 16;  // first column of this 16-wide patch
     if (cb >= e.N) break;           // warp-uniform
-    tc_epi_loads<MODE>(e, row0, cb + 16, lane, pb, bb);
-    r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
+    tc_epi_loads<MODE, ELSRC>(e, row0, cb + 16, lane, pb, bb);
+    r += tc_epi_patch<MODE, SUB, ACT, ELSRC>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
     if (cb + 16 >= e.N) break;
-    if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE>(e, row0, cb + 32, lane, pa, ba);
-    r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
+    if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC>(e, row0, cb + 32, lane, pa, ba);
+    r += tc_epi_patch<MODE, SUB, ACT, ELSRC>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
   }
 #else
   EpiPre pa[4];
   float ba[4] = {0.f, 0.f, 0.f, 0.f};
-  tc_epi_loads<MODE>(e, row0, col0, lane, pa, ba);
+  tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pa, ba);
   mbar_wait(tfull, tphase);  // accumulator of this tile complete
   tc_fence_after();
 #pragma unroll 1
   for (int ch = 0; ch < TC_EPI_PATCHES; ++ch) {
     const int cb = col0 + ch * 16;
     if (cb >= e.N) break;
-    if (ch > 0) tc_epi_loads<MODE>(e, row0, cb, lane, pa, ba);
-    r += tc_epi_patch<MODE, SUB, ACT>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
+    if (ch > 0) tc_epi_loads<MODE, ELSRC>(e, row0, cb, lane, pa, ba);
+    r += tc_epi_patch<MODE, SUB, ACT, ELSRC>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
   }
 #endif
   return r;
 }
 
 // ---------------------------------------------------------------------------------------------
-// MODE/SUB/ACT >= 0: every task of the launch has that epilogue mode / GRAD sub-mode / activation
-// (the host checks), compiled in; -1 = generic descriptor-driven epilogue.
-template <int CG, int MODE, int SUB, int ACT>
+// MODE/SUB/ACT/ELSRC >= 0: every task of the launch has that epilogue mode / GRAD sub-mode /
+// activation / e_l source (the host checks), compiled in; -1 = generic descriptor-driven epilogue.
+template <int CG, int MODE, int SUB, int ACT, int ELSRC>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
   using Cfg = TcCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
@@ -476,7 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + part * TC_EPI_COLS);
       // (waits for the accumulator inside, after the first patch's loads are in flight)
-      float r = tc_epi_warp<MODE, SUB, ACT>(e, m0 + q * 32, n0 + part * TC_EPI_COLS, lane, t_row, xp, tfull_bar(as), aphase);
+      float r = tc_epi_warp<MODE, SUB, ACT, ELSRC>(e, m0 + q * 32, n0 + part * TC_EPI_COLS, lane, t_row, xp, tfull_bar(as), aphase);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): release the stage
       tc_fence_before();
       __syncwarp();
