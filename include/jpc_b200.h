@@ -73,7 +73,7 @@ typedef struct jpcb_pc_desc {
   uint8_t skip[JPCB_MAX_LAYERS];     /* identity skip at layer l (jpc/_utils.py:122-126) */
   float scalings[JPCB_MAX_LAYERS];   /* a_l of _get_param_scalings (jpc/_core/_energies.py:879-933) */
   int32_t dtype;                     /* JPCB_DTYPE_* */
-  int32_t loss;                      /* JPCB_LOSS_* (only MSE on this path so far) */
+  int32_t loss;                      /* JPCB_LOSS_*: output-layer energy (mse, or cross-entropy of softmax(logits)) */
   float output_energy_scaling;       /* lambda; 1 when the reference passes None */
   float activity_decay;
   int32_t solver;                    /* JPCB_SOLVER_* */
@@ -93,8 +93,8 @@ size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc);
 /* init_activities_with_ffwd  (jpc/_core/_init.py:12-82).
  * A_out[l] (l = 0..L-1) receives z_{l+1} = a_l f_l(z_l) (+ z_l where skip[l]); A_out[L-1] is the
  * network output.  If `loss_out` and `y` are non-NULL, *loss_out (device float) receives this
- * rank's part of mse_loss(A_out[L-1], y) = 1/(2B) sum (y - out)^2  (jpc/_utils.py:129-130,
- * jpc/_train.py:159-162). */
+ * rank's part of mse_loss(A_out[L-1], y) = 1/(2B) sum (y - out)^2, or of cross_entropy_loss when
+ * desc->loss is JPCB_LOSS_CE  (jpc/_utils.py:129-136, jpc/_train.py:159-164). */
 int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
                       const float* x, float* const* A_out, const float* y, float* loss_out,
                       void* workspace, size_t workspace_bytes, void* stream);

@@ -77,8 +77,7 @@ int validate(const jpcb_pc_desc* d) {
   }
   for (int l = 0; l <= d->n_layers; ++l)
     if ((long long)d->batch_local * d->dims[l] >= (1LL << 31)) return fail(JPCB_ENOTIMPL, "batch_local * dims[%d] must be < 2^31 (32-bit element indices)", l);
-  if (d->loss == JPCB_LOSS_CE) return fail(JPCB_ENOTIMPL, "cross-entropy output energy is not on the B200 path yet");
-  if (d->loss != JPCB_LOSS_MSE) return fail(JPCB_EINVAL, "`mse` and `ce` are the only valid losses.");
+  if (d->loss != JPCB_LOSS_MSE && d->loss != JPCB_LOSS_CE) return fail(JPCB_EINVAL, "`mse` and `ce` are the only valid losses.");
   if (d->dtype != JPCB_DTYPE_F32 && d->dtype != JPCB_DTYPE_BF16) return fail(JPCB_EINVAL, "bad dtype %d", d->dtype);
   if (d->solver != JPCB_SOLVER_EULER && d->solver != JPCB_SOLVER_HEUN) return fail(JPCB_EINVAL, "bad solver %d", d->solver);
   if (d->n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", d->n_steps);
@@ -113,6 +112,7 @@ struct Ws {
   float* red = nullptr;
   std::vector<float*> err;   // [L]  err[l]: [Bl, d_{l+1}] fp32 (F32 path)
   float* P1 = nullptr;       // hoisted layer-0 prediction [Bl, d_1]
+  float* logits = nullptr;   // cross-entropy output: the output layer's prediction [Bl, d_L]
   std::vector<float*> Zt;    // [L-1] Heun stage state of A[l]
   std::vector<float*> G1;    // [L-1] Heun first-stage gradient of A[l]
   // bf16 operand copies (tensor-core path)
@@ -134,6 +134,7 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
   w->Zt.assign(L, nullptr);
   w->G1.assign(L, nullptr);
   w->P1 = b.take<float>(Bl * d->dims[1]);
+  if (d->loss == JPCB_LOSS_CE) w->logits = b.take<float>(Bl * d->dims[L]);
   const bool tc = d->dtype == JPCB_DTYPE_BF16, heun = d->solver == JPCB_SOLVER_HEUN;
   for (int l = 0; l < L; ++l) w->err[l] = tc ? nullptr : b.take<float>(Bl * d->dims[l + 1]);
   if (heun)
@@ -301,8 +302,11 @@ struct Run {
       t.e.O = A_out[l];
       if (l == 0 && keep_p1) t.e.O2 = ws.P1;
       if (tc && l + 1 < L) { t.e.Ob = ws.Hb[l + 1]; t.e.act = d->act[l + 1]; }
-      if (l == L - 1 && loss_acc && y) { t.e.red = loss_acc; t.e.Y = y; }
+      const bool ce = d->loss == JPCB_LOSS_CE;
+      if (l == L - 1 && loss_acc && y && !ce) { t.e.red = loss_acc; t.e.Y = y; }
       RET(launch({t}));
+      // cross_entropy_loss(logits = network output, y)  (jpc/_utils.py:133-136)
+      if (l == L - 1 && loss_acc && y && ce) RET(ce_rows(A_out[L - 1], 1.f, nullptr, nullptr, loss_acc));
     }
     return JPCB_OK;
   }
@@ -317,11 +321,27 @@ struct Run {
   }
 
   // prediction errors err[l] for l in [lo, L) on state S; optional per-layer energy sums
+  // one warp per row: cross-entropy error / energy of the output layer from its logits
+  int ce_rows(const float* lg, float lam, float* err, bf16* err_b, float* red) {
+    const int wpb = 8, blocks = (Bl + wpb - 1) / wpb;
+    ce_rows_kernel<<<blocks < num_sms() * 4 ? blocks : num_sms() * 4, wpb * 32, 0, st>>>(lg, y, Bl, d->dims[L], lam, err, err_b, red);
+    count_launch();
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+
   int errors(int lo, const float* const* S, const std::vector<bf16*>& H, bool energy) {
     std::vector<GTask> ts;
+    const bool ce = d->loss == JPCB_LOSS_CE;
     for (int l = lo; l < L; ++l) {
       GTask t;
       fwd_operands(t, l, S, H);
+      if (ce && l == L - 1) {  // logits only; the softmax error follows in ce_rows (needs whole rows)
+        t.e.mode = EPI_FFWD;
+        t.e.O = ws.logits;
+        ts.push_back(t);
+        continue;
+      }
       t.e.mode = EPI_ERR;
       t.e.skip = eskip(l);
       t.e.U = l == 0 ? x : S[l - 1];
@@ -332,7 +352,9 @@ struct Run {
       if (energy) t.e.red = ws.red + l;
       ts.push_back(t);
     }
-    return launch(ts);
+    RET(launch(ts));
+    if (ce) RET(ce_rows(ws.logits, d->output_energy_scaling, ws.err[L - 1], ws.Eb[L - 1], energy ? ws.red + (L - 1) : nullptr));
+    return JPCB_OK;
   }
   // err[0] = S[0] - P1 without a GEMM (K = 0 task on the CUDA-core kernel), optional energy
   int error0_from_p1(const float* const* S, bool energy) {

@@ -215,7 +215,9 @@ __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int 
 // `nvalid` (1..4) columns are inside the matrix; `vec` says 16-byte vector access is legal
 // (N % 4 == 0 and nvalid == 4).  Returns this thread's contribution to the reduction (`red`).
 // `have_bias4`: the caller already holds the 4 bias values of columns col..col+3 in `bias4`.
-template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1, int ELSRC = -1>
+// PLAIN: the task has no skip term, no bias, no partial-gradient input, unit weights (gscale = escale = 1)
+// and no activity decay -- the common case, checked on the host -- so those branches compile away.
+template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1, int ELSRC = -1, bool PLAIN = false>
 __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec,
                                             const EpiPre& p, bool have_bias4, const float (&bias4)[4]) {
   const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
@@ -234,10 +236,10 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     float pred[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float bj = have_bias4 ? bias4[j] : ((e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f);
+      float bj = PLAIN ? 0.f : (have_bias4 ? bias4[j] : ((e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f));
       pred[j] = e.alpha * (acc[j] + bj);
     }
-    if (e.skip != 0.f) {
+    if (!PLAIN && e.skip != 0.f) {
       float u[4];
       ld4(e.U, idx, nvalid, vec, u);
 #pragma unroll
@@ -260,8 +262,9 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float d = j < nvalid ? p.a[j] - pred[j] : 0.f;
-      r += 0.5f * e.escale * d * d;
-      out[j] = e.escale * d;
+      const float es = PLAIN ? 1.f : e.escale;
+      r += 0.5f * es * d * d;
+      out[j] = es * d;
     }
     if (e.O) st4(e.O, idx, nvalid, vec, out);
     if (e.Ob) st4(e.Ob, idx, nvalid, vec, out);
@@ -290,16 +293,18 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) g[j] = el[j] - act_bwd<FAST>(act, z[j]) * (e.alpha * acc[j]);
-  if (e.skip != 0.f) {
+  if (!PLAIN && e.skip != 0.f) {
     float en[4];
     if (e.En) ld4(e.En, idx, nvalid, vec, en);
     else ld4(e.Enb, idx, nvalid, vec, en);
 #pragma unroll
     for (int j = 0; j < 4; ++j) g[j] -= e.skip * en[j];
   }
+  if (!PLAIN) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) g[j] = e.gscale * g[j] + e.ad * z[j];
-  if (e.Gin) {
+    for (int j = 0; j < 4; ++j) g[j] = e.gscale * g[j] + e.ad * z[j];
+  }
+  if (!PLAIN && e.Gin) {
     float gi[4];
     ld4(e.Gin, idx, nvalid, vec, gi);
 #pragma unroll

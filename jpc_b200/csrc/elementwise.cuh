@@ -91,6 +91,39 @@ static __global__ void scale_kernel(const float* src, float* dst, size_t n, floa
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = s * src[i];
 }
 
+// Cross-entropy output layer (jpc/_core/_energies.py:107-109): one warp per batch row.
+//   E_out += -lam * sum_j y_j log_softmax(logits)_j            (into *red, if red)
+//   err    = -dE_out/dlogits = lam * (y - softmax(logits) * sum_j y_j)   (fp32 and/or bf16 copies, if given)
+static __global__ void ce_rows_kernel(const float* __restrict__ logits, const float* __restrict__ y, int M, int N, float lam,
+                                      float* err, __nv_bfloat16* err_b, float* red) {
+  const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float* lr = logits + (size_t)row * N;
+    const float* yr = y + (size_t)row * N;
+    float mx = -INFINITY, sy = 0.f;
+    for (int j = lane; j < N; j += 32) { mx = fmaxf(mx, lr[j]); sy += yr[j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sy = warp_sum(sy);
+    float se = 0.f;
+    for (int j = lane; j < N; j += 32) se += expf(lr[j] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    for (int j = lane; j < N; j += 32) {
+      const float lp = lr[j] - lse;  // log_softmax
+      acc -= lam * yr[j] * lp;
+      const float e = lam * (yr[j] - expf(lp) * sy);
+      if (err) err[(size_t)row * N + j] = e;
+      if (err_b) err_b[(size_t)row * N + j] = __float2bfloat16_rn(e);
+    }
+  }
+  if (red) {
+    acc = warp_sum(acc);
+    if (lane == 0 && acc != 0.f) atomicAdd(red, acc);
+  }
+}
+
 // Turns raw per-layer sums acc[l] = lam/2 * sum err_l^2 into the reference's outputs:
 //   E_layers (order [output, hidden 1..L-2, first], each / B)   jpc/_core/_energies.py:155-156
 //   F = sum(acc)/B + ad/(2B) * sumsq                             jpc/_core/_energies.py:145-153

@@ -37,12 +37,12 @@ int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   return JPCB_OK;
 }
 
-template <int CG, int MODE, int SUB, int ACT, int ELSRC>
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
 int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   using Cfg = TcCfg<CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -58,7 +58,7 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC>, g));
+  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN>, g));
   count_launch();
   return JPCB_OK;
 }
@@ -68,23 +68,29 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
 // weight-gradient outputs).  Anything else takes the generic descriptor-driven kernel.
 int variant_key(const Epi& e) {
   if (tc_flags() & 4) return 0;
-  if (e.mode == EPI_ERR) return 1;
+  const bool plain = e.skip == 0.f && e.bias == nullptr && e.Gin == nullptr && e.gscale == 1.f && e.escale == 1.f && e.ad == 0.f;
+  if (e.mode == EPI_ERR) return plain ? 1 : 7;
   if (e.mode == EPI_SCALE) return 2;
-  if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && (e.act == ACT_TANH || e.act == ACT_RELU) && !e.El && (e.Elb || e.P))
+  if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && plain && (e.act == ACT_TANH || e.act == ACT_RELU) && !e.El && (e.Elb || e.P))
     return 3 + (e.act == ACT_RELU ? 2 : 0) + (e.Elb ? 0 : 1);
+  if (e.mode == EPI_FFWD && (e.act == ACT_TANH || e.act == ACT_RELU || e.act == ACT_LINEAR)) return e.act == ACT_TANH ? 8 : (e.act == ACT_RELU ? 9 : 10);
   return 0;
 }
 
 template <int CG>
 int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
   switch (key) {
-    case 1: return launch_variant<CG, EPI_ERR, 0, 0, -1>(g, grid, st);
-    case 2: return launch_variant<CG, EPI_SCALE, 0, 0, -1>(g, grid, st);
-    case 3: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0>(g, grid, st);
-    case 4: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 1>(g, grid, st);
-    case 5: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0>(g, grid, st);
-    case 6: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 1>(g, grid, st);
-    default: return launch_variant<CG, -1, -1, -1, -1>(g, grid, st);
+    case 1: return launch_variant<CG, EPI_ERR, 0, 0, -1, true>(g, grid, st);
+    case 7: return launch_variant<CG, EPI_ERR, 0, 0, -1, false>(g, grid, st);
+    case 2: return launch_variant<CG, EPI_SCALE, 0, 0, -1, false>(g, grid, st);
+    case 3: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, true>(g, grid, st);
+    case 4: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 1, true>(g, grid, st);
+    case 5: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, true>(g, grid, st);
+    case 6: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 1, true>(g, grid, st);
+    case 8: return launch_variant<CG, EPI_FFWD, 0, ACT_TANH, -1, false>(g, grid, st);
+    case 9: return launch_variant<CG, EPI_FFWD, 0, ACT_RELU, -1, false>(g, grid, st);
+    case 10: return launch_variant<CG, EPI_FFWD, 0, ACT_LINEAR, -1, false>(g, grid, st);
+    default: return launch_variant<CG, -1, -1, -1, -1, false>(g, grid, st);
   }
 }
 

@@ -287,7 +287,7 @@ __device__ __forceinline__ void tc_epi_loads(const Epi& e, int row0, int cb, int
   }
 }
 
-template <int MODE, int SUB, int ACT, int ELSRC>
+template <int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
 __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, int lane, uint32_t taddr, float* xp,
                                               const EpiPre (&pre)[4], const float (&bias4)[4]) {
   const int c4 = lane & 3, rq = lane >> 2;
@@ -310,14 +310,14 @@ __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, in
     const int row = row0 + rl;
     if (cok && row < e.M) {
       const float a4[4] = {a.x, a.y, a.z, a.w};
-      r += epi_finish<true, MODE, SUB, ACT, ELSRC>(e, row, col, a4, 4, true, pre[i], true, bias4);
+      r += epi_finish<true, MODE, SUB, ACT, ELSRC, PLAIN>(e, row, col, a4, 4, true, pre[i], true, bias4);
     }
   }
   __syncwarp();
   return r;
 }
 
-template <int MODE, int SUB, int ACT, int ELSRC>
+template <int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
 __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
                                              uint32_t tphase) {
   float r = 0.f;
@@ -332,10 +332,10 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
     const int cb = col0 + ch * 16;  // first column of this 16-wide patch
     if (cb >= e.N) break;           // warp-uniform
     tc_epi_loads<MODE, ELSRC>(e, row0, cb + 16, lane, pb, bb);
-    r += tc_epi_patch<MODE, SUB, ACT, ELSRC>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
+    r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
     if (cb + 16 >= e.N) break;
     if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC>(e, row0, cb + 32, lane, pa, ba);
-    r += tc_epi_patch<MODE, SUB, ACT, ELSRC>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
+    r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
   }
 #else
   EpiPre pa[4];
@@ -348,7 +348,7 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
     const int cb = col0 + ch * 16;
     if (cb >= e.N) break;
     if (ch > 0) tc_epi_loads<MODE, ELSRC>(e, row0, cb, lane, pa, ba);
-    r += tc_epi_patch<MODE, SUB, ACT, ELSRC>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
+    r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
   }
 #endif
   return r;
@@ -357,7 +357,8 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
 // ---------------------------------------------------------------------------------------------
 // MODE/SUB/ACT/ELSRC >= 0: every task of the launch has that epilogue mode / GRAD sub-mode /
 // activation / e_l source (the host checks), compiled in; -1 = generic descriptor-driven epilogue.
-template <int CG, int MODE, int SUB, int ACT, int ELSRC>
+// PLAIN: no task of the launch has a skip term, bias, partial-gradient input, non-unit weight or decay.
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
   using Cfg = TcCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + part * TC_EPI_COLS);
       // (waits for the accumulator inside, after the first patch's loads are in flight)
-      float r = tc_epi_warp<MODE, SUB, ACT, ELSRC>(e, m0 + q * 32, n0 + part * TC_EPI_COLS, lane, t_row, xp, tfull_bar(as), aphase);
+      float r = tc_epi_warp<MODE, SUB, ACT, ELSRC, PLAIN>(e, m0 + q * 32, n0 + part * TC_EPI_COLS, lane, t_row, xp, tfull_bar(as), aphase);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): release the stage
       tc_fence_before();
       __syncwarp();

@@ -390,3 +390,58 @@ def test_config5_bpc_full_size():
     c = _bpc_case(10, 1024, 6, 784, "relu", 1024)
     _check_bpc(*c, TOL32)
     _check_bpc_infer(*c, TOL32, T=30, dt=0.5)
+
+
+# ---- cross-entropy output energy (jpc/_core/_energies.py:107-109) ------------------------------
+def _check_ce(om, sk, x, y, tol, param_type="sp", lam=None, fused=("euler", 3.0, 0.5)):
+    import jpc_b200 as J
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    gx, gy = dev(x), dev(y)
+    a0 = O.init_activities_with_ffwd(om, x, skips=sk, param_type=param_type)
+    acts = [a.float().double() for a in perturb(a0)]
+    gacts = devs(acts)
+    okw = dict(x=x, loss="ce", param_type=param_type, output_energy_scaling=lam)
+    E = O.pc_energy_fn(om, sk, acts, y, record_layers=True, **okw)
+    gE = J.pc_energy_fn((gm, gsk), gacts, gy, x=gx, loss="ce", param_type=param_type, output_energy_scaling=lam, record_layers=True)
+    assert rel(gE, E) < tol
+    F, g = O.compute_pc_activity_grad(om, sk, acts, y, **okw)
+    gF, gg = J.compute_pc_activity_grad((gm, gsk), gacts, gy, x=gx, loss_id="ce", param_type=param_type, output_energy_scaling=lam)
+    assert abs(float(gF) - float(F)) <= tol * abs(float(F))
+    gmax = max(float(t.abs().max()) for t in g)
+    for p, q in zip(gg, g):
+        assert rel(p, q) < tol or float((p.double().cpu() - q).abs().max()) < tol * gmax
+    pg = O.compute_pc_param_grads(om, sk, acts, y, **okw)
+    gpg, _ = J.compute_pc_param_grads((gm, gsk), gacts, gy, x=gx, loss_id="ce", param_type=param_type, output_energy_scaling=lam)
+    for l, q in enumerate(pg):
+        assert rel(gpg[l][1].weight, q["W"]) < tol
+        if q["b"] is not None:
+            assert rel(gpg[l][1].bias, q["b"]) < tol
+    # fused train step: loss is cross_entropy_loss at the init (jpc/_train.py:159-164)
+    solver, max_t1, dt = fused
+    ref = O.pc_train_step(om, sk, x, y, solver=solver, max_t1=max_t1, dt=dt, loss_id="ce", param_type=param_type)
+    opt = J.optim.sgd(0.0)
+    out = J.make_pc_step(gm, opt, opt.init((gm, gsk)), gy, input=gx, loss_id="ce", param_type=param_type,
+                         ode_solver=J.Euler() if solver == "euler" else J.Heun(), max_t1=max_t1, dt=dt,
+                         stepsize_controller=J.ConstantStepSize(), skip_model=gsk)
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+    assert rel(out["energies"], ref["energies"]) < tol
+    amax = max(float(t.abs().max()) for t in ref["activities"][:-1])
+    for p, q in zip(out["activities"][:-1], ref["activities"][:-1]):
+        assert float((p[0].double().cpu() - q).abs().max()) < tol * amax
+
+
+def test_cross_entropy_fp32():
+    om, sk, x, y = _case(10, 20, 3, 5, "tanh", 6, use_bias=True)            # one-hot targets
+    _check_ce(om, sk, x, y, TOL32)
+    _check_ce(om, sk, x, y, TOL32, lam=2.5, fused=("heun", 2.0, 0.5))
+    om, sk, x, y = _case(12, 16, 4, 37, "relu", 5, onehot_out=False)         # targets that do not sum to 1
+    _check_ce(om, sk, x, y.abs(), TOL32)
+    om, sk, x, y = _case(784, 300, 3, 10, "tanh", 64)                         # config-1 shape with the ce energy
+    _check_ce(om, sk, x, y, TOL32, fused=("euler", 10.0, 0.5))
+
+
+def test_cross_entropy_bf16():
+    import jpc_b200 as J
+    J.set_compute_dtype("bf16")
+    om, sk, x, y = _case(256, 512, 3, 16, "tanh", 256, use_bias=True)
+    _check_ce(om, sk, x, y, TOLBF, fused=("euler", 2.0, 0.5))
