@@ -371,9 +371,9 @@ struct Run {
   // gradient/update of A[l-1], l = 1..L-1.  Z: state where act' is evaluated; p1_hoisted: err[0]
   // is formed on the fly as Z[0] - P1.
   int grads(int sub, float c, const float* const* Z, const float* const* Z0, float* const* Out, const std::vector<bf16*>& Hout,
-            bool p1_hoisted) {
+            bool p1_hoisted, int lo = 1) {
     std::vector<GTask> ts;
-    for (int l = 1; l < L; ++l) {
+    for (int l = lo; l < L; ++l) {
       GTask t;
       t.e.mode = EPI_GRAD; t.e.sub = sub; t.e.act = d->act[l];
       t.e.M = Bl; t.e.N = d->dims[l]; t.K = d->dims[l + 1];
@@ -404,15 +404,30 @@ struct Run {
 
   // T fixed steps of Euler / Heun, in place on A (jpc/_core/_infer.py:109-132; diffrax Euler.step /
   // Heun tableau).  Requires P1 and, on the tensor-core path, Hb[l] = act_l(A[l-1]).
-  int infer_loop(float* const* A) {
+  //
+  // `from_ffwd`: A is exactly the feed-forward init (make_pc_step).  Then every hidden prediction error is
+  // exactly zero and only the output error is not, so after s Euler steps only the top s+1 activities have
+  // moved (the error wavefront travels one layer per step).  Step s therefore only
+  // evaluates layers l >= L-1-s; the error buffer just below the front is read as the zeros it was set to.
+  // Same result as evaluating every layer (whose contributions would be exact zeros), fewer GEMMs.
+  int infer_loop(float* const* A, bool from_ffwd = false) {
     const int T = d->n_steps;
     const size_t n_dummy = (size_t)Bl * d->dims[L];
+    const bool front = from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !(tc_flags() & 8);
+    if (front) {
+      if (tc) {
+        for (int l = (L - 2 - T > 0 ? L - 2 - T : 0); l < L - 1; ++l) CK(cudaMemsetAsync(ws.Eb[l], 0, (size_t)Bl * d->dims[l + 1] * sizeof(bf16), st));
+      } else {
+        CK(cudaMemsetAsync(ws.err[0], 0, (size_t)(reinterpret_cast<char*>(ws.err[L - 1]) - reinterpret_cast<char*>(ws.err[0])), st));
+      }
+    }
     for (int s = 0; s < T; ++s) {
       const float h = s == T - 1 ? d->dt_last : d->dt;
       const float c = h * invB;
       if (d->solver == JPCB_SOLVER_EULER) {
-        RET(errors(1, A, ws.Hb, false));
-        RET(grads(GRAD_EULER, c, A, nullptr, A, ws.Hb, true));
+        const int lo = front ? (L - 1 - s > 1 ? L - 1 - s : 1) : 1;
+        RET(errors(lo, A, ws.Hb, false));
+        RET(grads(GRAD_EULER, c, A, nullptr, A, ws.Hb, true, lo));
         if (d->activity_decay != 0.f) RET(scale_inplace(A[L - 1], n_dummy, 1.f - c * d->activity_decay));
       } else {
         std::vector<float*> zt(ws.Zt.begin(), ws.Zt.begin() + (L - 1));
@@ -593,7 +608,7 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
   RET(r.prep_weights());
   RET(r.prep_inputs(nullptr, r.ws.Hb));
   RET(r.ffwd(A_out, r.ws.red + RED_LOSS, true));   // init + loss at the init + hoisted P1 + bf16 operands
-  RET(r.infer_loop(A_out));
+  RET(r.infer_loop(A_out, true));
   RET(r.errors(1, A_out, r.ws.Hb, true));           // errors + layer energies at the solution
   RET(r.error0_from_p1(A_out, true));
   RET(r.wgrads(A_out, gW, gb));
