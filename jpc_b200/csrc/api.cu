@@ -120,8 +120,6 @@ struct Ws {
   std::vector<bf16*> Hb;       // [L]   act_l(u_l)  [Bl, d_l]
   std::vector<bf16*> Htb;      // [L]   same for the Heun stage state
   std::vector<bf16*> Eb;       // [L]   err[l] [Bl, d_{l+1}]
-  std::vector<bf16*> EbT;      // [L]   err[l]^T [d_{l+1}, Bl]
-  std::vector<bf16*> HbT;      // [L]   act_l(u_l)^T [d_l, Bl]
   size_t bytes = 0;
 };
 
@@ -143,7 +141,7 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
       w->G1[l] = b.take<float>(Bl * d->dims[l + 1]);
     }
   w->Wb.assign(L, nullptr); w->WTb.assign(L, nullptr); w->Hb.assign(L, nullptr); w->Htb.assign(L, nullptr);
-  w->Eb.assign(L, nullptr); w->EbT.assign(L, nullptr); w->HbT.assign(L, nullptr);
+  w->Eb.assign(L, nullptr);
   if (tc) {
     for (int l = 0; l < L; ++l) {
       const size_t wn = (size_t)d->dims[l] * d->dims[l + 1];
@@ -152,8 +150,6 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
       w->Hb[l] = b.take<bf16>(Bl * d->dims[l]);
       if (heun && l >= 1) w->Htb[l] = b.take<bf16>(Bl * d->dims[l]);
       w->Eb[l] = b.take<bf16>(Bl * d->dims[l + 1]);
-      w->EbT[l] = b.take<bf16>(Bl * d->dims[l + 1]);
-      w->HbT[l] = b.take<bf16>(Bl * d->dims[l]);
     }
   }
   w->bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
@@ -447,14 +443,8 @@ struct Run {
 
   // parameter gradients from err[] (already computed on state S) -- jpc/_core/_grads.py:487-499
   int wgrads(const float* const* S, float* const* gW, float* const* gb) {
-    if (tc) {
-      for (int l = 0; l < L; ++l) {
-        const int dn = d->dims[l + 1], dk = d->dims[l];
-        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dn + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Eb[l], ws.EbT[l], Bl, dn); count_launch();
-        transpose_to_bf16_kernel<bf16><<<ew_grid(((Bl + 31) / 32) * ((dk + 31) / 32), 1), dim3(32, 8), 0, st>>>(ws.Hb[l], ws.HbT[l], Bl, dk); count_launch();
-      }
-      CK(cudaGetLastError());
-    }
+    // tensor-core path: gW_l = -(a_l/B) Eb[l]^T Hb[l] with both operands read MN-major straight from
+    // the [batch, d] bf16 copies the inference phases already keep (K = batch runs across their rows)
     std::vector<GTask> ts;
     for (int l = 0; l < L; ++l) {
       GTask t;
@@ -462,7 +452,7 @@ struct Run {
       t.e.M = d->dims[l + 1]; t.e.N = d->dims[l]; t.K = Bl;
       t.a_p = ws.err[l]; t.a_smn = 1; t.a_sk = d->dims[l + 1];
       t.b_p = l == 0 ? x : S[l - 1]; t.b_smn = 1; t.b_sk = d->dims[l]; t.b_act = d->act[l];
-      t.a_b = ws.EbT[l]; t.b_b = ws.HbT[l];
+      t.a_b = ws.Eb[l]; t.b_b = ws.Hb[l]; t.mn_major = tc;
       t.e.alpha = -d->scalings[l] * invB;
       t.e.O = gW[l];
       ts.push_back(t);

@@ -41,8 +41,9 @@ struct GTask {
   int K = 0;
   const float* a_p = nullptr; long long a_smn = 0, a_sk = 0; int a_act = ACT_LINEAR;
   const float* b_p = nullptr; long long b_smn = 0, b_sk = 0; int b_act = ACT_LINEAR;
-  const __nv_bfloat16* a_b = nullptr;  // [M, K] K-major
-  const __nv_bfloat16* b_b = nullptr;  // [N, K] K-major
+  const __nv_bfloat16* a_b = nullptr;  // [M, K] K-major   (mn_major: [K, M] row-major)
+  const __nv_bfloat16* b_b = nullptr;  // [N, K] K-major   (mn_major: [K, N] row-major)
+  bool mn_major = false;               // tensor-core path: D = a_b^T b_b, operands read MN-major (no transposed copies)
   GTask() { memset(&e, 0, sizeof(e)); e.gscale = 1.f; e.escale = 1.f; }
 };
 

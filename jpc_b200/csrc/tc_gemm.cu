@@ -24,6 +24,7 @@ EncodeTiledFn encode_tiled() {
 }
 
 // bf16 [rows, cols] row-major, box = {64 cols, box_rows}, SWIZZLE_128B, OOB reads give zeros
+// (K-major operand: rows = M/N, cols = K; MN-major operand: rows = K, cols = M/N, box_rows = 64)
 int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -37,12 +38,12 @@ int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   return JPCB_OK;
 }
 
-template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN, bool MNMAJ = false>
 int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   using Cfg = TcCfg<CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN, MNMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -51,14 +52,18 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: the kernel's prologue may overlap the previous kernel's tail; it
+  // executes griddepcontrol.wait before its first global-memory access (tc_gemm.cuh)
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN>, g));
+  cfg.numAttrs = (tc_flags() & 16) ? 1 : 2;
+  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN, MNMAJ>, g));
   count_launch();
   return JPCB_OK;
 }
@@ -66,7 +71,9 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
 // Epilogue specialisations compiled in: what the timed configurations run (errors, tanh / relu
 // Euler updates with e_l from the bf16 error copy or from the hoisted layer-0 prediction, scaled
 // weight-gradient outputs).  Anything else takes the generic descriptor-driven kernel.
-int variant_key(const Epi& e) {
+int variant_key(const GTask& t) {
+  const Epi& e = t.e;
+  if (t.mn_major) return 11;  // (only the weight-gradient SCALE tasks use MN-major operands)
   if (tc_flags() & 4) return 0;
   const bool plain = e.skip == 0.f && e.bias == nullptr && e.Gin == nullptr && e.gscale == 1.f && e.escale == 1.f && e.ad == 0.f;
   if (e.mode == EPI_ERR) return plain ? 1 : 7;
@@ -90,6 +97,7 @@ int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
     case 8: return launch_variant<CG, EPI_FFWD, 0, ACT_TANH, -1, false>(g, grid, st);
     case 9: return launch_variant<CG, EPI_FFWD, 0, ACT_RELU, -1, false>(g, grid, st);
     case 10: return launch_variant<CG, EPI_FFWD, 0, ACT_LINEAR, -1, false>(g, grid, st);
+    case 11: return launch_variant<CG, EPI_SCALE, 0, 0, -1, false, true>(g, grid, st);
     default: return launch_variant<CG, -1, -1, -1, -1, false>(g, grid, st);
   }
 }
@@ -101,7 +109,10 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
   // tasks of one phase are independent: launch them grouped by epilogue specialisation
   std::vector<int> keys(tasks.size());
   std::vector<char> done(tasks.size(), 0);
-  for (size_t i = 0; i < tasks.size(); ++i) keys[i] = variant_key(tasks[i].e);
+  for (size_t i = 0; i < tasks.size(); ++i) {
+    if (tasks[i].mn_major && tasks[i].e.mode != EPI_SCALE) return fail(JPCB_EINVAL, "internal: MN-major operands are only built for SCALE tasks");
+    keys[i] = variant_key(tasks[i]);
+  }
   for (size_t first = 0; first < tasks.size(); ++first) {
     if (done[first]) continue;
     const int key = keys[first];
@@ -116,8 +127,13 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
         const GTask& t = tasks[i];
         if (t.K <= 0 || !t.a_b || !t.b_b) return fail(JPCB_EINVAL, "internal: tensor-core task without bf16 operands");
         TcTask& s = g.t[n];
-        RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
-        RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, Cfg::B_ROWS));
+        if (t.mn_major) {
+          RET(make_map(&s.tmA, t.a_b, t.K, t.e.M, 64));
+          RET(make_map(&s.tmB, t.b_b, t.K, t.e.N, 64));
+        } else {
+          RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
+          RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, Cfg::B_ROWS));
+        }
         s.K = t.K;
         s.tile_begin = tiles;
         s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;

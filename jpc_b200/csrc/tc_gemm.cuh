@@ -62,8 +62,8 @@ struct TcCfg {
 };
 
 struct alignas(64) TcTask {
-  CUtensorMap tmA;  // bf16 [M, K] row-major, box {64, 128}
-  CUtensorMap tmB;  // bf16 [N, K] row-major, box {64, 256 / CG}
+  CUtensorMap tmA;  // bf16 [M, K] row-major, box {64, 128}        (MN-major launches: [K, M] row-major, box {64, 64})
+  CUtensorMap tmB;  // bf16 [N, K] row-major, box {64, 256 / CG}   (MN-major launches: [K, N] row-major, box {64, 64})
   int K;
   int tile_begin;
   int tiles_n;
@@ -253,9 +253,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major operand (the GEMM's K runs across ROWS of the source tensor: weight gradients, K = batch),
+// SWIZZLE_128B: the tile is a grid of atoms of 8 K-rows x 128 B (64 bf16 along M/N), as TMA boxes of
+// {64 elements, 64 rows} lay them down: 8-row groups 1024 B apart (SBO), the next 64 M/N elements in
+// the next box, TC_MN_BOX_BYTES further (LBO).
+constexpr int TC_MN_BOX_BYTES = 64 * TC_BLOCK_K * 2;  // one {64 x 64} bf16 box = 8 KB
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_MN_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor for kind::f16: D=f32, A=B=bf16, M x N tile; both operands K-major, or both MN-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ int tc_find_task(const TcGroup& g, int tile) {
@@ -358,7 +367,9 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
 // MODE/SUB/ACT/ELSRC >= 0: every task of the launch has that epilogue mode / GRAD sub-mode /
 // activation / e_l source (the host checks), compiled in; -1 = generic descriptor-driven epilogue.
 // PLAIN: no task of the launch has a skip term, bias, partial-gradient input, non-unit weight or decay.
-template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
+// MNMAJ: both operands are read MN-major, i.e. D = A^T B with A [K, M] and B [K, N] row-major in HBM
+// (weight gradients e^T phi(z), K = batch) -- no transposed operand copies are ever materialised.
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN, bool MNMAJ = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
   using Cfg = TcCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
@@ -398,6 +409,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation) touched no global
+  // memory and may overlap the tail of the previous kernel in the stream; from here on we read what it
+  // wrote.  Our own dependents may be scheduled as soon as SMs free up (they wait the same way).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -417,8 +433,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
           const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CG);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d<CG>(sa, &t.tmA, fb, kb * TC_BLOCK_K, m0);
-          tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0);
+          if constexpr (!MNMAJ) {
+            tma_load_2d<CG>(sa, &t.tmA, fb, kb * TC_BLOCK_K, m0);
+            tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0);
+          } else {  // boxes of {64 M/N elements, 64 K rows}
+#pragma unroll
+            for (int i = 0; i < TC_BLOCK_M / 64; ++i) tma_load_2d<CG>(sa + i * TC_MN_BOX_BYTES, &t.tmA, fb, m0 + 64 * i, kb * TC_BLOCK_K);
+#pragma unroll
+            for (int i = 0; i < Cfg::B_ROWS / 64; ++i)
+              tma_load_2d<CG>(sa + TC_A_BYTES + i * TC_MN_BOX_BYTES, &t.tmB, fb, n0 + 64 * i, kb * TC_BLOCK_K);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -427,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M * CG, TC_BLOCK_N);
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M * CG, TC_BLOCK_N, MNMAJ);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -443,13 +467,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-            const uint64_t da = umma_desc_kmajor_sw128(sa);
-            const uint64_t db = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
+            const uint64_t da = MNMAJ ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
+            const uint64_t db = MNMAJ ? umma_desc_mnmajor_sw128(sa + TC_A_BYTES) : umma_desc_kmajor_sw128(sa + TC_A_BYTES);
+            // advancing K by 16: K-major: +32 B inside the 128-byte swizzle row; MN-major: +16 rows of 128 B
+            constexpr uint64_t kstep = MNMAJ ? (uint64_t)((TC_UMMA_K * 128) >> 4) : 2u;
 #pragma unroll
-            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-              // advancing K inside the 128-byte swizzle row: +32 B => +2 in the (addr >> 4) field
-              umma_f16<CG>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+              umma_f16<CG>(d_tmem, da + kstep * (uint64_t)k, db + kstep * (uint64_t)k, idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit<CG>(empty_bar(stage));  // ring slot reusable once these MMAs have read it
             if (kb == nkb - 1) umma_commit<CG>(tfull_bar(as));  // accumulator complete
           }
