@@ -20,6 +20,7 @@
 #include "elementwise.cuh"
 #include "host.cuh"
 #include "simt_gemm.cuh"
+#include "warp_gemm.cuh"
 
 using namespace jpcb;
 typedef __nv_bfloat16 bf16;
@@ -115,6 +116,9 @@ struct Ws {
   float* logits = nullptr;   // cross-entropy output: the output layer's prediction [Bl, d_L]
   std::vector<float*> Zt;    // [L-1] Heun stage state of A[l]
   std::vector<float*> G1;    // [L-1] Heun first-stage gradient of A[l]
+  // fp32 operand copies (fp32 path): act_l(u_l) [Bl, d_l] (+ Heun stage twin) and W_l^T [d_l, d_{l+1}], so that
+  // every inference GEMM reads two K-contiguous fp32 operands with no activation left to apply on load
+  std::vector<float*> Hf, Hft, WTf;
   // bf16 operand copies (tensor-core path)
   std::vector<bf16*> Wb, WTb;  // [L]   W_l [d_{l+1}, d_l] and its transpose [d_l, d_{l+1}]
   std::vector<bf16*> Hb;       // [L]   act_l(u_l)  [Bl, d_l]
@@ -140,6 +144,14 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
       w->Zt[l] = b.take<float>(Bl * d->dims[l + 1]);
       w->G1[l] = b.take<float>(Bl * d->dims[l + 1]);
     }
+  w->Hf.assign(L, nullptr); w->Hft.assign(L, nullptr); w->WTf.assign(L, nullptr);
+  if (!tc) {
+    for (int l = 0; l < L; ++l) {
+      if (l >= 1 || d->act[0] != JPCB_ACT_LINEAR) w->Hf[l] = b.take<float>(Bl * d->dims[l]);
+      if (heun && l >= 1) w->Hft[l] = b.take<float>(Bl * d->dims[l]);
+      if (l >= 1) w->WTf[l] = b.take<float>((size_t)d->dims[l] * d->dims[l + 1]);
+    }
+  }
   w->Wb.assign(L, nullptr); w->WTb.assign(L, nullptr); w->Hb.assign(L, nullptr); w->Htb.assign(L, nullptr);
   w->Eb.assign(L, nullptr);
   if (tc) {
@@ -187,17 +199,67 @@ int launch_simt_cfg(const std::vector<GTask>& tasks, cudaStream_t st) {
   return JPCB_OK;
 }
 
+// narrow-layer path: one warp per MT x 4 output patch (warp_gemm.cuh); needs K-contiguous, activation-free operands
+template <int MT>
+int launch_warp_mt(const std::vector<GTask>& tasks, cudaStream_t st) {
+  size_t i = 0;
+  while (i < tasks.size()) {
+    SimtGroup g;
+    memset(&g, 0, sizeof(int) * 2);
+    int n = 0, tiles = 0;
+    for (; i < tasks.size() && n < SIMT_MAX_TASKS; ++i, ++n) {
+      const GTask& t = tasks[i];
+      SimtTask& s = g.t[n];
+      s.A = Opnd{t.a_p, t.a_smn, 1, ACT_LINEAR, 0};
+      s.B = Opnd{t.b_p, t.b_smn, 1, ACT_LINEAR, 0};
+      s.K = t.K;
+      s.tile_begin = tiles;
+      s.tiles_n = (t.e.N + WG_NT - 1) / WG_NT;
+      s.pad_ = 0;
+      s.e = t.e;
+      tiles += s.tiles_n * ((t.e.M + MT - 1) / MT);
+    }
+    g.ntasks = n;
+    g.total_tiles = tiles;
+    if (tiles == 0) continue;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((tiles + WG_WARPS - 1) / WG_WARPS);
+    cfg.blockDim = dim3(WG_WARPS * 32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // the kernel starts with griddepcontrol.wait
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, warp_grouped_gemm<MT>, g));
+    count_launch();
+  }
+  return JPCB_OK;
+}
+
+int launch_warp(const std::vector<GTask>& tasks, cudaStream_t st) {
+  long long w8 = 0;
+  for (const GTask& t : tasks) w8 += (long long)((t.e.M + 7) / 8) * ((t.e.N + WG_NT - 1) / WG_NT);
+  // 8-row patches move less operand data per multiply-add; use them while they still give every SM >= 16 warps
+  return w8 >= 16LL * num_sms() ? launch_warp_mt<8>(tasks, st) : launch_warp_mt<4>(tasks, st);
+}
+
 }  // namespace
 
 int jpcb::launch_simt(const std::vector<GTask>& tasks, cudaStream_t st) {
   if (tasks.empty()) return JPCB_OK;
-  // pick the tile shape from the amount of parallelism the phase offers
+  // pick the kernel / tile shape from the amount of parallelism the phase offers
   long long t128 = 0, t64 = 0;
+  bool warp_ok = !(tc_flags() & 32);
   for (const GTask& t : tasks) {
     t128 += (long long)((t.e.M + 127) / 128) * ((t.e.N + 127) / 128);
     t64 += (long long)((t.e.M + 63) / 64) * ((t.e.N + 63) / 64);
+    warp_ok = warp_ok && (t.K == 0 || (t.a_sk == 1 && t.b_sk == 1 && t.a_act == ACT_LINEAR && t.b_act == ACT_LINEAR));
   }
   const int sms = num_sms();
+  // fewer 64 x 64 tiles than two per SM: a tiled GEMM cannot fill the machine, the warp-level path can
+  if (warp_ok && t64 < 2LL * sms) return launch_warp(tasks, st);
   if (t128 >= 2LL * sms) return launch_simt_cfg<128, 128, 16, 2, 2>(tasks, st);
   if (t64 >= sms) return launch_simt_cfg<64, 64, 16, 1, 1>(tasks, st);
   return launch_simt_cfg<32, 32, 16, 1, 1>(tasks, st);  // (8x8 threads) latency-bound small layers
@@ -249,7 +311,14 @@ struct Run {
 
   // ---- bf16 operand preparation ----
   int prep_weights() {
-    if (!tc) return JPCB_OK;
+    if (!tc) {
+      for (int l = 1; l < L; ++l) {
+        const int R = d->dims[l + 1], C = d->dims[l];
+        transpose_f32_kernel<<<ew_grid(((R + 31) / 32) * ((C + 31) / 32), 1), dim3(32, 8), 0, st>>>(W[l], ws.WTf[l], R, C); count_launch();
+      }
+      CK(cudaGetLastError());
+      return JPCB_OK;
+    }
     for (int l = 0; l < L; ++l) {
       const size_t n = (size_t)d->dims[l] * d->dims[l + 1];
       cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR); count_launch();
@@ -262,15 +331,25 @@ struct Run {
     CK(cudaGetLastError());
     return JPCB_OK;
   }
-  // Hb[0] = bf16(act_0(x)); when `S` is given also Hdst[l] = bf16(act_l(S[l-1])) for l = 1..L-1
-  int prep_inputs(const float* const* S, std::vector<bf16*>& Hdst) {
-    if (!tc) return JPCB_OK;
+  // operand copies of the layer inputs on state S: (Hb | Hf)[0] = act_0(x); when `S` is given also
+  // (Hb | Hf)[l] = act_l(S[l-1]) for l = 1..L-1  (bf16 on the tensor-core path, fp32 otherwise)
+  int prep_inputs(const float* const* S) {
+    if (!tc) {
+      if (ws.Hf[0]) { const size_t n0 = (size_t)Bl * d->dims[0]; act_f32_kernel<<<ew_grid(n0, 256), 256, 0, st>>>(x, ws.Hf[0], n0, d->act[0]); count_launch(); }
+      if (S)
+        for (int l = 1; l < L; ++l) {
+          const size_t n = (size_t)Bl * d->dims[l];
+          act_f32_kernel<<<ew_grid(n, 256), 256, 0, st>>>(S[l - 1], ws.Hf[l], n, d->act[l]); count_launch();
+        }
+      CK(cudaGetLastError());
+      return JPCB_OK;
+    }
     const size_t n0 = (size_t)Bl * d->dims[0];
     cast_act_bf16_kernel<<<ew_grid(n0 / 4 + 1, 256), 256, 0, st>>>(x, ws.Hb[0], n0, d->act[0]); count_launch();
     if (S)
       for (int l = 1; l < L; ++l) {
         const size_t n = (size_t)Bl * d->dims[l];
-        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], Hdst[l], n, d->act[l]); count_launch();
+        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], ws.Hb[l], n, d->act[l]); count_launch();
       }
     CK(cudaGetLastError());
     return JPCB_OK;
@@ -278,9 +357,13 @@ struct Run {
 
   // ---- task builders ----
   // forward GEMM of layer l on state S (u_l = x or S[l-1]); H = bf16 operand list for that state
-  void fwd_operands(GTask& t, int l, const float* const* S, const std::vector<bf16*>& H) const {
+  // `stage`: the operand copies of the Heun stage state (Htb / Hft) instead of the current state's
+  void fwd_operands(GTask& t, int l, const float* const* S, bool stage) const {
+    const std::vector<bf16*>& H = stage ? ws.Htb : ws.Hb;
+    const std::vector<float*>& Hf = stage ? ws.Hft : ws.Hf;
     t.e.M = Bl; t.e.N = d->dims[l + 1]; t.K = d->dims[l];
-    t.a_p = l == 0 ? x : S[l - 1]; t.a_smn = d->dims[l]; t.a_sk = 1; t.a_act = d->act[l];
+    (void)S;
+    t.a_p = l == 0 ? (ws.Hf[0] ? ws.Hf[0] : x) : Hf[l]; t.a_smn = d->dims[l]; t.a_sk = 1; t.a_act = ACT_LINEAR;
     t.b_p = W[l]; t.b_smn = d->dims[l]; t.b_sk = 1;
     t.a_b = l == 0 ? ws.Hb[0] : H[l]; t.b_b = ws.Wb[l];
     t.e.alpha = d->scalings[l];
@@ -291,13 +374,13 @@ struct Run {
   int ffwd(float* const* A_out, float* loss_acc, bool keep_p1) {
     for (int l = 0; l < L; ++l) {
       GTask t;
-      fwd_operands(t, l, A_out, ws.Hb);
+      fwd_operands(t, l, A_out, false);
       t.e.mode = EPI_FFWD;
       t.e.skip = d->skip[l] ? 1.f : 0.f;  // the init honours any non-None skip (_init.py:69-78)
       t.e.U = l == 0 ? x : A_out[l - 1];
       t.e.O = A_out[l];
       if (l == 0 && keep_p1) t.e.O2 = ws.P1;
-      if (tc && l + 1 < L) { t.e.Ob = ws.Hb[l + 1]; t.e.act = d->act[l + 1]; }
+      if (l + 1 < L) { t.e.act = d->act[l + 1]; if (tc) t.e.Ob = ws.Hb[l + 1]; else t.e.Oh = ws.Hf[l + 1]; }
       const bool ce = d->loss == JPCB_LOSS_CE;
       if (l == L - 1 && loss_acc && y && !ce) { t.e.red = loss_acc; t.e.Y = y; }
       RET(launch({t}));
@@ -310,7 +393,7 @@ struct Run {
   // hoisted layer-0 prediction P1 = a_0 (W_0 act_0(x) + b_0)  (constant during inference)
   int predict_p1() {
     GTask t;
-    fwd_operands(t, 0, nullptr, ws.Hb);
+    fwd_operands(t, 0, nullptr, false);
     t.e.mode = EPI_FFWD;
     t.e.O = ws.P1;
     return launch({t});
@@ -326,12 +409,12 @@ struct Run {
     return JPCB_OK;
   }
 
-  int errors(int lo, const float* const* S, const std::vector<bf16*>& H, bool energy) {
+  int errors(int lo, const float* const* S, bool stage, bool energy) {
     std::vector<GTask> ts;
     const bool ce = d->loss == JPCB_LOSS_CE;
     for (int l = lo; l < L; ++l) {
       GTask t;
-      fwd_operands(t, l, S, H);
+      fwd_operands(t, l, S, stage);
       if (ce && l == L - 1) {  // logits only; the softmax error follows in ce_rows (needs whole rows)
         t.e.mode = EPI_FFWD;
         t.e.O = ws.logits;
@@ -366,7 +449,8 @@ struct Run {
 
   // gradient/update of A[l-1], l = 1..L-1.  Z: state where act' is evaluated; p1_hoisted: err[0]
   // is formed on the fly as Z[0] - P1.
-  int grads(int sub, float c, const float* const* Z, const float* const* Z0, float* const* Out, const std::vector<bf16*>& Hout,
+  // `stage_out`: the updated state is the Heun stage state (operand copies go to Htb / Hft)
+  int grads(int sub, float c, const float* const* Z, const float* const* Z0, float* const* Out, bool stage_out,
             bool p1_hoisted, int lo = 1) {
     std::vector<GTask> ts;
     for (int l = lo; l < L; ++l) {
@@ -374,7 +458,7 @@ struct Run {
       t.e.mode = EPI_GRAD; t.e.sub = sub; t.e.act = d->act[l];
       t.e.M = Bl; t.e.N = d->dims[l]; t.K = d->dims[l + 1];
       t.a_p = ws.err[l]; t.a_smn = d->dims[l + 1]; t.a_sk = 1;
-      t.b_p = W[l]; t.b_smn = 1; t.b_sk = d->dims[l];  // B(n,k) = W_l[k][n]
+      t.b_p = ws.WTf[l]; t.b_smn = d->dims[l + 1]; t.b_sk = 1;  // B(n,k) = W_l[k][n] = WTf_l[n][k]
       t.a_b = ws.Eb[l]; t.b_b = ws.WTb[l];
       t.e.alpha = d->scalings[l];
       t.e.skip = eskip(l);
@@ -386,7 +470,7 @@ struct Run {
       t.e.O = Out[l - 1];
       if (sub == GRAD_HEUN1 || sub == GRAD_HEUN2) t.e.G1 = ws.G1[l - 1];
       if (sub == GRAD_HEUN2) t.e.Z0 = Z0[l - 1];
-      if (tc && sub != GRAD_OUT) t.e.Ob = Hout[l];
+      if (sub != GRAD_OUT) { if (tc) t.e.Ob = (stage_out ? ws.Htb : ws.Hb)[l]; else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[l]; }
       ts.push_back(t);
     }
     return launch(ts);
@@ -422,16 +506,16 @@ struct Run {
       const float c = h * invB;
       if (d->solver == JPCB_SOLVER_EULER) {
         const int lo = front ? (L - 1 - s > 1 ? L - 1 - s : 1) : 1;
-        RET(errors(lo, A, ws.Hb, false));
-        RET(grads(GRAD_EULER, c, A, nullptr, A, ws.Hb, true, lo));
+        RET(errors(lo, A, false, false));
+        RET(grads(GRAD_EULER, c, A, nullptr, A, false, true, lo));
         if (d->activity_decay != 0.f) RET(scale_inplace(A[L - 1], n_dummy, 1.f - c * d->activity_decay));
       } else {
         std::vector<float*> zt(ws.Zt.begin(), ws.Zt.begin() + (L - 1));
         zt.push_back(A[L - 1]);  // dummy slot is never read by the error tasks
-        RET(errors(1, A, ws.Hb, false));
-        RET(grads(GRAD_HEUN1, c, A, nullptr, zt.data(), ws.Htb, true));
-        RET(errors(1, zt.data(), ws.Htb, false));
-        RET(grads(GRAD_HEUN2, c, zt.data(), A, A, ws.Hb, true));
+        RET(errors(1, A, false, false));
+        RET(grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, true));
+        RET(errors(1, zt.data(), true, false));
+        RET(grads(GRAD_HEUN2, c, zt.data(), A, A, false, true));
         if (d->activity_decay != 0.f) {
           const float q = c * d->activity_decay;
           RET(scale_inplace(A[L - 1], n_dummy, 1.f - q + 0.5f * q * q));
@@ -451,7 +535,8 @@ struct Run {
       t.e.mode = EPI_SCALE;
       t.e.M = d->dims[l + 1]; t.e.N = d->dims[l]; t.K = Bl;
       t.a_p = ws.err[l]; t.a_smn = 1; t.a_sk = d->dims[l + 1];
-      t.b_p = l == 0 ? x : S[l - 1]; t.b_smn = 1; t.b_sk = d->dims[l]; t.b_act = d->act[l];
+      t.b_p = l == 0 ? (ws.Hf[0] ? ws.Hf[0] : x) : ws.Hf[l]; t.b_smn = 1; t.b_sk = d->dims[l];  // act already applied
+      (void)S;
       t.a_b = ws.Eb[l]; t.b_b = ws.Hb[l]; t.mn_major = tc;
       t.e.alpha = -d->scalings[l] * invB;
       t.e.O = gW[l];
@@ -512,7 +597,7 @@ int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const flo
   if (!A_out) return fail(JPCB_EINVAL, "null activity list");
   RET(r.zero_red());
   RET(r.prep_weights());
-  RET(r.prep_inputs(nullptr, r.ws.Hb));
+  RET(r.prep_inputs(nullptr));
   const bool want_loss = loss_out && y;
   RET(r.ffwd(A_out, want_loss ? r.ws.red + RED_LOSS : nullptr, false));
   if (want_loss) RET(r.finalize(nullptr, nullptr, false, loss_out));
@@ -526,8 +611,8 @@ int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float*
   if (!A || !y || !E_layers) return fail(JPCB_EINVAL, "null activities / target / output");
   RET(r.zero_red());
   RET(r.prep_weights());
-  RET(r.prep_inputs(A, r.ws.Hb));
-  RET(r.errors(0, A, r.ws.Hb, true));
+  RET(r.prep_inputs(A));
+  RET(r.errors(0, A, false, true));
   return r.finalize(E_layers, nullptr, false, nullptr);
 }
 
@@ -539,9 +624,9 @@ int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const
   if (!A || !y || !gA) return fail(JPCB_EINVAL, "null activities / target / output");
   RET(r.zero_red());
   RET(r.prep_weights());
-  RET(r.prep_inputs(A, r.ws.Hb));
-  RET(r.errors(0, A, r.ws.Hb, true));
-  RET(r.grads(GRAD_OUT, r.invB, A, nullptr, gA, r.ws.Hb, false));
+  RET(r.prep_inputs(A));
+  RET(r.errors(0, A, false, true));
+  RET(r.grads(GRAD_OUT, r.invB, A, nullptr, gA, false, false));
   const size_t n_dummy = (size_t)r.Bl * desc->dims[r.L];
   scale_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[r.L - 1], gA[r.L - 1], n_dummy, desc->activity_decay * r.invB); count_launch();
   CK(cudaGetLastError());
@@ -559,7 +644,7 @@ int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* 
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A || !y) return fail(JPCB_EINVAL, "null activities / target");
   RET(r.prep_weights());
-  RET(r.prep_inputs(A, r.ws.Hb));
+  RET(r.prep_inputs(A));
   RET(r.predict_p1());
   RET(r.infer_loop(A));
   if (sumsq_out) {
@@ -581,8 +666,8 @@ int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const f
   if (!A || !y || !gW) return fail(JPCB_EINVAL, "null activities / target / output");
   RET(r.zero_red());
   RET(r.prep_weights());
-  RET(r.prep_inputs(A, r.ws.Hb));
-  RET(r.errors(0, A, r.ws.Hb, E_layers != nullptr));
+  RET(r.prep_inputs(A));
+  RET(r.errors(0, A, false, E_layers != nullptr));
   RET(r.wgrads(A, gW, gb));
   if (E_layers) RET(r.finalize(E_layers, nullptr, false, nullptr));
   return JPCB_OK;
@@ -596,10 +681,10 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
   if (!A_out || !y || !gW) return fail(JPCB_EINVAL, "null activities / target / output");
   RET(r.zero_red());
   RET(r.prep_weights());
-  RET(r.prep_inputs(nullptr, r.ws.Hb));
+  RET(r.prep_inputs(nullptr));
   RET(r.ffwd(A_out, r.ws.red + RED_LOSS, true));   // init + loss at the init + hoisted P1 + bf16 operands
   RET(r.infer_loop(A_out, true));
-  RET(r.errors(1, A_out, r.ws.Hb, true));           // errors + layer energies at the solution
+  RET(r.errors(1, A_out, false, true));           // errors + layer energies at the solution
   RET(r.error0_from_p1(A_out, true));
   RET(r.wgrads(A_out, gW, gb));
   return r.finalize(E_layers, nullptr, false, loss_out);

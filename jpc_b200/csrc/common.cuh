@@ -109,6 +109,7 @@ struct Epi {
   float* O;                    // fp32 out (z_out / e / g / scaled D)
   float* O2;                   // FFWD: optional second fp32 copy
   __nv_bfloat16* Ob;           // bf16 out: act(z_out) (FFWD / GRAD updates) or e (ERR)
+  float* Oh;                   // fp32 out: act(z_out) (FFWD / GRAD updates) -- the fp32 path's GEMM operand copy
   float* red;                  // ERR: energy accumulator; FFWD: loss accumulator (needs Y)
   const float* Y;              // FFWD: loss target
 };
@@ -123,7 +124,7 @@ __device__ __forceinline__ Epi epi_pin(const Epi& src) {
   asm volatile("" : "+r"(e.mode), "+r"(e.sub), "+r"(e.act), "+r"(e.M), "+r"(e.N), "+r"(e.accum));
   asm volatile("" : "+f"(e.alpha), "+f"(e.skip), "+f"(e.escale), "+f"(e.c), "+f"(e.ad), "+f"(e.gscale));
   asm volatile("" : "+l"(e.bias), "+l"(e.T), "+l"(e.U), "+l"(e.Z), "+l"(e.Z0), "+l"(e.El), "+l"(e.Elb), "+l"(e.P));
-  asm volatile("" : "+l"(e.En), "+l"(e.Enb), "+l"(e.Gin), "+l"(e.G1), "+l"(e.O), "+l"(e.O2), "+l"(e.Ob), "+l"(e.red), "+l"(e.Y));
+  asm volatile("" : "+l"(e.En), "+l"(e.Enb), "+l"(e.Gin), "+l"(e.G1), "+l"(e.O), "+l"(e.O2), "+l"(e.Ob), "+l"(e.Oh), "+l"(e.red), "+l"(e.Y));
   return e;
 }
 
@@ -248,10 +249,11 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     if (mode == EPI_FFWD) {
       st4(e.O, idx, nvalid, vec, pred);
       if (e.O2) st4(e.O2, idx, nvalid, vec, pred);
-      if (e.Ob) {
+      if (e.Ob || e.Oh) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) out[j] = act_fwd<FAST>(act, pred[j]);
-        st4(e.Ob, idx, nvalid, vec, out);
+        if (e.Ob) st4(e.Ob, idx, nvalid, vec, out);
+        if (e.Oh) st4(e.Oh, idx, nvalid, vec, out);
       }
       if (e.red) {
 #pragma unroll
@@ -331,11 +333,12 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     for (int j = 0; j < 4; ++j) out[j] = z0[j] - 0.5f * e.c * (g1[j] + g[j]);
   }
   st4(e.O, idx, nvalid, vec, out);
-  if (e.Ob) {
+  if (e.Ob || e.Oh) {
     float h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = act_fwd<FAST>(act, out[j]);
-    st4(e.Ob, idx, nvalid, vec, h);
+    if (e.Ob) st4(e.Ob, idx, nvalid, vec, h);
+    if (e.Oh) st4(e.Oh, idx, nvalid, vec, h);
   }
   return 0.f;
 }

@@ -20,6 +20,30 @@ static __global__ void cast_act_bf16_kernel(const float* __restrict__ src, __nv_
   }
 }
 
+// dst[i] = act(src[i]) in fp32 (accurate libm-grade activation: the fp32 path's GEMM operand copy)
+static __global__ void act_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int act) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = act_fwd<false>(act, src[i]);
+}
+
+// dst[c][r] = src[r][c] in fp32; src is [R, C] row-major, dst [C, R] row-major.
+static __global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+  __shared__ float tile[32][33];
+  const int tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      tile[i][threadIdx.x] = (r < R && c < C) ? src[(size_t)r * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) dst[(size_t)c * R + r] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
 // dst[c][r] = bf16(src[r][c]); src is [R, C] row-major (fp32 or bf16), dst [C, R] row-major.
 template <typename TIn>
 static __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {
