@@ -8,7 +8,7 @@ host-framework work outside the kernels, as in the reference (jpc/_train.py:234-
 included in the `e2e` number, which goes through the public `jpc_b200.make_pc_step` API from
 pinned HOST buffers.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c1|c2|c3] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c1|c2|c3|c5] [--impl reference]
 
 Launched under torchrun for N > 1 (one rank per GPU, NCCL).  Weak scaling: every rank holds the
 workload's full batch; the energy normalisation uses the GLOBAL batch.
@@ -44,6 +44,10 @@ WORKLOADS = {
                solver="euler", max_t1=10.0, dt=0.5, dtype="bf16",
                desc="wide MLP width 2048 depth 8 (2048-in, 2048-out), batch 4096 per GPU, bf16 operands / fp32 "
                     "accumulate+master, 20 Euler steps"),
+    "c5": dict(d_in=10, width=1024, depth=6, d_out=784, act="relu", bias=False, ptype="sp", skips=False, B=1024,
+               solver="euler", max_t1=15.0, dt=0.5, dtype="f32", bpc=True,
+               desc="bidirectional PC (bPC) MLP width 1024 depth 6 (10 -> 784 top-down, 784 -> 10 bottom-up), batch 1024, "
+                    "30 Euler steps, fp32"),
 }
 METRIC = "PC train samples/sec (T inference iters)"
 UNIT = "samples/s"
@@ -196,6 +200,83 @@ def run_reference(args, w):
     return 0
 
 
+def run_bpc(args, w):
+    """BASELINE config 5: one bPC train step = feed-forward init of the bottom-up chain (image -> label,
+    examples/bidirectional_pc.ipynb cell 8) + T fused Euler steps on the bPC energy + both models' parameter
+    gradients.  fp32 CUDA-core path in round 1 (the bf16 tensor-core schedule for bPC is not built yet)."""
+    import torch
+    import jpc_b200 as J
+    from jpc_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    J.set_compute_dtype("f32")
+    gen_l, lab_h, img_h = make_inputs(dict(w, d_in=w["d_in"], d_out=w["d_out"]), seed_w=0)       # top-down: label -> image
+    amo_l, _, _ = make_inputs(dict(w, d_in=w["d_out"], d_out=w["d_in"]), seed_w=1)               # amortiser: image -> label
+    g = torch.Generator().manual_seed(1)
+    img_h = torch.randn(w["B"], w["d_out"], generator=g)
+    lab_h = torch.nn.functional.one_hot(torch.randint(0, w["d_in"], (w["B"],), generator=g), w["d_in"]).float()
+    td = to_device_model(gen_l, dev)
+    amort = to_device_model(amo_l, dev)
+    bu = amort[::-1]
+    img_p, lab_p = img_h.pin_memory(), lab_h.pin_memory()
+    img, lab = img_p.to(dev), lab_p.to(dev)
+    T = n_steps(w)
+
+    def step(x_lab, y_img):
+        acts = J.init_activities_with_ffwd(amort, y_img)          # (reference order: amortiser sweep, image side first)
+        acts = J.solve_bpc_inference(td, bu, acts, y_img, input=x_lab, n_steps=T, dt=w["dt"])
+        return J.compute_bpc_param_grads(td, bu, acts, y_img, x=x_lab)
+
+    for _ in range(max(3, args.warmup)):
+        step(lab, img)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    l0 = _lib.lib.jpcb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(lab, img)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.lib.jpcb_launch_count() - l0
+    clocks = sampler.stop()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gr = step(lab_p.to(dev, non_blocking=True), img_p.to(dev, non_blocking=True))
+        float(gr[0][0][1].weight[0, 0])  # device -> host read of a result
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    dims = [w["d_in"]] + [w["width"]] * (w["depth"] - 1) + [w["d_out"]]
+    gl = [2.0 * w["B"] * dims[l] * dims[l + 1] for l in range(w["depth"])]
+    per_step = 4 * sum(gl) - 2 * gl[0] - 2 * gl[-1]            # 2 directions x (prediction + transposed) GEMMs, clamped ends hoisted
+    total = sum(gl) + T * per_step + 2 * sum(gl) + 2 * sum(gl)  # init + inference + errors at the solution + 2 x weight gradients
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    ach = total / (ms / args.steps * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    line = {"metric": METRIC, "value": w["B"] * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "global_batch": w["B"], "inference_steps": T, "solver": "euler", "parallelism": "dp1",
+                       "l2": "working set fits L2; no flush", "algorithmic_gflop_per_step": total / 1e9},
+            "e2e": {"value": w["B"] * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * (img_p.numel() + lab_p.numel()),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "kernel": "simt_grouped_gemm<128,128,16,2,2> (fp32 CUDA-core FMA: round 1 runs bPC at fp32 parity; the "
+                                   "tensor-core bPC schedule is the next step, hence the small fraction of the bf16 tensor peak)"},
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,7 +289,11 @@ def main():
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
+        if w.get("bpc"):
+            raise SystemExit("--impl reference is implemented for the PC workloads (c1-c4)")
         return run_reference(args, w)
+    if w.get("bpc"):
+        return run_bpc(args, w)
     args.warmup = max(args.warmup, 3)
 
     import torch
