@@ -454,7 +454,8 @@ def main():
             peak = peaks.get("hbm_gbs", 6650.0)
             ach = (wbytes + abytes) / (per_launch_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "kernel": "simt_grouped_gemm (one inference phase)", "launch_ms": per_launch_ms,
+                    "kernel": "warp_grouped_gemm (narrow-layer fp32 path; one inference phase = all layers' GEMMs + fused epilogue)",
+                    "launch_ms": per_launch_ms,
                     "bytes_per_launch": wbytes + abytes,
                     "whole_step_tflops": fl["total"] / (ms / args.steps * 1e-3) / 1e12}
 
