@@ -121,6 +121,18 @@ int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* 
                   float* const* A, const float* x, const float* y, float* sumsq_out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* One TRIAL step of diffrax.Heun of size dt from state A (which is not modified), for solve_inference with an
+ * adaptive step-size controller (jpc/_core/_infer.py:109-132 with PIDController; the accept / reject / next-dt
+ * logic is scalar host code in the caller, as it is host-side controller code in diffrax).  desc->solver must be
+ * JPCB_SOLVER_HEUN.  A_new[l] (l = 0..L-1) receives the candidate state; out2 (device float[2]) receives
+ *   out2[0] = sum over every activity entry of ( y_err / (atol + rtol * max(|y0|, |y1|)) )^2,
+ *             y_err = dt (k1 - k2) / 2 the embedded error estimate (the dummy slot contributes 0),
+ *   out2[1] = sum of A_new^2 over all L slots (the reference's steady-state Event, _infer.py:136-145). */
+int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                       const float* const* A, const float* x, const float* y, float dt, float rtol,
+                       float atol, float* const* A_new, float* out2, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* compute_pc_param_grads  (jpc/_core/_grads.py:436-499).  gW[l]: [d_{l+1}, d_l]; gb[l]:
  * [d_{l+1}] (ignored when !has_bias; gb may then be NULL).  Partial sums over local rows,
  * already divided by batch_global.  E_layers (may be NULL) as in jpcb_pc_energy, for free. */

@@ -335,20 +335,106 @@ def _solver_id(solver) -> int:
     raise NotImplementedError(f"solver {solver!r} is not on the B200 path (Euler and Heun are)")
 
 
+MAX_STEPS = 4096  # diffrax.diffeqsolve default
+
+
+def _rms(tensors) -> float:
+    """optimistix.rms_norm over a list of arrays (host read-back of one scalar; controller logic only)."""
+    tot = sum(float(torch.sum(t.double() ** 2)) for t in tensors)
+    n = sum(t.numel() for t in tensors)
+    return math.sqrt(tot / n)
+
+
+def _solve_adaptive(params, activities, output, input, loss_id, param_type, solver, max_t1, dt0, ctrl, weight_decay,
+                    spectral_penalty, activity_decay, gamma, output_energy_scaling, batch_global=None):
+    """solve_inference with diffrax.Heun + PIDController (the reference's default, jpc/_core/_infer.py:28-33):
+    every trial step (two gradient evaluations, candidate state, embedded-error and activity sums of squares) is
+    one C-ABI call; accept/reject and the next step size are the controller's scalar arithmetic on the host
+    (solvers.PIDController), one 8-byte read-back per trial step.  The steady-state Event of the reference
+    (`_infer.py:136-145`) is evaluated after every accepted step."""
+    if not isinstance(solver, Heun):
+        if isinstance(solver, Euler):
+            raise RuntimeError("Cannot use adaptive step sizes with a solver that does not provide error estimates.")
+        raise NotImplementedError(f"solver {solver!r} is not on the B200 path (Euler and Heun are)")
+    model, skip_model = _unpack_params(params)
+    net = _Net(model, skip_model, input, output, param_type=param_type, loss_id=loss_id, gamma=gamma,
+               output_energy_scaling=output_energy_scaling, activity_decay=activity_decay, weight_decay=weight_decay,
+               spectral_penalty=spectral_penalty, solver=_lib.SOLVER_HEUN, n_steps=1, dt=0.0, dt_last=0.0,
+               batch_global=batch_global)
+    net.check_acts(activities)
+    order = 2.0  # diffrax: error order of Heun (2nd order with an embedded 1st-order estimate)
+    t1 = float(max_t1)
+    A = [a.clone() for a in activities]
+    B_ = [torch.empty_like(a) for a in activities]
+    ws = net.workspace()
+    out2 = torch.zeros(2, dtype=torch.float32, device=net.dev)
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    numel = sum(a.numel() for a in A) * world
+    kw = dict(x=input, loss_id=loss_id, param_type=param_type, weight_decay=weight_decay, spectral_penalty=spectral_penalty,
+              activity_decay=activity_decay, gamma=gamma, output_energy_scaling=output_energy_scaling)
+    if dt0 is None:
+        # Hairer / Wanner initial step, as diffrax's PIDController.init does when dt0 is None
+        _, g0 = compute_pc_activity_grad(params, A, output, **kw)
+        f0 = [-g for g in g0]
+        scale = [ctrl.atol + a.abs() * ctrl.rtol for a in A]
+        d0 = _rms([a / s for a, s in zip(A, scale)])
+        d1 = _rms([f / s for f, s in zip(f0, scale)])
+        small = d0 < 1e-5 or d1 < 1e-5
+        h0 = 1e-6 if small else 0.01 * d0 / d1
+        y1 = [a + h0 * f for a, f in zip(A, f0)]
+        _, g1 = compute_pc_activity_grad(params, y1, output, **kw)
+        d2 = _rms([(-gb - f) / s for gb, f, s in zip(g1, f0, scale)]) / h0
+        max_d = max(d1, d2)
+        h1 = max(1e-6, h0 * 1e-3) if max_d <= 1e-15 else (0.01 / max_d) ** (1.0 / order)
+        dt = min(100.0 * h0, h1)
+    else:
+        dt = float(dt0)
+    t, steps, state = 0.0, 0, ctrl.init_state()
+    stats = {"accepted": 0, "rejected": 0, "event": False}
+    while t < t1:
+        if steps >= MAX_STEPS:
+            raise RuntimeError("The maximum number of solver steps was reached. Try increasing `max_steps`.")
+        h = min(dt, t1 - t)
+        _lib.check(_lib.lib.jpcb_pc_heun_trial(net.desc, net.W, net.b, _lib.ptr_array(A), _lib.ptr(input), _lib.ptr(output),
+                                               h, ctrl.rtol, ctrl.atol, _lib.ptr_array(B_), _lib.ptr(out2), _lib.ptr(ws),
+                                               ws.numel(), net.stream()))
+        if world > 1:  # the controller's norms are global over the batch (SURVEY 8e): one scalar all-reduce per trial step
+            dist.all_reduce(out2, op=dist.ReduceOp.SUM)
+        err_ss, act_ss = out2.tolist()  # the one host read-back per trial step
+        keep, dt, state = ctrl.adapt(h, math.sqrt(err_ss / numel), order, state)
+        steps += 1
+        if keep:
+            t = t1 if t1 - (t + h) < 1e-6 * max(1.0, t1) else t + h
+            A, B_ = B_, A
+            stats["accepted"] += 1
+            rms = math.sqrt(act_ss / numel)
+            if rms < ctrl.atol + ctrl.rtol * rms:  # steady_state_event_with_timeout
+                stats["event"] = True
+                break
+        else:
+            stats["rejected"] += 1
+    solve_inference.last_stats = stats
+    return [a.unsqueeze(0) for a in A]
+
+
 def solve_inference(params, activities, output, *, input=None, loss_id="mse", param_type="sp", solver=None,
                     max_t1=20, dt=None, stepsize_controller=None, weight_decay=0.0, spectral_penalty=0.0,
                     activity_decay=0.0, gamma=None, output_energy_scaling=None, record_iters=False,
-                    record_every=None):
-    """jpc/_core/_infer.py:20-133 for fixed-step solvers: all T steps x L layers run on the device
-    without returning to the host.  Returns leaves with the reference's leading time axis (1, B, d)
-    (SaveAt(t1=True)).  The reference's steady-state Event (`_infer.py:136-145`) tests the RMS of
-    the ACTIVITIES against ~1e-3; it is evaluated here on the final state and reported through
-    `solve_inference.last_event` rather than stopping the fused loop early."""
+                    record_every=None, batch_global=None):
+    """jpc/_core/_infer.py:20-133.  Fixed-step solvers (ConstantStepSize): all T steps x L layers run on the
+    device without returning to the host (the reference's steady-state Event, `_infer.py:136-145`, tests the
+    RMS of the ACTIVITIES against ~1e-3 and never fires on real activities; it is not checked inside the fused
+    loop).  PIDController (the default): controller-driven trial steps, see `_solve_adaptive`.  Returns leaves
+    with the reference's leading time axis (1, B, d) (SaveAt(t1=True)).  `batch_global` (not in the reference
+    signature) is the 1/B of the energy when `activities` is one rank's shard of a data-parallel batch."""
     solver = Heun() if solver is None else solver
     stepsize_controller = PIDController(rtol=1e-3, atol=1e-3) if stepsize_controller is None else stepsize_controller
     if isinstance(stepsize_controller, PIDController):
-        raise NotImplementedError("adaptive PIDController stepping is not on the B200 path yet; pass "
-                                  "stepsize_controller=ConstantStepSize() and dt")
+        if record_iters or record_every is not None:
+            raise NotImplementedError("record_iters / record_every are not on the B200 path yet")
+        return _solve_adaptive(params, activities, output, input, loss_id, param_type, solver, max_t1, dt, stepsize_controller,
+                               weight_decay, spectral_penalty, activity_decay, gamma, output_energy_scaling, batch_global)
     if not isinstance(stepsize_controller, ConstantStepSize):
         raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
     if record_iters or record_every is not None:
@@ -360,7 +446,7 @@ def solve_inference(params, activities, output, *, input=None, loss_id="mse", pa
     net = _Net(model, skip_model, input, output, param_type=param_type, loss_id=loss_id, gamma=gamma,
                output_energy_scaling=output_energy_scaling, activity_decay=activity_decay,
                weight_decay=weight_decay, spectral_penalty=spectral_penalty,
-               solver=_solver_id(solver), n_steps=T, dt=h, dt_last=h_last)
+               solver=_solver_id(solver), n_steps=T, dt=h, dt_last=h_last, batch_global=batch_global)
     net.check_acts(activities)
     A = [a.clone() for a in activities]  # functional API: inputs are never mutated
     ws = net.workspace()

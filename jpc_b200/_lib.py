@@ -63,6 +63,8 @@ SIGNATURES = {
     "jpcb_pc_energy": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
     "jpcb_pc_activity_grad": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _PP, _P, C.c_size_t, _P]),
     "jpcb_pc_infer": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
+    "jpcb_pc_heun_trial": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, C.c_float, C.c_float, C.c_float, _PP, _P, _P,
+                                     C.c_size_t, _P]),
     "jpcb_pc_param_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _PP, _PP, _P, _P, C.c_size_t, _P]),
     "jpcb_pc_train_step": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _P, _P, _PP, _P, _P, _PP, _PP, _P, C.c_size_t, _P]),
     "jpcb_bpc_workspace_bytes": (C.c_size_t, [C.POINTER(BpcDesc)]),

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_with_ffwd)
+from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_with_ffwd, solve_inference)
 from ._errors import _check_param_type
 from ._utils import compute_accuracy, compute_activity_norms, compute_param_norms
 from .optim import apply_updates
@@ -93,26 +93,45 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         raise NotImplementedError("record_activities / record_energies / record_every are not on the B200 path yet")
     ode_solver = Heun() if ode_solver is None else ode_solver
     stepsize_controller = PIDController(rtol=1e-3, atol=1e-3) if stepsize_controller is None else stepsize_controller
-    if not isinstance(stepsize_controller, ConstantStepSize):
-        raise NotImplementedError("adaptive PIDController stepping is not on the B200 path yet; pass "
-                                  "stepsize_controller=ConstantStepSize() and dt")
-    T, h, h_last = _time_grid(max_t1, dt)
-    if T > 4096:
-        raise RuntimeError("The maximum number of solver steps (4096) was reached.")
     world = _world()
-    net = _Net(model, skip_model, input, output, param_type=param_type, loss_id=loss_id, gamma=None,
-               output_energy_scaling=None, activity_decay=activity_decay, weight_decay=weight_decay,
-               spectral_penalty=spectral_penalty, solver=_solver_id(ode_solver), n_steps=T, dt=h, dt_last=h_last,
-               batch_global=input.shape[0] * world)
-    if tuple(output.shape) != (net.B, net.dims[-1]):
-        raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.dims[-1])}")
-    arena = _Arena(net)
-    acts = net.new_acts()
-    ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_pc_train_step(
-        net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr(output), _lib.ptr_array(acts), _lib.ptr(arena.loss),
-        _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
-        _lib.ptr(ws), ws.numel(), net.stream()))
+    common = dict(param_type=param_type, loss_id=loss_id, gamma=None, output_energy_scaling=None, activity_decay=activity_decay,
+                  weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=input.shape[0] * world)
+    if isinstance(stepsize_controller, ConstantStepSize):
+        # fixed steps: the whole step up to the optimiser is ONE C-ABI call
+        T, h, h_last = _time_grid(max_t1, dt)
+        if T > 4096:
+            raise RuntimeError("The maximum number of solver steps (4096) was reached.")
+        net = _Net(model, skip_model, input, output, solver=_solver_id(ode_solver), n_steps=T, dt=h, dt_last=h_last, **common)
+        if tuple(output.shape) != (net.B, net.dims[-1]):
+            raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.dims[-1])}")
+        arena = _Arena(net)
+        acts = net.new_acts()
+        ws = net.workspace()
+        _lib.check(_lib.lib.jpcb_pc_train_step(
+            net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr(output), _lib.ptr_array(acts), _lib.ptr(arena.loss),
+            _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
+            _lib.ptr(ws), ws.numel(), net.stream()))
+    elif isinstance(stepsize_controller, PIDController):
+        # adaptive steps (the reference's default): init + loss, the controller-driven solve, then energies + gradients
+        net = _Net(model, skip_model, input, output, **common)
+        if tuple(output.shape) != (net.B, net.dims[-1]):
+            raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.dims[-1])}")
+        arena = _Arena(net)
+        acts0 = net.new_acts()
+        ws = net.workspace()
+        _lib.check(_lib.lib.jpcb_pc_ffwd_init(net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr_array(acts0), _lib.ptr(output),
+                                              _lib.ptr(arena.loss), _lib.ptr(ws), ws.numel(), net.stream()))
+        sol = solve_inference((model, skip_model), acts0, output, input=input, loss_id=loss_id, param_type=param_type,
+                              solver=ode_solver, max_t1=max_t1, dt=dt, stepsize_controller=stepsize_controller,
+                              weight_decay=weight_decay, spectral_penalty=spectral_penalty, activity_decay=activity_decay,
+                              batch_global=input.shape[0] * world)
+        acts = [a[0].contiguous() for a in sol]
+        ws = net.workspace()
+        _lib.check(_lib.lib.jpcb_pc_param_grads(net.desc, net.W, net.b, _lib.ptr_array(acts), _lib.ptr(input), _lib.ptr(output),
+                                                _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
+                                                _lib.ptr(arena.E), _lib.ptr(ws), ws.numel(), net.stream()))
+    else:
+        raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
     arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
     param_grads = _grads_pytree(net, arena.gW, arena.gb)
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)

@@ -450,8 +450,9 @@ struct Run {
   // gradient/update of A[l-1], l = 1..L-1.  Z: state where act' is evaluated; p1_hoisted: err[0]
   // is formed on the fly as Z[0] - P1.
   // `stage_out`: the updated state is the Heun stage state (operand copies go to Htb / Hft)
+  // `err_red` (GRAD_HEUN2 only): accumulates the scaled embedded-error sum of squares of an adaptive trial step
   int grads(int sub, float c, const float* const* Z, const float* const* Z0, float* const* Out, bool stage_out,
-            bool p1_hoisted, int lo = 1) {
+            bool p1_hoisted, int lo = 1, float* err_red = nullptr, float rtol = 0.f, float atol = 0.f) {
     std::vector<GTask> ts;
     for (int l = lo; l < L; ++l) {
       GTask t;
@@ -469,7 +470,7 @@ struct Run {
       t.e.c = c; t.e.ad = d->activity_decay; t.e.gscale = 1.f;
       t.e.O = Out[l - 1];
       if (sub == GRAD_HEUN1 || sub == GRAD_HEUN2) t.e.G1 = ws.G1[l - 1];
-      if (sub == GRAD_HEUN2) t.e.Z0 = Z0[l - 1];
+      if (sub == GRAD_HEUN2) { t.e.Z0 = Z0[l - 1]; t.e.red = err_red; t.e.tol_r = rtol; t.e.tol_a = atol; }
       if (sub != GRAD_OUT) { if (tc) t.e.Ob = (stage_out ? ws.Htb : ws.Hb)[l]; else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[l]; }
       ts.push_back(t);
     }
@@ -655,6 +656,31 @@ int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* 
     const float nf = (float)numel;
     CK(cudaMemcpyAsync(sumsq_out + 1, &nf, sizeof(float), cudaMemcpyHostToDevice, r.st));
   }
+  return JPCB_OK;
+}
+
+int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A, const float* x,
+                       const float* y, float dt, float rtol, float atol, float* const* A_new, float* out2, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!A || !y || !A_new || !out2) return fail(JPCB_EINVAL, "null activities / target / outputs");
+  if (desc->solver != JPCB_SOLVER_HEUN) return fail(JPCB_EINVAL, "jpcb_pc_heun_trial needs desc->solver == JPCB_SOLVER_HEUN");
+  if (desc->activity_decay != 0.f) return fail(JPCB_ENOTIMPL, "adaptive stepping with activity_decay is not on the B200 path");
+  const int L = r.L;
+  CK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), r.st));
+  RET(r.prep_weights());
+  RET(r.prep_inputs(A));
+  RET(r.predict_p1());
+  const float c = dt * r.invB;
+  std::vector<float*> zt(r.ws.Zt.begin(), r.ws.Zt.begin() + (L - 1));
+  zt.push_back(A_new[L - 1]);  // dummy slot is never read by the error tasks
+  RET(r.errors(1, A, false, false));
+  RET(r.grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, true));
+  RET(r.errors(1, zt.data(), true, false));
+  RET(r.grads(GRAD_HEUN2, c, zt.data(), A, A_new, false, true, 1, out2, rtol, atol));
+  CK(cudaMemcpyAsync(A_new[L - 1], A[L - 1], (size_t)r.Bl * desc->dims[L] * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+  RET(r.sumsq_all(A_new, out2 + 1));
   return JPCB_OK;
 }
 

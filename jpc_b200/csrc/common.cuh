@@ -94,6 +94,7 @@ struct Epi {
   float c;       // GRAD: OUT -> multiplier of g (1/B); EULER/HEUN -> dt/B
   float ad;      // GRAD: activity_decay
   float gscale;  // GRAD: weight w of this term (bPC alpha_f / alpha_b; 1 for PC)
+  float tol_r, tol_a;  // GRAD_HEUN2 with `red`: rtol / atol of the embedded-error norm (adaptive stepping)
   const float* bias;           // [N] or null
   const float* T;              // ERR: target
   const float* U;              // FFWD/ERR: skip input
@@ -122,7 +123,7 @@ struct Epi {
 __device__ __forceinline__ Epi epi_pin(const Epi& src) {
   Epi e = src;
   asm volatile("" : "+r"(e.mode), "+r"(e.sub), "+r"(e.act), "+r"(e.M), "+r"(e.N), "+r"(e.accum));
-  asm volatile("" : "+f"(e.alpha), "+f"(e.skip), "+f"(e.escale), "+f"(e.c), "+f"(e.ad), "+f"(e.gscale));
+  asm volatile("" : "+f"(e.alpha), "+f"(e.skip), "+f"(e.escale), "+f"(e.c), "+f"(e.ad), "+f"(e.gscale), "+f"(e.tol_r), "+f"(e.tol_a));
   asm volatile("" : "+l"(e.bias), "+l"(e.T), "+l"(e.U), "+l"(e.Z), "+l"(e.Z0), "+l"(e.El), "+l"(e.Elb), "+l"(e.P));
   asm volatile("" : "+l"(e.En), "+l"(e.Enb), "+l"(e.Gin), "+l"(e.G1), "+l"(e.O), "+l"(e.O2), "+l"(e.Ob), "+l"(e.Oh), "+l"(e.red), "+l"(e.Y));
   return e;
@@ -331,6 +332,17 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     ld4(e.G1, idx, nvalid, vec, g1);
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[j] = z0[j] - 0.5f * e.c * (g1[j] + g[j]);
+    if (e.red) {
+      // diffrax.Heun's embedded error estimate y_err = dt (k1 - k2) / 2 = -(c/2)(g1 - g2), scaled as
+      // PIDController does: y_err / (atol + rtol * max(|y0|, |y1|)); the caller takes the RMS over all entries
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) {
+          const float ye = 0.5f * e.c * (g[j] - g1[j]);
+          const float sc = ye / (e.tol_a + e.tol_r * fmaxf(fabsf(z0[j]), fabsf(out[j])));
+          r += sc * sc;
+        }
+    }
   }
   st4(e.O, idx, nvalid, vec, out);
   if (e.Ob || e.Oh) {
@@ -340,7 +352,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     if (e.Ob) st4(e.Ob, idx, nvalid, vec, h);
     if (e.Oh) st4(e.Oh, idx, nvalid, vec, h);
   }
-  return 0.f;
+  return r;
 }
 
 // Applies the fused epilogue to 4 horizontally adjacent accumulator values D[row, col..col+3].

@@ -381,6 +381,67 @@ def solve_inference(model, skips, activities, y, *, x, solver="euler", max_t1=20
     return acts, steps
 
 
+def solve_inference_adaptive(model, skips, activities, y, *, x, max_t1=20.0, dt0=None, rtol=1e-3, atol=1e-3,
+                             safety=0.9, factormin=0.2, factormax=10.0, max_steps=4096, **kw):
+    """diffrax.Heun + PIDController(rtol, atol) (I-controller defaults) + the reference's steady-state Event:
+    what `jpc.solve_inference` does when called with its defaults (jpc/_core/_infer.py:28-33,109-132).
+
+    diffrax is a third-party dependency that is not under /root/reference; the controller below restates
+    upstream diffrax 0.6-0.7 from memory: embedded error y_err = dt (k1 - k2) / 2, scaled
+    error = rms_norm(y_err / (atol + rtol max(|y0|, |y1|))), accept iff < 1, factor = clip(safety *
+    err^(-1/order), [1 if accepted else factormin, factormax]) with order = 2; Hairer initial step when dt0 is
+    None.  PARITY UNPINNED against a live diffrax run.  Returns (activities, stats)."""
+    acts = [a.detach().clone() for a in activities]
+    order = 2.0
+
+    def vf(a_list):
+        _, g = compute_pc_activity_grad(model, skips, a_list, y, x=x, **kw)
+        return [-gi for gi in g]
+
+    if dt0 is None:
+        f0 = vf(acts)
+        scale = [atol + a.abs() * rtol for a in acts]
+        d0 = rms_norm([a / s for a, s in zip(acts, scale)])
+        d1 = rms_norm([f / s for f, s in zip(f0, scale)])
+        small = d0 < 1e-5 or d1 < 1e-5
+        h0 = 1e-6 if small else 0.01 * d0 / d1
+        f1 = vf([a + h0 * f for a, f in zip(acts, f0)])
+        d2 = rms_norm([(fb - fa) / s for fa, fb, s in zip(f0, f1, scale)]) / h0
+        max_d = max(d1, d2)
+        h1 = max(1e-6, h0 * 1e-3) if max_d <= 1e-15 else (0.01 / max_d) ** (1.0 / order)
+        dt = min(100.0 * h0, h1)
+    else:
+        dt = float(dt0)
+    t, steps = 0.0, 0
+    stats = {"accepted": 0, "rejected": 0, "event": False, "dts": []}
+    while t < max_t1:
+        if steps >= max_steps:
+            raise RuntimeError("The maximum number of solver steps was reached. Try increasing `max_steps`.")
+        h = min(dt, max_t1 - t)
+        k1 = vf(acts)
+        k2 = vf([a + h * k for a, k in zip(acts, k1)])
+        cand = [a + h * (0.5 * ka + 0.5 * kb) for a, ka, kb in zip(acts, k1, k2)]
+        yerr = [h * (0.5 * ka - 0.5 * kb) for ka, kb in zip(k1, k2)]
+        err = rms_norm([e / (atol + rtol * torch.maximum(a.abs(), c.abs())) for e, a, c in zip(yerr, acts, cand)])
+        keep = err < 1.0
+        inv = float("inf") if err == 0.0 else 1.0 / err
+        factor = min(max(safety * inv ** (1.0 / order), 1.0 if keep else factormin), factormax)
+        dt = h * factor
+        steps += 1
+        if keep:
+            t = max_t1 if max_t1 - (t + h) < 1e-6 * max(1.0, max_t1) else t + h
+            acts = cand
+            stats["accepted"] += 1
+            stats["dts"].append(h)
+            r = rms_norm(acts)
+            if r < atol + rtol * r:
+                stats["event"] = True
+                break
+        else:
+            stats["rejected"] += 1
+    return acts, stats
+
+
 def pc_train_step(model, skips, x, y, *, solver="euler", max_t1=20.0, dt=0.5, loss_id="mse",
                   param_type="sp", activity_decay=0.0):
     """What make_pc_step computes before the optimiser (jpc/_train.py:135-232): ffwd init, loss at

@@ -289,8 +289,6 @@ def test_error_behaviour():
     opt = J.optim.sgd(0.1)
     with pytest.raises(ValueError):
         J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=None)
-    with pytest.raises(NotImplementedError):  # adaptive default controller: 'next' row
-        J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx)
     with pytest.raises(RuntimeError):  # no CPU path
         J.init_activities_with_ffwd(to_gpu_model(om, device="cpu"), x.float())
 
@@ -445,3 +443,57 @@ def test_cross_entropy_bf16():
     J.set_compute_dtype("bf16")
     om, sk, x, y = _case(256, 512, 3, 16, "tanh", 256, use_bias=True)
     _check_ce(om, sk, x, y, TOLBF, fused=("euler", 2.0, 0.5))
+
+
+# ---- adaptive solve: Heun + PIDController, the reference's default ----------------
+def _adaptive_case(om, sk, x, y, tol, max_t1, dt0, rtol=1e-3, atol=1e-3, param_type="sp"):
+    import jpc_b200 as J
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    gx, gy = dev(x), dev(y)
+    a0 = O.init_activities_with_ffwd(om, x, skips=sk, param_type=param_type)
+    ref, st = O.solve_inference_adaptive(om, sk, a0, y, x=x, max_t1=max_t1, dt0=dt0, rtol=rtol, atol=atol, param_type=param_type)
+    sol = J.solve_inference((gm, gsk), devs(a0), gy, input=gx, param_type=param_type, solver=J.Heun(), max_t1=max_t1, dt=dt0,
+                            stepsize_controller=J.PIDController(rtol=rtol, atol=atol))
+    got = J.solve_inference.last_stats
+    assert (got["accepted"], got["rejected"], got["event"]) == (st["accepted"], st["rejected"], st["event"])
+    amax = max(float(t.abs().max()) for t in ref[:-1])
+    for p, q in zip(sol, ref):
+        assert p.ndim == 3 and p.shape[0] == 1
+        assert float((p[0].double().cpu() - q).abs().max()) < tol * amax
+    return st
+
+
+def test_adaptive_heun_pid_matches_oracle_controller():
+    om, sk, x, y = _case(10, 20, 3, 5, "tanh", 8, use_bias=True)
+    st = _adaptive_case(om, sk, x, y, 2e-5, 5.0, None)            # Hairer initial step
+    assert st["accepted"] >= 3
+    _adaptive_case(om, sk, x, y, 2e-5, 5.0, 0.05)                  # given dt0
+    st = _adaptive_case(om, sk, x, y, 2e-5, 3.0, 50.0, rtol=1e-5, atol=1e-5)   # first step rejected
+    assert st["rejected"] >= 1
+    om, sk, x, y = _case(12, 16, 6, 3, "relu", 5, param_type="mupc", skips=True)
+    _adaptive_case(om, sk, x, y, 2e-5, 4.0, None, param_type="mupc")
+
+
+def test_make_pc_step_default_arguments_run_the_adaptive_solve():
+    """make_pc_step(model, optim, opt_state, output, input=...) with the reference's defaults (Heun, PIDController
+    1e-3, max_t1=20, dt=None) -- the call every example notebook makes."""
+    import jpc_b200 as J
+    om, sk, x, y = _case(784, 300, 3, 10, "relu", 64, use_bias=True)
+    gm = to_gpu_model(om)
+    gx, gy = dev(x), dev(y)
+    opt = J.optim.adam(1e-3)
+    out = J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx)
+    a0 = O.init_activities_with_ffwd(om, x)
+    ref, st = O.solve_inference_adaptive(om, None, a0, y, x=x, max_t1=20.0)
+    assert abs(float(out["loss"]) - float(O.mse_loss(a0[-1], y))) <= TOL32 * float(O.mse_loss(a0[-1], y))
+    E = O.pc_energy_fn(om, None, ref, y, x=x, record_layers=True)
+    assert rel(out["energies"], E) < 1e-4
+    amax = max(float(t.abs().max()) for t in ref[:-1])
+    for p, q in zip(out["activities"][:-1], ref[:-1]):
+        assert float((p[0].double().cpu() - q).abs().max()) < 2e-5 * amax
+    pg = O.compute_pc_param_grads(om, None, ref, y, x=x)
+    g, _ = J.compute_pc_param_grads((gm, None), [a[0].contiguous() for a in out["activities"]], gy, x=gx)
+    for l, q in enumerate(pg):
+        assert rel(g[l][1].weight, q["W"]) < 1e-4
+    with pytest.raises(RuntimeError):  # Euler has no error estimate: diffrax refuses, so do we
+        J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx, ode_solver=J.Euler())

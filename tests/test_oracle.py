@@ -209,3 +209,20 @@ def test_errors():
         O.check_param_type("bogus")
     with pytest.raises(ValueError):
         O.act_fn("bogus", torch.zeros(1))
+
+
+def test_adaptive_heun_matches_fine_fixed_step():
+    """The PID-controlled Heun solve agrees with a very fine fixed-step solve to the controller's tolerance,
+    takes far fewer steps, and shrinks/accepts as the I-controller prescribes."""
+    om = O.make_mlp(0, 10, 20, 3, 5, "tanh", use_bias=True)
+    x, y = _data(6, 10, 5)
+    a0 = O.init_activities_with_ffwd(om, x)
+    fine, _ = O.solve_inference(om, None, a0, y, x=x, solver="heun", max_t1=4.0, dt=4.0 / 4000, event_atol=0.0, event_rtol=0.0)
+    ada, st = O.solve_inference_adaptive(om, None, a0, y, x=x, max_t1=4.0, dt0=None, rtol=1e-3, atol=1e-3)
+    assert st["accepted"] + st["rejected"] < 400 and st["accepted"] >= 2
+    assert abs(sum(st["dts"]) - 4.0) < 1e-9
+    for p, q in zip(ada[:-1], fine[:-1]):
+        assert float((p - q).abs().max()) < 5e-2 * max(float(q.abs().max()), 1.0)
+    # a huge first step must be rejected and shrunk by at least factormin
+    _, st2 = O.solve_inference_adaptive(om, None, a0, y, x=x, max_t1=4.0, dt0=1e4, rtol=1e-6, atol=1e-6)
+    assert st2["rejected"] >= 1
