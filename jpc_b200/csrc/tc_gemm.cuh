@@ -326,40 +326,48 @@ __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, in
   return r;
 }
 
+// Loads run TC_EPI_DEPTH - 1 patches ahead of their use (register ring of TC_EPI_DEPTH patch buffers);
+// the ring index must be static, so the 8-patch loop is fully unrolled when the depth is 3.
+#ifndef JPCB_TC_EPI_DEPTH
+#define JPCB_TC_EPI_DEPTH 3
+#endif
 template <int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
 __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
                                              uint32_t tphase) {
   float r = 0.f;
-#if 1
-  EpiPre pa[4], pb[4];
-  float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-  tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pa, ba);
-  mbar_wait(tfull, tphase);  // accumulator of this tile complete
-  tc_fence_after();
+  constexpr int DEPTH = (PLAIN && JPCB_TC_EPI_DEPTH == 3) ? 3 : 2;
+  if constexpr (DEPTH == 3) {
+    EpiPre pre[3][4];
+    float bias[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pre[0], bias[0]);
+    tc_epi_loads<MODE, ELSRC>(e, row0, col0 + 16, lane, pre[1], bias[1]);
+    mbar_wait(tfull, tphase);  // accumulator of this tile complete
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < TC_EPI_PATCHES; ++ch) {
+      const int cb = col0 + ch * 16;  // first column of this 16-wide patch
+      if (cb < e.N) {                 // warp-uniform
+        if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC>(e, row0, cb + 32, lane, pre[(ch + 2) % 3], bias[(ch + 2) % 3]);
+        r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pre[ch % 3], bias[ch % 3]);
+      }
+    }
+  } else {
+    EpiPre pa[4], pb[4];
+    float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+    tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pa, ba);
+    mbar_wait(tfull, tphase);  // accumulator of this tile complete
+    tc_fence_after();
 #pragma unroll 1
-  for (int ch = 0; ch < TC_EPI_PATCHES; ch += 2) {
-    const int cb = col0 + ch * 16;  // first column of this 16-wide patch
-    if (cb >= e.N) break;           // warp-uniform
-    tc_epi_loads<MODE, ELSRC>(e, row0, cb + 16, lane, pb, bb);
-    r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
-    if (cb + 16 >= e.N) break;
-    if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC>(e, row0, cb + 32, lane, pa, ba);
-    r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
+    for (int ch = 0; ch < TC_EPI_PATCHES; ch += 2) {
+      const int cb = col0 + ch * 16;  // first column of this 16-wide patch
+      if (cb >= e.N) break;           // warp-uniform
+      tc_epi_loads<MODE, ELSRC>(e, row0, cb + 16, lane, pb, bb);
+      r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
+      if (cb + 16 >= e.N) break;
+      if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC>(e, row0, cb + 32, lane, pa, ba);
+      r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
+    }
   }
-#else
-  EpiPre pa[4];
-  float ba[4] = {0.f, 0.f, 0.f, 0.f};
-  tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pa, ba);
-  mbar_wait(tfull, tphase);  // accumulator of this tile complete
-  tc_fence_after();
-#pragma unroll 1
-  for (int ch = 0; ch < TC_EPI_PATCHES; ++ch) {
-    const int cb = col0 + ch * 16;
-    if (cb >= e.N) break;
-    if (ch > 0) tc_epi_loads<MODE, ELSRC>(e, row0, cb, lane, pa, ba);
-    r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
-  }
-#endif
   return r;
 }
 
