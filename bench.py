@@ -45,9 +45,9 @@ WORKLOADS = {
                desc="wide MLP width 2048 depth 8 (2048-in, 2048-out), batch 4096 per GPU, bf16 operands / fp32 "
                     "accumulate+master, 20 Euler steps"),
     "c5": dict(d_in=10, width=1024, depth=6, d_out=784, act="relu", bias=False, ptype="sp", skips=False, B=1024,
-               solver="euler", max_t1=15.0, dt=0.5, dtype="f32", bpc=True,
+               solver="euler", max_t1=15.0, dt=0.5, dtype="bf16", bpc=True,
                desc="bidirectional PC (bPC) MLP width 1024 depth 6 (10 -> 784 top-down, 784 -> 10 bottom-up), batch 1024, "
-                    "30 Euler steps, fp32"),
+                    "30 Euler steps, bf16 operands / fp32 accumulate+master (--bpc-f32 for the fp32 CUDA-core path)"),
 }
 METRIC = "PC train samples/sec (T inference iters)"
 UNIT = "samples/s"
@@ -211,7 +211,7 @@ def run_bpc(args, w):
         raise SystemExit("bench.py needs a CUDA device")
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    J.set_compute_dtype("f32")
+    dtype = "f32" if args.bpc_f32 else "bf16"
     gen_l, lab_h, img_h = make_inputs(dict(w, d_in=w["d_in"], d_out=w["d_out"]), seed_w=0)       # top-down: label -> image
     amo_l, _, _ = make_inputs(dict(w, d_in=w["d_out"], d_out=w["d_in"]), seed_w=1)               # amortiser: image -> label
     g = torch.Generator().manual_seed(1)
@@ -225,7 +225,9 @@ def run_bpc(args, w):
     T = n_steps(w)
 
     def step(x_lab, y_img):
+        J.set_compute_dtype("f32")                                # the amortiser sweep has a 10-wide output: fp32 path
         acts = J.init_activities_with_ffwd(amort, y_img)          # (reference order: amortiser sweep, image side first)
+        J.set_compute_dtype(dtype)
         acts = J.solve_bpc_inference(td, bu, acts, y_img, input=x_lab, n_steps=T, dt=w["dt"])
         return J.compute_bpc_param_grads(td, bu, acts, y_img, x=x_lab)
 
@@ -263,15 +265,15 @@ def run_bpc(args, w):
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     line = {"metric": METRIC, "value": w["B"] * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": w["desc"], "global_batch": w["B"], "inference_steps": T, "solver": "euler", "parallelism": "dp1",
                        "l2": "working set fits L2; no flush", "algorithmic_gflop_per_step": total / 1e9},
             "e2e": {"value": w["B"] * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * (img_p.numel() + lab_p.numel()),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "simt_grouped_gemm<128,128,16,2,2> (fp32 CUDA-core FMA: round 1 runs bPC at fp32 parity; the "
-                                   "tensor-core bPC schedule is the next step, hence the small fraction of the bf16 tensor peak)"},
+                         "kernel": "tc_grouped_gemm (bPC phases: errors / forward half / backward half + update), whole step"
+                         if dtype == "bf16" else "simt_grouped_gemm<128,128,16,2,2> (fp32 CUDA-core FMA path), whole step"},
             "cpu_baseline": None}
     print(json.dumps(line), flush=True)
     return 0
@@ -286,6 +288,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-rows", type=int, default=256, help="rows per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bpc-f32", action="store_true", help="c5: run bPC on the fp32 CUDA-core path instead of bf16 tensor cores")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from . import _core
 from ._core import _layer_parts, _skip_flags, _WS_CACHE
 from ._errors import _check_param_type
 from .nn import tree_unflatten_like
@@ -46,6 +47,7 @@ class _BpcNet:
             if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
         dims = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+        self.true_dims = list(dims)
         for j in range(n):
             if Ws[j].shape[1] != dims[j]:
                 raise ValueError(f"top-down layer {j}: weight shape {tuple(Ws[j].shape)} does not chain from {dims[j]}")
@@ -59,6 +61,25 @@ class _BpcNet:
             raise NotImplementedError("mixed bias / no-bias layers are not on the B200 path")
         skips = _skip_flags(skip_model, n)
         B = x.shape[0]
+        self.bf16 = _core.get_compute_dtype() == "bf16"
+        bWs = [l.bias for l in self.td_lin] if all(td_bias) else None
+        bVs = [l.bias for l in self.bu_lin] if all(bu_bias) else None
+        if self.bf16:
+            # The tensor-core path needs every feature dim to be a multiple of 8 (TMA row pitch, 16-byte vectors):
+            # zero-pad.  Padded weights / inputs / activities are zero and stay zero (act(0) = 0 for all 8
+            # activations; zero weight rows and columns), so energies and the un-padded parts of every result are
+            # unchanged; results are sliced back.  (Data layout only -- no arithmetic happens here.)
+            pd = [(v + 7) // 8 * 8 for v in dims]
+            P = torch.nn.functional.pad
+            Ws = [P(Ws[j], (0, pd[j] - dims[j], 0, pd[j + 1] - dims[j + 1])).contiguous() for j in range(n)]
+            Vs = [P(Vs[j], (0, pd[j + 1] - dims[j + 1], 0, pd[j] - dims[j])).contiguous() for j in range(n)]
+            if bWs is not None:
+                bWs = [P(bWs[j], (0, pd[j + 1] - dims[j + 1])).contiguous() for j in range(n)]
+            if bVs is not None:
+                bVs = [P(bVs[j], (0, pd[j] - dims[j])).contiguous() for j in range(n)]
+            x = P(x, (0, pd[0] - dims[0])).contiguous()
+            y = P(y, (0, pd[-1] - dims[-1])).contiguous()
+            dims = pd
         d = _lib.BpcDesc()
         d.td.n_layers, d.td.batch_local = n, B
         d.td.batch_global = B if batch_global is None else int(batch_global)
@@ -70,7 +91,7 @@ class _BpcNet:
             d.td.skip[j] = 1 if skips[j] else 0
             d.td.scalings[j] = 1.0
         d.td.has_bias, d.bu_has_bias = int(all(td_bias)), int(all(bu_bias))
-        d.td.dtype, d.td.loss = _lib.DTYPE_F32, _lib.LOSS_MSE
+        d.td.dtype, d.td.loss = (_lib.DTYPE_BF16 if self.bf16 else _lib.DTYPE_F32), _lib.LOSS_MSE
         d.td.output_energy_scaling, d.td.activity_decay = 1.0, 0.0
         d.td.solver, d.td.n_steps, d.td.dt, d.td.dt_last = _lib.SOLVER_EULER, int(n_steps), float(dt), float(dt)
         d.forward_energy_weight, d.backward_energy_weight = float(forward_energy_weight), float(backward_energy_weight)
@@ -81,9 +102,9 @@ class _BpcNet:
         self.H, self.B, self.dims, self.dev = H, B, dims, dev
         self.td_bias, self.bu_bias = all(td_bias), all(bu_bias)
         self.W, self.V = _lib.ptr_array(Ws), _lib.ptr_array(Vs)
-        self.bW = _lib.ptr_array([l.bias for l in self.td_lin]) if self.td_bias else None
-        self.bV = _lib.ptr_array([l.bias for l in self.bu_lin]) if self.bu_bias else None
-        self._keep = (Ws, Vs)
+        self.bW = _lib.ptr_array(bWs) if self.td_bias else None
+        self.bV = _lib.ptr_array(bVs) if self.bu_bias else None
+        self._keep = (Ws, Vs, bWs, bVs)
         self.x, self.y = x, y
 
     def workspace(self):
@@ -102,11 +123,25 @@ class _BpcNet:
         if len(activities) != self.H + 1:
             raise ValueError(f"expected {self.H + 1} activity arrays (z_0..z_{self.H - 1} + the unused output slot), got {len(activities)}")
         for k, a in enumerate(activities[:-1]):
-            if tuple(a.shape) != (self.B, self.dims[k + 1]):
-                raise ValueError(f"activities[{k}] has shape {tuple(a.shape)}, expected {(self.B, self.dims[k + 1])}")
+            if tuple(a.shape) != (self.B, self.true_dims[k + 1]):
+                raise ValueError(f"activities[{k}] has shape {tuple(a.shape)}, expected {(self.B, self.true_dims[k + 1])}")
         for a in activities:
             if a.device != self.dev or a.dtype != torch.float32 or not a.is_contiguous():
                 raise ValueError("activities must be contiguous fp32 CUDA tensors")
+
+    def pad_acts(self, activities, clone=False):
+        """Activities in the layout the library sees (zero-padded feature dims on the bf16 path)."""
+        if not self.bf16:
+            return [a.clone() for a in activities] if clone else list(activities)
+        P = torch.nn.functional.pad
+        out = [P(a, (0, self.dims[k + 1] - a.shape[1])).contiguous() for k, a in enumerate(activities[:-1])]
+        out.append(torch.zeros(self.B, self.dims[-1], dtype=torch.float32, device=self.dev))
+        return out
+
+    def unpad_acts(self, padded, like):
+        if not self.bf16:
+            return padded
+        return [p[:, :a.shape[1]].contiguous() if p.shape[1] >= a.shape[1] else a.clone() for p, a in zip(padded, like)]
 
     def args(self):
         return (self.desc, self.W, self.bW, self.V, self.bV)
@@ -124,7 +159,7 @@ def bpc_energy_fn(top_down_model, bottom_up_model, activities, y, *, x=None, ski
     net.check_acts(activities)
     ws = net.workspace()
     E = torch.empty(2 * (net.H + 1), dtype=torch.float32, device=net.dev)
-    _lib.check(_lib.lib.jpcb_bpc_energy(*net.args(), _lib.ptr_array(activities), _lib.ptr(x), _lib.ptr(y), _lib.ptr(E),
+    _lib.check(_lib.lib.jpcb_bpc_energy(*net.args(), _lib.ptr_array(net.pad_acts(activities)), _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr(E),
                                         _lib.ptr(ws), ws.numel(), net.stream()))
     return E if record_layers else E.sum()
 
@@ -136,23 +171,34 @@ def compute_bpc_activity_grad(top_down_model, bottom_up_model, activities, y, *,
     net.check_acts(activities)
     ws = net.workspace()
     F = torch.empty((), dtype=torch.float32, device=net.dev)
-    g = [torch.empty_like(a) for a in activities]
-    _lib.check(_lib.lib.jpcb_bpc_activity_grad(*net.args(), _lib.ptr_array(activities), _lib.ptr(x), _lib.ptr(y), _lib.ptr(F),
+    pa = net.pad_acts(activities)
+    # (the unused last slot may have any shape in the reference; its gradient is zero)
+    g = [torch.empty_like(a) for a in pa[:-1]] + [torch.empty(net.B, net.dims[-1], dtype=torch.float32, device=net.dev)]
+    _lib.check(_lib.lib.jpcb_bpc_activity_grad(*net.args(), _lib.ptr_array(pa), _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr(F),
                                                _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
-    return F, g
+    return F, net.unpad_acts(g[:-1], activities[:-1]) + [torch.zeros_like(activities[-1])]
 
 
 def _param_grads(net, activities, want_energies=False):
-    gW = [torch.empty_like(l.weight) for l in net.td_lin]
-    gV = [torch.empty_like(l.weight) for l in net.bu_lin]
-    gbW = [torch.empty_like(l.bias) for l in net.td_lin] if net.td_bias else None
-    gbV = [torch.empty_like(l.bias) for l in net.bu_lin] if net.bu_bias else None
+    D, n = net.dims, net.H + 1
+    f32 = dict(dtype=torch.float32, device=net.dev)
+    gW = [torch.empty(D[j + 1], D[j], **f32) for j in range(n)]
+    gV = [torch.empty(D[j], D[j + 1], **f32) for j in range(n)]
+    gbW = [torch.empty(D[j + 1], **f32) for j in range(n)] if net.td_bias else None
+    gbV = [torch.empty(D[j], **f32) for j in range(n)] if net.bu_bias else None
     E = torch.empty(2 * (net.H + 1), dtype=torch.float32, device=net.dev) if want_energies else None
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_bpc_param_grads(*net.args(), _lib.ptr_array(activities), _lib.ptr(net.x), _lib.ptr(net.y),
+    _lib.check(_lib.lib.jpcb_bpc_param_grads(*net.args(), _lib.ptr_array(net.pad_acts(activities)), _lib.ptr(net.x), _lib.ptr(net.y),
                                              _lib.ptr_array(gW), _lib.ptr_array(gbW) if gbW else None, _lib.ptr_array(gV),
                                              _lib.ptr_array(gbV) if gbV else None, _lib.ptr(E), _lib.ptr(ws), ws.numel(),
                                              net.stream()))
+
+    if net.bf16:  # slice the zero-padded rows / columns off again
+        T = net.true_dims
+        gW = [g[:T[j + 1], :T[j]].contiguous() for j, g in enumerate(gW)]
+        gV = [g[:T[j], :T[j + 1]].contiguous() for j, g in enumerate(gV)]
+        gbW = [g[:T[j + 1]].contiguous() for j, g in enumerate(gbW)] if gbW else None
+        gbV = [g[:T[j]].contiguous() for j, g in enumerate(gbV)] if gbV else None
 
     def tree(model, gw, gb):
         leaves = []
@@ -207,8 +253,8 @@ def solve_bpc_inference(top_down_model, bottom_up_model, activities, output, *, 
     net = _net(top_down_model, bottom_up_model, input, output, skip_model, param_type, backward_energy_weight,
                forward_energy_weight, n_steps=n_steps, dt=dt)
     net.check_acts(activities)
-    A = [a.clone() for a in activities]
+    A = net.pad_acts(activities, clone=True)
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_bpc_infer(*net.args(), _lib.ptr_array(A), _lib.ptr(input), _lib.ptr(output), _lib.ptr(ws),
+    _lib.check(_lib.lib.jpcb_bpc_infer(*net.args(), _lib.ptr_array(A), _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr(ws),
                                        ws.numel(), net.stream()))
-    return A
+    return net.unpad_acts(A, activities)

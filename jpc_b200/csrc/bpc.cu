@@ -15,8 +15,12 @@
 // activity gradient (into a scratch buffer); the backward-direction half + combination + Euler
 // update.  The two constant predictions (W_0 phi_0(x) and V_H psi_H(y)) are hoisted out of the loop.
 //
-// This first version runs the fp32 CUDA-core path (1e-5 parity, BASELINE config 5 is fp32); the
-// bf16 tensor-core schedule for bPC is the next step.
+// td.dtype selects the arithmetic of the GEMM operands exactly as on the PC path: JPCB_DTYPE_F32 = CUDA-core
+// fp32 FMA (1e-5 parity); JPCB_DTYPE_BF16 = the tcgen05 grouped GEMM on bf16 operand copies with fp32
+// accumulation and fp32 master activities (2e-2 parity).  The bf16 path keeps ONE operand copy bf16(act(z_k))
+// per activity, so it needs the two directions to apply the same activation to z_k
+// (td.act[k+1] == bu_act[k], true for make_mlp models), and every dim / the batch to be multiples of 8
+// (the host mirror zero-pads feature dims).
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -25,6 +29,7 @@
 #include "host.cuh"
 
 using namespace jpcb;
+typedef __nv_bfloat16 bf16;
 
 namespace {
 
@@ -61,8 +66,17 @@ int validate_bpc(const jpcb_bpc_desc* d) {
     if (t.skip[l] && l >= 1 && l <= t.n_layers - 2 && t.dims[l] != t.dims[l + 1])
       return fail(JPCB_EINVAL, "identity skip at layer %d needs equal dims (%d vs %d)", l, t.dims[l], t.dims[l + 1]);
   }
-  if (t.dtype == JPCB_DTYPE_BF16) return fail(JPCB_ENOTIMPL, "bPC runs the fp32 path; the bf16 tensor-core schedule for bPC is not built yet");
-  if (t.dtype != JPCB_DTYPE_F32) return fail(JPCB_EINVAL, "bad dtype %d", t.dtype);
+  if (t.dtype != JPCB_DTYPE_F32 && t.dtype != JPCB_DTYPE_BF16) return fail(JPCB_EINVAL, "bad dtype %d", t.dtype);
+  if (t.dtype == JPCB_DTYPE_BF16) {
+    if (t.batch_local % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs batch_local %% 8 == 0 (got %d)", t.batch_local);
+    for (int l = 0; l <= t.n_layers; ++l)
+      if (t.dims[l] % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs every dim %% 8 == 0 (dims[%d]=%d)", l, t.dims[l]);
+    for (int k = 0; k + 1 < t.n_layers; ++k)
+      if (t.act[k + 1] != d->bu_act[k])
+        return fail(JPCB_ENOTIMPL, "bf16 bPC path needs td.act[%d] == bu_act[%d] (one bf16 operand copy per activity)", k + 1, k);
+  }
+  for (int l = 0; l <= t.n_layers; ++l)
+    if ((long long)t.batch_local * t.dims[l] >= (1LL << 31)) return fail(JPCB_ENOTIMPL, "batch_local * dims[%d] must be < 2^31", l);
   if (t.solver != JPCB_SOLVER_EULER) return fail(JPCB_ENOTIMPL, "bPC inference is Euler (update_bpc_activities with optax.sgd); Heun is not on this path");
   if (t.n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", t.n_steps);
   if (t.activity_decay != 0.f) return fail(JPCB_EINVAL, "bpc_energy_fn has no activity_decay");
@@ -95,14 +109,37 @@ struct BpcRun {
   std::vector<float*> e, dl, Gf;    // e_j [Bl, D[j+1]], delta_j [Bl, D[j]], forward half of dF/dz_k [Bl, D[k+1]]
   float* P0 = nullptr;              // W_0 phi_0(x) + b_0        [Bl, D[1]]
   float* QH = nullptr;              // V_H psi_H(y) + c_H        [Bl, D[H]]
+  // bf16 operand copies (tensor-core path)
+  bool tc = false;
+  std::vector<bf16*> Wb, WTb, Vb, VTb;  // W_j, W_j^T (j >= 1), V_j, V_j^T (j <= H-1)
+  std::vector<bf16*> Hz;                // act(z_k)      [Bl, D[k+1]], k = 0..H-1
+  bf16* Hx = nullptr;                   // phi_0(x)      [Bl, D[0]]
+  bf16* Hy = nullptr;                   // psi_H(y)      [Bl, D[H+1]]
+  std::vector<bf16*> Eb, Db;            // bf16 copies of e_j / delta_j
   size_t bytes = 0;
 
   void carve(void* base) {
     Bump b{reinterpret_cast<char*>(base)};
     red = b.take<float>(2 * (H + 1) + 8);
-    e.resize(H + 1); dl.resize(H + 1); Gf.resize(H);
-    for (int j = 0; j <= H; ++j) e[j] = b.take<float>((size_t)Bl * D[j + 1]);
-    for (int j = 0; j <= H; ++j) dl[j] = b.take<float>((size_t)Bl * D[j]);
+    e.assign(H + 1, nullptr); dl.assign(H + 1, nullptr); Gf.resize(H);
+    Wb.assign(H + 1, nullptr); WTb.assign(H + 1, nullptr); Vb.assign(H + 1, nullptr); VTb.assign(H + 1, nullptr);
+    Hz.assign(H, nullptr); Eb.assign(H + 1, nullptr); Db.assign(H + 1, nullptr);
+    if (!tc) {
+      for (int j = 0; j <= H; ++j) e[j] = b.take<float>((size_t)Bl * D[j + 1]);
+      for (int j = 0; j <= H; ++j) dl[j] = b.take<float>((size_t)Bl * D[j]);
+    } else {
+      for (int j = 0; j <= H; ++j) {
+        const size_t wn = (size_t)D[j] * D[j + 1];
+        Wb[j] = b.take<bf16>(wn); Vb[j] = b.take<bf16>(wn);
+        if (j >= 1) WTb[j] = b.take<bf16>(wn);
+        if (j <= H - 1) VTb[j] = b.take<bf16>(wn);
+        Eb[j] = b.take<bf16>((size_t)Bl * D[j + 1]);
+        Db[j] = b.take<bf16>((size_t)Bl * D[j]);
+      }
+      for (int k = 0; k < H; ++k) Hz[k] = b.take<bf16>((size_t)Bl * D[k + 1]);
+      Hx = b.take<bf16>((size_t)Bl * D[0]);
+      Hy = b.take<bf16>((size_t)Bl * D[H + 1]);
+    }
     for (int k = 0; k < H; ++k) Gf[k] = b.take<float>((size_t)Bl * D[k + 1]);
     P0 = b.take<float>((size_t)Bl * D[1]);
     QH = b.take<float>((size_t)Bl * D[H]);
@@ -116,6 +153,7 @@ struct BpcRun {
     st = reinterpret_cast<cudaStream_t>(stream);
     H = d->td.n_layers - 1; Bl = d->td.batch_local; D = d->td.dims;
     invB = 1.f / (float)d->td.batch_global; af = d->forward_energy_weight; ab = d->backward_energy_weight;
+    tc = d->td.dtype == JPCB_DTYPE_BF16;
     if (!W || !V || !x || !y) return fail(JPCB_EINVAL, "null weight lists / input / target");
     if (d->td.has_bias && !bW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias list");
     if (d->bu_has_bias && !bV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias list");
@@ -127,11 +165,47 @@ struct BpcRun {
   const float* biasW(int j) const { return d->td.has_bias ? bW[j] : nullptr; }
   const float* biasV(int j) const { return d->bu_has_bias ? bV[j] : nullptr; }
 
+  int launch(const std::vector<GTask>& t) { return tc ? launch_tc(t, st) : launch_simt(t, st); }
+  static int ew_grid(size_t items, int per_block) {
+    size_t blocks = (items + per_block - 1) / per_block;
+    const size_t cap = (size_t)num_sms() * 8;
+    return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+  }
+  // bf16 operand copies of the weights (both directions, plus the transposes the gradient GEMMs read) and of
+  // the clamped inputs; with `S` also of every activity
+  int prep(const float* const* S) {
+    if (!tc) return JPCB_OK;
+    for (int j = 0; j <= H; ++j) {
+      const size_t wn = (size_t)D[j] * D[j + 1];
+      cast_act_bf16_kernel<<<ew_grid(wn / 4 + 1, 256), 256, 0, st>>>(W[j], Wb[j], wn, ACT_LINEAR); count_launch();
+      cast_act_bf16_kernel<<<ew_grid(wn / 4 + 1, 256), 256, 0, st>>>(V[j], Vb[j], wn, ACT_LINEAR); count_launch();
+      if (j >= 1) {  // W_j [D[j+1], D[j]] -> [D[j], D[j+1]]
+        transpose_to_bf16_kernel<float><<<ew_grid(((D[j + 1] + 31) / 32) * ((D[j] + 31) / 32), 1), dim3(32, 8), 0, st>>>(W[j], WTb[j], D[j + 1], D[j]);
+        count_launch();
+      }
+      if (j <= H - 1) {  // V_j [D[j], D[j+1]] -> [D[j+1], D[j]]
+        transpose_to_bf16_kernel<float><<<ew_grid(((D[j] + 31) / 32) * ((D[j + 1] + 31) / 32), 1), dim3(32, 8), 0, st>>>(V[j], VTb[j], D[j], D[j + 1]);
+        count_launch();
+      }
+    }
+    const size_t nx = (size_t)Bl * D[0], ny = (size_t)Bl * D[H + 1];
+    cast_act_bf16_kernel<<<ew_grid(nx / 4 + 1, 256), 256, 0, st>>>(x, Hx, nx, d->td.act[0]); count_launch();
+    cast_act_bf16_kernel<<<ew_grid(ny / 4 + 1, 256), 256, 0, st>>>(y, Hy, ny, d->bu_act[H]); count_launch();
+    if (S)
+      for (int k = 0; k < H; ++k) {
+        const size_t n = (size_t)Bl * D[k + 1];
+        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[k], Hz[k], n, d->td.act[k + 1]); count_launch();
+      }
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+
   // top-down prediction GEMM of layer j on state S: phi_j(u_j) W_j^T
   void td_operands(GTask& t, int j, const float* const* S) const {
     t.e.M = Bl; t.e.N = D[j + 1]; t.K = D[j];
     t.a_p = j == 0 ? x : S[j - 1]; t.a_smn = D[j]; t.a_sk = 1; t.a_act = d->td.act[j];
     t.b_p = W[j]; t.b_smn = D[j]; t.b_sk = 1;
+    t.a_b = j == 0 ? Hx : Hz[j - 1]; t.b_b = Wb[j];
     t.e.alpha = 1.f; t.e.bias = biasW(j);
   }
   // bottom-up prediction GEMM of layer j on state S: psi_j(v_j) V_j^T
@@ -139,6 +213,7 @@ struct BpcRun {
     t.e.M = Bl; t.e.N = D[j]; t.K = D[j + 1];
     t.a_p = j == H ? y : S[j]; t.a_smn = D[j + 1]; t.a_sk = 1; t.a_act = d->bu_act[j];
     t.b_p = V[j]; t.b_smn = D[j + 1]; t.b_sk = 1;
+    t.a_b = j == H ? Hy : Hz[j]; t.b_b = Vb[j];
     t.e.alpha = 1.f; t.e.bias = biasV(j);
   }
 
@@ -147,12 +222,12 @@ struct BpcRun {
     GTask a, b;
     td_operands(a, 0, nullptr); a.e.mode = EPI_FFWD; a.e.O = P0;
     bu_operands(b, H, nullptr); b.e.mode = EPI_FFWD; b.e.O = QH;
-    return launch_simt({a, b}, st);
+    return launch({a, b});
   }
 
   // all 2(H+1) prediction errors on state S (+ energy sums when `energy`)
   int errors(const float* const* S, bool energy, bool hoisted) {
-    std::vector<GTask> ts;
+    std::vector<GTask> ts, k0;  // k0: the two GEMM-free tasks (always on the CUDA-core kernel)
     for (int j = 0; j <= H; ++j) {
       GTask t;
       t.e.mode = EPI_ERR; t.e.escale = 1.f;
@@ -164,9 +239,9 @@ struct BpcRun {
         t.e.skip = skip(j); t.e.U = j == 0 ? x : S[j - 1];
       }
       t.e.T = j == H ? y : S[j];
-      t.e.O = e[j];
+      t.e.O = e[j]; t.e.Ob = Eb[j];
       if (energy) t.e.red = red + j;
-      ts.push_back(t);
+      (t.K == 0 ? k0 : ts).push_back(t);
     }
     for (int j = 0; j <= H; ++j) {
       GTask t;
@@ -179,11 +254,13 @@ struct BpcRun {
         t.e.skip = skip(j); t.e.U = j == H ? y : S[j];
       }
       t.e.T = j == 0 ? x : S[j - 1];
-      t.e.O = dl[j];
+      t.e.O = dl[j]; t.e.Ob = Db[j];
       if (energy) t.e.red = red + H + 1 + j;
-      ts.push_back(t);
+      (t.K == 0 ? k0 : ts).push_back(t);
     }
-    return launch_simt(ts, st);
+    if (!tc) { ts.insert(ts.end(), k0.begin(), k0.end()); return launch_simt(ts, st); }
+    RET(launch_tc(ts, st));
+    return launch_simt(k0, st);
   }
 
   // dF/dz_k (sub = GRAD_OUT, c = 1/B, into Out[k]) or the Euler update z_k -= c * B dF/dz_k (in place)
@@ -195,8 +272,9 @@ struct BpcRun {
       t.e.M = Bl; t.e.N = D[k + 1]; t.K = D[k + 2];
       t.a_p = e[k + 1]; t.a_smn = D[k + 2]; t.a_sk = 1;
       t.b_p = W[k + 1]; t.b_smn = 1; t.b_sk = D[k + 1];  // B(n,k') = W_{k+1}[k'][n]
-      t.e.alpha = 1.f; t.e.skip = skip(k + 1); t.e.En = e[k + 1];
-      t.e.Z = Z[k]; t.e.El = e[k];
+      t.a_b = Eb[k + 1]; t.b_b = WTb[k + 1];
+      t.e.alpha = 1.f; t.e.skip = skip(k + 1); t.e.En = e[k + 1]; t.e.Enb = Eb[k + 1];
+      t.e.Z = Z[k]; t.e.El = e[k]; t.e.Elb = Eb[k];
       t.e.gscale = af; t.e.c = 1.f; t.e.O = Gf[k];
       f.push_back(t);
       GTask u;  // backward-direction half + combination (+ update)
@@ -204,13 +282,15 @@ struct BpcRun {
       u.e.M = Bl; u.e.N = D[k + 1]; u.K = D[k];
       u.a_p = dl[k]; u.a_smn = D[k]; u.a_sk = 1;
       u.b_p = V[k]; u.b_smn = 1; u.b_sk = D[k + 1];       // B(n,k') = V_k[k'][n]
-      u.e.alpha = 1.f; u.e.skip = skip(k); u.e.En = dl[k];
-      u.e.Z = Z[k]; u.e.El = dl[k + 1];
+      u.a_b = Db[k]; u.b_b = VTb[k];
+      u.e.alpha = 1.f; u.e.skip = skip(k); u.e.En = dl[k]; u.e.Enb = Db[k];
+      u.e.Z = Z[k]; u.e.El = dl[k + 1]; u.e.Elb = Db[k + 1];
       u.e.gscale = ab; u.e.Gin = Gf[k]; u.e.c = c; u.e.O = Out[k];
+      if (tc && sub != GRAD_OUT) u.e.Ob = Hz[k];  // act(z_new): the next evaluation's operand (both directions)
       b.push_back(u);
     }
-    RET(launch_simt(f, st));
-    return launch_simt(b, st);
+    RET(launch(f));
+    return launch(b);
   }
 
   int finalize(float* E_pairs, float* F) {
@@ -230,6 +310,7 @@ size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc) {
   if (validate_bpc(desc) != JPCB_OK) return 0;
   BpcRun r;
   r.d = desc; r.H = desc->td.n_layers - 1; r.Bl = desc->td.batch_local; r.D = desc->td.dims;
+  r.tc = desc->td.dtype == JPCB_DTYPE_BF16;
   r.carve(nullptr);
   return r.bytes;
 }
@@ -241,6 +322,7 @@ int jpcb_bpc_energy(const jpcb_bpc_desc* desc, const float* const* W, const floa
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A || !E_pairs) return fail(JPCB_EINVAL, "null activities / output");
   RET(r.zero_red());
+  RET(r.prep(A));
   RET(r.errors(A, true, false));
   return r.finalize(E_pairs, nullptr);
 }
@@ -252,6 +334,7 @@ int jpcb_bpc_activity_grad(const jpcb_bpc_desc* desc, const float* const* W, con
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A || !gA) return fail(JPCB_EINVAL, "null activities / output");
   RET(r.zero_red());
+  RET(r.prep(A));
   RET(r.errors(A, true, false));
   RET(r.grads(GRAD_OUT, r.invB, A, gA));
   CK(cudaMemsetAsync(gA[r.H], 0, (size_t)r.Bl * r.D[r.H + 1] * sizeof(float), r.st));  // dummy slot: dF/dA[-1] = 0
@@ -265,6 +348,7 @@ int jpcb_bpc_infer(const jpcb_bpc_desc* desc, const float* const* W, const float
   BpcRun r;
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A) return fail(JPCB_EINVAL, "null activities");
+  RET(r.prep(A));
   RET(r.hoist());
   const int T = desc->td.n_steps;
   for (int s = 0; s < T; ++s) {
@@ -283,6 +367,7 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A || !gW || !gV) return fail(JPCB_EINVAL, "null activities / outputs");
   RET(r.zero_red());
+  RET(r.prep(A));
   RET(r.errors(A, E_pairs != nullptr, false));
   const int H = r.H, Bl = r.Bl;
   const int32_t* D = r.D;
@@ -292,27 +377,31 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
     t.e.mode = EPI_SCALE; t.e.M = D[j + 1]; t.e.N = D[j]; t.K = Bl;
     t.a_p = r.e[j]; t.a_smn = 1; t.a_sk = D[j + 1];
     t.b_p = j == 0 ? x : A[j - 1]; t.b_smn = 1; t.b_sk = D[j]; t.b_act = desc->td.act[j];
+    t.a_b = r.Eb[j]; t.b_b = j == 0 ? r.Hx : r.Hz[j - 1]; t.mn_major = r.tc;  // both read MN-major: no transposes
     t.e.alpha = -r.af * r.invB; t.e.O = gW[j];
     ts.push_back(t);
     GTask u;  // gV_j = -(alpha_b/B) delta_j^T psi_j(v_j)
     u.e.mode = EPI_SCALE; u.e.M = D[j]; u.e.N = D[j + 1]; u.K = Bl;
     u.a_p = r.dl[j]; u.a_smn = 1; u.a_sk = D[j];
     u.b_p = j == H ? y : A[j]; u.b_smn = 1; u.b_sk = D[j + 1]; u.b_act = desc->bu_act[j];
+    u.a_b = r.Db[j]; u.b_b = j == H ? r.Hy : r.Hz[j]; u.mn_major = r.tc;
     u.e.alpha = -r.ab * r.invB; u.e.O = gV[j];
     ts.push_back(u);
   }
-  RET(launch_simt(ts, r.st));
+  RET(r.launch(ts));
   if (desc->td.has_bias) {
     if (!gbW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias-gradient list");
     for (int j = 0; j <= H; ++j) {
-      colsum_kernel<float><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.e[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
+      if (r.tc) colsum_kernel<bf16><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Eb[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
+      else colsum_kernel<float><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.e[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
       count_launch();
     }
   }
   if (desc->bu_has_bias) {
     if (!gbV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias-gradient list");
     for (int j = 0; j <= H; ++j) {
-      colsum_kernel<float><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.dl[j], gbV[j], Bl, D[j], -r.ab * r.invB);
+      if (r.tc) colsum_kernel<bf16><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Db[j], gbV[j], Bl, D[j], -r.ab * r.invB);
+      else colsum_kernel<float><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.dl[j], gbV[j], Bl, D[j], -r.ab * r.invB);
       count_launch();
     }
   }
