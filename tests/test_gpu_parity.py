@@ -521,3 +521,35 @@ def test_config5_bpc_full_size_bf16():
     c = _bpc_case(10, 1024, 6, 784, "relu", 1024)
     _check_bpc(*c, TOLBF)
     _check_bpc_infer(*c, TOLBF, T=30, dt=0.5)
+
+
+# ---- tensor-core GEMM shape sweep (tile / TMA box boundaries) -----------------------------------
+@pytest.mark.parametrize("B,d_in,d_out", [(8, 8, 8), (8, 64, 8), (136, 72, 200), (128, 64, 256), (256, 2048, 264),
+                                          (264, 520, 136), (520, 8, 1032), (1024, 136, 24), (40, 1000, 512)])
+def test_tc_gemm_shape_sweep(B, d_in, d_out):
+    """One FFWD GEMM + bias through the tcgen05 path for shapes around the 256x256x64 tile and the TMA boxes
+    (M, N, K below / at / above one tile, K not a multiple of 64), against fp64 on the bf16-rounded operands."""
+    import jpc_b200 as J
+    from jpc_b200 import nn
+    J.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(B * 7 + d_in * 3 + d_out)
+    W = (torch.rand(d_out, d_in, generator=g, dtype=torch.float64) * 2 - 1) / math.sqrt(d_in)
+    b = torch.rand(d_out, generator=g, dtype=torch.float64) - 0.5
+    x = torch.randn(B, d_in, generator=g, dtype=torch.float64)
+    W2 = (torch.rand(d_out, d_out, generator=g, dtype=torch.float64) * 2 - 1) / math.sqrt(d_out)
+    layers = []
+    for Wl, bl, act in ((W, b, "linear"), (W2, None, "tanh")):
+        lin = nn.Linear.__new__(nn.Linear)
+        lin.weight, lin.bias = dev(Wl), (None if bl is None else dev(bl))
+        lin.out_features, lin.in_features = Wl.shape
+        lin.use_bias = bl is not None
+        layers.append(nn.Sequential([nn.Lambda(nn.get_act_fn(act)), lin]))
+    # mixed bias is not on the path: give the second layer a zero bias
+    layers[1].layers[1].bias = torch.zeros(d_out, device="cuda")
+    layers[1].layers[1].use_bias = True
+    out = J.init_activities_with_ffwd(layers, dev(x))
+    r = lambda t: t.float().bfloat16().double()
+    want = r(x) @ r(W).T + b.float().double()
+    assert float((out[0].double().cpu() - want).abs().max()) < 2e-5 * max(float(want.abs().max()), 1.0)
+    want2 = r(torch.tanh(want)) @ r(W2).T
+    assert float((out[1].double().cpu() - want2).abs().max()) < 2e-2 * max(float(want2.abs().max()), 1.0)
