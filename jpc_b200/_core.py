@@ -145,6 +145,26 @@ class _Net:
         B = x.shape[0]
         skips = _skip_flags(skip_model, L)
         scal = _get_param_scalings(model, x, skip_model=skip_model, param_type=param_type, gamma=gamma)
+        self.true_dims = list(dims)
+        bs = [lin.bias for lin in self.linears] if all(has_bias) else None
+        self.padded = _COMPUTE_DTYPE == "bf16" and any(v % 8 for v in dims)
+        if self.padded:
+            # The tensor-core path needs every feature dim to be a multiple of 8 (TMA row pitch, 16-byte vectors):
+            # zero-pad weights, biases, inputs, targets and activities.  Padded entries are zero and stay zero
+            # (act(0) = 0 for all 8 activations; zero weight rows / columns), so energies and the un-padded part of
+            # every result are unchanged; results are sliced back.  Data layout only -- no arithmetic happens here.
+            if loss_id == "ce" and dims[-1] % 8:
+                raise NotImplementedError("bf16 path: a cross-entropy output layer must have a multiple of 8 classes "
+                                          "(zero-padded logits would enter the softmax)")
+            pd = [(v + 7) // 8 * 8 for v in dims]
+            P = torch.nn.functional.pad
+            Ws = [P(Ws[l], (0, pd[l] - dims[l], 0, pd[l + 1] - dims[l + 1])).contiguous() for l in range(L)]
+            if bs is not None:
+                bs = [P(bs[l], (0, pd[l + 1] - dims[l + 1])).contiguous() for l in range(L)]
+            x = P(x, (0, pd[0] - dims[0])).contiguous()
+            if y is not None:
+                y = P(y, (0, pd[-1] - dims[-1])).contiguous()
+            dims = pd
         lam = 1.0 if output_energy_scaling is None else float(output_energy_scaling)
         bg = B if batch_global is None else int(batch_global)
         key = (L, B, bg, tuple(dims), tuple(p[0] for p in parts), all(has_bias), tuple(skips), tuple(scal),
@@ -176,9 +196,11 @@ class _Net:
         self.L, self.B, self.dims, self.dev = L, B, dims, dev
         self.has_bias = all(has_bias)
         self.W = _lib.ptr_array(Ws)
-        self.b = _lib.ptr_array([lin.bias for lin in self.linears]) if self.has_bias else None
-        self._keep = Ws  # keep tensors alive while pointer arrays exist
-        self.x, self.y = x, y
+        self.b = _lib.ptr_array(bs) if self.has_bias else None
+        self._keep = (Ws, bs)  # keep tensors alive while pointer arrays exist
+        self.x, self.y = x, y   # (zero-padded copies when self.padded)
+        self.w_shapes = [tuple(w.shape) for w in Ws]
+        self.b_shapes = [tuple(b_.shape) for b_ in bs] if bs is not None else None
 
     def workspace(self) -> torch.Tensor:
         k = (self.dev, )
@@ -195,13 +217,35 @@ class _Net:
         if len(activities) != self.L:
             raise ValueError(f"expected {self.L} activity arrays (one per layer, last = dummy output slot), got {len(activities)}")
         for l, a in enumerate(activities):
-            if tuple(a.shape) != (self.B, self.dims[l + 1]):
-                raise ValueError(f"activities[{l}] has shape {tuple(a.shape)}, expected {(self.B, self.dims[l + 1])}")
+            if tuple(a.shape) != (self.B, self.true_dims[l + 1]):
+                raise ValueError(f"activities[{l}] has shape {tuple(a.shape)}, expected {(self.B, self.true_dims[l + 1])}")
             if a.device != self.dev or a.dtype != torch.float32 or not a.is_contiguous():
                 raise ValueError("activities must be contiguous fp32 CUDA tensors")
 
     def new_acts(self):
+        """Output buffers in the layout the library sees (padded feature dims when self.padded)."""
         return [torch.empty(self.B, self.dims[l + 1], dtype=torch.float32, device=self.dev) for l in range(self.L)]
+
+    def in_acts(self, activities, clone=False):
+        """User activities -> the layout the library sees."""
+        if not self.padded:
+            return [a.clone() for a in activities] if clone else list(activities)
+        P = torch.nn.functional.pad
+        return [P(a, (0, self.dims[l + 1] - a.shape[1])).contiguous() for l, a in enumerate(activities)]
+
+    def out_acts(self, bufs):
+        """Library-layout activity-shaped results -> the user's shapes."""
+        if not self.padded:
+            return bufs
+        return [b_[:, :self.true_dims[l + 1]].contiguous() for l, b_ in enumerate(bufs)]
+
+    def out_grads(self, gW, gb):
+        if not self.padded:
+            return gW, gb
+        T = self.true_dims
+        gW = [g[:T[l + 1], :T[l]].contiguous() for l, g in enumerate(gW)]
+        gb = [g[:T[l + 1]].contiguous() for l, g in enumerate(gb)] if gb is not None else None
+        return gW, gb
 
 
 def _probe_error(desc) -> int:
@@ -235,9 +279,9 @@ def init_activities_with_ffwd(model, input, *, skip_model=None, param_type="sp",
                output_energy_scaling=None, activity_decay=0.0, weight_decay=0.0, spectral_penalty=0.0)
     acts = net.new_acts()
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_pc_ffwd_init(net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr_array(acts), None, None,
+    _lib.check(_lib.lib.jpcb_pc_ffwd_init(net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr_array(acts), None, None,
                                           _lib.ptr(ws), ws.numel(), net.stream()))
-    return acts
+    return net.out_acts(acts)
 
 
 def pc_energy_fn(params, activities, y, *, x=None, loss="mse", param_type="sp", weight_decay=0.0,
@@ -253,13 +297,13 @@ def pc_energy_fn(params, activities, y, *, x=None, loss="mse", param_type="sp", 
     ws = net.workspace()
     if record_layers:
         E = torch.empty(net.L, dtype=torch.float32, device=net.dev)
-        _lib.check(_lib.lib.jpcb_pc_energy(net.desc, net.W, net.b, _lib.ptr_array(activities), _lib.ptr(x), _lib.ptr(y),
+        _lib.check(_lib.lib.jpcb_pc_energy(net.desc, net.W, net.b, _lib.ptr_array(net.in_acts(activities)), _lib.ptr(net.x), _lib.ptr(net.y),
                                            _lib.ptr(E), _lib.ptr(ws), ws.numel(), net.stream()))
         return E
     F = torch.empty((), dtype=torch.float32, device=net.dev)
     g = net.new_acts()
-    _lib.check(_lib.lib.jpcb_pc_activity_grad(net.desc, net.W, net.b, _lib.ptr_array(activities), _lib.ptr(x), _lib.ptr(y),
-                                              _lib.ptr(F), _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
+    _lib.check(_lib.lib.jpcb_pc_activity_grad(net.desc, net.W, net.b, _lib.ptr_array(net.in_acts(activities)), _lib.ptr(net.x),
+                                              _lib.ptr(net.y), _lib.ptr(F), _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
     return F
 
 
@@ -274,9 +318,9 @@ def compute_pc_activity_grad(params, activities, y, *, x=None, loss_id="mse", pa
     ws = net.workspace()
     F = torch.empty((), dtype=torch.float32, device=net.dev)
     g = net.new_acts()
-    _lib.check(_lib.lib.jpcb_pc_activity_grad(net.desc, net.W, net.b, _lib.ptr_array(activities), _lib.ptr(x), _lib.ptr(y),
-                                              _lib.ptr(F), _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
-    return F, g
+    _lib.check(_lib.lib.jpcb_pc_activity_grad(net.desc, net.W, net.b, _lib.ptr_array(net.in_acts(activities)), _lib.ptr(net.x),
+                                              _lib.ptr(net.y), _lib.ptr(F), _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
+    return F, net.out_acts(g)
 
 
 def neg_pc_activity_grad(t, activities, args):
@@ -292,13 +336,15 @@ def neg_pc_activity_grad(t, activities, args):
 
 def _param_grads_raw(net: _Net, activities, want_energies=False, arena=None):
     """Runs jpcb_pc_param_grads; returns (gW list, gb list or None, E_layers or None)."""
-    gW = [torch.empty_like(lin.weight) for lin in net.linears]
-    gb = [torch.empty_like(lin.bias) for lin in net.linears] if net.has_bias else None
+    f32 = dict(dtype=torch.float32, device=net.dev)
+    gW = [torch.empty(sh, **f32) for sh in net.w_shapes]
+    gb = [torch.empty(sh, **f32) for sh in net.b_shapes] if net.has_bias else None
     E = torch.empty(net.L, dtype=torch.float32, device=net.dev) if want_energies else None
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_pc_param_grads(net.desc, net.W, net.b, _lib.ptr_array(activities), _lib.ptr(net.x), _lib.ptr(net.y),
-                                            _lib.ptr_array(gW), _lib.ptr_array(gb) if gb else None, _lib.ptr(E),
+    _lib.check(_lib.lib.jpcb_pc_param_grads(net.desc, net.W, net.b, _lib.ptr_array(net.in_acts(activities)), _lib.ptr(net.x),
+                                            _lib.ptr(net.y), _lib.ptr_array(gW), _lib.ptr_array(gb) if gb else None, _lib.ptr(E),
                                             _lib.ptr(ws), ws.numel(), net.stream()))
+    gW, gb = net.out_grads(gW, gb)
     return gW, gb, E
 
 
@@ -363,27 +409,30 @@ def _solve_adaptive(params, activities, output, input, loss_id, param_type, solv
                batch_global=batch_global)
     net.check_acts(activities)
     order = 2.0  # diffrax: error order of Heun (2nd order with an embedded 1st-order estimate)
-    t1 = float(max_t1)
-    A = [a.clone() for a in activities]
-    B_ = [torch.empty_like(a) for a in activities]
-    ws = net.workspace()
-    out2 = torch.zeros(2, dtype=torch.float32, device=net.dev)
-    import torch.distributed as dist
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    numel = sum(a.numel() for a in A) * world
+    kw_out = output  # (user-shaped tensors for the two gradient evaluations of the initial-step heuristic)
     kw = dict(x=input, loss_id=loss_id, param_type=param_type, weight_decay=weight_decay, spectral_penalty=spectral_penalty,
               activity_decay=activity_decay, gamma=gamma, output_energy_scaling=output_energy_scaling)
+    t1 = float(max_t1)
+    A = net.in_acts(activities, clone=True)
+    B_ = [torch.empty_like(a) for a in A]
+    ws = net.workspace()
+    out2 = torch.zeros(2, dtype=torch.float32, device=net.dev)
+    input, output = net.x, net.y
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    numel = sum(a.numel() for a in activities) * world  # (padding entries are zero: they add nothing to the sums)
     if dt0 is None:
         # Hairer / Wanner initial step, as diffrax's PIDController.init does when dt0 is None
-        _, g0 = compute_pc_activity_grad(params, A, output, **kw)
+        A0 = [a.contiguous() for a in activities]
+        _, g0 = compute_pc_activity_grad(params, A0, kw_out, **kw)
         f0 = [-g for g in g0]
-        scale = [ctrl.atol + a.abs() * ctrl.rtol for a in A]
-        d0 = _rms([a / s for a, s in zip(A, scale)])
+        scale = [ctrl.atol + a.abs() * ctrl.rtol for a in A0]
+        d0 = _rms([a / s for a, s in zip(A0, scale)])
         d1 = _rms([f / s for f, s in zip(f0, scale)])
         small = d0 < 1e-5 or d1 < 1e-5
         h0 = 1e-6 if small else 0.01 * d0 / d1
-        y1 = [a + h0 * f for a, f in zip(A, f0)]
-        _, g1 = compute_pc_activity_grad(params, y1, output, **kw)
+        y1 = [a + h0 * f for a, f in zip(A0, f0)]
+        _, g1 = compute_pc_activity_grad(params, y1, kw_out, **kw)
         d2 = _rms([(-gb - f) / s for gb, f, s in zip(g1, f0, scale)]) / h0
         max_d = max(d1, d2)
         h1 = max(1e-6, h0 * 1e-3) if max_d <= 1e-15 else (0.01 / max_d) ** (1.0 / order)
@@ -415,7 +464,7 @@ def _solve_adaptive(params, activities, output, input, loss_id, param_type, solv
         else:
             stats["rejected"] += 1
     solve_inference.last_stats = stats
-    return [a.unsqueeze(0) for a in A]
+    return [a.unsqueeze(0) for a in net.out_acts(A)]
 
 
 def solve_inference(params, activities, output, *, input=None, loss_id="mse", param_type="sp", solver=None,
@@ -448,11 +497,11 @@ def solve_inference(params, activities, output, *, input=None, loss_id="mse", pa
                weight_decay=weight_decay, spectral_penalty=spectral_penalty,
                solver=_solver_id(solver), n_steps=T, dt=h, dt_last=h_last, batch_global=batch_global)
     net.check_acts(activities)
-    A = [a.clone() for a in activities]  # functional API: inputs are never mutated
+    A = net.in_acts(activities, clone=True)  # functional API: inputs are never mutated
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_pc_infer(net.desc, net.W, net.b, _lib.ptr_array(A), _lib.ptr(input), _lib.ptr(output),
+    _lib.check(_lib.lib.jpcb_pc_infer(net.desc, net.W, net.b, _lib.ptr_array(A), _lib.ptr(net.x), _lib.ptr(net.y),
                                       None, _lib.ptr(ws), ws.numel(), net.stream()))
-    return [a.unsqueeze(0) for a in A]
+    return [a.unsqueeze(0) for a in net.out_acts(A)]
 
 
 def update_pc_activities(params, activities, optim, opt_state, output, *, input=None, loss_id="mse", param_type="sp",

@@ -32,9 +32,9 @@ class _Arena:
     256-byte boundaries (the kernels use 16-byte vector stores)."""
 
     def __init__(self, net=None, *, weight_shapes=None, bias_shapes=None, device=None):
-        if net is not None:
-            weight_shapes = [tuple(lin.weight.shape) for lin in net.linears]
-            bias_shapes = [tuple(lin.bias.shape) for lin in net.linears] if net.has_bias else None
+        if net is not None:  # (library-layout shapes: zero-padded feature dims on the bf16 path)
+            weight_shapes = net.w_shapes
+            bias_shapes = net.b_shapes if net.has_bias else None
             device = net.dev
         L = len(weight_shapes)
         shapes = []
@@ -102,38 +102,39 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         if T > 4096:
             raise RuntimeError("The maximum number of solver steps (4096) was reached.")
         net = _Net(model, skip_model, input, output, solver=_solver_id(ode_solver), n_steps=T, dt=h, dt_last=h_last, **common)
-        if tuple(output.shape) != (net.B, net.dims[-1]):
-            raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.dims[-1])}")
+        if tuple(output.shape) != (net.B, net.true_dims[-1]):
+            raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.true_dims[-1])}")
         arena = _Arena(net)
         acts = net.new_acts()
         ws = net.workspace()
         _lib.check(_lib.lib.jpcb_pc_train_step(
-            net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr(output), _lib.ptr_array(acts), _lib.ptr(arena.loss),
+            net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr_array(acts), _lib.ptr(arena.loss),
             _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
             _lib.ptr(ws), ws.numel(), net.stream()))
     elif isinstance(stepsize_controller, PIDController):
         # adaptive steps (the reference's default): init + loss, the controller-driven solve, then energies + gradients
         net = _Net(model, skip_model, input, output, **common)
-        if tuple(output.shape) != (net.B, net.dims[-1]):
-            raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.dims[-1])}")
+        if tuple(output.shape) != (net.B, net.true_dims[-1]):
+            raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.true_dims[-1])}")
         arena = _Arena(net)
         acts0 = net.new_acts()
         ws = net.workspace()
-        _lib.check(_lib.lib.jpcb_pc_ffwd_init(net.desc, net.W, net.b, _lib.ptr(input), _lib.ptr_array(acts0), _lib.ptr(output),
+        _lib.check(_lib.lib.jpcb_pc_ffwd_init(net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr_array(acts0), _lib.ptr(net.y),
                                               _lib.ptr(arena.loss), _lib.ptr(ws), ws.numel(), net.stream()))
-        sol = solve_inference((model, skip_model), acts0, output, input=input, loss_id=loss_id, param_type=param_type,
+        sol = solve_inference((model, skip_model), net.out_acts(acts0), output, input=input, loss_id=loss_id, param_type=param_type,
                               solver=ode_solver, max_t1=max_t1, dt=dt, stepsize_controller=stepsize_controller,
                               weight_decay=weight_decay, spectral_penalty=spectral_penalty, activity_decay=activity_decay,
                               batch_global=input.shape[0] * world)
-        acts = [a[0].contiguous() for a in sol]
+        acts = net.in_acts([a[0].contiguous() for a in sol])
         ws = net.workspace()
-        _lib.check(_lib.lib.jpcb_pc_param_grads(net.desc, net.W, net.b, _lib.ptr_array(acts), _lib.ptr(input), _lib.ptr(output),
+        _lib.check(_lib.lib.jpcb_pc_param_grads(net.desc, net.W, net.b, _lib.ptr_array(acts), _lib.ptr(net.x), _lib.ptr(net.y),
                                                 _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
                                                 _lib.ptr(arena.E), _lib.ptr(ws), ws.numel(), net.stream()))
     else:
         raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
     arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
-    param_grads = _grads_pytree(net, arena.gW, arena.gb)
+    acts = net.out_acts(acts)
+    param_grads = _grads_pytree(net, *net.out_grads(arena.gW, arena.gb))
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)
     g_norms = compute_param_norms(param_grads) if grad_norms else (None, None)
     a_norms = compute_activity_norms(acts) if activity_norms else None

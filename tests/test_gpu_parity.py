@@ -204,12 +204,13 @@ def _fused_step_raw(om, sk, x, y, solver, max_t1, dt, param_type="sp"):
     arena = _Arena(net)
     acts = net.new_acts()
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(gx), _lib.ptr(gy), _lib.ptr_array(acts),
+    _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr_array(acts),
                                            _lib.ptr(arena.loss), _lib.ptr(arena.E), _lib.ptr_array(arena.gW),
                                            _lib.ptr_array(arena.gb) if arena.gb else None, _lib.ptr(ws), ws.numel(),
                                            net.stream()))
     torch.cuda.synchronize()
-    return acts, arena
+    arena.gW, arena.gb = net.out_grads(arena.gW, arena.gb)  # (slices the zero padding of the bf16 path off again)
+    return net.out_acts(acts), arena
 
 
 def _check_fused(om, sk, x, y, solver, max_t1, dt, tol, param_type="sp"):
@@ -553,3 +554,18 @@ def test_tc_gemm_shape_sweep(B, d_in, d_out):
     assert float((out[0].double().cpu() - want).abs().max()) < 2e-5 * max(float(want.abs().max()), 1.0)
     want2 = r(torch.tanh(want)) @ r(W2).T
     assert float((out[1].double().cpu() - want2).abs().max()) < 2e-2 * max(float(want2.abs().max()), 1.0)
+
+
+def test_bf16_path_odd_feature_dims_are_zero_padded():
+    """MNIST-shaped net on the tensor-core path: 10 classes / a 20-wide layer are not multiples of 8; the host
+    mirror zero-pads feature dims and slices every result back (energies, gradients, activities unchanged)."""
+    import jpc_b200 as J
+    J.set_compute_dtype("bf16")
+    om, sk, x, y = _case(784, 260, 4, 10, "tanh", 128, use_bias=True)
+    _check_all(om, sk, x, y, TOLBF)
+    _check_fused(om, sk, x, y, "euler", 5.0, 0.5, TOLBF)
+    _check_fused(om, sk, x, y, "heun", 2.0, 0.5, TOLBF)
+    om, sk, x, y = _case(20, 36, 5, 12, "tanh", 128, skips=True)
+    _check_all(om, sk, x, y, TOLBF)
+    with pytest.raises(NotImplementedError):  # zero-padded logits would enter the softmax
+        J.pc_energy_fn((to_gpu_model(om), None), devs(O.init_activities_with_ffwd(om, x)), dev(y), x=dev(x), loss="ce")
