@@ -212,6 +212,7 @@ def run_bpc(args, w):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     dtype = "f32" if args.bpc_f32 else "bf16"
+    J.set_compute_dtype(dtype)
     gen_l, lab_h, img_h = make_inputs(dict(w, d_in=w["d_in"], d_out=w["d_out"]), seed_w=0)       # top-down: label -> image
     amo_l, _, _ = make_inputs(dict(w, d_in=w["d_out"], d_out=w["d_in"]), seed_w=1)               # amortiser: image -> label
     g = torch.Generator().manual_seed(1)
@@ -225,9 +226,7 @@ def run_bpc(args, w):
     T = n_steps(w)
 
     def step(x_lab, y_img):
-        J.set_compute_dtype("f32")                                # the amortiser sweep has a 10-wide output: fp32 path
         acts = J.init_activities_with_ffwd(amort, y_img)          # (reference order: amortiser sweep, image side first)
-        J.set_compute_dtype(dtype)
         acts = J.solve_bpc_inference(td, bu, acts, y_img, input=x_lab, n_steps=T, dt=w["dt"])
         return J.compute_bpc_param_grads(td, bu, acts, y_img, x=x_lab)
 

@@ -258,8 +258,9 @@ int jpcb::launch_simt(const std::vector<GTask>& tasks, cudaStream_t st) {
     warp_ok = warp_ok && (t.K == 0 || (t.a_sk == 1 && t.b_sk == 1 && t.a_act == ACT_LINEAR && t.b_act == ACT_LINEAR));
   }
   const int sms = num_sms();
-  // fewer 64 x 64 tiles than two per SM: a tiled GEMM cannot fill the machine, the warp-level path can
-  if (warp_ok && t64 < 2LL * sms) return launch_warp(tasks, st);
+  // fewer 64 x 64 tiles than one per SM: a tiled GEMM cannot fill the machine, the warp-level path can
+  static const int warp_q = [] { const char* v = getenv("JPCB_WARP_Q"); return v ? atoi(v) : 4; }();  // threshold in quarter-SMs
+  if (warp_ok && 4 * t64 < (long long)warp_q * sms) return launch_warp(tasks, st);
   if (t128 >= 2LL * sms) return launch_simt_cfg<128, 128, 16, 2, 2>(tasks, st);
   if (t64 >= sms) return launch_simt_cfg<64, 64, 16, 1, 1>(tasks, st);
   return launch_simt_cfg<32, 32, 16, 1, 1>(tasks, st);  // (8x8 threads) latency-bound small layers

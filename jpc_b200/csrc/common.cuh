@@ -194,14 +194,17 @@ __device__ __forceinline__ void unpack_bf16x4(const uint2& t, float (&v)[4]) {
 // epilogue dispatches once per tile so that its inner loop is straight-line code); -1 = read it
 // from the descriptor at run time.
 // ELSRC fixes where GRAD takes e_l from: 0 = Elb (packed bf16), 1 = z - P (hoisted prediction), -1 = run time.
-template <int MODE = -1, int ELSRC = -1>
+// PLAIN == 2 (ELSRC == 0 only): the partial-gradient input Gin is part of the task and is loaded here into p.b.
+template <int MODE = -1, int ELSRC = -1, int PLAIN = 0>
 __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int nvalid, bool vec, EpiPre& p) {
   const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
   const int mode = MODE >= 0 ? MODE : e.mode;
   if (mode == EPI_GRAD) {
     ld4(e.Z, idx, nvalid, vec, p.a);
-    if (ELSRC == 0) p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
-    else if (ELSRC == 1) ld4(e.P, idx, nvalid, vec, p.b);
+    if (ELSRC == 0) {
+      p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
+      if (PLAIN == 2) ld4(e.Gin, idx, nvalid, vec, p.b);
+    } else if (ELSRC == 1) ld4(e.P, idx, nvalid, vec, p.b);
     else if (e.El || !e.Elb) ld4(e.El ? e.El : e.P, idx, nvalid, vec, p.b);
     else if (vec) p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
     else ld4(e.Elb, idx, nvalid, false, p.b);
@@ -217,9 +220,10 @@ __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int 
 // `nvalid` (1..4) columns are inside the matrix; `vec` says 16-byte vector access is legal
 // (N % 4 == 0 and nvalid == 4).  Returns this thread's contribution to the reduction (`red`).
 // `have_bias4`: the caller already holds the 4 bias values of columns col..col+3 in `bias4`.
-// PLAIN: the task has no skip term, no bias, no partial-gradient input, unit weights (gscale = escale = 1)
-// and no activity decay -- the common case, checked on the host -- so those branches compile away.
-template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1, int ELSRC = -1, bool PLAIN = false>
+// PLAIN >= 1: the task has no skip term, no bias, unit output-energy weight and no activity decay -- the common
+// case, checked on the host -- so those branches compile away; PLAIN == 1: no partial-gradient input either;
+// PLAIN == 2: a partial-gradient input Gin, already loaded by epi_preload (bPC: the other direction's half).
+template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1, int ELSRC = -1, int PLAIN = 0>
 __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec,
                                             const EpiPre& p, bool have_bias4, const float (&bias4)[4]) {
   const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
@@ -306,6 +310,13 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
   if (!PLAIN) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) g[j] = e.gscale * g[j] + e.ad * z[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] *= e.gscale;
+  }
+  if (PLAIN == 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] += p.b[j];
   }
   if (!PLAIN && e.Gin) {
     float gi[4];

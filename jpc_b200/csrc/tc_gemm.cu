@@ -38,7 +38,7 @@ int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   return JPCB_OK;
 }
 
-template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN, bool MNMAJ = false>
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false>
 int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   using Cfg = TcCfg<CG>;
   static bool attr_set = false;
@@ -75,30 +75,41 @@ int variant_key(const GTask& t) {
   const Epi& e = t.e;
   if (t.mn_major) return 11;  // (only the weight-gradient SCALE tasks use MN-major operands)
   if (tc_flags() & 4) return 0;
-  const bool plain = e.skip == 0.f && e.bias == nullptr && e.Gin == nullptr && e.gscale == 1.f && e.escale == 1.f && e.ad == 0.f;
+  const bool noextra = e.skip == 0.f && e.bias == nullptr && e.escale == 1.f && e.ad == 0.f;
+  const bool plain = noextra && e.Gin == nullptr && e.gscale == 1.f;
   if (e.mode == EPI_ERR) return plain ? 1 : 7;
   if (e.mode == EPI_SCALE) return 2;
-  if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && plain && (e.act == ACT_TANH || e.act == ACT_RELU) && !e.El && (e.Elb || e.P))
+  const bool act_ok = e.act == ACT_TANH || e.act == ACT_RELU;
+  if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && plain && act_ok && !e.El && (e.Elb || e.P))
     return 3 + (e.act == ACT_RELU ? 2 : 0) + (e.Elb ? 0 : 1);
-  if (e.mode == EPI_FFWD && (e.act == ACT_TANH || e.act == ACT_RELU || e.act == ACT_LINEAR)) return e.act == ACT_TANH ? 8 : (e.act == ACT_RELU ? 9 : 10);
+  // bPC: forward-direction half (GRAD_OUT into scratch) and backward-direction half + combination (Gin) + Euler update
+  if (e.mode == EPI_GRAD && noextra && act_ok && !e.El && e.Elb) {
+    if (e.sub == GRAD_OUT && e.Gin == nullptr) return e.act == ACT_TANH ? 12 : 13;
+    if (e.sub == GRAD_EULER && e.Gin != nullptr) return e.act == ACT_TANH ? 14 : 15;
+  }
+  if (e.mode == EPI_FFWD && (act_ok || e.act == ACT_LINEAR)) return e.act == ACT_TANH ? 8 : (e.act == ACT_RELU ? 9 : 10);
   return 0;
 }
 
 template <int CG>
 int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
   switch (key) {
-    case 1: return launch_variant<CG, EPI_ERR, 0, 0, -1, true>(g, grid, st);
-    case 7: return launch_variant<CG, EPI_ERR, 0, 0, -1, false>(g, grid, st);
-    case 2: return launch_variant<CG, EPI_SCALE, 0, 0, -1, false>(g, grid, st);
-    case 3: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, true>(g, grid, st);
-    case 4: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 1, true>(g, grid, st);
-    case 5: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, true>(g, grid, st);
-    case 6: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 1, true>(g, grid, st);
-    case 8: return launch_variant<CG, EPI_FFWD, 0, ACT_TANH, -1, false>(g, grid, st);
-    case 9: return launch_variant<CG, EPI_FFWD, 0, ACT_RELU, -1, false>(g, grid, st);
-    case 10: return launch_variant<CG, EPI_FFWD, 0, ACT_LINEAR, -1, false>(g, grid, st);
-    case 11: return launch_variant<CG, EPI_SCALE, 0, 0, -1, false, true>(g, grid, st);
-    default: return launch_variant<CG, -1, -1, -1, -1, false>(g, grid, st);
+    case 1: return launch_variant<CG, EPI_ERR, 0, 0, -1, 1>(g, grid, st);
+    case 7: return launch_variant<CG, EPI_ERR, 0, 0, -1, 0>(g, grid, st);
+    case 2: return launch_variant<CG, EPI_SCALE, 0, 0, -1, 0>(g, grid, st);
+    case 3: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, 1>(g, grid, st);
+    case 4: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 1, 1>(g, grid, st);
+    case 5: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 1>(g, grid, st);
+    case 6: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 1, 1>(g, grid, st);
+    case 8: return launch_variant<CG, EPI_FFWD, 0, ACT_TANH, -1, 0>(g, grid, st);
+    case 9: return launch_variant<CG, EPI_FFWD, 0, ACT_RELU, -1, 0>(g, grid, st);
+    case 10: return launch_variant<CG, EPI_FFWD, 0, ACT_LINEAR, -1, 0>(g, grid, st);
+    case 11: return launch_variant<CG, EPI_SCALE, 0, 0, -1, 0, true>(g, grid, st);
+    case 12: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_TANH, 0, 1>(g, grid, st);
+    case 13: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_RELU, 0, 1>(g, grid, st);
+    case 14: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, 2>(g, grid, st);
+    case 15: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 2>(g, grid, st);
+    default: return launch_variant<CG, -1, -1, -1, -1, 0>(g, grid, st);
   }
 }
 

@@ -282,12 +282,12 @@ __device__ __forceinline__ int tc_find_task(const TcGroup& g, int tile) {
 // row); (3) transpose it through XOR-swizzled shared memory into the same coalesced layout;
 // (4) finish + store.  MODE/SUB/ACT are compile-time so that (4) is straight-line code
 // (-1 = generic: read from the descriptor).
-template <int MODE, int ELSRC>
+template <int MODE, int ELSRC, int PLAIN>
 __device__ __forceinline__ void tc_epi_loads(const Epi& e, int row0, int cb, int lane, EpiPre (&pre)[4], float (&bias4)[4]) {
   const int c4 = lane & 3, rq = lane >> 2;
   const int colc = min(cb + 4 * c4, e.N - 4);  // N % 8 == 0 on this path
 #pragma unroll
-  for (int i = 0; i < 4; ++i) epi_preload<MODE, ELSRC>(e, min(row0 + rq + 8 * i, e.M - 1), colc, 4, true, pre[i]);
+  for (int i = 0; i < 4; ++i) epi_preload<MODE, ELSRC, PLAIN>(e, min(row0 + rq + 8 * i, e.M - 1), colc, 4, true, pre[i]);
   if (MODE == EPI_FFWD || MODE == EPI_ERR || MODE < 0) {
     if (e.bias != nullptr) {
       const float4 bv = *reinterpret_cast<const float4*>(e.bias + colc);
@@ -296,7 +296,7 @@ __device__ __forceinline__ void tc_epi_loads(const Epi& e, int row0, int cb, int
   }
 }
 
-template <int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
+template <int MODE, int SUB, int ACT, int ELSRC, int PLAIN>
 __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, int lane, uint32_t taddr, float* xp,
                                               const EpiPre (&pre)[4], const float (&bias4)[4]) {
   const int c4 = lane & 3, rq = lane >> 2;
@@ -331,40 +331,40 @@ __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, in
 #ifndef JPCB_TC_EPI_DEPTH
 #define JPCB_TC_EPI_DEPTH 3
 #endif
-template <int MODE, int SUB, int ACT, int ELSRC, bool PLAIN>
+template <int MODE, int SUB, int ACT, int ELSRC, int PLAIN>
 __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
                                              uint32_t tphase) {
   float r = 0.f;
-  constexpr int DEPTH = (PLAIN && JPCB_TC_EPI_DEPTH == 3) ? 3 : 2;
+  constexpr int DEPTH = (PLAIN == 1 && JPCB_TC_EPI_DEPTH == 3) ? 3 : 2;
   if constexpr (DEPTH == 3) {
     EpiPre pre[3][4];
     float bias[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pre[0], bias[0]);
-    tc_epi_loads<MODE, ELSRC>(e, row0, col0 + 16, lane, pre[1], bias[1]);
+    tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, col0, lane, pre[0], bias[0]);
+    tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, col0 + 16, lane, pre[1], bias[1]);
     mbar_wait(tfull, tphase);  // accumulator of this tile complete
     tc_fence_after();
 #pragma unroll
     for (int ch = 0; ch < TC_EPI_PATCHES; ++ch) {
       const int cb = col0 + ch * 16;  // first column of this 16-wide patch
       if (cb < e.N) {                 // warp-uniform
-        if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC>(e, row0, cb + 32, lane, pre[(ch + 2) % 3], bias[(ch + 2) % 3]);
+        if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pre[(ch + 2) % 3], bias[(ch + 2) % 3]);
         r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pre[ch % 3], bias[ch % 3]);
       }
     }
   } else {
     EpiPre pa[4], pb[4];
     float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-    tc_epi_loads<MODE, ELSRC>(e, row0, col0, lane, pa, ba);
+    tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, col0, lane, pa, ba);
     mbar_wait(tfull, tphase);  // accumulator of this tile complete
     tc_fence_after();
 #pragma unroll 1
     for (int ch = 0; ch < TC_EPI_PATCHES; ch += 2) {
       const int cb = col0 + ch * 16;  // first column of this 16-wide patch
       if (cb >= e.N) break;           // warp-uniform
-      tc_epi_loads<MODE, ELSRC>(e, row0, cb + 16, lane, pb, bb);
+      tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 16, lane, pb, bb);
       r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
       if (cb + 16 >= e.N) break;
-      if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC>(e, row0, cb + 32, lane, pa, ba);
+      if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pa, ba);
       r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
     }
   }
@@ -374,10 +374,10 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
 // ---------------------------------------------------------------------------------------------
 // MODE/SUB/ACT/ELSRC >= 0: every task of the launch has that epilogue mode / GRAD sub-mode /
 // activation / e_l source (the host checks), compiled in; -1 = generic descriptor-driven epilogue.
-// PLAIN: no task of the launch has a skip term, bias, partial-gradient input, non-unit weight or decay.
+// PLAIN (1 / 2): no task of the launch has a skip term, bias or decay (2: each has a partial-gradient input).
 // MNMAJ: both operands are read MN-major, i.e. D = A^T B with A [K, M] and B [K, N] row-major in HBM
 // (weight gradients e^T phi(z), K = batch) -- no transposed operand copies are ever materialised.
-template <int CG, int MODE, int SUB, int ACT, int ELSRC, bool PLAIN, bool MNMAJ = false>
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
   using Cfg = TcCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
