@@ -20,6 +20,7 @@ from ._core import (
 from ._bpc import (bpc_energy_fn, compute_bpc_activity_grad, compute_bpc_param_grads, solve_bpc_inference,
                    update_bpc_activities, update_bpc_params)
 from ._errors import _check_param_type
+from ._eval import test_discriminative_pc
 from ._train import make_pc_step
 from ._utils import (compute_accuracy, compute_activity_norms, compute_param_norms, cross_entropy_loss,
                      mse_loss)
