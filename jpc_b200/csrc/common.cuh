@@ -131,7 +131,9 @@ __device__ __forceinline__ Epi epi_pin(const Epi& src) {
 
 __device__ __forceinline__ void ld4(const float* __restrict__ p, uint32_t idx, int nvalid, bool vec, float (&v)[4]) {
   if (vec) {
-    float4 t = *reinterpret_cast<const float4*>(p + idx);
+    // __ldcg / __stcg: explicit GLOBAL-space accesses (the descriptor pointers lose their address space in
+    // epi_pin, and generic LD/ST cost extra descriptor moves), cached at L2 only -- these are streaming tensors
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p + idx));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   } else {
 #pragma unroll
@@ -140,7 +142,7 @@ __device__ __forceinline__ void ld4(const float* __restrict__ p, uint32_t idx, i
 }
 __device__ __forceinline__ void ld4(const __nv_bfloat16* __restrict__ p, uint32_t idx, int nvalid, bool vec, float (&v)[4]) {
   if (vec) {
-    uint2 t = *reinterpret_cast<const uint2*>(p + idx);
+    uint2 t = __ldcg(reinterpret_cast<const uint2*>(p + idx));
     __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
     __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
     v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
@@ -151,7 +153,7 @@ __device__ __forceinline__ void ld4(const __nv_bfloat16* __restrict__ p, uint32_
 }
 __device__ __forceinline__ void st4(float* __restrict__ p, uint32_t idx, int nvalid, bool vec, const float (&v)[4]) {
   if (vec) {
-    *reinterpret_cast<float4*>(p + idx) = make_float4(v[0], v[1], v[2], v[3]);
+    __stcg(reinterpret_cast<float4*>(p + idx), make_float4(v[0], v[1], v[2], v[3]));
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) if (j < nvalid) p[idx + j] = v[j];
@@ -164,7 +166,7 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, uint32_t idx,
     uint2 t;
     t.x = *reinterpret_cast<uint32_t*>(&a);
     t.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p + idx) = t;
+    __stcg(reinterpret_cast<uint2*>(p + idx), t);
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) if (j < nvalid) p[idx + j] = __float2bfloat16_rn(v[j]);
@@ -202,11 +204,11 @@ __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int 
   if (mode == EPI_GRAD) {
     ld4(e.Z, idx, nvalid, vec, p.a);
     if (ELSRC == 0) {
-      p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
+      p.h = __ldcg(reinterpret_cast<const uint2*>(e.Elb + idx));
       if (PLAIN == 2) ld4(e.Gin, idx, nvalid, vec, p.b);
     } else if (ELSRC == 1) ld4(e.P, idx, nvalid, vec, p.b);
     else if (e.El || !e.Elb) ld4(e.El ? e.El : e.P, idx, nvalid, vec, p.b);
-    else if (vec) p.h = *reinterpret_cast<const uint2*>(e.Elb + idx);
+    else if (vec) p.h = __ldcg(reinterpret_cast<const uint2*>(e.Elb + idx));
     else ld4(e.Elb, idx, nvalid, false, p.b);
   } else if (mode == EPI_ERR) {
     ld4(e.T, idx, nvalid, vec, p.a);  // (the skip input U, rare, is read in epi_finish)
@@ -227,6 +229,7 @@ template <bool FAST, int MODE = -1, int SUB = -1, int ACT = -1, int ELSRC = -1, 
 __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, const float (&acc)[4], int nvalid, bool vec,
                                             const EpiPre& p, bool have_bias4, const float (&bias4)[4]) {
   const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
+  static_assert(PLAIN == 0 || MODE != EPI_GRAD || SUB == GRAD_EULER || SUB == GRAD_OUT, "plain GRAD variants exist for OUT / EULER only");
   const int mode = MODE >= 0 ? MODE : e.mode;
   const int sub = SUB >= 0 ? SUB : e.sub;
   const int act = ACT >= 0 ? ACT : e.act;
@@ -242,8 +245,12 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     float pred[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float bj = PLAIN ? 0.f : (have_bias4 ? bias4[j] : ((e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f));
-      pred[j] = e.alpha * (acc[j] + bj);
+      if (PLAIN) {
+        pred[j] = e.alpha * acc[j];
+      } else {
+        float bj = have_bias4 ? bias4[j] : ((e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f);
+        pred[j] = e.alpha * (acc[j] + bj);
+      }
     }
     if (!PLAIN && e.skip != 0.f) {
       float u[4];
@@ -268,14 +275,17 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float d = j < nvalid ? p.a[j] - pred[j] : 0.f;
-      const float es = PLAIN ? 1.f : e.escale;
-      r += 0.5f * es * d * d;
-      out[j] = es * d;
+      const float d = j < nvalid ? p.a[j] - pred[j] : 0.f;
+      out[j] = PLAIN ? d : e.escale * d;
     }
     if (e.O) st4(e.O, idx, nvalid, vec, out);
     if (e.Ob) st4(e.Ob, idx, nvalid, vec, out);
-    return e.red ? r : 0.f;
+    if (e.red) {  // layer energy (lam/2) sum d^2 -- only the launches that report energies pay for it
+      const float half = PLAIN ? 0.5f : (e.escale != 0.f ? 0.5f / e.escale : 0.f);  // out = lam d  =>  lam/2 d^2 = out^2 / (2 lam)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r += half * out[j] * out[j];
+    }
+    return r;
   }
   // ---- EPI_GRAD ----
   float el[4], g[4];
@@ -310,29 +320,24 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
   if (!PLAIN) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) g[j] = e.gscale * g[j] + e.ad * z[j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) g[j] *= e.gscale;
   }
-  if (PLAIN == 2) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) g[j] += p.b[j];
-  }
+  // PLAIN: the weight gscale is folded into the coefficient of g below (cg); PLAIN == 2 adds the other half Gin
   if (!PLAIN && e.Gin) {
     float gi[4];
     ld4(e.Gin, idx, nvalid, vec, gi);
 #pragma unroll
     for (int j = 0; j < 4; ++j) g[j] += gi[j];
   }
+  const float cg = PLAIN ? e.c * e.gscale : e.c;  // (uniform: hoisted out of the patch loop)
   if (sub == GRAD_OUT) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = e.c * g[j];
+    for (int j = 0; j < 4; ++j) out[j] = PLAIN == 2 ? fmaf(cg, g[j], e.c * p.b[j]) : cg * g[j];
     st4(e.O, idx, nvalid, vec, out);
     return 0.f;
   }
   if (sub == GRAD_EULER) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = z[j] - e.c * g[j];
+    for (int j = 0; j < 4; ++j) out[j] = PLAIN == 2 ? fmaf(-cg, g[j], fmaf(-e.c, p.b[j], z[j])) : fmaf(-cg, g[j], z[j]);
   } else if (sub == GRAD_HEUN1) {
     st4(e.G1, idx, nvalid, vec, g);
 #pragma unroll
