@@ -193,6 +193,25 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
                          float* const* gV, float* const* gbV, float* E_pairs, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ---- parameter update ----------------------------------------------------------
+ * The last two lines of the reference's train step, `optim.update(updates=param_grads, state, params)`
+ * followed by `eqx.apply_updates` (jpc/_train.py:234-242; jpc/_core/_updates.py:189-194), for the two
+ * optimisers its examples use.  optax is a third-party dependency (pins: SURVEY 8c); restated:
+ *   optax.sgd(lr):                p' = p - lr g
+ *   optax.adam(lr, b1, b2, eps):  mu' = b1 mu + (1-b1) g;  nu' = b2 nu + (1-b2) g^2;
+ *                                 p' = p - lr (mu'/(1-b1^t)) / (sqrt(nu'/(1-b2^t)) + eps),  t = step >= 1
+ * One pass over `n_tensors` device tensors of `numel[i]` floats each (pointer tables are HOST arrays of
+ * device pointers).  Hyper-parameters are doubles: 1-b, 1-b^t are formed in double and rounded once to fp32,
+ * as optax does with Python floats.  Outputs may alias their inputs (in place) or be fresh buffers (the reference's
+ * functional convention). */
+int jpcb_optim_sgd(int n_tensors, const long long* numel, const float* const* params,
+                   const float* const* grads, double learning_rate, float* const* params_out,
+                   void* stream);
+int jpcb_optim_adam(int n_tensors, const long long* numel, const float* const* params,
+                    const float* const* grads, const float* const* mu, const float* const* nu,
+                    double learning_rate, double b1, double b2, double eps, int step,
+                    float* const* params_out, float* const* mu_out, float* const* nu_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,8 +22,8 @@ from ._bpc import (bpc_energy_fn, compute_bpc_activity_grad, compute_bpc_param_g
 from ._errors import _check_param_type
 from ._eval import test_discriminative_pc
 from ._train import make_pc_step
-from ._utils import (compute_accuracy, compute_activity_norms, compute_param_norms, cross_entropy_loss,
-                     mse_loss)
+from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,
+                     cross_entropy_loss, get_t_max, mse_loss)
 from .nn import get_act_fn, make_mlp, make_skip_model
 from .solvers import ConstantStepSize, Euler, Heun, PIDController
 from . import nn, optim  # noqa: F401

@@ -20,7 +20,7 @@ from . import _core
 from ._core import _layer_parts, _skip_flags, _WS_CACHE
 from ._errors import _check_param_type
 from .nn import tree_unflatten_like
-from .optim import apply_updates
+from .optim import update_and_apply
 
 
 class _BpcNet:
@@ -226,8 +226,7 @@ def update_bpc_activities(top_down_model, bottom_up_model, activities, optim, op
                                               skip_model=skip_model, param_type=param_type,
                                               backward_energy_weight=backward_energy_weight,
                                               forward_energy_weight=forward_energy_weight)
-    updates, opt_state = optim.update(grads, opt_state, activities)
-    activities = apply_updates(activities, updates)
+    activities, opt_state = update_and_apply(optim, grads, opt_state, activities)
     return {"energy": energy, "activities": activities, "grads": grads, "opt_state": opt_state}
 
 
@@ -238,10 +237,8 @@ def update_bpc_params(top_down_model, bottom_up_model, activities, top_down_opti
     td_g, bu_g = compute_bpc_param_grads(top_down_model, bottom_up_model, activities, output, x=input, skip_model=skip_model,
                                          param_type=param_type, backward_energy_weight=backward_energy_weight,
                                          forward_energy_weight=forward_energy_weight)
-    td_u, top_down_opt_state = top_down_optim.update(td_g, top_down_opt_state, top_down_model)
-    bu_u, bottom_up_opt_state = bottom_up_optim.update(bu_g, bottom_up_opt_state, bottom_up_model)
-    top_down_model = apply_updates(top_down_model, td_u)
-    bottom_up_model = apply_updates(bottom_up_model, bu_u)
+    top_down_model, top_down_opt_state = update_and_apply(top_down_optim, td_g, top_down_opt_state, top_down_model)
+    bottom_up_model, bottom_up_opt_state = update_and_apply(bottom_up_optim, bu_g, bottom_up_opt_state, bottom_up_model)
     return {"models": (top_down_model, bottom_up_model), "grads": (td_g, bu_g),
             "opt_states": (top_down_opt_state, bottom_up_opt_state)}
 

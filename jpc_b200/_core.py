@@ -26,7 +26,7 @@ import torch
 from . import _lib
 from ._errors import _check_param_type
 from .nn import Identity, Lambda, Linear, Sequential, tree_unflatten_like
-from .optim import apply_updates
+from .optim import update_and_apply
 from .solvers import ConstantStepSize, Euler, Heun, PIDController
 
 # ---------------------------------------------------------------------------------------------
@@ -213,6 +213,12 @@ class _Net:
     def stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
+    def with_steps(self, n_steps, dt, dt_last):
+        """A copy of the descriptor with another fixed-step schedule (same shapes, same workspace size)."""
+        d = _lib.PcDesc.from_buffer_copy(self.desc)
+        d.n_steps, d.dt, d.dt_last = int(n_steps), float(dt), float(dt_last)
+        return d
+
     def check_acts(self, activities):
         if len(activities) != self.L:
             raise ValueError(f"expected {self.L} activity arrays (one per layer, last = dummy output slot), got {len(activities)}")
@@ -391,8 +397,63 @@ def _rms(tensors) -> float:
     return math.sqrt(tot / n)
 
 
+class _SaveAt:
+    """The `SaveAt` of jpc/_core/_infer.py:103-107, restated (diffrax is third-party, recalled: SURVEY App. B).
+    * neither flag: `SaveAt(t1=True)` -> one row, the final state: leaves (1, B, d).
+    * `record_iters`: `SaveAt(t1=True, steps=True)` -> one row per accepted step, leaves (4096, B, d) padded with
+      inf after the last step (diffrax `max_steps`; the final state is the last finite row, `get_t_max`).
+    * `record_every`: `SaveAt(t1=True, ts=arange(0, max_t1, record_every))` -> one row per requested time, taken
+      by linear interpolation inside the accepted step that contains it (diffrax LocalLinearInterpolation, the
+      dense output of both Euler and Heun), inf where the solve stopped early, then one row with the final state.
+    Rows are device copies of the activity buffers made between C-ABI calls: bookkeeping, no arithmetic other
+    than the interpolation `torch.lerp`."""
+
+    def __init__(self, net, max_t1, record_iters, record_every):
+        self.net = net
+        self.ts = None
+        if record_every is not None:
+            self.ts = torch.arange(0, max_t1, record_every).tolist()
+            rows = len(self.ts) + 1
+        elif record_iters:
+            rows = MAX_STEPS
+        else:
+            rows = 1
+        self.steps = bool(record_iters) and self.ts is None
+        self.ys = [torch.full((rows, net.B, net.true_dims[l + 1]), float("inf"), dtype=torch.float32, device=net.dev)
+                   for l in range(net.L)]
+        self.i = 0
+
+    @property
+    def needs_prev(self):
+        return self.ts is not None
+
+    def _put(self, row, bufs, prev=None, w=None):
+        for l, y in enumerate(self.ys):
+            d = self.net.true_dims[l + 1]
+            if prev is None:
+                y[row].copy_(bufs[l][:, :d])
+            else:
+                torch.lerp(prev[l][:, :d], bufs[l][:, :d], w, out=y[row])
+
+    def step(self, t0, prev, t1, cur):
+        """One accepted step from (t0, prev) to (t1, cur); buffers in the library's (possibly padded) layout."""
+        if self.ts is not None:
+            while self.i < len(self.ts) and self.ts[self.i] <= t1:
+                self._put(self.i, cur, prev, (self.ts[self.i] - t0) / (t1 - t0))
+                self.i += 1
+        elif self.steps:
+            self._put(self.i, cur)
+            self.i += 1
+
+    def finish(self, cur):
+        if not self.steps:
+            self._put(-1, cur)
+        return self.ys
+
+
 def _solve_adaptive(params, activities, output, input, loss_id, param_type, solver, max_t1, dt0, ctrl, weight_decay,
-                    spectral_penalty, activity_decay, gamma, output_energy_scaling, batch_global=None):
+                    spectral_penalty, activity_decay, gamma, output_energy_scaling, batch_global=None, record_iters=False,
+                    record_every=None):
     """solve_inference with diffrax.Heun + PIDController (the reference's default, jpc/_core/_infer.py:28-33):
     every trial step (two gradient evaluations, candidate state, embedded-error and activity sums of squares) is
     one C-ABI call; accept/reject and the next step size are the controller's scalar arithmetic on the host
@@ -441,6 +502,7 @@ def _solve_adaptive(params, activities, output, input, loss_id, param_type, solv
         dt = float(dt0)
     t, steps, state = 0.0, 0, ctrl.init_state()
     stats = {"accepted": 0, "rejected": 0, "event": False}
+    save = _SaveAt(net, max_t1, record_iters, record_every)
     while t < t1:
         if steps >= MAX_STEPS:
             raise RuntimeError("The maximum number of solver steps was reached. Try increasing `max_steps`.")
@@ -454,8 +516,9 @@ def _solve_adaptive(params, activities, output, input, loss_id, param_type, solv
         keep, dt, state = ctrl.adapt(h, math.sqrt(err_ss / numel), order, state)
         steps += 1
         if keep:
-            t = t1 if t1 - (t + h) < 1e-6 * max(1.0, t1) else t + h
+            t_prev, t = t, (t1 if t1 - (t + h) < 1e-6 * max(1.0, t1) else t + h)
             A, B_ = B_, A
+            save.step(t_prev, B_, t, A)
             stats["accepted"] += 1
             rms = math.sqrt(act_ss / numel)
             if rms < ctrl.atol + ctrl.rtol * rms:  # steady_state_event_with_timeout
@@ -464,7 +527,7 @@ def _solve_adaptive(params, activities, output, input, loss_id, param_type, solv
         else:
             stats["rejected"] += 1
     solve_inference.last_stats = stats
-    return [a.unsqueeze(0) for a in net.out_acts(A)]
+    return save.finish(A)
 
 
 def solve_inference(params, activities, output, *, input=None, loss_id="mse", param_type="sp", solver=None,
@@ -475,19 +538,17 @@ def solve_inference(params, activities, output, *, input=None, loss_id="mse", pa
     device without returning to the host (the reference's steady-state Event, `_infer.py:136-145`, tests the
     RMS of the ACTIVITIES against ~1e-3 and never fires on real activities; it is not checked inside the fused
     loop).  PIDController (the default): controller-driven trial steps, see `_solve_adaptive`.  Returns leaves
-    with the reference's leading time axis (1, B, d) (SaveAt(t1=True)).  `batch_global` (not in the reference
+    with the reference's leading time axis: (1, B, d) by default (SaveAt(t1=True)), (4096, B, d) inf-padded with
+    `record_iters`, (len(ts) + 1, B, d) with `record_every` (see `_SaveAt`).  `batch_global` (not in the reference
     signature) is the 1/B of the energy when `activities` is one rank's shard of a data-parallel batch."""
     solver = Heun() if solver is None else solver
     stepsize_controller = PIDController(rtol=1e-3, atol=1e-3) if stepsize_controller is None else stepsize_controller
     if isinstance(stepsize_controller, PIDController):
-        if record_iters or record_every is not None:
-            raise NotImplementedError("record_iters / record_every are not on the B200 path yet")
         return _solve_adaptive(params, activities, output, input, loss_id, param_type, solver, max_t1, dt, stepsize_controller,
-                               weight_decay, spectral_penalty, activity_decay, gamma, output_energy_scaling, batch_global)
+                               weight_decay, spectral_penalty, activity_decay, gamma, output_energy_scaling, batch_global,
+                               record_iters, record_every)
     if not isinstance(stepsize_controller, ConstantStepSize):
         raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
-    if record_iters or record_every is not None:
-        raise NotImplementedError("record_iters / record_every are not on the B200 path yet")
     model, skip_model = _unpack_params(params)
     T, h, h_last = _time_grid(max_t1, dt)
     if T > 4096:
@@ -499,9 +560,23 @@ def solve_inference(params, activities, output, *, input=None, loss_id="mse", pa
     net.check_acts(activities)
     A = net.in_acts(activities, clone=True)  # functional API: inputs are never mutated
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_pc_infer(net.desc, net.W, net.b, _lib.ptr_array(A), _lib.ptr(net.x), _lib.ptr(net.y),
-                                      None, _lib.ptr(ws), ws.numel(), net.stream()))
-    return [a.unsqueeze(0) for a in net.out_acts(A)]
+    if not record_iters and record_every is None:
+        _lib.check(_lib.lib.jpcb_pc_infer(net.desc, net.W, net.b, _lib.ptr_array(A), _lib.ptr(net.x), _lib.ptr(net.y),
+                                          None, _lib.ptr(ws), ws.numel(), net.stream()))
+        return [a.unsqueeze(0) for a in net.out_acts(A)]
+    # recording: the same entry point, one solver step per call, rows copied out in between (`_SaveAt`)
+    save = _SaveAt(net, max_t1, record_iters, record_every)
+    one, last = net.with_steps(1, h, h), net.with_steps(1, h_last, h_last)
+    prev = [torch.empty_like(a) for a in A] if save.needs_prev else None
+    for i in range(T):
+        if prev is not None:
+            for p_, a in zip(prev, A):
+                p_.copy_(a)
+        d = last if i == T - 1 else one
+        _lib.check(_lib.lib.jpcb_pc_infer(d, net.W, net.b, _lib.ptr_array(A), _lib.ptr(net.x), _lib.ptr(net.y),
+                                          None, _lib.ptr(ws), ws.numel(), net.stream()))
+        save.step(i * h, prev, float(max_t1) if i == T - 1 else (i + 1) * h, A)
+    return save.finish(A)
 
 
 def update_pc_activities(params, activities, optim, opt_state, output, *, input=None, loss_id="mse", param_type="sp",
@@ -512,8 +587,7 @@ def update_pc_activities(params, activities, optim, opt_state, output, *, input=
                                              weight_decay=weight_decay, spectral_penalty=spectral_penalty,
                                              activity_decay=activity_decay, gamma=gamma,
                                              output_energy_scaling=output_energy_scaling)
-    updates, opt_state = optim.update(grads, opt_state, activities)
-    activities = apply_updates(activities, updates)
+    activities, opt_state = update_and_apply(optim, grads, opt_state, activities)
     return {"energy": energy, "activities": activities, "grads": grads, "opt_state": opt_state}
 
 
@@ -524,6 +598,5 @@ def update_pc_params(params, activities, optim, opt_state, output, *, input=None
                                    weight_decay=weight_decay, spectral_penalty=spectral_penalty,
                                    activity_decay=activity_decay, gamma=gamma,
                                    output_energy_scaling=output_energy_scaling)
-    updates, opt_state = optim.update(grads, opt_state, tuple(params))
-    model, skip_model = apply_updates(tuple(params), updates)
+    (model, skip_model), opt_state = update_and_apply(optim, grads, opt_state, tuple(params))
     return {"model": model, "skip_model": skip_model, "grads": grads, "opt_state": opt_state}

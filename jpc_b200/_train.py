@@ -13,8 +13,9 @@ import torch
 from . import _lib
 from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_with_ffwd, solve_inference)
 from ._errors import _check_param_type
-from ._utils import compute_accuracy, compute_activity_norms, compute_param_norms
-from .optim import apply_updates
+from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,
+                     get_t_max)
+from .optim import update_and_apply
 from .solvers import ConstantStepSize, Heun, PIDController
 
 
@@ -89,14 +90,18 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         """)
     if loss_id not in ("mse", "ce"):
         raise ValueError("`mse` and `ce` are the only valid losses.")
-    if record_activities or record_energies or record_every is not None:
-        raise NotImplementedError("record_activities / record_energies / record_every are not on the B200 path yet")
+    if record_energies:
+        record_activities = True
+    recording = record_activities or record_every is not None
     ode_solver = Heun() if ode_solver is None else ode_solver
     stepsize_controller = PIDController(rtol=1e-3, atol=1e-3) if stepsize_controller is None else stepsize_controller
     world = _world()
+    if recording and world > 1:
+        raise NotImplementedError("recorded trajectories are per-process: not available under data parallelism")
     common = dict(param_type=param_type, loss_id=loss_id, gamma=None, output_energy_scaling=None, activity_decay=activity_decay,
                   weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=input.shape[0] * world)
-    if isinstance(stepsize_controller, ConstantStepSize):
+    t_max, sol, rec_energies = 0, None, None
+    if isinstance(stepsize_controller, ConstantStepSize) and not recording:
         # fixed steps: the whole step up to the optimiser is ONE C-ABI call
         T, h, h_last = _time_grid(max_t1, dt)
         if T > 4096:
@@ -111,8 +116,9 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
             net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr_array(acts), _lib.ptr(arena.loss),
             _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
             _lib.ptr(ws), ws.numel(), net.stream()))
-    elif isinstance(stepsize_controller, PIDController):
-        # adaptive steps (the reference's default): init + loss, the controller-driven solve, then energies + gradients
+    elif isinstance(stepsize_controller, (PIDController, ConstantStepSize)):
+        # adaptive steps (the reference's default) or a recorded trajectory: init + loss, the solve (controller-driven
+        # trial steps / one step per call when rows are saved), then energies + gradients at the selected row
         net = _Net(model, skip_model, input, output, **common)
         if tuple(output.shape) != (net.B, net.true_dims[-1]):
             raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.true_dims[-1])}")
@@ -124,8 +130,16 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         sol = solve_inference((model, skip_model), net.out_acts(acts0), output, input=input, loss_id=loss_id, param_type=param_type,
                               solver=ode_solver, max_t1=max_t1, dt=dt, stepsize_controller=stepsize_controller,
                               weight_decay=weight_decay, spectral_penalty=spectral_penalty, activity_decay=activity_decay,
-                              batch_global=input.shape[0] * world)
-        acts = net.in_acts([a[0].contiguous() for a in sol])
+                              batch_global=input.shape[0] * world, record_iters=record_activities,
+                              record_every=record_every)
+        # jpc/_train.py:183,199-201,223-225: row t_max of a recorded trajectory, row 0 otherwise (with `record_every`
+        # alone row 0 is the state at ts[0] = 0, i.e. the initial activities -- the reference does the same)
+        t_max = get_t_max(sol) if record_activities else 0
+        acts = net.in_acts([a[t_max].contiguous() for a in sol])
+        if record_energies:
+            rec_energies = compute_infer_energies((model, skip_model), sol, t_max, output, x=input, loss=loss_id,
+                                                  param_type=param_type, weight_decay=weight_decay,
+                                                  spectral_penalty=spectral_penalty, activity_decay=activity_decay)
         ws = net.workspace()
         _lib.check(_lib.lib.jpcb_pc_param_grads(net.desc, net.W, net.b, _lib.ptr_array(acts), _lib.ptr(net.x), _lib.ptr(net.y),
                                                 _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
@@ -138,8 +152,7 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)
     g_norms = compute_param_norms(param_grads) if grad_norms else (None, None)
     a_norms = compute_activity_norms(acts) if activity_norms else None
-    updates, opt_state = optim.update(param_grads, opt_state, (model, skip_model))
-    model, skip_model = apply_updates((model, skip_model), updates)
+    (model, skip_model), opt_state = update_and_apply(optim, param_grads, opt_state, (model, skip_model))
     acc = compute_accuracy(output, init_activities_with_ffwd(model, input, skip_model=skip_model,
                                                              param_type=param_type)[-1]) if calculate_accuracy else None
     return {
@@ -148,9 +161,9 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         "opt_state": opt_state,
         "loss": arena.loss,
         "acc": acc,
-        "activities": [a.unsqueeze(0) for a in acts],
-        "t_max": 0,
-        "energies": arena.E,
+        "activities": sol if recording else [a.unsqueeze(0) for a in acts],
+        "t_max": t_max,
+        "energies": arena.E if rec_energies is None else rec_energies,
         "activity_norms": a_norms,
         "model_param_norms": p_norms[0],
         "skip_model_param_norms": p_norms[1],

@@ -1,4 +1,4 @@
-"""User-side helpers of jpc/_utils.py:129-142,219-260 (losses, accuracy, norms).  These are
+"""User-side helpers of jpc/_utils.py:129-260 (losses, accuracy, recorded-trajectory helpers, norms).  These are
 evaluation/metric utilities outside the train-step kernels; they run as torch device ops on
 whatever device their inputs live on."""
 from __future__ import annotations
@@ -37,3 +37,25 @@ def compute_param_norms(params):
         return torch.stack([torch.linalg.vector_norm(p.reshape(-1), ord=2) for p in leaves])
     model_params, skip_model_params = params
     return proc(model_params), (proc(skip_model_params) if skip_model_params is not None else None)
+
+
+def get_t_max(activities_iters):
+    """jpc/_utils.py:145-146: index of the last recorded step = (first inf row of the first leaf) - 1.
+    Stays on the device like the reference's traced value; rows past the last step are inf
+    (`solve_inference(record_iters=True)`)."""
+    return torch.argmax(activities_iters[0][:, 0, 0]) - 1
+
+
+def compute_infer_energies(params, activities_iters, t_max, y, *, x=None, loss="mse", param_type="sp", weight_decay=0.0,
+                           spectral_penalty=0.0, activity_decay=0.0):
+    """jpc/_utils.py:149-216: layer energies at recorded steps 0..t_max-1, as a (len(model), 500) array that is
+    zero past t_max, rows in the reference's order (`pc_energy_fn(record_layers=True)` reversed, `:216`).
+    One `jpcb_pc_energy` call per recorded step."""
+    from ._core import pc_energy_fn
+    model, _ = params
+    out = torch.zeros(len(model), 500, dtype=torch.float32, device=y.device)
+    for t in range(min(int(t_max), 500)):
+        out[:, t] = pc_energy_fn(params, [a[t] for a in activities_iters], y, x=x, loss=loss, param_type=param_type,
+                                 weight_decay=weight_decay, spectral_penalty=spectral_penalty,
+                                 activity_decay=activity_decay, record_layers=True)
+    return out.flip(0)

@@ -598,3 +598,105 @@ def test_training_loop_learns_a_synthetic_task():
     loss1, acc1 = J.test_discriminative_pc(model, yt, xt)
     assert float(loss1) < 0.6 * float(loss0)
     assert float(acc1) > 70.0 > 40.0 > float(acc0) - 15.0
+
+
+# ---- recorded trajectories: record_iters / record_every / record_energies -----------
+@pytest.mark.parametrize("solver", ["euler", "heun"])
+def test_solve_inference_record_iters_and_record_every(solver):
+    import jpc_b200 as J
+    om, sk, x, y = _case(10, 20, 3, 5, "tanh", 8, use_bias=True)
+    gm, gx, gy = to_gpu_model(om), dev(x), dev(y)
+    a0 = [a.float().double() for a in perturb(O.init_activities_with_ffwd(om, x))]
+    traj = []
+    O.solve_inference(om, sk, a0, y, x=x, solver=solver, max_t1=2.0, dt=0.3, use_closed_form=True, event_atol=0.0,
+                      event_rtol=0.0, trajectory=traj)
+    kw = dict(input=gx, solver=J.Euler() if solver == "euler" else J.Heun(), max_t1=2.0, dt=0.3,
+              stepsize_controller=J.ConstantStepSize())
+    # SaveAt(steps=True): (4096, B, d), one row per step (7 here, the last one clipped), inf after
+    sol = J.solve_inference((gm, None), devs(a0), gy, record_iters=True, **kw)
+    assert int(J.get_t_max(sol)) == 6
+    for l, s in enumerate(sol):
+        assert tuple(s.shape) == (4096,) + tuple(a0[l].shape)
+        assert bool(torch.isinf(s[7:]).all())
+        for i in range(7):
+            assert rel(s[i], traj[i + 1][1][l]) < TOL32
+    # SaveAt(ts=arange(0, max_t1, 1), t1=True): rows at t = 0, 1 (interpolated inside a step), then the final state
+    sol = J.solve_inference((gm, None), devs(a0), gy, record_every=1, **kw)
+    want = O.saveat_ts(traj, [0.0, 1.0])
+    for l, s in enumerate(sol):
+        assert tuple(s.shape) == (3,) + tuple(a0[l].shape)
+        assert rel(s[0], a0[l]) < 1e-7 and rel(s[1], want[1][l]) < TOL32 and rel(s[2], traj[-1][1][l]) < TOL32
+
+
+def test_make_pc_step_record_energies_and_adaptive_recording():
+    import jpc_b200 as J
+    om, sk, x, y = _case(12, 24, 3, 6, "relu", 8, use_bias=True)
+    gm, gx, gy = to_gpu_model(om), dev(x), dev(y)
+    opt = J.optim.sgd(1e-2)
+    out = J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx, ode_solver=J.Euler(), max_t1=3, dt=0.5,
+                         stepsize_controller=J.ConstantStepSize(), record_energies=True, activity_norms=True)
+    a0 = O.init_activities_with_ffwd(om, x)
+    traj = []
+    O.solve_inference(om, sk, a0, y, x=x, solver="euler", max_t1=3.0, dt=0.5, use_closed_form=True, event_atol=0.0,
+                      event_rtol=0.0, trajectory=traj)
+    assert int(out["t_max"]) == 5 and tuple(out["energies"].shape) == (3, 500)
+    for t in range(5):  # jpc/_utils.py:203-216: steps 0..t_max-1, layer rows reversed
+        E = O.pc_energy_fn(om, None, traj[t + 1][1], y, x=x, record_layers=True)
+        assert rel(out["energies"][:, t], torch.flip(E, [0])) < 1e-5
+    assert float(out["energies"][:, 5:].abs().max()) == 0.0
+    # the parameter update uses the last recorded row
+    fin = traj[-1][1]
+    pg = O.compute_pc_param_grads(om, None, fin, y, x=x)
+    new = out["model"]
+    for l, q in enumerate(pg):
+        assert rel(new[l][1].weight, om[l]["W"] - 1e-2 * q["W"]) < 1e-6
+    norms = torch.stack([a.norm(dim=-1).mean() for a in fin])
+    assert rel(out["activity_norms"], norms) < 1e-5
+    # default adaptive solve with every accepted step recorded
+    out = J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx, max_t1=5, record_activities=True)
+    ref, st = O.solve_inference_adaptive(om, None, a0, y, x=x, max_t1=5.0)
+    tm = int(out["t_max"])
+    assert tm == st["accepted"] - 1
+    for p, q in zip(out["activities"][:-1], ref[:-1]):
+        assert tuple(p.shape)[0] == 4096 and rel(p[tm], q) < 1e-4
+
+
+# ---- fused parameter update ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["sgd", "adam"])
+def test_fused_optimiser_matches_optax_protocol(name):
+    """jpcb_optim_sgd / jpcb_optim_adam (one pass) against the optax-protocol path (update + apply_updates) and
+    the fp64 oracle, over ragged tensor sizes, an unaligned view, an empty tensor and > 32 tensors (two launches)."""
+    import jpc_b200 as J
+    from jpc_b200.optim import apply_updates, update_and_apply
+    g_ = torch.Generator().manual_seed(0)
+    sizes = [(7, 5), (1,), (0,), (33, 129), (1024, 64)] + [(3, k + 1) for k in range(36)]
+    base = torch.randn(8, generator=g_, dtype=torch.float64).float().cuda()
+    p64 = [torch.randn(s, generator=g_, dtype=torch.float64) for s in sizes] + [base[1:8].double().cpu()]
+    params = [dev(p) for p in p64[:-1]] + [base[1:8]]  # last leaf: contiguous but not 16-byte aligned
+    opt = J.optim.sgd(0.3) if name == "sgd" else J.optim.adam(1e-2)
+    st_f, st_p, st_o = opt.init(params), opt.init(params), None
+    pf, pp, po = params, params, p64
+    n0 = J._lib.lib.jpcb_launch_count()
+    for it in range(3):
+        g64 = [torch.randn(p.shape, generator=g_, dtype=torch.float64) for p in p64]
+        g = devs(g64)
+        pf, st_f = update_and_apply(opt, g, st_f, pf)
+        u, st_p = opt.update(g, st_p, pp)
+        pp = apply_updates(pp, u)
+        if name == "sgd":
+            po = O.sgd_update(po, g64, 0.3)
+        else:
+            po, st_o = O.adam_update(po, g64, st_o, 1e-2)
+    assert J._lib.lib.jpcb_launch_count() - n0 == 6  # 42 tensors -> two launches per update: the fused path ran
+    for a, b, c in zip(pf, pp, po):
+        if a.numel():
+            assert rel(a, c) < 2e-6 and rel(b, c) < 2e-6
+    assert params[0] is not pf[0] and rel(params[0], p64[0]) < 1e-7  # functional: inputs untouched
+    if name == "adam":
+        for a, c in zip(st_f["mu"] + st_f["nu"], st_o["mu"] + st_o["nu"]):
+            if a.numel():
+                assert rel(a, c) < 2e-6
+    # CPU tensors: the protocol path (no device kernel) still serves them
+    cp = [torch.ones(3)]
+    out, _ = update_and_apply(J.optim.sgd(0.5), [torch.ones(3)], (), cp)
+    assert torch.equal(out[0], torch.full((3,), 0.5))

@@ -226,3 +226,35 @@ def test_adaptive_heun_matches_fine_fixed_step():
     # a huge first step must be rejected and shrunk by at least factormin
     _, st2 = O.solve_inference_adaptive(om, None, a0, y, x=x, max_t1=4.0, dt0=1e4, rtol=1e-6, atol=1e-6)
     assert st2["rejected"] >= 1
+
+
+def test_saveat_bookkeeping_matches_oracle_interpolation():
+    """jpc_b200._core._SaveAt (host-side row bookkeeping of record_iters / record_every) against the oracle's
+    `saveat_ts` on a synthetic trajectory -- no device work involved."""
+    import types
+    from jpc_b200._core import _SaveAt
+    g = torch.Generator().manual_seed(0)
+    ts_steps = [0.0, 0.4, 0.8, 1.2, 1.5]
+    traj = [(t, [torch.randn(3, 4, generator=g), torch.randn(3, 2, generator=g)]) for t in ts_steps]
+    net = types.SimpleNamespace(B=3, L=2, true_dims=[5, 4, 2], dev=torch.device("cpu"))
+    save = _SaveAt(net, 1.5, False, 0.5)     # ts = [0, 0.5, 1.0]
+    for (t0, y0), (t1, y1) in zip(traj[:-1], traj[1:]):
+        save.step(t0, y0, t1, y1)
+    ys = save.finish(traj[-1][1])
+    want = O.saveat_ts(traj, [0.0, 0.5, 1.0])
+    for l in range(2):
+        assert tuple(ys[l].shape) == (4,) + tuple(traj[0][1][l].shape)
+        for i in range(3):
+            assert torch.allclose(ys[l][i], want[i][l], atol=1e-6)
+        assert torch.equal(ys[l][3], traj[-1][1][l])
+    save = _SaveAt(net, 1.5, True, None)     # every step, inf-padded to diffrax's max_steps
+    for (t0, y0), (t1, y1) in zip(traj[:-1], traj[1:]):
+        save.step(t0, y0, t1, y1)
+    ys = save.finish(traj[-1][1])
+    assert ys[0].shape[0] == 4096 and torch.equal(ys[0][3], traj[-1][1][0]) and bool(torch.isinf(ys[0][4:]).all())
+    from jpc_b200._utils import get_t_max
+    assert int(get_t_max(ys)) == 3
+    # an early stop leaves the unreached ts rows at inf
+    save = _SaveAt(net, 1.5, False, 0.5)
+    save.step(*traj[0], *traj[1])
+    assert bool(torch.isinf(save.finish(traj[1][1])[0][1:3]).all())
