@@ -80,6 +80,13 @@ typedef struct jpcb_pc_desc {
   int32_t n_steps;                   /* T fixed steps */
   float dt;                          /* step size of steps 0..T-2 */
   float dt_last;                     /* step size of the last step (ConstantStepSize clips to t1) */
+  int32_t free_input;                /* unsupervised PC (`x = None` in the reference, jpc/_core/_energies.py:86,
+                                      * 123-124): there is no input; z_0 is a free activity.  Every activity list
+                                      * (A, gA, A_new) then has n_layers + 1 entries [z_0, z_1 .. z_{L-1}, dummy]
+                                      * exactly like the reference's, and the `x` argument must be NULL.  The first
+                                      * layer's prediction is used as the reference uses it (scalings[0] must be 1:
+                                      * "sp" is the only parameterisation the reference's unsupervised branch
+                                      * accepts).  jpcb_pc_ffwd_init / jpcb_pc_train_step need an input. */
 } jpcb_pc_desc;
 
 int jpcb_version(void);

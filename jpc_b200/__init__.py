@@ -9,6 +9,7 @@ from ._core import (
     compute_pc_activity_grad,
     compute_pc_param_grads,
     get_compute_dtype,
+    init_activities_from_normal,
     init_activities_with_ffwd,
     neg_pc_activity_grad,
     pc_energy_fn,

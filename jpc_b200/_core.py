@@ -115,8 +115,14 @@ class _Net:
         _check_param_type(param_type)
         if loss_id not in ("mse", "ce"):
             raise ValueError("`mse` and `ce` are the only valid losses.")
-        if x is None:
-            raise NotImplementedError("unsupervised mode (input=None) is not on the B200 path yet")
+        # x is None: unsupervised PC (jpc/_core/_energies.py:86,123-124) -- z_0 = activities[0] is a free activity,
+        # every activity list has L + 1 entries and the first layer's prediction carries no scaling
+        self.free = x is None
+        if self.free and y is None:
+            raise ValueError("unsupervised mode (input=None) needs the target to size the batch")
+        if self.free and param_type != "sp":
+            raise ValueError("unsupervised mode (input=None) supports param_type='sp' only: the reference's "
+                             "`_get_param_scalings` needs the input's width for 'mupc' / 'ntp'")
         L = len(model)
         parts = [_layer_parts(l) for l in model]
         bare = any(isinstance(l, Linear) for l in model)
@@ -130,7 +136,7 @@ class _Net:
         dev = Ws[0].device
         if dev.type != "cuda":
             raise RuntimeError("jpc_b200 has no CPU path: model weights must be CUDA tensors")
-        for t in Ws + [x] + ([y] if y is not None else []):
+        for t in Ws + ([x] if x is not None else []) + ([y] if y is not None else []):
             if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
         has_bias = [lin.bias is not None for lin in self.linears]
@@ -140,9 +146,9 @@ class _Net:
         for l in range(L):
             if Ws[l].shape[1] != dims[l]:
                 raise ValueError(f"layer {l}: weight shape {tuple(Ws[l].shape)} does not chain from {dims[l]}")
-        if x.shape[1] != dims[0]:
+        if x is not None and x.shape[1] != dims[0]:
             raise ValueError("input feature dim does not match the first layer")
-        B = x.shape[0]
+        B = y.shape[0] if self.free else x.shape[0]
         skips = _skip_flags(skip_model, L)
         scal = _get_param_scalings(model, x, skip_model=skip_model, param_type=param_type, gamma=gamma)
         self.true_dims = list(dims)
@@ -161,14 +167,15 @@ class _Net:
             Ws = [P(Ws[l], (0, pd[l] - dims[l], 0, pd[l + 1] - dims[l + 1])).contiguous() for l in range(L)]
             if bs is not None:
                 bs = [P(bs[l], (0, pd[l + 1] - dims[l + 1])).contiguous() for l in range(L)]
-            x = P(x, (0, pd[0] - dims[0])).contiguous()
+            if x is not None:
+                x = P(x, (0, pd[0] - dims[0])).contiguous()
             if y is not None:
                 y = P(y, (0, pd[-1] - dims[-1])).contiguous()
             dims = pd
         lam = 1.0 if output_energy_scaling is None else float(output_energy_scaling)
         bg = B if batch_global is None else int(batch_global)
         key = (L, B, bg, tuple(dims), tuple(p[0] for p in parts), all(has_bias), tuple(skips), tuple(scal),
-               _COMPUTE_DTYPE, loss_id, lam, float(activity_decay), solver, n_steps, float(dt), float(dt_last))
+               _COMPUTE_DTYPE, loss_id, lam, float(activity_decay), solver, n_steps, float(dt), float(dt_last), self.free)
         cached = _DESC_CACHE.get(key)
         if cached is None:
             d = _lib.PcDesc()
@@ -185,6 +192,7 @@ class _Net:
             d.output_energy_scaling = lam
             d.activity_decay = float(activity_decay)
             d.solver, d.n_steps, d.dt, d.dt_last = solver, n_steps, float(dt), float(dt_last)
+            d.free_input = 1 if self.free else 0
             ws_bytes = _lib.lib.jpcb_pc_workspace_bytes(d)
             if ws_bytes == 0:
                 _lib.check(_probe_error(d))
@@ -194,6 +202,9 @@ class _Net:
             _DESC_CACHE[key] = cached
         self.desc, self.ws_bytes = cached
         self.L, self.B, self.dims, self.dev = L, B, dims, dev
+        # widths of the entries of an activity list: [d_1 .. d_L], preceded by d_0 when z_0 is free
+        self.adims = dims[0 if self.free else 1:]
+        self.true_adims = self.true_dims[0 if self.free else 1:]
         self.has_bias = all(has_bias)
         self.W = _lib.ptr_array(Ws)
         self.b = _lib.ptr_array(bs) if self.has_bias else None
@@ -220,30 +231,32 @@ class _Net:
         return d
 
     def check_acts(self, activities):
-        if len(activities) != self.L:
-            raise ValueError(f"expected {self.L} activity arrays (one per layer, last = dummy output slot), got {len(activities)}")
+        n = len(self.adims)
+        if len(activities) != n:
+            raise ValueError(f"expected {n} activity arrays ({'z_0, ' if self.free else ''}one per layer, last = dummy "
+                             f"output slot), got {len(activities)}")
         for l, a in enumerate(activities):
-            if tuple(a.shape) != (self.B, self.true_dims[l + 1]):
-                raise ValueError(f"activities[{l}] has shape {tuple(a.shape)}, expected {(self.B, self.true_dims[l + 1])}")
+            if tuple(a.shape) != (self.B, self.true_adims[l]):
+                raise ValueError(f"activities[{l}] has shape {tuple(a.shape)}, expected {(self.B, self.true_adims[l])}")
             if a.device != self.dev or a.dtype != torch.float32 or not a.is_contiguous():
                 raise ValueError("activities must be contiguous fp32 CUDA tensors")
 
     def new_acts(self):
         """Output buffers in the layout the library sees (padded feature dims when self.padded)."""
-        return [torch.empty(self.B, self.dims[l + 1], dtype=torch.float32, device=self.dev) for l in range(self.L)]
+        return [torch.empty(self.B, w, dtype=torch.float32, device=self.dev) for w in self.adims]
 
     def in_acts(self, activities, clone=False):
         """User activities -> the layout the library sees."""
         if not self.padded:
             return [a.clone() for a in activities] if clone else list(activities)
         P = torch.nn.functional.pad
-        return [P(a, (0, self.dims[l + 1] - a.shape[1])).contiguous() for l, a in enumerate(activities)]
+        return [P(a, (0, self.adims[l] - a.shape[1])).contiguous() for l, a in enumerate(activities)]
 
     def out_acts(self, bufs):
         """Library-layout activity-shaped results -> the user's shapes."""
         if not self.padded:
             return bufs
-        return [b_[:, :self.true_dims[l + 1]].contiguous() for l, b_ in enumerate(bufs)]
+        return [b_[:, :self.true_adims[l]].contiguous() for l, b_ in enumerate(bufs)]
 
     def out_grads(self, gW, gb):
         if not self.padded:
@@ -288,6 +301,25 @@ def init_activities_with_ffwd(model, input, *, skip_model=None, param_type="sp",
     _lib.check(_lib.lib.jpcb_pc_ffwd_init(net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr_array(acts), None, None,
                                           _lib.ptr(ws), ws.numel(), net.stream()))
     return net.out_acts(acts)
+
+
+def init_activities_from_normal(key, layer_sizes, mode, batch_size, sigma=0.05, device=None):
+    """jpc/_core/_init.py:85-123: z_l ~ N(0, sigma^2) for every layer that is free to vary -- hidden layers and the
+    (dummy) output slot in "supervised" mode, also z_0 in "unsupervised" mode.  `key` is a `torch.Generator` or an
+    int seed (the reference's is a JAX PRNG key: same law, a different random stream -- a data-side difference,
+    not an arithmetic one).  Drawn by torch's device generator directly into device memory."""
+    if mode not in ("supervised", "unsupervised"):
+        raise ValueError("`mode` must be 'supervised' or 'unsupervised'")
+    device = torch.device("cuda" if device is None else device)
+    if isinstance(key, torch.Generator):
+        gen = key
+    else:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(int(key))
+    start_l = 0 if mode == "unsupervised" else 1
+    return [float(sigma) * torch.randn(int(batch_size), int(layer_sizes[l]), generator=gen, device=gen.device,
+                                       dtype=torch.float32).to(device)
+            for l in range(start_l, len(layer_sizes))]
 
 
 def pc_energy_fn(params, activities, y, *, x=None, loss="mse", param_type="sp", weight_decay=0.0,
@@ -419,8 +451,7 @@ class _SaveAt:
         else:
             rows = 1
         self.steps = bool(record_iters) and self.ts is None
-        self.ys = [torch.full((rows, net.B, net.true_dims[l + 1]), float("inf"), dtype=torch.float32, device=net.dev)
-                   for l in range(net.L)]
+        self.ys = [torch.full((rows, net.B, w), float("inf"), dtype=torch.float32, device=net.dev) for w in net.true_adims]
         self.i = 0
 
     @property
@@ -429,7 +460,7 @@ class _SaveAt:
 
     def _put(self, row, bufs, prev=None, w=None):
         for l, y in enumerate(self.ys):
-            d = self.net.true_dims[l + 1]
+            d = self.net.true_adims[l]
             if prev is None:
                 y[row].copy_(bufs[l][:, :d])
             else:

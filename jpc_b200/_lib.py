@@ -37,6 +37,7 @@ class PcDesc(C.Structure):
         ("n_steps", C.c_int32),
         ("dt", C.c_float),
         ("dt_last", C.c_float),
+        ("free_input", C.c_int32),
     ]
 
 

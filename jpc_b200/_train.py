@@ -11,7 +11,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_with_ffwd, solve_inference)
+from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_from_normal, init_activities_with_ffwd,
+                    solve_inference)
 from ._errors import _check_param_type
 from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,
                      get_t_max)
@@ -99,9 +100,36 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     if recording and world > 1:
         raise NotImplementedError("recorded trajectories are per-process: not available under data parallelism")
     common = dict(param_type=param_type, loss_id=loss_id, gamma=None, output_energy_scaling=None, activity_decay=activity_decay,
-                  weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=input.shape[0] * world)
+                  weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=output.shape[0] * world)
     t_max, sol, rec_energies = 0, None, None
-    if isinstance(stepsize_controller, ConstantStepSize) and not recording:
+    if input is None and not isinstance(stepsize_controller, (PIDController, ConstantStepSize)):
+        raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
+    if input is None:
+        # unsupervised PC (jpc/_train.py:143-149,159-161): random-normal activities incl. z_0, no loss, then the same
+        # solve -> energies -> parameter gradients; every activity list has L + 1 entries
+        if batch_size != output.shape[0]:
+            raise ValueError(f"batch_size={batch_size} does not match the target's {output.shape[0]} rows")
+        net = _Net(model, skip_model, None, output, **common)
+        arena = _Arena(net)
+        arena.loss.zero_()
+        arena.loss = None  # the reference returns loss=None without an input
+        acts0 = init_activities_from_normal(key, layer_sizes, "unsupervised", batch_size, sigma, device=output.device)
+        sol = solve_inference((model, skip_model), acts0, output, input=None, loss_id=loss_id, param_type=param_type,
+                              solver=ode_solver, max_t1=max_t1, dt=dt, stepsize_controller=stepsize_controller,
+                              weight_decay=weight_decay, spectral_penalty=spectral_penalty, activity_decay=activity_decay,
+                              batch_global=output.shape[0] * world, record_iters=record_activities,
+                              record_every=record_every)
+        t_max = get_t_max(sol) if record_activities else 0
+        acts = net.in_acts([a[t_max].contiguous() for a in sol])
+        if record_energies:
+            rec_energies = compute_infer_energies((model, skip_model), sol, t_max, output, x=None, loss=loss_id,
+                                                  param_type=param_type, weight_decay=weight_decay,
+                                                  spectral_penalty=spectral_penalty, activity_decay=activity_decay)
+        ws = net.workspace()
+        _lib.check(_lib.lib.jpcb_pc_param_grads(net.desc, net.W, net.b, _lib.ptr_array(acts), None, _lib.ptr(net.y),
+                                                _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
+                                                _lib.ptr(arena.E), _lib.ptr(ws), ws.numel(), net.stream()))
+    elif isinstance(stepsize_controller, ConstantStepSize) and not recording:
         # fixed steps: the whole step up to the optimiser is ONE C-ABI call
         T, h, h_last = _time_grid(max_t1, dt)
         if T > 4096:
@@ -153,6 +181,8 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     g_norms = compute_param_norms(param_grads) if grad_norms else (None, None)
     a_norms = compute_activity_norms(acts) if activity_norms else None
     (model, skip_model), opt_state = update_and_apply(optim, param_grads, opt_state, (model, skip_model))
+    if calculate_accuracy and input is None:
+        raise ValueError("calculate_accuracy needs an input (the accuracy is that of the feed-forward pass)")
     acc = compute_accuracy(output, init_activities_with_ffwd(model, input, skip_model=skip_model,
                                                              param_type=param_type)[-1]) if calculate_accuracy else None
     return {

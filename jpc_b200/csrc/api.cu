@@ -82,6 +82,7 @@ int validate(const jpcb_pc_desc* d) {
   if (d->dtype != JPCB_DTYPE_F32 && d->dtype != JPCB_DTYPE_BF16) return fail(JPCB_EINVAL, "bad dtype %d", d->dtype);
   if (d->solver != JPCB_SOLVER_EULER && d->solver != JPCB_SOLVER_HEUN) return fail(JPCB_EINVAL, "bad solver %d", d->solver);
   if (d->n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", d->n_steps);
+  if (d->free_input && d->scalings[0] != 1.f) return fail(JPCB_EINVAL, "free_input (unsupervised) needs scalings[0] == 1: the reference's branch is unscaled");
   if (d->dtype == JPCB_DTYPE_BF16) {
     if (d->batch_local % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs batch_local %% 8 == 0 (got %d)", d->batch_local);
     for (int l = 0; l <= d->n_layers; ++l)
@@ -116,6 +117,8 @@ struct Ws {
   float* logits = nullptr;   // cross-entropy output: the output layer's prediction [Bl, d_L]
   std::vector<float*> Zt;    // [L-1] Heun stage state of A[l]
   std::vector<float*> G1;    // [L-1] Heun first-stage gradient of A[l]
+  float* Zx = nullptr;       // free_input + Heun: stage state / first-stage gradient of z_0
+  float* G1x = nullptr;
   // fp32 operand copies (fp32 path): act_l(u_l) [Bl, d_l] (+ Heun stage twin) and W_l^T [d_l, d_{l+1}], so that
   // every inference GEMM reads two K-contiguous fp32 operands with no activation left to apply on load
   std::vector<float*> Hf, Hft, WTf;
@@ -139,17 +142,23 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
   if (d->loss == JPCB_LOSS_CE) w->logits = b.take<float>(Bl * d->dims[L]);
   const bool tc = d->dtype == JPCB_DTYPE_BF16, heun = d->solver == JPCB_SOLVER_HEUN;
   for (int l = 0; l < L; ++l) w->err[l] = tc ? nullptr : b.take<float>(Bl * d->dims[l + 1]);
-  if (heun)
+  const bool fr = d->free_input != 0;
+  if (heun) {
     for (int l = 0; l < L - 1; ++l) {
       w->Zt[l] = b.take<float>(Bl * d->dims[l + 1]);
       w->G1[l] = b.take<float>(Bl * d->dims[l + 1]);
     }
+    if (fr) {
+      w->Zx = b.take<float>(Bl * d->dims[0]);
+      w->G1x = b.take<float>(Bl * d->dims[0]);
+    }
+  }
   w->Hf.assign(L, nullptr); w->Hft.assign(L, nullptr); w->WTf.assign(L, nullptr);
   if (!tc) {
     for (int l = 0; l < L; ++l) {
       if (l >= 1 || d->act[0] != JPCB_ACT_LINEAR) w->Hf[l] = b.take<float>(Bl * d->dims[l]);
-      if (heun && l >= 1) w->Hft[l] = b.take<float>(Bl * d->dims[l]);
-      if (l >= 1) w->WTf[l] = b.take<float>((size_t)d->dims[l] * d->dims[l + 1]);
+      if (heun && (l >= 1 || (fr && w->Hf[0]))) w->Hft[l] = b.take<float>(Bl * d->dims[l]);
+      if (l >= 1 || fr) w->WTf[l] = b.take<float>((size_t)d->dims[l] * d->dims[l + 1]);
     }
   }
   w->Wb.assign(L, nullptr); w->WTb.assign(L, nullptr); w->Hb.assign(L, nullptr); w->Htb.assign(L, nullptr);
@@ -158,9 +167,9 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
     for (int l = 0; l < L; ++l) {
       const size_t wn = (size_t)d->dims[l] * d->dims[l + 1];
       w->Wb[l] = b.take<bf16>(wn);
-      if (l >= 1) w->WTb[l] = b.take<bf16>(wn);
+      if (l >= 1 || fr) w->WTb[l] = b.take<bf16>(wn);
       w->Hb[l] = b.take<bf16>(Bl * d->dims[l]);
-      if (heun && l >= 1) w->Htb[l] = b.take<bf16>(Bl * d->dims[l]);
+      if (heun && (l >= 1 || fr)) w->Htb[l] = b.take<bf16>(Bl * d->dims[l]);
       w->Eb[l] = b.take<bf16>(Bl * d->dims[l + 1]);
     }
   }
@@ -283,13 +292,16 @@ struct Run {
   const jpcb_pc_desc* d;
   const float* const* W;
   const float* const* b;
-  const float* x;
+  const float* x;        // the input -- or, with free_input, z_0 of the current state
   const float* y;
   Ws ws;
   cudaStream_t st;
   int L, Bl;
   float invB;
   bool tc;
+  bool fr = false;                // desc->free_input: z_0 is a free activity (unsupervised PC)
+  const float* x_stage = nullptr; // free_input: z_0 of the Heun stage state (else the input)
+  float* x_out = nullptr;         // free_input: where the next grads() call writes z_0's gradient / new value
 
   int init(const jpcb_pc_desc* desc, const float* const* W_, const float* const* b_, const float* x_, const float* y_, void* wsp,
            size_t ws_bytes, void* stream) {
@@ -302,6 +314,8 @@ struct Run {
     if (d->has_bias && !b) return fail(JPCB_EINVAL, "has_bias set but no bias list");
     carve(d, wsp, &ws);
     if (!wsp || ws_bytes < ws.bytes) return fail(JPCB_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, ws_bytes);
+    fr = d->free_input != 0;
+    x_stage = fr && ws.Zx ? ws.Zx : x;
     return JPCB_OK;
   }
   const float* bias(int l) const { return d->has_bias ? b[l] : nullptr; }
@@ -313,7 +327,7 @@ struct Run {
   // ---- bf16 operand preparation ----
   int prep_weights() {
     if (!tc) {
-      for (int l = 1; l < L; ++l) {
+      for (int l = fr ? 0 : 1; l < L; ++l) {
         const int R = d->dims[l + 1], C = d->dims[l];
         transpose_f32_kernel<<<ew_grid(((R + 31) / 32) * ((C + 31) / 32), 1), dim3(32, 8), 0, st>>>(W[l], ws.WTf[l], R, C); count_launch();
       }
@@ -323,7 +337,7 @@ struct Run {
     for (int l = 0; l < L; ++l) {
       const size_t n = (size_t)d->dims[l] * d->dims[l + 1];
       cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR); count_launch();
-      if (l >= 1) {
+      if (l >= 1 || fr) {
         const int R = d->dims[l + 1], C = d->dims[l];
         const int tiles = ((R + 31) / 32) * ((C + 31) / 32);
         transpose_to_bf16_kernel<float><<<ew_grid(tiles, 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C); count_launch();
@@ -364,9 +378,11 @@ struct Run {
     const std::vector<float*>& Hf = stage ? ws.Hft : ws.Hf;
     t.e.M = Bl; t.e.N = d->dims[l + 1]; t.K = d->dims[l];
     (void)S;
-    t.a_p = l == 0 ? (ws.Hf[0] ? ws.Hf[0] : x) : Hf[l]; t.a_smn = d->dims[l]; t.a_sk = 1; t.a_act = ACT_LINEAR;
+    const bool st0 = stage && fr;  // layer 0 reads the stage state's z_0 only when z_0 is free
+    t.a_p = l == 0 ? (st0 ? (ws.Hft[0] ? ws.Hft[0] : x_stage) : (ws.Hf[0] ? ws.Hf[0] : x)) : Hf[l];
+    t.a_smn = d->dims[l]; t.a_sk = 1; t.a_act = ACT_LINEAR;
     t.b_p = W[l]; t.b_smn = d->dims[l]; t.b_sk = 1;
-    t.a_b = l == 0 ? ws.Hb[0] : H[l]; t.b_b = ws.Wb[l];
+    t.a_b = l == 0 ? (st0 ? ws.Htb[0] : ws.Hb[0]) : H[l]; t.b_b = ws.Wb[l];
     t.e.alpha = d->scalings[l];
     t.e.bias = bias(l);
   }
@@ -475,6 +491,28 @@ struct Run {
       if (sub != GRAD_OUT) { if (tc) t.e.Ob = (stage_out ? ws.Htb : ws.Hb)[l]; else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[l]; }
       ts.push_back(t);
     }
+    if (fr) {
+      // unsupervised PC: z_0 is free.  It has no prediction error of its own, so its gradient is only the
+      // term sent down by layer 0: dF/dz_0 = -(1/B) act_0'(z_0) . (a_0 e_1 W_0)  (+ decay).  "e_0 = 0" is
+      // expressed with the hoisted-prediction source: e = Z - P with P = Z.
+      if (!x_out) return fail(JPCB_EINVAL, "free_input: no destination for z_0");
+      const float* zx = sub == GRAD_HEUN2 ? x_stage : x;
+      GTask t;
+      t.e.mode = EPI_GRAD; t.e.sub = sub; t.e.act = d->act[0];
+      t.e.M = Bl; t.e.N = d->dims[0]; t.K = d->dims[1];
+      t.a_p = ws.err[0]; t.a_smn = d->dims[1]; t.a_sk = 1;
+      t.b_p = ws.WTf[0]; t.b_smn = d->dims[1]; t.b_sk = 1;
+      t.a_b = ws.Eb[0]; t.b_b = ws.WTb[0];
+      t.e.alpha = d->scalings[0];
+      t.e.Z = zx; t.e.P = zx;
+      t.e.c = c; t.e.ad = d->activity_decay; t.e.gscale = 1.f;
+      t.e.O = x_out;
+      if (sub == GRAD_HEUN1 || sub == GRAD_HEUN2) t.e.G1 = ws.G1x;
+      if (sub == GRAD_HEUN2) { t.e.Z0 = x; t.e.red = err_red; t.e.tol_r = rtol; t.e.tol_a = atol; }
+      if (sub != GRAD_OUT) { if (tc) t.e.Ob = (stage_out ? ws.Htb : ws.Hb)[0]; else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[0]; }
+      ts.push_back(t);
+      x_out = nullptr;
+    }
     return launch(ts);
   }
 
@@ -495,7 +533,8 @@ struct Run {
   int infer_loop(float* const* A, bool from_ffwd = false) {
     const int T = d->n_steps;
     const size_t n_dummy = (size_t)Bl * d->dims[L];
-    const bool front = from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !(tc_flags() & 8);
+    float* const xw = const_cast<float*>(x);  // free_input: z_0 is updated in place like every other activity
+    const bool front = !fr && from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !(tc_flags() & 8);
     if (front) {
       if (tc) {
         for (int l = (L - 2 - T > 0 ? L - 2 - T : 0); l < L - 1; ++l) CK(cudaMemsetAsync(ws.Eb[l], 0, (size_t)Bl * d->dims[l + 1] * sizeof(bf16), st));
@@ -508,16 +547,19 @@ struct Run {
       const float c = h * invB;
       if (d->solver == JPCB_SOLVER_EULER) {
         const int lo = front ? (L - 1 - s > 1 ? L - 1 - s : 1) : 1;
-        RET(errors(lo, A, false, false));
-        RET(grads(GRAD_EULER, c, A, nullptr, A, false, true, lo));
+        RET(errors(fr ? 0 : lo, A, false, false));
+        x_out = fr ? xw : nullptr;
+        RET(grads(GRAD_EULER, c, A, nullptr, A, false, !fr, lo));
         if (d->activity_decay != 0.f) RET(scale_inplace(A[L - 1], n_dummy, 1.f - c * d->activity_decay));
       } else {
         std::vector<float*> zt(ws.Zt.begin(), ws.Zt.begin() + (L - 1));
         zt.push_back(A[L - 1]);  // dummy slot is never read by the error tasks
-        RET(errors(1, A, false, false));
-        RET(grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, true));
-        RET(errors(1, zt.data(), true, false));
-        RET(grads(GRAD_HEUN2, c, zt.data(), A, A, false, true));
+        RET(errors(fr ? 0 : 1, A, false, false));
+        x_out = fr ? ws.Zx : nullptr;
+        RET(grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, !fr));
+        RET(errors(fr ? 0 : 1, zt.data(), true, false));
+        x_out = fr ? xw : nullptr;
+        RET(grads(GRAD_HEUN2, c, zt.data(), A, A, false, !fr));
         if (d->activity_decay != 0.f) {
           const float q = c * d->activity_decay;
           RET(scale_inplace(A[L - 1], n_dummy, 1.f - q + 0.5f * q * q));
@@ -566,7 +608,11 @@ struct Run {
     CK(cudaGetLastError());
     return JPCB_OK;
   }
-  int sumsq_all(const float* const* A, float* out) {
+  int sumsq_all(const float* const* A, float* out, const float* z0 = nullptr) {
+    if (fr) {  // z_0 is one of the activities
+      const size_t n = (size_t)Bl * d->dims[0];
+      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, st>>>(z0 ? z0 : x, n, out); count_launch();
+    }
     for (int l = 0; l < L; ++l) {
       const size_t n = (size_t)Bl * d->dims[l + 1];
       sumsq_kernel<<<ew_grid(n, 1024), 256, 0, st>>>(A[l], n, out); count_launch();
@@ -575,6 +621,18 @@ struct Run {
     return JPCB_OK;
   }
 };
+
+// desc->free_input: the caller's activity lists have L + 1 entries [z_0, z_1 .. z_{L-1}, dummy] and there is no
+// input; internally z_0 takes the input's place and the lists are seen from their second entry on.
+template <typename PP>
+int split_free(const jpcb_pc_desc* d, const float*& x, PP& A) {
+  if (!d || !d->free_input) return JPCB_OK;
+  if (x) return fail(JPCB_EINVAL, "free_input (unsupervised): `x` must be NULL, z_0 is activities[0]");
+  if (!A || !A[0]) return fail(JPCB_EINVAL, "free_input (unsupervised): null activity list");
+  x = A[0];
+  A = A + 1;
+  return JPCB_OK;
+}
 
 }  // namespace
 
@@ -594,6 +652,7 @@ size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc) {
 
 int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, float* const* A_out,
                       const float* y, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (desc && desc->free_input) return fail(JPCB_EINVAL, "init_activities_with_ffwd needs an input (free_input is set)");
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A_out) return fail(JPCB_EINVAL, "null activity list");
@@ -608,6 +667,7 @@ int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const flo
 
 int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A, const float* x,
                    const float* y, float* E_layers, void* workspace, size_t workspace_bytes, void* stream) {
+  RET(split_free(desc, x, A));
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A || !y || !E_layers) return fail(JPCB_EINVAL, "null activities / target / output");
@@ -621,6 +681,10 @@ int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float*
 int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
                           const float* x, const float* y, float* F, float* const* gA, void* workspace, size_t workspace_bytes,
                           void* stream) {
+  if (!gA) return fail(JPCB_EINVAL, "null activities / target / output");
+  float* gx = nullptr;
+  if (desc && desc->free_input) { gx = gA[0]; gA = gA + 1; }
+  RET(split_free(desc, x, A));
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A || !y || !gA) return fail(JPCB_EINVAL, "null activities / target / output");
@@ -628,6 +692,7 @@ int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const
   RET(r.prep_weights());
   RET(r.prep_inputs(A));
   RET(r.errors(0, A, false, true));
+  r.x_out = gx;
   RET(r.grads(GRAD_OUT, r.invB, A, nullptr, gA, false, false));
   const size_t n_dummy = (size_t)r.Bl * desc->dims[r.L];
   scale_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[r.L - 1], gA[r.L - 1], n_dummy, desc->activity_decay * r.invB); count_launch();
@@ -642,18 +707,19 @@ int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const
 
 int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, float* const* A, const float* x,
                   const float* y, float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
+  RET(split_free(desc, x, A));
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A || !y) return fail(JPCB_EINVAL, "null activities / target");
   RET(r.prep_weights());
   RET(r.prep_inputs(A));
-  RET(r.predict_p1());
+  if (!r.fr) RET(r.predict_p1());
   RET(r.infer_loop(A));
   if (sumsq_out) {
     CK(cudaMemsetAsync(sumsq_out, 0, 2 * sizeof(float), r.st));
     RET(r.sumsq_all(A, sumsq_out));
     size_t numel = 0;
-    for (int l = 0; l < r.L; ++l) numel += (size_t)r.Bl * desc->dims[l + 1];
+    for (int l = r.fr ? -1 : 0; l < r.L; ++l) numel += (size_t)r.Bl * desc->dims[l + 1];
     const float nf = (float)numel;
     CK(cudaMemcpyAsync(sumsq_out + 1, &nf, sizeof(float), cudaMemcpyHostToDevice, r.st));
   }
@@ -663,6 +729,10 @@ int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* 
 int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A, const float* x,
                        const float* y, float dt, float rtol, float atol, float* const* A_new, float* out2, void* workspace,
                        size_t workspace_bytes, void* stream) {
+  if (!A_new) return fail(JPCB_EINVAL, "null activities / target / outputs");
+  float* x_new = nullptr;
+  if (desc && desc->free_input) { x_new = A_new[0]; A_new = A_new + 1; }
+  RET(split_free(desc, x, A));
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A || !y || !A_new || !out2) return fail(JPCB_EINVAL, "null activities / target / outputs");
@@ -672,22 +742,26 @@ int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const fl
   CK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), r.st));
   RET(r.prep_weights());
   RET(r.prep_inputs(A));
-  RET(r.predict_p1());
+  const bool fr = r.fr;
+  if (!fr) RET(r.predict_p1());
   const float c = dt * r.invB;
   std::vector<float*> zt(r.ws.Zt.begin(), r.ws.Zt.begin() + (L - 1));
   zt.push_back(A_new[L - 1]);  // dummy slot is never read by the error tasks
-  RET(r.errors(1, A, false, false));
-  RET(r.grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, true));
-  RET(r.errors(1, zt.data(), true, false));
-  RET(r.grads(GRAD_HEUN2, c, zt.data(), A, A_new, false, true, 1, out2, rtol, atol));
+  RET(r.errors(fr ? 0 : 1, A, false, false));
+  r.x_out = fr ? r.ws.Zx : nullptr;
+  RET(r.grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, !fr));
+  RET(r.errors(fr ? 0 : 1, zt.data(), true, false));
+  r.x_out = x_new;
+  RET(r.grads(GRAD_HEUN2, c, zt.data(), A, A_new, false, !fr, 1, out2, rtol, atol));
   CK(cudaMemcpyAsync(A_new[L - 1], A[L - 1], (size_t)r.Bl * desc->dims[L] * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
-  RET(r.sumsq_all(A_new, out2 + 1));
+  RET(r.sumsq_all(A_new, out2 + 1, x_new));
   return JPCB_OK;
 }
 
 int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
                         const float* x, const float* y, float* const* gW, float* const* gb, float* E_layers, void* workspace,
                         size_t workspace_bytes, void* stream) {
+  RET(split_free(desc, x, A));
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A || !y || !gW) return fail(JPCB_EINVAL, "null activities / target / output");
@@ -703,6 +777,9 @@ int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const f
 int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, const float* y,
                        float* const* A_out, float* loss_out, float* E_layers, float* const* gW, float* const* gb, void* workspace,
                        size_t workspace_bytes, void* stream) {
+  if (desc && desc->free_input)
+    return fail(JPCB_ENOTIMPL, "the fused train step starts from the feed-forward init, which needs an input; "
+                               "unsupervised steps are jpcb_pc_infer + jpcb_pc_param_grads on caller-initialised activities");
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A_out || !y || !gW) return fail(JPCB_EINVAL, "null activities / target / output");

@@ -700,3 +700,105 @@ def test_fused_optimiser_matches_optax_protocol(name):
     cp = [torch.ones(3)]
     out, _ = update_and_apply(J.optim.sgd(0.5), [torch.ones(3)], (), cp)
     assert torch.equal(out[0], torch.full((3,), 0.5))
+
+
+# ---- unsupervised PC: input=None, z_0 is a free activity -----------------------------
+def _unsup_case(dims_in, width, depth, d_out, act, B, use_bias, act0="linear", seed=0):
+    om, sk, x, y = _case(dims_in, width, depth, d_out, act, B, use_bias=use_bias, seed=seed)
+    om[0]["act"] = act0
+    g = torch.Generator().manual_seed(5)
+    dims = [dims_in] + [l["W"].shape[0] for l in om]
+    acts = [(0.5 * torch.randn(B, w, generator=g, dtype=torch.float64)).float().double() for w in dims]
+    return om, y, acts
+
+
+def _check_unsup(om, y, acts, tol, ad=0.0, lam=None, solves=True):
+    import jpc_b200 as J
+    gm, gy, ga = to_gpu_model(om), dev(y), devs(acts)
+    fm = f32_model(om)
+    kw = dict(x=None, activity_decay=ad, output_energy_scaling=lam)
+    E = O.pc_energy_fn(fm, None, acts, y, record_layers=True, **kw)
+    assert rel(J.pc_energy_fn((gm, None), ga, gy, record_layers=True, **kw), E) < tol
+    F, g = O.compute_pc_activity_grad(fm, None, acts, y, **kw)
+    gF, gg = J.compute_pc_activity_grad((gm, None), ga, gy, **kw)
+    assert abs(float(gF) - float(F)) <= tol * abs(float(F))
+    assert len(gg) == len(om) + 1
+    gmax = max(float(t.abs().max()) for t in g)
+    for p, q in zip(gg, g):
+        assert float((p.double().cpu() - q).abs().max()) <= tol * gmax
+    pg = O.compute_pc_param_grads(fm, None, acts, y, **kw)
+    gp, _ = J.compute_pc_param_grads((gm, None), ga, gy, **kw)
+    for l, q in enumerate(pg):
+        assert rel(gp[l][1].weight, q["W"]) < tol
+        if q["b"] is not None:
+            assert rel(gp[l][1].bias, q["b"]) < tol
+    if not solves:
+        return
+    for solver in ("euler", "heun"):
+        ref, _ = O.solve_inference(fm, None, acts, y, x=None, solver=solver, max_t1=2.0, dt=0.3 * y.shape[0], event_atol=0.0,
+                                   event_rtol=0.0, activity_decay=ad, output_energy_scaling=lam)
+        sol = J.solve_inference((gm, None), ga, gy, input=None, solver=J.Euler() if solver == "euler" else J.Heun(),
+                                max_t1=2.0, dt=0.3 * y.shape[0], stepsize_controller=J.ConstantStepSize(), activity_decay=ad,
+                                output_energy_scaling=lam)
+        amax = max(float(t.abs().max()) for t in ref)
+        assert len(sol) == len(om) + 1
+        for p, q in zip(sol, ref):
+            assert float((p[0].double().cpu() - q).abs().max()) <= 4 * tol * amax
+        assert float((sol[0][0].double().cpu() - acts[0]).abs().max()) > 1e-3  # z_0 did move
+
+
+def test_unsupervised_free_input_fp32():
+    om, y, acts = _unsup_case(12, 20, 3, 6, "tanh", 8, True)
+    _check_unsup(om, y, acts, TOL32)
+    _check_unsup(om, y, acts, TOL32, ad=0.05, lam=0.7)
+    om, y, acts = _unsup_case(9, 17, 4, 5, "relu", 6, False, act0="tanh")   # ragged dims, non-linear first layer
+    _check_unsup(om, y, acts, TOL32)
+    import jpc_b200 as J
+    gm, gy, ga = to_gpu_model(om), dev(y), devs(acts)
+    with pytest.raises(ValueError):   # L entries instead of L + 1
+        J.pc_energy_fn((gm, None), ga[1:], gy, x=None)
+    with pytest.raises(ValueError):   # the reference's scalings need the input's width
+        J.pc_energy_fn((gm, None), ga, gy, x=None, param_type="mupc")
+
+
+def test_unsupervised_free_input_bf16():
+    import jpc_b200 as J
+    om, y, acts = _unsup_case(64, 128, 3, 32, "tanh", 64, True, act0="relu")
+    J.set_compute_dtype("bf16")
+    _check_unsup(om, y, acts, TOLBF)
+    om, y, acts = _unsup_case(50, 100, 3, 10, "relu", 32, False)           # padded odd dims, linear first layer
+    _check_unsup(om, y, acts, TOLBF)
+
+
+def test_unsupervised_adaptive_and_make_pc_step():
+    import jpc_b200 as J
+    om, y, acts = _unsup_case(12, 24, 3, 6, "tanh", 8, True)
+    gm, gy, ga = to_gpu_model(om), dev(y), devs(acts)
+    fm = f32_model(om)
+    # default solve (Heun + PID) from given activities
+    ref, st = O.solve_inference_adaptive(fm, None, acts, y, x=None, max_t1=6.0)
+    sol = J.solve_inference((gm, None), ga, gy, input=None, max_t1=6)
+    got = J.solve_inference.last_stats
+    assert (got["accepted"], got["rejected"]) == (st["accepted"], st["rejected"])
+    amax = max(float(t.abs().max()) for t in ref)
+    for p, q in zip(sol, ref):
+        assert float((p[0].double().cpu() - q).abs().max()) <= 2e-5 * amax
+    # make_pc_step(input=None): random-normal init (same seed -> same draw), no loss, L + 1 activities
+    sizes = [12, 24, 24, 6]
+    a0 = J.init_activities_from_normal(3, sizes, "unsupervised", 8, sigma=0.05)
+    assert [tuple(a.shape) for a in a0] == [(8, w) for w in sizes]
+    assert 0.03 < float(torch.cat([a.flatten() for a in a0]).std()) < 0.07
+    opt = J.optim.sgd(1e-2)
+    out = J.make_pc_step(gm, opt, opt.init((gm, None)), gy, key=3, layer_sizes=sizes, batch_size=8, ode_solver=J.Euler(),
+                         max_t1=3, dt=0.5, stepsize_controller=J.ConstantStepSize())
+    assert out["loss"] is None and len(out["activities"]) == 4
+    a064 = [a.double().cpu() for a in a0]
+    ref, _ = O.solve_inference(fm, None, a064, y, x=None, solver="euler", max_t1=3.0, dt=0.5, event_atol=0.0, event_rtol=0.0)
+    for p, q in zip(out["activities"], ref):
+        assert rel(p[0], q) < 1e-5
+    assert rel(out["energies"], O.pc_energy_fn(fm, None, ref, y, x=None, record_layers=True)) < 1e-5
+    pg = O.compute_pc_param_grads(fm, None, ref, y, x=None)
+    for l, q in enumerate(pg):
+        assert rel(out["model"][l][1].weight, fm[l]["W"] - 1e-2 * q["W"]) < 1e-6
+    with pytest.raises(ValueError):   # jpc/_train.py:136-141
+        J.make_pc_step(gm, opt, opt.init((gm, None)), gy)

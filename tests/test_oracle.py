@@ -236,7 +236,7 @@ def test_saveat_bookkeeping_matches_oracle_interpolation():
     g = torch.Generator().manual_seed(0)
     ts_steps = [0.0, 0.4, 0.8, 1.2, 1.5]
     traj = [(t, [torch.randn(3, 4, generator=g), torch.randn(3, 2, generator=g)]) for t in ts_steps]
-    net = types.SimpleNamespace(B=3, L=2, true_dims=[5, 4, 2], dev=torch.device("cpu"))
+    net = types.SimpleNamespace(B=3, L=2, true_adims=[4, 2], dev=torch.device("cpu"))
     save = _SaveAt(net, 1.5, False, 0.5)     # ts = [0, 0.5, 1.0]
     for (t0, y0), (t1, y1) in zip(traj[:-1], traj[1:]):
         save.step(t0, y0, t1, y1)
