@@ -200,6 +200,20 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
                          float* const* gV, float* const* gbV, float* E_pairs, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ---- hybrid PC: the amortiser's layer-wise regression -------------------------------
+ * hpc_energy_fn (jpc/_core/_energies.py:161-243) and compute_hpc_param_grads (jpc/_core/_grads.py:502-541):
+ * for every layer l of the amortiser `desc` describes (unit scalings, no skips, mse),
+ *   e_l = T[l] - (W_l act_l(U[l]) + b_l),   E_l = sum e_l^2 / B   (no 1/2 in this energy),
+ *   gW[l] = -(2/B) e_l^T act_l(U[l]),       gb[l] = -(2/B) sum_rows e_l.
+ * U[l] = the layer's input (U[0] = the amortiser's input, U[l] = its own feed-forward guess of layer l-1),
+ * T[l] = the layer's target (the generator's equilibrated activity; T[L-1] = the amortiser's target).
+ * E_layers (nullable): device float[L] in pc_energy_fn's order [last layer, 1..L-2, first layer].
+ * gW / gb nullable as a pair (energy only). */
+int jpcb_hpc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                         const float* const* U, const float* const* T, float* const* gW,
+                         float* const* gb, float* E_layers, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* ---- parameter update ----------------------------------------------------------
  * The last two lines of the reference's train step, `optim.update(updates=param_grads, state, params)`
  * followed by `eqx.apply_updates` (jpc/_train.py:234-242; jpc/_core/_updates.py:189-194), for the two

@@ -66,9 +66,9 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // descriptor validation
 // ---------------------------------------------------------------------------------------------
-int validate(const jpcb_pc_desc* d) {
+int validate(const jpcb_pc_desc* d, int min_layers = 2) {
   if (!d) return fail(JPCB_EINVAL, "null descriptor");
-  if (d->n_layers < 2 || d->n_layers > JPCB_MAX_LAYERS) return fail(JPCB_EINVAL, "n_layers=%d outside [2,%d]", d->n_layers, JPCB_MAX_LAYERS);
+  if (d->n_layers < min_layers || d->n_layers > JPCB_MAX_LAYERS) return fail(JPCB_EINVAL, "n_layers=%d outside [%d,%d]", d->n_layers, min_layers, JPCB_MAX_LAYERS);
   if (d->batch_local <= 0 || d->batch_global < d->batch_local) return fail(JPCB_EINVAL, "bad batch sizes local=%d global=%d", d->batch_local, d->batch_global);
   for (int l = 0; l <= d->n_layers; ++l)
     if (d->dims[l] <= 0) return fail(JPCB_EINVAL, "dims[%d]=%d", l, d->dims[l]);
@@ -304,8 +304,8 @@ struct Run {
   float* x_out = nullptr;         // free_input: where the next grads() call writes z_0's gradient / new value
 
   int init(const jpcb_pc_desc* desc, const float* const* W_, const float* const* b_, const float* x_, const float* y_, void* wsp,
-           size_t ws_bytes, void* stream) {
-    RET(validate(desc));
+           size_t ws_bytes, void* stream, int min_layers = 2) {
+    RET(validate(desc, min_layers));
     d = desc; W = W_; b = b_; x = x_; y = y_;
     st = reinterpret_cast<cudaStream_t>(stream);
     L = d->n_layers; Bl = d->batch_local; invB = 1.f / (float)d->batch_global;
@@ -426,7 +426,9 @@ struct Run {
     return JPCB_OK;
   }
 
-  int errors(int lo, const float* const* S, bool stage, bool energy) {
+  // `Tl` / `esc_all` (layer-wise regression, jpcb_hpc_param_grads): per-layer targets instead of the next
+  // activity, and one error weight for every layer instead of lambda on the output layer only
+  int errors(int lo, const float* const* S, bool stage, bool energy, const float* const* Tl = nullptr, float esc_all = 0.f) {
     std::vector<GTask> ts;
     const bool ce = d->loss == JPCB_LOSS_CE;
     for (int l = lo; l < L; ++l) {
@@ -441,8 +443,8 @@ struct Run {
       t.e.mode = EPI_ERR;
       t.e.skip = eskip(l);
       t.e.U = l == 0 ? x : S[l - 1];
-      t.e.T = l == L - 1 ? y : S[l];
-      t.e.escale = l == L - 1 ? d->output_energy_scaling : 1.f;
+      t.e.T = Tl ? Tl[l] : (l == L - 1 ? y : S[l]);
+      t.e.escale = esc_all != 0.f ? esc_all : (l == L - 1 ? d->output_energy_scaling : 1.f);
       t.e.O = ws.err[l];
       t.e.Ob = ws.Eb[l];
       if (energy) t.e.red = ws.red + l;
@@ -644,7 +646,7 @@ const char* jpcb_last_error(void) { return g_err.c_str(); }
 unsigned long long jpcb_launch_count(void) { return g_launches.load(); }
 
 size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc) {
-  if (validate(desc) != JPCB_OK) return 0;
+  if (validate(desc, 1) != JPCB_OK) return 0;  // (a single layer is enough for jpcb_pc_ffwd_init)
   Ws w;
   carve(desc, nullptr, &w);
   return w.bytes;
@@ -654,7 +656,7 @@ int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const flo
                       const float* y, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (desc && desc->free_input) return fail(JPCB_EINVAL, "init_activities_with_ffwd needs an input (free_input is set)");
   Run r;
-  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream, 1));
   if (!A_out) return fail(JPCB_EINVAL, "null activity list");
   RET(r.zero_red());
   RET(r.prep_weights());
@@ -770,6 +772,30 @@ int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const f
   RET(r.prep_inputs(A));
   RET(r.errors(0, A, false, E_layers != nullptr));
   RET(r.wgrads(A, gW, gb));
+  if (E_layers) RET(r.finalize(E_layers, nullptr, false, nullptr));
+  return JPCB_OK;
+}
+
+int jpcb_hpc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* U,
+                         const float* const* T, float* const* gW, float* const* gb, float* E_layers, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!U || !T || !U[0]) return fail(JPCB_EINVAL, "null layer input / target lists");
+  if (desc) {
+    if (desc->free_input || desc->loss != JPCB_LOSS_MSE) return fail(JPCB_EINVAL, "layer-wise regression: mse, with an input");
+    for (int l = 0; l < desc->n_layers && l < JPCB_MAX_LAYERS; ++l)
+      if (desc->skip[l] || desc->scalings[l] != 1.f) return fail(JPCB_EINVAL, "layer-wise regression: no skips, unit scalings (layer %d)", l);
+  }
+  Run r;
+  RET(r.init(desc, W, b, U[0], T[desc ? desc->n_layers - 1 : 0], workspace, workspace_bytes, stream));
+  for (int l = 0; l < r.L; ++l)
+    if (!U[l] || !T[l]) return fail(JPCB_EINVAL, "null input / target of layer %d", l);
+  RET(r.zero_red());
+  RET(r.prep_weights());
+  RET(r.prep_inputs(U + 1));  // layer l >= 1 reads act_l(U[l])
+  // e_l = 2 (T_l - f_l(U_l)): the energy sum e_l^2 / 4 = |T_l - f_l|^2 and the gradients -(1/B) e_l^T act_l(U_l) then
+  // carry hpc_energy_fn's missing 1/2 (jpc/_core/_energies.py:228-243)
+  RET(r.errors(0, U + 1, false, E_layers != nullptr, T, 2.f));
+  if (gW) RET(r.wgrads(U + 1, gW, gb));
   if (E_layers) RET(r.finalize(E_layers, nullptr, false, nullptr));
   return JPCB_OK;
 }

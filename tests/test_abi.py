@@ -50,7 +50,7 @@ def test_workspace_sizing_and_validation_without_a_gpu():
     heun.solver = 1
     assert L.jpcb_pc_workspace_bytes(heun) > L.jpcb_pc_workspace_bytes(_desc())  # stage state + first-stage gradient
     bad = _desc()
-    bad.n_layers = 1
+    bad.n_layers = 0  # (a single layer is legal: jpcb_pc_ffwd_init serves one-layer feed-forward passes)
     assert L.jpcb_pc_workspace_bytes(bad) == 0 and b"n_layers" in L.jpcb_last_error()
     bad = _desc()
     bad.act[1] = 99

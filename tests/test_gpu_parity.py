@@ -802,3 +802,87 @@ def test_unsupervised_adaptive_and_make_pc_step():
         assert rel(out["model"][l][1].weight, fm[l]["W"] - 1e-2 * q["W"]) < 1e-6
     with pytest.raises(ValueError):   # jpc/_train.py:136-141
         J.make_pc_step(gm, opt, opt.init((gm, None)), gy)
+
+
+# ---- hybrid PC: amortiser + generator -------------------------------------------------
+def _hpc_models(d_in, width, depth, d_out, act, use_bias, seed=0):
+    """generator d_in -> d_out and amortiser d_out -> d_in of the same depth (examples/hybrid_pc.ipynb)."""
+    gen = O.make_mlp(seed, d_in, width, depth, d_out, act, use_bias=use_bias)
+    amo = O.make_mlp(seed + 1, d_out, width, depth, d_in, act, use_bias=use_bias)
+    return gen, amo
+
+
+@pytest.mark.parametrize("supervised", [True, False])
+def test_hybrid_pc_step_matches_oracle(supervised):
+    import jpc_b200 as J
+    B = 8
+    gen, amo = _hpc_models(10, 24, 3, 14, "tanh", True)
+    x, y = data(B, 10, 14, onehot_out=False, onehot_in=True)
+    ggen, gamo = to_gpu_model(gen), to_gpu_model(amo)
+    gx, gy = dev(x), dev(y)
+    fgen, famo = f32_model(gen), f32_model(amo)
+    inp, ginp = (x, gx) if supervised else (None, None)
+    # amortised initialisation
+    aa = O.init_activities_with_amort(famo, fgen, y)
+    gaa = J.init_activities_with_amort(gamo, ggen, gy)
+    assert len(gaa) == len(aa) == 4
+    for p, q in zip(gaa, aa):
+        assert rel(p, q) < TOL32
+    # one hybrid step with a fixed-step solve
+    opts = (J.optim.sgd(1e-2), J.optim.sgd(1e-2))
+    states = (opts[0].init((ggen, None)), opts[1].init(gamo))
+    out = J.make_hpc_step(ggen, gamo, opts, states, gy, input=ginp, ode_solver=J.Euler(), max_t1=3, dt=0.5,
+                          stepsize_controller=J.ConstantStepSize(), record_energies=True)
+    a0 = aa[1:] if supervised else aa
+    traj = []
+    eq, _ = O.solve_inference(fgen, None, a0, y, x=inp, solver="euler", max_t1=3.0, dt=0.5, event_atol=0.0, event_rtol=0.0,
+                              trajectory=traj)
+    assert int(out["t_max"]) == 5
+    for p, q in zip(out["activities"][1], eq):
+        assert rel(p[5], q) < TOL32
+    for_amort = eq[::-1][1:]
+    E = O.hpc_energy_fn(famo, for_amort, aa, y, inp)
+    assert abs(float(out["energies"][1]) - float(E)) <= TOL32 * float(E)
+    El = O.hpc_energy_fn(famo, for_amort, aa, y, inp, record_layers=True)
+    assert rel(J.hpc_energy_fn(gamo, devs(for_amort), gaa, gy, ginp, record_layers=True), El) < TOL32
+    gg = O.compute_pc_param_grads(fgen, None, eq, y, x=inp)
+    ag = O.compute_hpc_param_grads(famo, for_amort, aa, y, inp)
+    for l in range(3):
+        assert rel(out["generator"][l][1].weight, fgen[l]["W"] - 1e-2 * gg[l]["W"]) < 1e-6
+        assert rel(out["amortiser"][l][1].weight, famo[l]["W"] - 1e-2 * ag[l]["W"]) < 1e-6
+        assert rel(out["amortiser"][l][1].bias, famo[l]["b"] - 1e-2 * ag[l]["b"]) < 1e-6
+    jg = J.compute_hpc_param_grads(gamo, devs(for_amort), gaa, gy, ginp)
+    for l in range(3):
+        assert rel(jg[l][1].weight, ag[l]["W"]) < TOL32 and rel(jg[l][1].bias, ag[l]["b"]) < TOL32
+    if supervised:
+        assert abs(float(out["losses"][0]) - float(torch.mean((y - O.init_activities_with_ffwd(fgen, x)[-1]) ** 2))) < 1e-5
+        assert abs(float(out["losses"][1]) - float(torch.mean((x - aa[0]) ** 2))) < 1e-5
+    else:
+        assert out["losses"][0] is None
+        assert abs(float(out["losses"][1]) - float(torch.mean((for_amort[-1] - aa[0]) ** 2))) < 1e-5
+    # evaluation helper runs end to end (default adaptive solves, amortised and random inits)
+    accs = J.test_hpc(ggen, gamo, gy, gx, 0, [10, 24, 24, 14], B, max_t1=5)
+    assert len(accs) == 4 and tuple(accs[3].shape) == (B, 14) and all(0.0 <= float(a) <= 100.0 for a in accs[:3])
+    acc, preds = J.test_generative_pc(ggen, gy, gx, 0, [10, 24, 24, 14], B, max_t1=5)
+    assert 0.0 <= float(acc) <= 100.0 and rel(preds, O.init_activities_with_ffwd(fgen, x)[-1]) < TOL32
+
+
+def test_hybrid_pc_bf16():
+    """(targets 0.5 away from the predictions: with nearly-converged targets the regression error is a small
+    difference of bf16-rounded numbers and its relative accuracy is that cancellation's, not the kernel's)"""
+    import jpc_b200 as J
+    B = 32
+    gen, amo = _hpc_models(16, 64, 3, 24, "relu", False)
+    x, y = data(B, 16, 24, onehot_out=False)
+    fgen, famo = f32_model(gen), f32_model(amo)
+    aa = O.init_activities_with_amort(famo, fgen, y)
+    eq = [a + 0.5 * torch.randn(a.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64) for a in aa[1:]]
+    for_amort = eq[::-1][1:]
+    J.set_compute_dtype("bf16")
+    gamo = to_gpu_model(amo)
+    ag = O.compute_hpc_param_grads(famo, for_amort, aa, y, x)
+    jg = J.compute_hpc_param_grads(gamo, devs(for_amort), devs(aa), dev(y), dev(x))
+    for l in range(3):
+        assert rel(jg[l][1].weight, ag[l]["W"]) < TOLBF
+    E = O.hpc_energy_fn(famo, for_amort, aa, y, x, record_layers=True)
+    assert rel(J.hpc_energy_fn(gamo, devs(for_amort), devs(aa), dev(y), dev(x), record_layers=True), E) < TOLBF
