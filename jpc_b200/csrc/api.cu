@@ -247,9 +247,60 @@ int launch_warp_mt(const std::vector<GTask>& tasks, cudaStream_t st) {
   return JPCB_OK;
 }
 
+// the 8 x 16-per-warp variant (warp8_grouped_gemm)
+int launch_warp8(const std::vector<GTask>& tasks, cudaStream_t st) {
+  size_t i = 0;
+  while (i < tasks.size()) {
+    SimtGroup g;
+    memset(&g, 0, sizeof(int) * 2);
+    int n = 0, tiles = 0;
+    for (; i < tasks.size() && n < SIMT_MAX_TASKS; ++i, ++n) {
+      const GTask& t = tasks[i];
+      SimtTask& s = g.t[n];
+      s.A = Opnd{t.a_p, t.a_smn, 1, ACT_LINEAR, 0};
+      s.B = Opnd{t.b_p, t.b_smn, 1, ACT_LINEAR, 0};
+      s.K = t.K;
+      s.tile_begin = tiles;
+      s.tiles_n = (t.e.N + WG8_NT - 1) / WG8_NT;
+      s.pad_ = 0;
+      s.e = t.e;
+      tiles += s.tiles_n * ((t.e.M + WG8_MT - 1) / WG8_MT);
+    }
+    g.ntasks = n;
+    g.total_tiles = tiles;
+    if (tiles == 0) continue;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((tiles + WG_WARPS - 1) / WG_WARPS);
+    cfg.blockDim = dim3(WG_WARPS * 32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, warp8_grouped_gemm, g));
+    count_launch();
+  }
+  return JPCB_OK;
+}
+
 int launch_warp(const std::vector<GTask>& tasks, cudaStream_t st) {
-  long long w8 = 0;
-  for (const GTask& t : tasks) w8 += (long long)((t.e.M + 7) / 8) * ((t.e.N + WG_NT - 1) / WG_NT);
+  long long w8 = 0, w16 = 0;
+  bool small_idx = true;
+  int kmax = 0;
+  for (const GTask& t : tasks) {
+    kmax = t.K > kmax ? t.K : kmax;
+    w8 += (long long)((t.e.M + 7) / 8) * ((t.e.N + WG_NT - 1) / WG_NT);
+    w16 += (long long)((t.e.M + WG8_MT - 1) / WG8_MT) * ((t.e.N + WG8_NT - 1) / WG8_NT);
+    small_idx = small_idx && (long long)t.e.M * t.a_smn < (1LL << 31) && (long long)t.e.N * t.b_smn < (1LL << 31);
+  }
+  // enough 8 x 16 warp tiles for several warps per SM: the wide variant amortises the per-warp fixed costs 4x
+  static const int w16_q = [] { const char* v = getenv("JPCB_WARP8_Q"); return v ? atoi(v) : 6; }();
+  // ... as long as K is short: with only 8 lanes on K a long reduction is a long chain of dependent L2 round trips
+  static const int w16_k = [] { const char* v = getenv("JPCB_WARP8_KMAX"); return v ? atoi(v) : 512; }();
+  if (small_idx && w16_q != 0 && kmax <= w16_k && w16 >= (long long)w16_q * num_sms())
+    return launch_warp8(tasks, st);  // (negative JPCB_WARP8_Q: always, for tests)
   // 8-row patches move less operand data per multiply-add; use them while they still give every SM >= 16 warps
   return w8 >= 16LL * num_sms() ? launch_warp_mt<8>(tasks, st) : launch_warp_mt<4>(tasks, st);
 }
