@@ -108,10 +108,11 @@ class _BpcNet:
         self.x, self.y = x, y
 
     def workspace(self):
-        ws = _WS_CACHE.get((self.dev,))
+        k = (self.dev, self.stream())  # one per stream (shared with the PC entry points on that stream)
+        ws = _WS_CACHE.get(k)
         if ws is None or ws.numel() < self.ws_bytes:
             ws = torch.empty(max(self.ws_bytes, 1 << 20), dtype=torch.uint8, device=self.dev)
-            _WS_CACHE[(self.dev,)] = ws
+            _WS_CACHE[k] = ws
         return ws
 
     def stream(self):

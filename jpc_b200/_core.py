@@ -214,7 +214,7 @@ class _Net:
         self.b_shapes = [tuple(b_.shape) for b_ in bs] if bs is not None else None
 
     def workspace(self) -> torch.Tensor:
-        k = (self.dev, )
+        k = (self.dev, self.stream())  # one per stream: calls on different streams may overlap on the device
         ws = _WS_CACHE.get(k)
         if ws is None or ws.numel() < self.ws_bytes:
             ws = torch.empty(max(self.ws_bytes, 1 << 20), dtype=torch.uint8, device=self.dev)

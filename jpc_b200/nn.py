@@ -171,50 +171,78 @@ def make_skip_model(depth: int) -> list:
 # ---------------------------------------------------------------------------------------------
 # tiny pytree utilities (equinox/jax.tree_util stand-ins for the structures above)
 # ---------------------------------------------------------------------------------------------
-def tree_leaves(tree) -> list:
-    """Array leaves (torch tensors) in a deterministic order."""
-    out = []
-    if tree is None:
-        return out
-    if torch.is_tensor(tree):
-        return [tree]
-    if isinstance(tree, (list, tuple)):
-        for t in tree:
-            out.extend(tree_leaves(t))
+def _leaves_into(tree, out: list) -> None:
+    t = type(tree)  # exact-type dispatch first: these walks run every train step over every layer
+    if t is Sequential:
+        for c in tree.layers:
+            _leaves_into(c, out)
+    elif t is Linear:
+        out.append(tree.weight)
+        if tree.bias is not None:
+            out.append(tree.bias)
+    elif t is list or t is tuple:
+        for c in tree:
+            _leaves_into(c, out)
+    elif tree is None or t is Lambda:
+        return
+    elif isinstance(tree, torch.Tensor):
+        out.append(tree)
+    elif isinstance(tree, (list, tuple)):
+        for c in tree:
+            _leaves_into(c, out)
     elif isinstance(tree, Sequential):
-        for t in tree.layers:
-            out.extend(tree_leaves(t))
+        for c in tree.layers:
+            _leaves_into(c, out)
     elif isinstance(tree, Linear):
         out.append(tree.weight)
         if tree.bias is not None:
             out.append(tree.bias)
     elif isinstance(tree, dict):
         for k in sorted(tree):
-            out.extend(tree_leaves(tree[k]))
+            _leaves_into(tree[k], out)
+
+
+def tree_leaves(tree) -> list:
+    """Array leaves (torch tensors) in a deterministic order."""
+    out: list = []
+    _leaves_into(tree, out)
     return out
 
 
-def tree_unflatten_like(tree, leaves: list):
-    """Rebuilds `tree`'s structure around new leaves (consumed front to back)."""
-    if tree is None:
-        return None
-    if torch.is_tensor(tree):
-        return leaves.pop(0)
-    if isinstance(tree, list):
-        return [tree_unflatten_like(t, leaves) for t in tree]
-    if isinstance(tree, tuple):
-        return tuple(tree_unflatten_like(t, leaves) for t in tree)
-    if isinstance(tree, Sequential):
-        return Sequential([tree_unflatten_like(t, leaves) for t in tree.layers])
-    if isinstance(tree, Linear):
+def _unflatten(tree, it):
+    t = type(tree)
+    if t is Sequential:
+        new = Sequential.__new__(Sequential)
+        new.layers = tuple(_unflatten(c, it) for c in tree.layers)
+        return new
+    if t is Linear or isinstance(tree, Linear):
         new = Linear.__new__(Linear)
         new.__dict__.update(tree.__dict__)
-        new.weight = leaves.pop(0)
-        new.bias = leaves.pop(0) if tree.bias is not None else None
+        new.weight = next(it)
+        new.bias = next(it) if tree.bias is not None else None
         return new
+    if t is list:
+        return [_unflatten(c, it) for c in tree]
+    if t is tuple:
+        return tuple(_unflatten(c, it) for c in tree)
+    if tree is None or t is Lambda:
+        return tree
+    if isinstance(tree, torch.Tensor):
+        return next(it)
+    if isinstance(tree, list):
+        return [_unflatten(c, it) for c in tree]
+    if isinstance(tree, tuple):
+        return tuple(_unflatten(c, it) for c in tree)
+    if isinstance(tree, Sequential):
+        return Sequential([_unflatten(c, it) for c in tree.layers])
     if isinstance(tree, dict):
-        return {k: tree_unflatten_like(tree[k], leaves) for k in sorted(tree)}
-    return tree  # Lambda / Identity / Activation: no leaves
+        return {k: _unflatten(tree[k], it) for k in sorted(tree)}
+    return tree  # Identity / Activation / other callables: no leaves
+
+
+def tree_unflatten_like(tree, leaves):
+    """Rebuilds `tree`'s structure around new leaves (taken front to back)."""
+    return _unflatten(tree, iter(leaves))
 
 
 def tree_map(fn, tree, *rest):
