@@ -51,6 +51,13 @@ def get_compute_dtype() -> str:
 # ---------------------------------------------------------------------------------------------
 # model -> descriptor
 # ---------------------------------------------------------------------------------------------
+# torch callables a user may wrap in Lambda instead of jpc_b200.get_act_fn(...).  (torch's gelu defaults to the erf
+# form while jax.nn.gelu -- the reference's -- defaults to the tanh approximation, so it is deliberately not mapped.)
+_F = torch.nn.functional
+_TORCH_ACT_NAMES = {torch.tanh: "tanh", _F.tanh: "tanh", torch.relu: "relu", _F.relu: "relu", _F.hardtanh: "hard_tanh",
+                    _F.leaky_relu: "leaky_relu", torch.selu: "selu", _F.selu: "selu", _F.silu: "silu"}
+
+
 def _layer_parts(layer) -> Tuple[str, Linear]:
     """(activation id, Linear) of one layer in the make_mlp form Sequential([Lambda(act), Linear])
     (jpc/_utils.py:102-106).  Anything else is outside the B200 path (no CPU fallback)."""
@@ -59,7 +66,7 @@ def _layer_parts(layer) -> Tuple[str, Linear]:
     subs = getattr(layer, "layers", None)
     if subs is not None and len(subs) == 2 and hasattr(subs[1], "weight"):
         fn = getattr(subs[0], "fn", subs[0])
-        name = getattr(fn, "name", None)
+        name = getattr(fn, "name", None) or _TORCH_ACT_NAMES.get(fn)
         if name in _lib.ACT_IDS:
             return name, subs[1]
     raise NotImplementedError(

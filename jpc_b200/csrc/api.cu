@@ -790,7 +790,6 @@ int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const fl
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!A || !y || !A_new || !out2) return fail(JPCB_EINVAL, "null activities / target / outputs");
   if (desc->solver != JPCB_SOLVER_HEUN) return fail(JPCB_EINVAL, "jpcb_pc_heun_trial needs desc->solver == JPCB_SOLVER_HEUN");
-  if (desc->activity_decay != 0.f) return fail(JPCB_ENOTIMPL, "adaptive stepping with activity_decay is not on the B200 path");
   const int L = r.L;
   CK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), r.st));
   RET(r.prep_weights());
@@ -806,7 +805,14 @@ int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const fl
   RET(r.errors(fr ? 0 : 1, zt.data(), true, false));
   r.x_out = x_new;
   RET(r.grads(GRAD_HEUN2, c, zt.data(), A, A_new, false, !fr, 1, out2, rtol, atol));
-  CK(cudaMemcpyAsync(A_new[L - 1], A[L - 1], (size_t)r.Bl * desc->dims[L] * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+  const size_t n_dummy = (size_t)r.Bl * desc->dims[L];
+  if (desc->activity_decay != 0.f) {  // the dummy slot decays like every other entry of the list
+    heun_dummy_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[L - 1], A_new[L - 1], n_dummy, c * desc->activity_decay, rtol, atol, out2);
+    count_launch();
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaMemcpyAsync(A_new[L - 1], A[L - 1], n_dummy * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+  }
   RET(r.sumsq_all(A_new, out2 + 1, x_new));
   return JPCB_OK;
 }

@@ -115,6 +115,22 @@ static __global__ void scale_kernel(const float* src, float* dst, size_t n, floa
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = s * src[i];
 }
 
+// Heun trial step of the dummy output slot under activity decay (its only force is -ad/B d, jpc/_core/_energies.py:
+// 145-150): with q = dt ad / B, k1 = -q d, k2 = -q (1 - q) d  =>  d_new = d (1 - q + q^2/2) and the embedded error
+// y_err = dt (k1 - k2) / 2 = -q^2 d / 2, added to *err_acc scaled as PIDController does (atol + rtol max(|d|, |d_new|)).
+static __global__ void heun_dummy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, float q, float rtol,
+                                         float atol, float* err_acc) {
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = src[i], dn = d * (1.f - q + 0.5f * q * q);
+    dst[i] = dn;
+    const float sc = (-0.5f * q * q * d) / (atol + rtol * fmaxf(fabsf(d), fabsf(dn)));
+    acc += sc * sc;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(err_acc, acc);
+}
+
 // Cross-entropy output layer (jpc/_core/_energies.py:107-109): one warp per batch row.
 //   E_out += -lam * sum_j y_j log_softmax(logits)_j            (into *red, if red)
 //   err    = -dE_out/dlogits = lam * (y - softmax(logits) * sum_j y_j)   (fp32 and/or bf16 copies, if given)

@@ -454,14 +454,15 @@ def test_cross_entropy_bf16():
 
 
 # ---- adaptive solve: Heun + PIDController, the reference's default ----------------
-def _adaptive_case(om, sk, x, y, tol, max_t1, dt0, rtol=1e-3, atol=1e-3, param_type="sp"):
+def _adaptive_case(om, sk, x, y, tol, max_t1, dt0, rtol=1e-3, atol=1e-3, param_type="sp", ad=0.0):
     import jpc_b200 as J
     gm, gsk = to_gpu_model(om), _gpu_skip(sk)
     gx, gy = dev(x), dev(y)
     a0 = O.init_activities_with_ffwd(om, x, skips=sk, param_type=param_type)
-    ref, st = O.solve_inference_adaptive(om, sk, a0, y, x=x, max_t1=max_t1, dt0=dt0, rtol=rtol, atol=atol, param_type=param_type)
+    ref, st = O.solve_inference_adaptive(om, sk, a0, y, x=x, max_t1=max_t1, dt0=dt0, rtol=rtol, atol=atol, param_type=param_type,
+                                         activity_decay=ad)
     sol = J.solve_inference((gm, gsk), devs(a0), gy, input=gx, param_type=param_type, solver=J.Heun(), max_t1=max_t1, dt=dt0,
-                            stepsize_controller=J.PIDController(rtol=rtol, atol=atol))
+                            stepsize_controller=J.PIDController(rtol=rtol, atol=atol), activity_decay=ad)
     got = J.solve_inference.last_stats
     assert (got["accepted"], got["rejected"], got["event"]) == (st["accepted"], st["rejected"], st["event"])
     amax = max(float(t.abs().max()) for t in ref[:-1])
@@ -480,6 +481,8 @@ def test_adaptive_heun_pid_matches_oracle_controller():
     assert st["rejected"] >= 1
     om, sk, x, y = _case(12, 16, 6, 3, "relu", 5, param_type="mupc", skips=True)
     _adaptive_case(om, sk, x, y, 2e-5, 4.0, None, param_type="mupc")
+    om, sk, x, y = _case(10, 20, 3, 5, "tanh", 8, use_bias=True)
+    _adaptive_case(om, sk, x, y, 2e-5, 5.0, None, ad=0.5)          # activity decay: the dummy output slot decays too
 
 
 def test_make_pc_step_default_arguments_run_the_adaptive_solve():
