@@ -214,6 +214,22 @@ int jpcb_hpc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const 
                          float* const* gb, float* E_layers, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- error-reparameterised PC, ePC -------------------------------------------------
+ * epc_energy_fn (jpc/_core/_energies.py:360-458), compute_epc_error_grad / compute_epc_param_grads
+ * (jpc/_core/_grads.py:857-949) for supervised networks.  The state is the error list
+ * E = [eps_1 .. eps_{L-1}, eps_L] (shapes of the PC activity list); activities follow from an error-perturbed
+ * forward pass z_{l+1} = a_l f_l(z_l) + eps_{l+1} (+ z_l where skip[l]), z_L = a f(z_{L-1}) - eps_L, and
+ *   F = ( sum_{l<L} 1/2 |eps_l|^2 + 1/2 |y - z_L|^2  [or the cross-entropy of z_L] ) / B.
+ * One call = the forward chain (L dependent GEMMs), and if gradients are requested the backward chain
+ * rho_l = act_l'(z_l) . (a_l rho_{l+1} W_l) + s_l rho_{l+1} from rho_L = y - z_L (L-1 dependent GEMMs):
+ *   gE[l-1] = (eps_l - rho_l) / B  (l < L),   gE[L-1] = rho_L / B,   gW[l] = -(a_l/B) rho_{l+1}^T act_l(z_l).
+ * F, gE, (gW, gb) are each nullable.  Workspace: jpcb_epc_workspace_bytes(desc) (larger than the PC one). */
+size_t jpcb_epc_workspace_bytes(const jpcb_pc_desc* desc);
+int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                   const float* const* E, const float* x, const float* y, float* F, float* const* gE,
+                   float* const* gW, float* const* gb, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* ---- parameter update ----------------------------------------------------------
  * The last two lines of the reference's train step, `optim.update(updates=param_grads, state, params)`
  * followed by `eqx.apply_updates` (jpc/_train.py:234-242; jpc/_core/_updates.py:189-194), for the two

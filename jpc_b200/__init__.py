@@ -22,6 +22,8 @@ from ._bpc import (bpc_energy_fn, compute_bpc_activity_grad, compute_bpc_param_g
                    update_bpc_activities, update_bpc_params)
 from ._errors import _check_param_type
 from ._eval import test_discriminative_pc, test_generative_pc
+from ._epc import (compute_epc_error_grad, compute_epc_param_grads, epc_energy_fn, init_epc_errors, update_epc_errors,
+                   update_epc_params)
 from ._hpc import (compute_hpc_param_grads, hpc_energy_fn, init_activities_with_amort, make_hpc_step, test_hpc)
 from ._train import make_pc_step
 from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,

@@ -74,6 +74,8 @@ SIGNATURES = {
     "jpcb_bpc_infer": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, C.c_size_t, _P]),
     "jpcb_bpc_param_grads": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
     "jpcb_hpc_param_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
+    "jpcb_epc_workspace_bytes": (C.c_size_t, [C.POINTER(PcDesc)]),
+    "jpcb_epc_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _PP, _PP, _PP, _P, C.c_size_t, _P]),
     "jpcb_optim_sgd": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), _PP, _PP, C.c_double, _PP, _P]),
     "jpcb_optim_adam": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), _PP, _PP, _PP, _PP, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int, _PP, _PP, _PP, _P]),

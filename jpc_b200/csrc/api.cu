@@ -857,6 +857,134 @@ int jpcb_hpc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const 
   return JPCB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// error-reparameterised PC: the state is the errors, the activities follow from them
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct EpcWs {
+  std::vector<float*> Z;    // [L-1] z_1 .. z_{L-1} of the error-perturbed forward pass
+  std::vector<float*> Rho;  // [L]   tensor-core path: fp32 back-propagated signal rho_{l+1} (the fp32 path keeps it in ws.err)
+  size_t bytes = 0;
+};
+void carve_epc(const jpcb_pc_desc* d, void* base, size_t pc_bytes, EpcWs* w) {
+  const int L = d->n_layers;
+  const size_t Bl = (size_t)d->batch_local;
+  Bump b{reinterpret_cast<char*>(base)};
+  b.off = pc_bytes;
+  w->Z.assign(L, nullptr);
+  w->Rho.assign(L, nullptr);
+  for (int l = 0; l + 1 < L; ++l) w->Z[l] = b.take<float>(Bl * d->dims[l + 1]);
+  if (d->dtype == JPCB_DTYPE_BF16)
+    for (int l = 0; l < L; ++l) w->Rho[l] = b.take<float>(Bl * d->dims[l + 1]);
+  w->bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
+}
+}  // namespace
+
+size_t jpcb_epc_workspace_bytes(const jpcb_pc_desc* desc) {
+  if (validate(desc) != JPCB_OK) return 0;
+  Ws w;
+  carve(desc, nullptr, &w);
+  EpcWs x;
+  carve_epc(desc, nullptr, w.bytes, &x);
+  return x.bytes;
+}
+
+int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* E, const float* x,
+                   const float* y, float* F, float* const* gE, float* const* gW, float* const* gb, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (desc && desc->free_input) return fail(JPCB_ENOTIMPL, "unsupervised ePC (x = None) is not on the B200 path");
+  Run r;
+  RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
+  if (!E || !y) return fail(JPCB_EINVAL, "null errors / target");
+  if (desc->activity_decay != 0.f || desc->output_energy_scaling != 1.f)
+    return fail(JPCB_EINVAL, "epc_energy_fn has no activity decay / output energy scaling");
+  EpcWs X;
+  carve_epc(desc, workspace, r.ws.bytes, &X);
+  if (workspace_bytes < X.bytes) return fail(JPCB_EWORKSPACE, "workspace too small: need %zu bytes (jpcb_epc_workspace_bytes), got %zu", X.bytes, workspace_bytes);
+  const int L = r.L, Bl = r.Bl;
+  const bool tc = r.tc, ce = desc->loss == JPCB_LOSS_CE;
+  auto rho = [&](int l) { return tc ? X.Rho[l] : r.ws.err[l]; };  // rho_{l+1}, fp32
+  RET(r.zero_red());
+  RET(r.prep_weights());
+  RET(r.prep_inputs(nullptr));
+  // ---- error-perturbed forward pass (jpc/_core/_energies.py:434-447): z_{l+1} = a_l f_l(z_l) + eps_{l+1} (+ z_l) ----
+  for (int l = 0; l + 1 < L; ++l) {
+    GTask t;
+    r.fwd_operands(t, l, nullptr, false);
+    t.e.mode = EPI_FFWD;
+    t.e.skip = 1.f; t.e.U = E[l];
+    if (desc->skip[l]) t.e.Gin = l == 0 ? x : X.Z[l - 1];  // any non-None skip below the output layer (:441-442)
+    t.e.O = X.Z[l];
+    t.e.act = desc->act[l + 1];
+    if (tc) t.e.Ob = r.ws.Hb[l + 1]; else t.e.Oh = r.ws.Hf[l + 1];
+    RET(r.launch({t}));
+  }
+  {  // output layer: z_L = a f(z_{L-1}) - eps_L; residual rho_L = y - z_L (or the softmax error) and its energy
+    GTask t;
+    r.fwd_operands(t, L - 1, nullptr, false);
+    t.e.skip = -1.f; t.e.U = E[L - 1];
+    if (ce) {
+      t.e.mode = EPI_FFWD;
+      t.e.O = r.ws.logits;
+      RET(r.launch({t}));
+      RET(r.ce_rows(r.ws.logits, 1.f, rho(L - 1), r.ws.Eb[L - 1], r.ws.red + (L - 1)));
+    } else {
+      t.e.mode = EPI_ERR;
+      t.e.T = y; t.e.escale = 1.f;
+      t.e.O = rho(L - 1); t.e.Ob = r.ws.Eb[L - 1];
+      t.e.red = r.ws.red + (L - 1);
+      RET(r.launch({t}));
+    }
+  }
+  // ---- energy: (sum_{l<L} 1/2 |eps_l|^2 + output term) / B  (:449-457) ----
+  if (F) {
+    for (int l = 0; l + 1 < L; ++l) {
+      const size_t n = (size_t)Bl * desc->dims[l + 1];
+      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, r.st>>>(E[l], n, r.ws.red + RED_SUMSQ); count_launch();
+    }
+    CK(cudaGetLastError());
+    finalize_kernel<<<1, 32, 0, r.st>>>(r.ws.red, L, r.invB, nullptr, F, r.ws.red + RED_SUMSQ, 1.f, r.ws.red + RED_LOSS, nullptr);
+    count_launch();
+    CK(cudaGetLastError());
+  }
+  if (!gE && !gW) return JPCB_OK;
+  // ---- backward pass: rho_l = act_l'(z_l) . (a_l rho_{l+1} W_l) + s_l rho_{l+1};  dF/d eps_l = (eps_l - rho_l) / B ----
+  // (the PC activity-gradient epilogue with "own error" 0 and coefficient -1 returns exactly rho_l)
+  for (int l = L - 1; l >= 1; --l) {
+    GTask t;
+    t.e.mode = EPI_GRAD; t.e.sub = GRAD_OUT; t.e.act = desc->act[l];
+    t.e.M = Bl; t.e.N = desc->dims[l]; t.K = desc->dims[l + 1];
+    t.a_p = rho(l); t.a_smn = desc->dims[l + 1]; t.a_sk = 1;
+    t.b_p = r.ws.WTf[l]; t.b_smn = desc->dims[l + 1]; t.b_sk = 1;
+    t.a_b = r.ws.Eb[l]; t.b_b = r.ws.WTb[l];
+    t.e.alpha = desc->scalings[l];
+    t.e.skip = (desc->skip[l] && l + 1 < L) ? 1.f : 0.f;  // (the output layer's forward pass has no skip term)
+    t.e.En = rho(l); t.e.Enb = r.ws.Eb[l];
+    t.e.Z = X.Z[l - 1]; t.e.P = X.Z[l - 1];
+    t.e.c = -1.f; t.e.gscale = 1.f;
+    t.e.O = rho(l - 1);
+    RET(r.launch({t}));
+    if (tc) {
+      const size_t n = (size_t)Bl * desc->dims[l];
+      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, r.st>>>(rho(l - 1), r.ws.Eb[l - 1], n, ACT_LINEAR); count_launch();
+      CK(cudaGetLastError());
+    }
+  }
+  if (gE) {
+    for (int l = 0; l < L; ++l) {
+      if (!gE[l]) return fail(JPCB_EINVAL, "null error-gradient buffer %d", l);
+      const size_t n = (size_t)Bl * desc->dims[l + 1];
+      // hidden errors: (eps - rho) / B; the output "error" enters z_L with a minus sign and carries no quadratic term: rho_L / B
+      if (l + 1 < L) axpby_kernel<<<ew_grid(n, 256), 256, 0, r.st>>>(E[l], rho(l), gE[l], n, r.invB, -r.invB);
+      else scale_kernel<<<ew_grid(n, 256), 256, 0, r.st>>>(rho(l), gE[l], n, r.invB);
+      count_launch();
+    }
+    CK(cudaGetLastError());
+  }
+  if (gW) RET(r.wgrads(nullptr, gW, gb));  // -(a_l / B) rho_{l+1}^T act_l(z_l): the PC weight-gradient schedule on rho
+  return JPCB_OK;
+}
+
 int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, const float* y,
                        float* const* A_out, float* loss_out, float* E_layers, float* const* gW, float* const* gb, void* workspace,
                        size_t workspace_bytes, void* stream) {

@@ -258,6 +258,12 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
 #pragma unroll
       for (int j = 0; j < 4; ++j) pred[j] += e.skip * u[j];
     }
+    if (!PLAIN && mode == EPI_FFWD && e.Gin != nullptr) {  // a second additive input (ePC: error perturbation AND skip)
+      float gi[4];
+      ld4(e.Gin, idx, nvalid, vec, gi);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pred[j] += gi[j];
+    }
     if (mode == EPI_FFWD) {
       st4(e.O, idx, nvalid, vec, pred);
       if (e.O2) st4(e.O2, idx, nvalid, vec, pred);

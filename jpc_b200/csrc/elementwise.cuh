@@ -115,6 +115,13 @@ static __global__ void scale_kernel(const float* src, float* dst, size_t n, floa
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = s * src[i];
 }
 
+// out[i] = a * x[i] + b * y[i]
+static __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, size_t n,
+                                    float a, float b) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + b * y[i];
+}
+
 // Heun trial step of the dummy output slot under activity decay (its only force is -ad/B d, jpc/_core/_energies.py:
 // 145-150): with q = dt ad / B, k1 = -q d, k2 = -q (1 - q) d  =>  d_new = d (1 - q + q^2/2) and the embedded error
 // y_err = dt (k1 - k2) / 2 = -q^2 d / 2, added to *err_acc scaled as PIDController does (atol + rtol max(|d|, |d_new|)).

@@ -896,3 +896,64 @@ def test_hybrid_pc_bf16():
         assert rel(jg[l][1].weight, ag[l]["W"]) < TOLBF
     E = O.hpc_energy_fn(famo, for_amort, aa, y, x, record_layers=True)
     assert rel(J.hpc_energy_fn(gamo, devs(for_amort), devs(aa), dev(y), dev(x), record_layers=True), E) < TOLBF
+
+
+# ---- error-reparameterised PC ------------------------------------------------------
+def _check_epc(om, sk, x, y, tol, param_type="sp", loss="mse", kink_frac=0.0):
+    """`kink_frac`: fraction of error-gradient entries allowed outside `tol`.  In ePC the activities are OUTPUTS of the
+    forward GEMMs, so on the bf16 path a relu pre-activation within ~1e-3 of zero can land on the other side of the
+    kink and flip relu'(z) for that one entry (measured, scripts/epc_check.py: 1-5 entries of ~3000 per tensor, none
+    with tanh, none in fp32).  PC proper does not have this: its activities are fp32 master state."""
+    import jpc_b200 as J
+    gm, gsk, gx, gy = to_gpu_model(om), _gpu_skip(sk), dev(x), dev(y)
+    g = torch.Generator().manual_seed(11)
+    dims = [l["W"].shape[0] for l in om]
+    errs = [(0.3 * torch.randn(x.shape[0], w, generator=g, dtype=torch.float64)).float().double() for w in dims]
+    kw = dict(x=x, param_type=param_type)
+    F, ge = O.compute_epc_error_grad(om, sk, errs, y, loss=loss, **kw)
+    gF, gge = J.compute_epc_error_grad((gm, gsk), devs(errs), gy, x=gx, loss_id=loss, param_type=param_type)
+    assert abs(float(gF) - float(F)) <= tol * abs(float(F))
+    assert abs(float(J.epc_energy_fn((gm, gsk), devs(errs), gy, x=gx, loss=loss, param_type=param_type)) - float(F)) <= tol * abs(float(F))
+    gmax = max(float(t.abs().max()) for t in ge)
+    for p, q in zip(gge, ge):
+        bad = ((p.double().cpu() - q).abs() > tol * gmax).double().mean()
+        assert float(bad) <= kink_frac
+    pg = O.compute_epc_param_grads(om, sk, errs, y, loss=loss, **kw)
+    mg, sg = J.compute_epc_param_grads((gm, gsk), devs(errs), gy, x=gx, loss_id=loss, param_type=param_type)
+    wmax = max(float(q["W"].abs().max()) for q in pg)
+    for l, q in enumerate(pg):
+        dW = (mg[l][1].weight.double().cpu() - q["W"]).abs()
+        lim = tol * max(wmax, float(q["W"].abs().max()))
+        assert float((dW > lim).double().mean()) <= kink_frac and float(dW.max()) < (10 if kink_frac else 1) * lim
+        if q["b"] is not None:
+            assert rel(mg[l][1].bias, q["b"]) < tol or float((mg[l][1].bias.double().cpu() - q["b"]).abs().max()) < tol * wmax
+    # one error update + one parameter update, the reference's loop body
+    opt = J.optim.sgd(0.1)
+    res = J.update_epc_errors((gm, gsk), devs(errs), opt, opt.init(devs(errs)), gy, input=gx, loss_id=loss, param_type=param_type)
+    for p, e0, q in zip(res["errors"], errs, gge):   # (the update applied to the library's own gradient)
+        assert float((p.double().cpu() - (e0 - 0.1 * q.double().cpu())).abs().max()) <= 1e-5 * max(1.0, float(e0.abs().max()))
+    res = J.update_epc_params((gm, gsk), devs(errs), opt, opt.init((gm, gsk)), gy, input=gx, loss_id=loss, param_type=param_type)
+    assert set(res) == {"model", "skip_model", "grads", "opt_state"} and len(res["model"]) == len(om)
+
+
+def test_epc_fp32():
+    om, sk, x, y = _case(10, 20, 3, 5, "tanh", 8, use_bias=True)
+    _check_epc(om, sk, x, y, TOL32)
+    om, sk, x, y = _case(9, 17, 4, 6, "relu", 6, onehot_out=True)
+    _check_epc(om, sk, x, y, TOL32, loss="ce")
+    om, sk, x, y = _case(12, 16, 6, 3, "relu", 5, param_type="mupc", skips=True)
+    _check_epc(om, sk, x, y, TOL32, param_type="mupc")
+    import jpc_b200 as J
+    errs = J.init_epc_errors([10, 20, 20, 5], 8)
+    assert [tuple(e.shape) for e in errs] == [(8, 20), (8, 20), (8, 5)] and float(sum(e.abs().sum() for e in errs)) == 0.0
+    with pytest.raises(NotImplementedError):
+        J.epc_energy_fn((to_gpu_model(om), None), errs, dev(y), x=None)
+
+
+def test_epc_bf16():
+    import jpc_b200 as J
+    om, sk, x, y = _case(64, 128, 4, 32, "tanh", 64, use_bias=True)
+    J.set_compute_dtype("bf16")
+    _check_epc(om, sk, x, y, TOLBF)
+    om, sk, x, y = _case(50, 96, 4, 10, "relu", 32, skips=True, onehot_out=False)
+    _check_epc(om, sk, x, y, TOLBF, kink_frac=5e-3)
