@@ -285,6 +285,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = the workload's batch on every rank (default, the driver's contract); strong = the "
+                         "workload's batch split over the ranks (SURVEY 8e: 4096 -> 2048/1024/512 rows)")
     ap.add_argument("--cpu-rows", type=int, default=256, help="rows per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bpc-f32", action="store_true", help="c5: run bPC on the fp32 CUDA-core path instead of bf16 tensor cores")
@@ -317,6 +320,10 @@ def main():
     from jpc_b200._train import _Arena
 
     J.set_compute_dtype(w["dtype"])
+    if args.scaling == "strong" and world > 1:
+        if w["B"] % (8 * world):
+            raise SystemExit(f"--scaling strong: batch {w['B']} does not split into {world} shards of a multiple of 8 rows")
+        w = dict(w, B=w["B"] // world, desc=w["desc"] + f" (strong scaling: {w['B'] // world} of {w['B']} rows per GPU)")
     om, x_h, y_h = make_inputs(w, seed_d=1 + rank)
     gm = to_device_model(om, dev)
     gsk = J.make_skip_model(w["depth"]) if w["skips"] else None
@@ -497,7 +504,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "vs_baseline": None,
             "dtype": w["dtype"], "data": "synthetic",
             "config": {"workload": w["desc"], "global_batch": B_global, "inference_steps": T, "solver": w["solver"],
                        "parallelism": f"dp{world}", "l2": "working set (activities + operand copies > 126 MB L2) exceeds L2; no flush"

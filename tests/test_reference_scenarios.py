@@ -3,7 +3,7 @@ syntax (keyword names, argument order, result keys) -- a user switching `import 
 `optax` -> `jpc.optim`, `diffrax` -> `jpc.{Heun, Euler, PIDController, ConstantStepSize}` keeps their code.
 Scenario list and fixture shapes follow /root/reference/tests/{conftest,test_train,test_infer,test_updates,
 test_init,test_energies,test_grads,test_utils,test_errors,test_test_functions}.py (batch 4, 10-20-20-5, relu,
-no bias); ePC / PDM / analytical scenarios are out of scope.  Like the reference's, these
+no bias); PDM / analytical / unsupervised-ePC scenarios are out of scope.  Like the reference's, these
 are smoke-level assertions (keys, shapes, finiteness); numerical parity is tests/test_gpu_parity.py's job."""
 import pytest
 import torch
@@ -277,6 +277,38 @@ def test_energies_and_grads(jpc, simple_model, x, y, y_onehot):
     assert len(grads) == len(bacts) and _finite(energy)
     tdg, bug = jpc.compute_bpc_param_grads(top_down_model=td, bottom_up_model=bu, activities=bacts, y=y, x=x)
     assert len(tdg) == len(td) and len(bug) == len(bu)
+
+
+# ---- ePC scenarios of test_init.py / test_energies.py / test_grads.py / test_updates.py ----------------------
+def test_epc_scenarios(jpc, simple_model, x, y, y_onehot):
+    errors = jpc.init_epc_errors(layer_sizes=SIZES, batch_size=x.shape[0], mode="supervised")
+    assert [tuple(e.shape) for e in errors] == [(B, HID), (B, HID), (B, D_OUT)] and all(float(e.abs().sum()) == 0 for e in errors)
+    assert len(jpc.init_epc_errors(layer_sizes=SIZES, batch_size=B, mode="unsupervised")) == len(SIZES)
+    params = (simple_model, None)
+    for loss, target in (("mse", y), ("ce", y_onehot)):
+        energy = jpc.epc_energy_fn(params=params, errors=errors, y=target, x=x, loss=loss, param_type="sp")
+        assert _finite(energy) and float(energy) >= 0
+        energy, grads = jpc.compute_epc_error_grad(params=params, errors=errors, y=target, x=x, loss_id=loss, param_type="sp")
+        assert len(grads) == len(errors) and _finite(energy)
+        optim = jpc.optim.sgd(learning_rate=0.01)
+        result = jpc.update_epc_errors(params=params, errors=errors, optim=optim, opt_state=optim.init(errors), output=target,
+                                       input=x, loss_id=loss, param_type="sp")
+        for k in ("energy", "errors", "grads", "opt_state"):
+            assert k in result
+        assert len(result["errors"]) == len(errors) and _finite(result["energy"])
+    for pt in ("sp", "mupc", "ntp"):
+        m = jpc.make_mlp(key=42, input_dim=D_IN, width=HID, depth=DEPTH, output_dim=D_OUT, act_fn="relu", use_bias=False,
+                         param_type=pt)
+        assert _finite(jpc.epc_energy_fn(params=(m, None), errors=errors, y=y, x=x, loss="mse", param_type=pt))
+        model_grads, skip_grads = jpc.compute_epc_param_grads(params=(m, None), errors=errors, y=y, x=x, loss_id="mse", param_type=pt)
+        assert len(model_grads) == len(m)
+        optim = jpc.optim.sgd(learning_rate=0.01)
+        result = jpc.update_epc_params(params=(m, None), errors=errors, optim=optim, opt_state=optim.init((m, None)), output=y,
+                                       input=x, loss_id="mse", param_type=pt)
+        for k in ("model", "skip_model", "grads", "opt_state"):
+            assert k in result
+    skip = jpc.make_skip_model(DEPTH)
+    assert _finite(jpc.epc_energy_fn(params=(simple_model, skip), errors=errors, y=y, x=x, loss="mse", param_type="sp"))
 
 
 # ---- test_utils.py / test_errors.py -------------------------------------------------------------
