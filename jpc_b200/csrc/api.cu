@@ -507,6 +507,13 @@ struct Run {
   }
   // err[0] = S[0] - P1 without a GEMM (K = 0 task on the CUDA-core kernel), optional energy
   int error0_from_p1(const float* const* S, bool energy) {
+    const size_t n0 = (size_t)Bl * d->dims[1];
+    if (n0 % 4 == 0 && (reinterpret_cast<uintptr_t>(S[0]) & 15) == 0) {  // plain streaming pass (the usual case)
+      err0_kernel<<<ew_grid(n0 / 4, 256), 256, 0, st>>>(S[0], ws.P1, ws.err[0], ws.Eb[0], n0 / 4, energy ? ws.red + 0 : nullptr);
+      count_launch();
+      CK(cudaGetLastError());
+      return JPCB_OK;
+    }
     GTask t;
     t.e.mode = EPI_ERR;
     t.e.M = Bl; t.e.N = d->dims[1]; t.K = 0;

@@ -115,6 +115,30 @@ static __global__ void scale_kernel(const float* src, float* dst, size_t n, floa
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = s * src[i];
 }
 
+// First-layer prediction error from the hoisted prediction: e = z_1 - P1 (fp32 and/or bf16 copies), optional energy
+// 1/2 sum e^2 into *red.  n % 4 == 0 and 16-byte aligned pointers (feature dims are multiples of 4 on this path).
+static __global__ void err0_kernel(const float* __restrict__ z, const float* __restrict__ p1, float* __restrict__ err,
+                                   __nv_bfloat16* __restrict__ err_b, size_t n4, float* red) {
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(z) + i), b = __ldcs(reinterpret_cast<const float4*>(p1) + i);
+    const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    if (err) reinterpret_cast<float4*>(err)[i] = d;
+    if (err_b) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+      uint2 t;
+      t.x = *reinterpret_cast<uint32_t*>(&lo);
+      t.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(err_b)[i] = t;
+    }
+    acc += 0.5f * (d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
+  }
+  if (red) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(red, acc);
+  }
+}
+
 // out[i] = a * x[i] + b * y[i]
 static __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, size_t n,
                                     float a, float b) {
