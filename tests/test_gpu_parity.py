@@ -957,3 +957,38 @@ def test_epc_bf16():
     _check_epc(om, sk, x, y, TOLBF)
     om, sk, x, y = _case(50, 96, 4, 10, "relu", 32, skips=True, onehot_out=False)
     _check_epc(om, sk, x, y, TOLBF, kink_frac=5e-3)
+
+
+# ---- BASELINE config 4 at full size (the bench line's workload) ------------------------------------
+def test_config4_wide_full_size_bf16():
+    """2048-wide, 8 layers, batch 4096, bf16 operands, 20 Euler steps -- the whole fused train step on the GPU, checked
+    with a bounded amount of oracle work through properties of the path:
+      * samples are independent during inference, so the first 48 rows of the full-batch result must equal
+        the fp64 oracle run on those 48 rows alone with the step size rescaled by 48/4096 (the energy's 1/B);
+      * every layer energy and the output layer's weight gradient are recomputed in fp64 from the activities the GPU
+        returned.  (Only the output layer: 20 steps of dt/B = 1.2e-4 move the hidden activities by less than the bf16
+        rounding of the feed-forward pass they started from, so an fp64 re-evaluation of a HIDDEN prediction error from
+        bf16-initialised activities measures that rounding, not the physical error -- scripts/c4_wgrad_check.py; the
+        hidden-layer gradients are covered at sizes the oracle can run end to end, and by the row-subset check here.)"""
+    import jpc_b200 as J
+    B, D, L, n = 4096, 2048, 8, 48
+    om, sk, x, y = _case(D, D, L, D, "tanh", B)
+    J.set_compute_dtype("bf16")
+    acts, arena = _fused_step_raw(om, sk, x, y, "euler", 10.0, 0.5)
+    xs, ys = x[:n], y[:n]
+    a0 = O.init_activities_with_ffwd(om, xs)
+    dt_s = 0.5 * n / B
+    ref, steps = O.solve_inference(om, None, a0, ys, x=xs, solver="euler", max_t1=20 * dt_s, dt=dt_s, use_closed_form=True,
+                                   event_atol=0.0, event_rtol=0.0)
+    assert steps == 20
+    for l in range(L - 1):
+        assert rel(acts[l][:n], ref[l]) < TOLBF
+    # energies and one weight gradient from the returned activities (fp64 on the host, layers 3 -> 4)
+    A = [a.double().cpu() for a in acts]
+    errs, scal = O.closed_form_errors(om, None, A, y, x)
+    E = torch.stack([0.5 * (e ** 2).sum() / B for e in errs])
+    E = torch.stack([E[L - 1]] + [E[k] for k in range(1, L - 1)] + [E[0]])   # reference order [output, hidden.., first]
+    assert rel(arena.E, E) < TOLBF
+    l = L - 1
+    gW = -(scal[l] / B) * errs[l].T @ O.act_fn(om[l]["act"], A[l - 1])
+    assert rel(arena.gW[l], gW) < TOLBF
