@@ -992,3 +992,18 @@ def test_config4_wide_full_size_bf16():
     l = L - 1
     gW = -(scal[l] / B) * errs[l].T @ O.act_fn(om[l]["act"], A[l - 1])
     assert rel(arena.gW[l], gW) < TOLBF
+    # stress step size dt = 0.1 B: every layer moves by O(1) and inference all but converges; same row-subset
+    # oracle and the output layer's weight gradient
+    acts, arena = _fused_step_raw(om, sk, x, y, "euler", 20 * 0.1 * B, 0.1 * B)
+    ref, steps = O.solve_inference(om, None, a0, ys, x=xs, solver="euler", max_t1=20 * 0.1 * n, dt=0.1 * n, use_closed_form=True,
+                                   event_atol=0.0, event_rtol=0.0)
+    assert steps == 20
+    amax = max(float(t.abs().max()) for t in ref[:-1])
+    for l in range(L - 1):
+        assert rel(acts[l][:n], ref[l]) < TOLBF or float((acts[l][:n].double().cpu() - ref[l]).abs().max()) < TOLBF * amax
+    A = [a.double().cpu() for a in acts]
+    errs, scal = O.closed_form_errors(om, None, A, y, x)
+    gmax = max(float(g.abs().max()) for g in arena.gW)
+    for l in (L - 1,):
+        gW = -(scal[l] / B) * errs[l].T @ O.act_fn(om[l]["act"], A[l - 1])
+        assert rel(arena.gW[l], gW) < TOLBF or float((arena.gW[l].double().cpu() - gW).abs().max()) < TOLBF * gmax
