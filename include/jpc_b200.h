@@ -44,6 +44,10 @@ extern "C" {
  * cores, bf16 operands, fp32 accumulation in TMEM, fp32 master activities (2e-2 parity). */
 #define JPCB_DTYPE_F32 0
 #define JPCB_DTYPE_BF16 1
+/* fp32 parity on the tensor cores (bPC entry points): every GEMM operand is a 3-way bf16 split hi + mid + lo (24
+ * mantissa bits) and every GEMM runs the six products hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi into one fp32
+ * accumulator; activities, errors and epilogue arithmetic stay fp32 with accurate activations (1e-5 parity). */
+#define JPCB_DTYPE_F32X3 2
 
 /* activation ids, order of jpc/_utils.py:13-15 */
 #define JPCB_ACT_LINEAR 0

@@ -61,7 +61,8 @@ class _BpcNet:
             raise NotImplementedError("mixed bias / no-bias layers are not on the B200 path")
         skips = _skip_flags(skip_model, n)
         B = x.shape[0]
-        self.bf16 = _core.get_compute_dtype() == "bf16"
+        self.dtype = _core.get_compute_dtype()
+        self.bf16 = self.dtype != "f32"  # either tensor-core path: same layout rules (dims / batch multiples of 8)
         bWs = [l.bias for l in self.td_lin] if all(td_bias) else None
         bVs = [l.bias for l in self.bu_lin] if all(bu_bias) else None
         if self.bf16:
@@ -91,7 +92,7 @@ class _BpcNet:
             d.td.skip[j] = 1 if skips[j] else 0
             d.td.scalings[j] = 1.0
         d.td.has_bias, d.bu_has_bias = int(all(td_bias)), int(all(bu_bias))
-        d.td.dtype, d.td.loss = (_lib.DTYPE_BF16 if self.bf16 else _lib.DTYPE_F32), _lib.LOSS_MSE
+        d.td.dtype, d.td.loss = _lib.DTYPE_IDS[self.dtype], _lib.LOSS_MSE
         d.td.output_energy_scaling, d.td.activity_decay = 1.0, 0.0
         d.td.solver, d.td.n_steps, d.td.dt, d.td.dt_last = _lib.SOLVER_EULER, int(n_steps), float(dt), float(dt)
         d.forward_energy_weight, d.backward_energy_weight = float(forward_energy_weight), float(backward_energy_weight)

@@ -37,10 +37,11 @@ _COMPUTE_DTYPE = "f32"
 
 
 def set_compute_dtype(name: str) -> None:
-    """"f32" (fp32 FMA, 1e-5 parity) or "bf16" (tcgen05 tensor cores, fp32 accumulate, 2e-2)."""
+    """"f32" (fp32 FMA, 1e-5 parity), "bf16" (tcgen05 tensor cores, fp32 accumulate, 2e-2) or "f32x3" (tcgen05 on 3-way
+    bf16 split operands, six products per GEMM: fp32 parity at tensor-core speed; bPC entry points only so far)."""
     global _COMPUTE_DTYPE
-    if name not in ("f32", "bf16"):
-        raise ValueError('compute dtype must be "f32" or "bf16"')
+    if name not in ("f32", "bf16", "f32x3"):
+        raise ValueError('compute dtype must be "f32", "bf16" or "f32x3"')
     _COMPUTE_DTYPE = name
 
 
@@ -160,6 +161,8 @@ class _Net:
         scal = _get_param_scalings(model, x, skip_model=skip_model, param_type=param_type, gamma=gamma)
         self.true_dims = list(dims)
         bs = [lin.bias for lin in self.linears] if all(has_bias) else None
+        if _COMPUTE_DTYPE == "f32x3":
+            raise NotImplementedError('compute dtype "f32x3" serves the bPC entry points; PC networks run "f32" or "bf16"')
         self.padded = _COMPUTE_DTYPE == "bf16" and any(v % 8 for v in dims)
         if self.padded:
             # The tensor-core path needs every feature dim to be a multiple of 8 (TMA row pitch, 16-byte vectors):

@@ -13,7 +13,8 @@ from . import _build
 MAX_LAYERS = 256
 
 OK, EINVAL, ENOTIMPL, EWORKSPACE, ECUDA = 0, 1, 2, 3, 4
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F32X3 = 0, 1, 2
+DTYPE_IDS = {"f32": DTYPE_F32, "bf16": DTYPE_BF16, "f32x3": DTYPE_F32X3}
 LOSS_MSE, LOSS_CE = 0, 1
 SOLVER_EULER, SOLVER_HEUN = 0, 1
 ACT_IDS = {"linear": 0, "tanh": 1, "hard_tanh": 2, "relu": 3, "leaky_relu": 4, "gelu": 5, "selu": 6, "silu": 7}

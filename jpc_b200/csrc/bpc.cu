@@ -23,6 +23,7 @@
 // (the host mirror zero-pads feature dims).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "elementwise.cuh"
@@ -66,8 +67,8 @@ int validate_bpc(const jpcb_bpc_desc* d) {
     if (t.skip[l] && l >= 1 && l <= t.n_layers - 2 && t.dims[l] != t.dims[l + 1])
       return fail(JPCB_EINVAL, "identity skip at layer %d needs equal dims (%d vs %d)", l, t.dims[l], t.dims[l + 1]);
   }
-  if (t.dtype != JPCB_DTYPE_F32 && t.dtype != JPCB_DTYPE_BF16) return fail(JPCB_EINVAL, "bad dtype %d", t.dtype);
-  if (t.dtype == JPCB_DTYPE_BF16) {
+  if (t.dtype != JPCB_DTYPE_F32 && t.dtype != JPCB_DTYPE_BF16 && t.dtype != JPCB_DTYPE_F32X3) return fail(JPCB_EINVAL, "bad dtype %d", t.dtype);
+  if (t.dtype != JPCB_DTYPE_F32) {
     if (t.batch_local % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs batch_local %% 8 == 0 (got %d)", t.batch_local);
     for (int l = 0; l <= t.n_layers; ++l)
       if (t.dims[l] % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs every dim %% 8 == 0 (dims[%d]=%d)", l, t.dims[l]);
@@ -109,8 +110,19 @@ struct BpcRun {
   std::vector<float*> e, dl, Gf;    // e_j [Bl, D[j+1]], delta_j [Bl, D[j]], forward half of dF/dz_k [Bl, D[k+1]]
   float* P0 = nullptr;              // W_0 phi_0(x) + b_0        [Bl, D[1]]
   float* QH = nullptr;              // V_H psi_H(y) + c_H        [Bl, D[H]]
-  // bf16 operand copies (tensor-core path)
-  bool tc = false;
+  // bf16 operand copies (tensor-core paths).  x3: the fp32-parity path -- every copy is a 3-way split [rows, 3 P(d)]
+  // (hi | mid | lo, P(d) = d rounded up to the 64-wide k-block, padding zero) and every GEMM runs six passes.
+  bool tc = false, x3 = false;
+  int P(int dd) const { return x3 ? (dd + 63) / 64 * 64 : dd; }
+  size_t cw(int dd) const { return x3 ? 3 * (size_t)P(dd) : (size_t)dd; }
+  void set_dtype(int dtype) { tc = dtype != JPCB_DTYPE_F32; x3 = dtype == JPCB_DTYPE_F32X3; }
+  // operand geometry of a tensor-core task whose concatenated dimension is `ka` (A) / `kb` (B) wide
+  void split_geom(GTask& t, int ka, int kb) const {
+    if (!x3) return;
+    static const int passes = [] { const char* v = getenv("JPCB_X3_PASSES"); const int n = v ? atoi(v) : 6; return n >= 3 && n <= 6 ? n : 6; }();
+    t.split = passes; t.a_ld = (int)cw(ka); t.b_ld = (int)cw(kb); t.a_part = P(ka); t.b_part = P(kb);
+  }
+  void set_ob(GTask& t, bf16* p) const { t.e.Ob = p; if (x3 && p) { t.e.ob_ld = (int)cw(t.e.N); t.e.ob_part = P(t.e.N); } }
   std::vector<bf16*> Wb, WTb, Vb, VTb;  // W_j, W_j^T (j >= 1), V_j, V_j^T (j <= H-1)
   std::vector<bf16*> Hz;                // act(z_k)      [Bl, D[k+1]], k = 0..H-1
   bf16* Hx = nullptr;                   // phi_0(x)      [Bl, D[0]]
@@ -124,21 +136,21 @@ struct BpcRun {
     e.assign(H + 1, nullptr); dl.assign(H + 1, nullptr); Gf.resize(H);
     Wb.assign(H + 1, nullptr); WTb.assign(H + 1, nullptr); Vb.assign(H + 1, nullptr); VTb.assign(H + 1, nullptr);
     Hz.assign(H, nullptr); Eb.assign(H + 1, nullptr); Db.assign(H + 1, nullptr);
-    if (!tc) {
+    if (!tc || x3) {  // fp32 errors (the split path keeps them too: e_l / skip sources of the gradient epilogue, bias gradients)
       for (int j = 0; j <= H; ++j) e[j] = b.take<float>((size_t)Bl * D[j + 1]);
       for (int j = 0; j <= H; ++j) dl[j] = b.take<float>((size_t)Bl * D[j]);
-    } else {
+    }
+    if (tc) {
       for (int j = 0; j <= H; ++j) {
-        const size_t wn = (size_t)D[j] * D[j + 1];
-        Wb[j] = b.take<bf16>(wn); Vb[j] = b.take<bf16>(wn);
-        if (j >= 1) WTb[j] = b.take<bf16>(wn);
-        if (j <= H - 1) VTb[j] = b.take<bf16>(wn);
-        Eb[j] = b.take<bf16>((size_t)Bl * D[j + 1]);
-        Db[j] = b.take<bf16>((size_t)Bl * D[j]);
+        Wb[j] = b.take<bf16>((size_t)D[j + 1] * cw(D[j])); Vb[j] = b.take<bf16>((size_t)D[j] * cw(D[j + 1]));
+        if (j >= 1) WTb[j] = b.take<bf16>((size_t)D[j] * cw(D[j + 1]));
+        if (j <= H - 1) VTb[j] = b.take<bf16>((size_t)D[j + 1] * cw(D[j]));
+        Eb[j] = b.take<bf16>((size_t)Bl * cw(D[j + 1]));
+        Db[j] = b.take<bf16>((size_t)Bl * cw(D[j]));
       }
-      for (int k = 0; k < H; ++k) Hz[k] = b.take<bf16>((size_t)Bl * D[k + 1]);
-      Hx = b.take<bf16>((size_t)Bl * D[0]);
-      Hy = b.take<bf16>((size_t)Bl * D[H + 1]);
+      for (int k = 0; k < H; ++k) Hz[k] = b.take<bf16>((size_t)Bl * cw(D[k + 1]));
+      Hx = b.take<bf16>((size_t)Bl * cw(D[0]));
+      Hy = b.take<bf16>((size_t)Bl * cw(D[H + 1]));
     }
     for (int k = 0; k < H; ++k) Gf[k] = b.take<float>((size_t)Bl * D[k + 1]);
     P0 = b.take<float>((size_t)Bl * D[1]);
@@ -153,7 +165,7 @@ struct BpcRun {
     st = reinterpret_cast<cudaStream_t>(stream);
     H = d->td.n_layers - 1; Bl = d->td.batch_local; D = d->td.dims;
     invB = 1.f / (float)d->td.batch_global; af = d->forward_energy_weight; ab = d->backward_energy_weight;
-    tc = d->td.dtype == JPCB_DTYPE_BF16;
+    set_dtype(d->td.dtype);
     if (!W || !V || !x || !y) return fail(JPCB_EINVAL, "null weight lists / input / target");
     if (d->td.has_bias && !bW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias list");
     if (d->bu_has_bias && !bV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias list");
@@ -173,8 +185,34 @@ struct BpcRun {
   }
   // bf16 operand copies of the weights (both directions, plus the transposes the gradient GEMMs read) and of
   // the clamped inputs; with `S` also of every activity
+  int split3(const float* src, bf16* dst, int R, int C, int act) {
+    split3_kernel<<<ew_grid((size_t)R * P(C), 256), 256, 0, st>>>(src, dst, R, C, P(C), act); count_launch();
+    return JPCB_OK;
+  }
+  int tsplit3(const float* src, bf16* dst, int R, int C) {  // src [R, C] -> split3(src^T) [C, 3 P(R)]
+    transpose_split3_kernel<<<ew_grid(((P(R) + 31) / 32) * ((C + 31) / 32), 1), dim3(32, 8), 0, st>>>(src, dst, R, C, P(R)); count_launch();
+    return JPCB_OK;
+  }
+  int prep_x3(const float* const* S) {
+    for (int j = 0; j <= H; ++j) {
+      split3(W[j], Wb[j], D[j + 1], D[j], ACT_LINEAR);
+      split3(V[j], Vb[j], D[j], D[j + 1], ACT_LINEAR);
+      if (j >= 1) tsplit3(W[j], WTb[j], D[j + 1], D[j]);
+      if (j <= H - 1) tsplit3(V[j], VTb[j], D[j], D[j + 1]);
+      // error copies are written by the epilogues (valid columns only): their padding columns must read as zero
+      CK(cudaMemsetAsync(Eb[j], 0, (size_t)Bl * cw(D[j + 1]) * sizeof(bf16), st));
+      CK(cudaMemsetAsync(Db[j], 0, (size_t)Bl * cw(D[j]) * sizeof(bf16), st));
+    }
+    split3(x, Hx, Bl, D[0], d->td.act[0]);
+    split3(y, Hy, Bl, D[H + 1], d->bu_act[H]);
+    if (S)
+      for (int k = 0; k < H; ++k) split3(S[k], Hz[k], Bl, D[k + 1], d->td.act[k + 1]);
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
   int prep(const float* const* S) {
     if (!tc) return JPCB_OK;
+    if (x3) return prep_x3(S);
     for (int j = 0; j <= H; ++j) {
       const size_t wn = (size_t)D[j] * D[j + 1];
       cast_act_bf16_kernel<<<ew_grid(wn / 4 + 1, 256), 256, 0, st>>>(W[j], Wb[j], wn, ACT_LINEAR); count_launch();
@@ -206,6 +244,7 @@ struct BpcRun {
     t.a_p = j == 0 ? x : S[j - 1]; t.a_smn = D[j]; t.a_sk = 1; t.a_act = d->td.act[j];
     t.b_p = W[j]; t.b_smn = D[j]; t.b_sk = 1;
     t.a_b = j == 0 ? Hx : Hz[j - 1]; t.b_b = Wb[j];
+    split_geom(t, D[j], D[j]);
     t.e.alpha = 1.f; t.e.bias = biasW(j);
   }
   // bottom-up prediction GEMM of layer j on state S: psi_j(v_j) V_j^T
@@ -214,6 +253,7 @@ struct BpcRun {
     t.a_p = j == H ? y : S[j]; t.a_smn = D[j + 1]; t.a_sk = 1; t.a_act = d->bu_act[j];
     t.b_p = V[j]; t.b_smn = D[j + 1]; t.b_sk = 1;
     t.a_b = j == H ? Hy : Hz[j]; t.b_b = Vb[j];
+    split_geom(t, D[j + 1], D[j + 1]);
     t.e.alpha = 1.f; t.e.bias = biasV(j);
   }
 
@@ -223,6 +263,15 @@ struct BpcRun {
     td_operands(a, 0, nullptr); a.e.mode = EPI_FFWD; a.e.O = P0;
     bu_operands(b, H, nullptr); b.e.mode = EPI_FFWD; b.e.O = QH;
     return launch({a, b});
+  }
+
+  // error against a hoisted prediction, e = z - P, as one streaming pass (no GEMM)
+  int hoisted_error(const float* z, const float* pred, float* err, bf16* err_b, int N, float* red_slot) {
+    const size_t n = (size_t)Bl * N;
+    err0_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(z, pred, err, err_b, n / 4, red_slot, N, x3 ? (int)cw(N) : 0, x3 ? P(N) : 0);
+    count_launch();
+    CK(cudaGetLastError());
+    return JPCB_OK;
   }
 
   // all 2(H+1) prediction errors on state S (+ energy sums when `energy`)
@@ -239,7 +288,7 @@ struct BpcRun {
         t.e.skip = skip(j); t.e.U = j == 0 ? x : S[j - 1];
       }
       t.e.T = j == H ? y : S[j];
-      t.e.O = e[j]; t.e.Ob = Eb[j];
+      t.e.O = e[j]; set_ob(t, Eb[j]);
       if (energy) t.e.red = red + j;
       (t.K == 0 ? k0 : ts).push_back(t);
     }
@@ -254,9 +303,15 @@ struct BpcRun {
         t.e.skip = skip(j); t.e.U = j == H ? y : S[j];
       }
       t.e.T = j == 0 ? x : S[j - 1];
-      t.e.O = dl[j]; t.e.Ob = Db[j];
+      t.e.O = dl[j]; set_ob(t, Db[j]);
       if (energy) t.e.red = red + H + 1 + j;
       (t.K == 0 ? k0 : ts).push_back(t);
+    }
+    // the two GEMM-free errors: streaming kernel when the layout allows 16-byte vectors, else the CUDA-core kernel's K = 0 path
+    if (hoisted && D[1] % 4 == 0 && D[H] % 4 == 0 && (reinterpret_cast<uintptr_t>(S[0]) & 15) == 0 && (reinterpret_cast<uintptr_t>(S[H - 1]) & 15) == 0) {
+      RET(launch(ts));
+      RET(hoisted_error(S[0], P0, e[0], Eb[0], D[1], energy ? red + 0 : nullptr));
+      return hoisted_error(S[H - 1], QH, dl[H], Db[H], D[H], energy ? red + H + 1 + H : nullptr);
     }
     if (!tc) { ts.insert(ts.end(), k0.begin(), k0.end()); return launch_simt(ts, st); }
     RET(launch_tc(ts, st));
@@ -273,8 +328,10 @@ struct BpcRun {
       t.a_p = e[k + 1]; t.a_smn = D[k + 2]; t.a_sk = 1;
       t.b_p = W[k + 1]; t.b_smn = 1; t.b_sk = D[k + 1];  // B(n,k') = W_{k+1}[k'][n]
       t.a_b = Eb[k + 1]; t.b_b = WTb[k + 1];
-      t.e.alpha = 1.f; t.e.skip = skip(k + 1); t.e.En = e[k + 1]; t.e.Enb = Eb[k + 1];
-      t.e.Z = Z[k]; t.e.El = e[k]; t.e.Elb = Eb[k];
+      split_geom(t, D[k + 2], D[k + 2]);
+      // (split path: the bf16 error copies are 3-part operand copies, not readable as plain bf16 -- fp32 errors instead)
+      t.e.alpha = 1.f; t.e.skip = skip(k + 1); t.e.En = e[k + 1]; t.e.Enb = x3 ? nullptr : Eb[k + 1];
+      t.e.Z = Z[k]; t.e.El = e[k]; t.e.Elb = x3 ? nullptr : Eb[k];
       t.e.gscale = af; t.e.c = 1.f; t.e.O = Gf[k];
       f.push_back(t);
       GTask u;  // backward-direction half + combination (+ update)
@@ -283,10 +340,11 @@ struct BpcRun {
       u.a_p = dl[k]; u.a_smn = D[k]; u.a_sk = 1;
       u.b_p = V[k]; u.b_smn = 1; u.b_sk = D[k + 1];       // B(n,k') = V_k[k'][n]
       u.a_b = Db[k]; u.b_b = VTb[k];
-      u.e.alpha = 1.f; u.e.skip = skip(k); u.e.En = dl[k]; u.e.Enb = Db[k];
-      u.e.Z = Z[k]; u.e.El = dl[k + 1]; u.e.Elb = Db[k + 1];
+      split_geom(u, D[k], D[k]);
+      u.e.alpha = 1.f; u.e.skip = skip(k); u.e.En = dl[k]; u.e.Enb = x3 ? nullptr : Db[k];
+      u.e.Z = Z[k]; u.e.El = dl[k + 1]; u.e.Elb = x3 ? nullptr : Db[k + 1];
       u.e.gscale = ab; u.e.Gin = Gf[k]; u.e.c = c; u.e.O = Out[k];
-      if (tc && sub != GRAD_OUT) u.e.Ob = Hz[k];  // act(z_new): the next evaluation's operand (both directions)
+      if (tc && sub != GRAD_OUT) set_ob(u, Hz[k]);  // act(z_new): the next evaluation's operand (both directions)
       b.push_back(u);
     }
     RET(launch(f));
@@ -310,7 +368,7 @@ size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc) {
   if (validate_bpc(desc) != JPCB_OK) return 0;
   BpcRun r;
   r.d = desc; r.H = desc->td.n_layers - 1; r.Bl = desc->td.batch_local; r.D = desc->td.dims;
-  r.tc = desc->td.dtype == JPCB_DTYPE_BF16;
+  r.set_dtype(desc->td.dtype);
   r.carve(nullptr);
   return r.bytes;
 }
@@ -378,6 +436,7 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
     t.a_p = r.e[j]; t.a_smn = 1; t.a_sk = D[j + 1];
     t.b_p = j == 0 ? x : A[j - 1]; t.b_smn = 1; t.b_sk = D[j]; t.b_act = desc->td.act[j];
     t.a_b = r.Eb[j]; t.b_b = j == 0 ? r.Hx : r.Hz[j - 1]; t.mn_major = r.tc;  // both read MN-major: no transposes
+    r.split_geom(t, D[j + 1], D[j]);
     t.e.alpha = -r.af * r.invB; t.e.O = gW[j];
     ts.push_back(t);
     GTask u;  // gV_j = -(alpha_b/B) delta_j^T psi_j(v_j)
@@ -385,6 +444,7 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
     u.a_p = r.dl[j]; u.a_smn = 1; u.a_sk = D[j];
     u.b_p = j == H ? y : A[j]; u.b_smn = 1; u.b_sk = D[j + 1]; u.b_act = desc->bu_act[j];
     u.a_b = r.Db[j]; u.b_b = j == H ? r.Hy : r.Hz[j]; u.mn_major = r.tc;
+    r.split_geom(u, D[j], D[j + 1]);
     u.e.alpha = -r.ab * r.invB; u.e.O = gV[j];
     ts.push_back(u);
   }
@@ -392,7 +452,7 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
   if (desc->td.has_bias) {
     if (!gbW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias-gradient list");
     for (int j = 0; j <= H; ++j) {
-      if (r.tc) colsum_kernel<bf16><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Eb[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
+      if (r.tc && !r.x3) colsum_kernel<bf16><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Eb[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
       else colsum_kernel<float><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.e[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
       count_launch();
     }
@@ -400,7 +460,7 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
   if (desc->bu_has_bias) {
     if (!gbV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias-gradient list");
     for (int j = 0; j <= H; ++j) {
-      if (r.tc) colsum_kernel<bf16><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Db[j], gbV[j], Bl, D[j], -r.ab * r.invB);
+      if (r.tc && !r.x3) colsum_kernel<bf16><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Db[j], gbV[j], Bl, D[j], -r.ab * r.invB);
       else colsum_kernel<float><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.dl[j], gbV[j], Bl, D[j], -r.ab * r.invB);
       count_launch();
     }

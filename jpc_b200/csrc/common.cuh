@@ -88,6 +88,9 @@ struct Epi {
   int act;    // activation id: act'(z) in GRAD, act(out) for the bf16 operand copy `Ob`
   int M, N;
   int accum;  // SCALE: out += a*D instead of =
+  // `Ob` as a 3-way split copy (fp32-parity tensor-core path): v = hi + mid + lo in bf16, stored at
+  // Ob[row * ob_ld + p * ob_part + col], p = 0, 1, 2.  ob_part == 0: plain bf16 copy with row pitch N.
+  int ob_ld, ob_part;
   float alpha;   // layer scaling a_l (SCALE: -(a_l/B))
   float skip;    // s_l (0 or 1)
   float escale;  // ERR: lam (output_energy_scaling on the output layer, else 1)
@@ -122,7 +125,7 @@ struct Epi {
 // of the epilogue's load stream would wait for every load in flight.
 __device__ __forceinline__ Epi epi_pin(const Epi& src) {
   Epi e = src;
-  asm volatile("" : "+r"(e.mode), "+r"(e.sub), "+r"(e.act), "+r"(e.M), "+r"(e.N), "+r"(e.accum));
+  asm volatile("" : "+r"(e.mode), "+r"(e.sub), "+r"(e.act), "+r"(e.M), "+r"(e.N), "+r"(e.accum), "+r"(e.ob_ld), "+r"(e.ob_part));
   asm volatile("" : "+f"(e.alpha), "+f"(e.skip), "+f"(e.escale), "+f"(e.c), "+f"(e.ad), "+f"(e.gscale), "+f"(e.tol_r), "+f"(e.tol_a));
   asm volatile("" : "+l"(e.bias), "+l"(e.T), "+l"(e.U), "+l"(e.Z), "+l"(e.Z0), "+l"(e.El), "+l"(e.Elb), "+l"(e.P));
   asm volatile("" : "+l"(e.En), "+l"(e.Enb), "+l"(e.Gin), "+l"(e.G1), "+l"(e.O), "+l"(e.O2), "+l"(e.Ob), "+l"(e.Oh), "+l"(e.red), "+l"(e.Y));
@@ -173,6 +176,26 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, uint32_t idx,
   }
 }
 
+// bf16 operand copy of 4 values: plain (row pitch N), or the 3-way split v = hi + mid + lo of the fp32-parity path
+__device__ __forceinline__ void st_ob(const Epi& e, int row, int col, uint32_t idx, int nvalid, bool vec, const float (&v)[4]) {
+  if (e.ob_part == 0) {
+    st4(e.Ob, idx, nvalid, vec, v);
+    return;
+  }
+  float hi[4], mid[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+    const float r1 = v[j] - hi[j];
+    mid[j] = __bfloat162float(__float2bfloat16_rn(r1));
+    lo[j] = r1 - mid[j];
+  }
+  const uint32_t b0 = (uint32_t)row * (uint32_t)e.ob_ld + (uint32_t)col;
+  st4(e.Ob, b0, nvalid, vec, hi);
+  st4(e.Ob, b0 + (uint32_t)e.ob_part, nvalid, vec, mid);
+  st4(e.Ob, b0 + 2u * (uint32_t)e.ob_part, nvalid, vec, lo);
+}
+
 // The fused epilogue is split in two so that callers can put many independent global loads in
 // flight before they consume any of them (the tensor-core epilogue issues a whole 32x32 patch of
 // loads, then reads the accumulator from TMEM, then finishes):
@@ -180,7 +203,8 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, uint32_t idx,
 //   epi_finish  : consumes them + the 4 accumulator values, stores, returns the reduction term
 struct EpiPre {
   float a[4];  // GRAD: z          ERR: target T    FFWD: loss target Y   SCALE(accum): old O
-  float b[4];  // GRAD: e_l (fp32) or P
+  float b[4];  // GRAD: e_l (fp32) or P; PLAIN == 2: the partial-gradient input Gin
+  float c[4];  // GRAD, ELSRC == 2 (fp32 e_l next to a Gin in b)
   uint2 h;     // GRAD: e_l as 4 packed bf16 when Elb is the source.  Deliberately NOT overlaid on b: two
                // differently predicated loads into the same registers make the second one wait for
                // every load that shares the first one's scoreboard slot.
@@ -195,8 +219,9 @@ __device__ __forceinline__ void unpack_bf16x4(const uint2& t, float (&v)[4]) {
 // MODE / SUB / ACT >= 0 fix the corresponding descriptor field at compile time (the tensor-core
 // epilogue dispatches once per tile so that its inner loop is straight-line code); -1 = read it
 // from the descriptor at run time.
-// ELSRC fixes where GRAD takes e_l from: 0 = Elb (packed bf16), 1 = z - P (hoisted prediction), -1 = run time.
-// PLAIN == 2 (ELSRC == 0 only): the partial-gradient input Gin is part of the task and is loaded here into p.b.
+// ELSRC fixes where GRAD takes e_l from: 0 = Elb (packed bf16), 1 = z - P (hoisted prediction), 2 = El (fp32: the
+// fp32-parity split path), -1 = run time.
+// PLAIN == 2 (ELSRC == 0 or 2): the partial-gradient input Gin is part of the task and is loaded here into p.b.
 template <int MODE = -1, int ELSRC = -1, int PLAIN = 0>
 __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int nvalid, bool vec, EpiPre& p) {
   const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
@@ -207,7 +232,10 @@ __device__ __forceinline__ void epi_preload(const Epi& e, int row, int col, int 
       p.h = __ldcg(reinterpret_cast<const uint2*>(e.Elb + idx));
       if (PLAIN == 2) ld4(e.Gin, idx, nvalid, vec, p.b);
     } else if (ELSRC == 1) ld4(e.P, idx, nvalid, vec, p.b);
-    else if (e.El || !e.Elb) ld4(e.El ? e.El : e.P, idx, nvalid, vec, p.b);
+    else if (ELSRC == 2) {
+      ld4(e.El, idx, nvalid, vec, p.c);
+      if (PLAIN == 2) ld4(e.Gin, idx, nvalid, vec, p.b);
+    } else if (e.El || !e.Elb) ld4(e.El ? e.El : e.P, idx, nvalid, vec, p.b);
     else if (vec) p.h = __ldcg(reinterpret_cast<const uint2*>(e.Elb + idx));
     else ld4(e.Elb, idx, nvalid, false, p.b);
   } else if (mode == EPI_ERR) {
@@ -270,7 +298,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
       if (e.Ob || e.Oh) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) out[j] = act_fwd<FAST>(act, pred[j]);
-        if (e.Ob) st4(e.Ob, idx, nvalid, vec, out);
+        if (e.Ob) st_ob(e, row, col, idx, nvalid, vec, out);
         if (e.Oh) st4(e.Oh, idx, nvalid, vec, out);
       }
       if (e.red) {
@@ -285,7 +313,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
       out[j] = PLAIN ? d : e.escale * d;
     }
     if (e.O) st4(e.O, idx, nvalid, vec, out);
-    if (e.Ob) st4(e.Ob, idx, nvalid, vec, out);
+    if (e.Ob) st_ob(e, row, col, idx, nvalid, vec, out);
     if (e.red) {  // layer energy (lam/2) sum d^2 -- only the launches that report energies pay for it
       const float half = PLAIN ? 0.5f : (e.escale != 0.f ? 0.5f / e.escale : 0.f);  // out = lam d  =>  lam/2 d^2 = out^2 / (2 lam)
 #pragma unroll
@@ -301,6 +329,9 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
   } else if (ELSRC == 1) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) el[j] = z[j] - p.b[j];
+  } else if (ELSRC == 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) el[j] = p.c[j];
   } else if (e.El) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) el[j] = p.b[j];
@@ -371,7 +402,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     float h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = act_fwd<FAST>(act, out[j]);
-    if (e.Ob) st4(e.Ob, idx, nvalid, vec, h);
+    if (e.Ob) st_ob(e, row, col, idx, nvalid, vec, h);
     if (e.Oh) st4(e.Oh, idx, nvalid, vec, h);
   }
   return r;

@@ -115,27 +115,81 @@ static __global__ void scale_kernel(const float* src, float* dst, size_t n, floa
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = s * src[i];
 }
 
-// First-layer prediction error from the hoisted prediction: e = z_1 - P1 (fp32 and/or bf16 copies), optional energy
-// 1/2 sum e^2 into *red.  n % 4 == 0 and 16-byte aligned pointers (feature dims are multiples of 4 on this path).
+// Prediction error from a hoisted (constant) prediction: e = z - P (fp32 and/or a bf16 operand copy), optional energy
+// 1/2 sum e^2 into *red.  n % 4 == 0 and 16-byte aligned pointers (feature dims are multiples of 4 on these paths).
+// ob_part > 0: the bf16 copy is the 3-way split [rows, ob_ld] of the fp32-parity path (row width N, parts ob_part apart).
 static __global__ void err0_kernel(const float* __restrict__ z, const float* __restrict__ p1, float* __restrict__ err,
-                                   __nv_bfloat16* __restrict__ err_b, size_t n4, float* red) {
+                                   __nv_bfloat16* __restrict__ err_b, size_t n4, float* red, int N = 0, int ob_ld = 0, int ob_part = 0) {
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(z) + i), b = __ldcs(reinterpret_cast<const float4*>(p1) + i);
     const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
     if (err) reinterpret_cast<float4*>(err)[i] = d;
     if (err_b) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
-      uint2 t;
-      t.x = *reinterpret_cast<uint32_t*>(&lo);
-      t.y = *reinterpret_cast<uint32_t*>(&hi);
-      reinterpret_cast<uint2*>(err_b)[i] = t;
+      if (ob_part == 0) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&lo);
+        t.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(err_b)[i] = t;
+      } else {
+        const size_t row = (i * 4) / (size_t)N, col = (i * 4) % (size_t)N;  // N % 4 == 0: the vector stays inside one row
+        const float v[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+          const float r1 = v[j] - __bfloat162float(h);
+          const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+          const size_t o = row * (size_t)ob_ld + col + j;
+          err_b[o] = h;
+          err_b[o + ob_part] = m;
+          err_b[o + 2 * (size_t)ob_part] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        }
+      }
     }
     acc += 0.5f * (d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
   }
   if (red) {
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(red, acc);
+  }
+}
+
+// 3-way bf16 split operand copies of the fp32-parity tensor-core path: v = act(src) = hi + mid + lo (each bf16, 24
+// mantissa bits together).  dst [R, 3 P] holds [hi | mid | lo] side by side, every part P >= C columns wide with the
+// columns C..P-1 ZERO (the GEMM's k-blocks run over whole parts).
+static __device__ __forceinline__ void split3_store(__nv_bfloat16* dst, size_t base, int P, float v) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  dst[base] = hi;
+  dst[base + P] = mid;
+  dst[base + 2 * (size_t)P] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+static __global__ void split3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int P, int act) {
+  const size_t n = (size_t)R * P;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / P), c = (int)(i % P);
+    const float v = c < C ? act_fwd<false>(act, src[(size_t)r * C + c]) : 0.f;
+    split3_store(dst, (size_t)r * 3 * P + c, P, v);
+  }
+}
+// src [R, C] fp32 -> dst [C, 3 P] = split3(src^T), P >= R (columns R..P-1 zero)
+static __global__ void transpose_split3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int P) {
+  __shared__ float tile[32][33];
+  const int tiles_c = (C + 31) / 32, tiles_r = (P + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      tile[i][threadIdx.x] = (r < R && c < C) ? src[(size_t)r * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;  // output row c, column r
+      if (c < C && r < P) split3_store(dst, (size_t)c * 3 * P + r, P, tile[threadIdx.x][i]);
+    }
+    __syncthreads();
   }
 }
 

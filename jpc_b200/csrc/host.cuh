@@ -44,6 +44,10 @@ struct GTask {
   const __nv_bfloat16* a_b = nullptr;  // [M, K] K-major   (mn_major: [K, M] row-major)
   const __nv_bfloat16* b_b = nullptr;  // [N, K] K-major   (mn_major: [K, N] row-major)
   bool mn_major = false;               // tensor-core path: D = a_b^T b_b, operands read MN-major (no transposed copies)
+  // fp32-parity tensor-core path: a_b / b_b are 3-way split copies [rows, 3 P] (elementwise.cuh: split3_kernel) and the
+  // GEMM runs six passes over K (hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi).  a_ld / b_ld: row pitch (3 P) of the
+  // copies; a_part / b_part: width P of one part (of the K dimension, or of the M / N dimension when mn_major).
+  int split = 0, a_ld = 0, b_ld = 0, a_part = 0, b_part = 0;
   GTask() { memset(&e, 0, sizeof(e)); e.gscale = 1.f; e.escale = 1.f; }
 };
 

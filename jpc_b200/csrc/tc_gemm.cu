@@ -77,8 +77,18 @@ int variant_key(const GTask& t) {
   if (tc_flags() & 4) return 0;
   const bool noextra = e.skip == 0.f && e.bias == nullptr && e.escale == 1.f && e.ad == 0.f;
   const bool plain = noextra && e.Gin == nullptr && e.gscale == 1.f;
-  if (e.mode == EPI_ERR) return plain ? 1 : 7;
+  if (e.mode == EPI_ERR) return plain ? 1 : 7;  // (no activation in this epilogue: also serves the fp32-parity split path)
   if (e.mode == EPI_SCALE) return 2;
+  if (t.split) {
+    // fp32-parity path: the specialised variants use fast activation approximations, so only activations that are exact
+    // either way (relu, identity) may take them; e_l comes from the fp32 error buffers (ELSRC == 2)
+    if (e.mode == EPI_FFWD && (e.act == ACT_RELU || e.act == ACT_LINEAR)) return e.act == ACT_RELU ? 9 : 10;
+    if (e.mode == EPI_GRAD && noextra && e.act == ACT_RELU && e.El) {
+      if (e.sub == GRAD_OUT && e.Gin == nullptr) return 17;
+      if (e.sub == GRAD_EULER && e.Gin != nullptr) return 18;
+    }
+    return 0;
+  }
   const bool act_ok = e.act == ACT_TANH || e.act == ACT_RELU;
   if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && plain && act_ok && !e.El && (e.Elb || e.P))
     return 3 + (e.act == ACT_RELU ? 2 : 0) + (e.Elb ? 0 : 1);
@@ -109,6 +119,8 @@ int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
     case 13: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_RELU, 0, 1>(g, grid, st);
     case 14: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, 2>(g, grid, st);
     case 15: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 2>(g, grid, st);
+    case 17: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_RELU, 2, 1>(g, grid, st);
+    case 18: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 2>(g, grid, st);
     default: return launch_variant<CG, -1, -1, -1, -1, 0>(g, grid, st);
   }
 }
@@ -138,17 +150,20 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
         const GTask& t = tasks[i];
         if (t.K <= 0 || !t.a_b || !t.b_b) return fail(JPCB_EINVAL, "internal: tensor-core task without bf16 operands");
         TcTask& s = g.t[n];
+        if (t.split && (t.a_ld <= 0 || t.b_ld <= 0 || t.a_part % TC_BLOCK_K || t.b_part % TC_BLOCK_K))
+          return fail(JPCB_EINVAL, "internal: split task without padded operand geometry");
         if (t.mn_major) {
-          RET(make_map(&s.tmA, t.a_b, t.K, t.e.M, 64));
-          RET(make_map(&s.tmB, t.b_b, t.K, t.e.N, 64));
+          RET(make_map(&s.tmA, t.a_b, t.K, t.split ? t.a_ld : t.e.M, 64));
+          RET(make_map(&s.tmB, t.b_b, t.K, t.split ? t.b_ld : t.e.N, 64));
         } else {
-          RET(make_map(&s.tmA, t.a_b, t.e.M, t.K, TC_BLOCK_M));
-          RET(make_map(&s.tmB, t.b_b, t.e.N, t.K, Cfg::B_ROWS));
+          RET(make_map(&s.tmA, t.a_b, t.e.M, t.split ? t.a_ld : t.K, TC_BLOCK_M));
+          RET(make_map(&s.tmB, t.b_b, t.e.N, t.split ? t.b_ld : t.K, Cfg::B_ROWS));
         }
+        s.split = t.split; s.a_part = t.a_part; s.b_part = t.b_part;
+        s.pad_[0] = s.pad_[1] = 0;
         s.K = t.K;
         s.tile_begin = tiles;
         s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;
-        s.pad_ = 0;
         s.e = t.e;
         tiles += s.tiles_n * ((t.e.M + BM - 1) / BM);
         ++n;

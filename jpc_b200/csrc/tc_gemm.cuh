@@ -67,9 +67,15 @@ struct alignas(64) TcTask {
   int K;
   int tile_begin;
   int tiles_n;
-  int pad_;
+  int split;           // 0: one pass over K; 3..6: that many products over 3-way split operand copies (fp32-parity path)
+  int a_part, b_part;  // split: width of one part of A / B along the concatenated dimension
+  int pad_[2];
   Epi e;
 };
+
+// the six (A part, B part) products of the split path, smallest terms first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
+__device__ __forceinline__ int tc_split_a(int pass) { return (0x052 >> (2 * pass)) & 3; }  // 2, 0, 1, 1, 0, 0 (2 bits each)
+__device__ __forceinline__ int tc_split_b(int pass) { return (0x118 >> (2 * pass)) & 3; }  // 0, 2, 1, 0, 1, 0
 
 constexpr int TC_MAX_TASKS = 16;
 struct alignas(64) TcGroup {
@@ -319,7 +325,9 @@ __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, in
     const int row = row0 + rl;
     if (cok && row < e.M) {
       const float a4[4] = {a.x, a.y, a.z, a.w};
-      r += epi_finish<true, MODE, SUB, ACT, ELSRC, PLAIN>(e, row, col, a4, 4, true, pre[i], true, bias4);
+      // (fast activation approximations only in the specialised bf16 variants; the generic instantiation, which
+      //  also serves the fp32-parity split path, evaluates them accurately)
+      r += epi_finish<(MODE >= 0), MODE, SUB, ACT, ELSRC, PLAIN>(e, row, col, a4, 4, true, pre[i], true, bias4);
     }
   }
   __syncwarp();
@@ -434,26 +442,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M;
       const int n0 = (local % t.tiles_n) * TC_BLOCK_N + (int)rank * Cfg::B_ROWS;
       const int nkb = (t.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+      // t.split = number of split products to run (6 = all; 4 drops the two hi*lo terms, 3 also mid*mid): the LAST
+      // t.split entries of the smallest-first list
+      const int pass0 = t.split ? 6 - t.split : 5;
       // the whole warp walks the ring (warp-uniform state); one elected lane issues
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (elect_one()) {
-          const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CG);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          if constexpr (!MNMAJ) {
-            tma_load_2d<CG>(sa, &t.tmA, fb, kb * TC_BLOCK_K, m0);
-            tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0);
-          } else {  // boxes of {64 M/N elements, 64 K rows}
+      for (int pass = pass0; pass < 6; ++pass) {
+        // split operands: this pass multiplies part pa of A with part pb of B (offsets along the concatenated dimension)
+        const int oa = t.split ? tc_split_a(pass) * t.a_part : 0, ob = t.split ? tc_split_b(pass) * t.b_part : 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CG);
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            if constexpr (!MNMAJ) {
+              tma_load_2d<CG>(sa, &t.tmA, fb, oa + kb * TC_BLOCK_K, m0);
+              tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, ob + kb * TC_BLOCK_K, n0);
+            } else {  // boxes of {64 M/N elements, 64 K rows}
 #pragma unroll
-            for (int i = 0; i < TC_BLOCK_M / 64; ++i) tma_load_2d<CG>(sa + i * TC_MN_BOX_BYTES, &t.tmA, fb, m0 + 64 * i, kb * TC_BLOCK_K);
+              for (int i = 0; i < TC_BLOCK_M / 64; ++i)
+                tma_load_2d<CG>(sa + i * TC_MN_BOX_BYTES, &t.tmA, fb, oa + m0 + 64 * i, kb * TC_BLOCK_K);
 #pragma unroll
-            for (int i = 0; i < Cfg::B_ROWS / 64; ++i)
-              tma_load_2d<CG>(sa + TC_A_BYTES + i * TC_MN_BOX_BYTES, &t.tmB, fb, n0 + 64 * i, kb * TC_BLOCK_K);
+              for (int i = 0; i < Cfg::B_ROWS / 64; ++i)
+                tma_load_2d<CG>(sa + TC_A_BYTES + i * TC_MN_BOX_BYTES, &t.tmB, fb, ob + n0 + 64 * i, kb * TC_BLOCK_K);
+            }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -466,7 +482,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       uint32_t aphase = 0;
       for (int tile = unit; tile < g.total_tiles; tile += nunits) {
         const int ti = tc_find_task(g, tile);
-        const int nkb = (g.t[ti].K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+        const int nkb = ((g.t[ti].K + TC_BLOCK_K - 1) / TC_BLOCK_K) * (g.t[ti].split ? g.t[ti].split : 1);  // k-blocks over all passes
         mbar_wait(tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BLOCK_N);

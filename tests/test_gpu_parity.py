@@ -340,8 +340,10 @@ def _check_bpc(td, bu, sk, x, y, acts, tol, af=1.0, ab=1.0):
                 assert rel(got[l][1].bias, q["b"]) < tol
 
 
-def _check_bpc_infer(td, bu, sk, x, y, acts, tol, T, dt, af=1.0, ab=1.0):
-    """fused T Euler steps == T x (oracle gradient step with sgd(dt))."""
+def _check_bpc_infer(td, bu, sk, x, y, acts, tol, T, dt, af=1.0, ab=1.0, kink_budget=0):
+    """fused T Euler steps == T x (oracle gradient step with sgd(dt)).  `kink_budget`: activity entries per tensor allowed
+    outside `tol` -- with relu, 1M entries x 30 steps, an fp32 pre-activation within rounding of 0 occasionally takes the
+    other branch for one step (scripts/x3_check.py: 1 entry of 1 048 576, all others at 1e-8)."""
     import jpc_b200 as J
     kw = dict(forward_energy_weight=af, backward_energy_weight=ab)
     a = [t.clone() for t in acts]
@@ -351,7 +353,8 @@ def _check_bpc_infer(td, bu, sk, x, y, acts, tol, T, dt, af=1.0, ab=1.0):
     gtd, gbu, gsk = to_gpu_model(td), to_gpu_model(bu), _gpu_skip(sk)
     ga = J.solve_bpc_inference(gtd, gbu, devs(acts), dev(y), input=dev(x), n_steps=T, dt=dt, skip_model=gsk, **kw)
     for p, q in zip(ga[:-1], a[:-1]):
-        assert rel(p, q) < tol
+        bad = int(((p.double().cpu() - q).abs() > tol * float(q.abs().max())).sum())
+        assert bad <= kink_budget and rel(p, q) < (100 if kink_budget else 1) * tol
     # and the reference-shaped discrete twin
     opt = J.optim.sgd(dt)
     b, st = devs(acts), opt.init(devs(acts))
@@ -1007,3 +1010,32 @@ def test_config4_wide_full_size_bf16():
     for l in (L - 1,):
         gW = -(scal[l] / B) * errs[l].T @ O.act_fn(om[l]["act"], A[l - 1])
         assert rel(arena.gW[l], gW) < TOLBF or float((arena.gW[l].double().cpu() - gW).abs().max()) < TOLBF * gmax
+
+
+# ---- fp32 parity on the tensor cores: 3-way bf16 split operands, six products per GEMM ("f32x3") ------------
+def test_bpc_f32x3_split_tensor_core_path():
+    """The same bPC checks as the fp32 CUDA-core path, at the SAME 1e-5 tolerance, but every GEMM on tcgen05:
+    ragged dims (padding of the split parts to the 64-wide k-block), biases, skips, tanh (accurate activations on this
+    path), energy weights, fused inference with the stress step."""
+    import jpc_b200 as J
+    J.set_compute_dtype("f32x3")
+    c = _bpc_case(10, 256, 4, 28, "tanh", 128, use_bias=True)
+    _check_bpc(*c, TOL32)
+    _check_bpc(*c, TOL32, af=0.5, ab=0.7)
+    _check_bpc_infer(*c, TOL32, T=6, dt=0.1 * 128)
+    c = _bpc_case(16, 128, 5, 72, "relu", 136, skips=True)
+    _check_bpc(*c, TOL32)
+    _check_bpc_infer(*c, TOL32, T=4, dt=0.5)
+    c = _bpc_case(24, 200, 3, 40, "silu", 64)
+    _check_bpc(*c, TOL32)
+    with pytest.raises(NotImplementedError):   # PC networks: "f32" or "bf16"
+        J.init_activities_with_ffwd(to_gpu_model(c[0]), dev(c[3]))
+
+
+def test_config5_bpc_full_size_f32x3():
+    """BASELINE config 5 at full size and fp32 parity on the tensor cores."""
+    import jpc_b200 as J
+    J.set_compute_dtype("f32x3")
+    c = _bpc_case(10, 1024, 6, 784, "relu", 1024)
+    _check_bpc(*c, TOL32)
+    _check_bpc_infer(*c, TOL32, T=30, dt=0.5, kink_budget=3)
