@@ -203,7 +203,7 @@ def run_reference(args, w):
 def run_bpc(args, w):
     """BASELINE config 5: one bPC train step = feed-forward init of the bottom-up chain (image -> label,
     examples/bidirectional_pc.ipynb cell 8) + T fused Euler steps on the bPC energy + both models' parameter
-    gradients.  fp32 CUDA-core path in round 1 (the bf16 tensor-core schedule for bPC is not built yet)."""
+    gradients.  Default arithmetic: fp32 parity on the tensor cores (f32x3; BASELINE's config 5 is fp32)."""
     import torch
     import jpc_b200 as J
     from jpc_b200 import _lib
@@ -226,10 +226,7 @@ def run_bpc(args, w):
     T = n_steps(w)
 
     def step(x_lab, y_img):
-        if dtype == "f32x3":  # (the PC feed-forward entry point has no split path yet: fp32 CUDA-core sweep)
-            J.set_compute_dtype("f32")
         acts = J.init_activities_with_ffwd(amort, y_img)          # (reference order: amortiser sweep, image side first)
-        J.set_compute_dtype(dtype)
         acts = J.solve_bpc_inference(td, bu, acts, y_img, input=x_lab, n_steps=T, dt=w["dt"])
         return J.compute_bpc_param_grads(td, bu, acts, y_img, x=x_lab)
 

@@ -38,7 +38,7 @@ _COMPUTE_DTYPE = "f32"
 
 def set_compute_dtype(name: str) -> None:
     """"f32" (fp32 FMA, 1e-5 parity), "bf16" (tcgen05 tensor cores, fp32 accumulate, 2e-2) or "f32x3" (tcgen05 on 3-way
-    bf16 split operands, six products per GEMM: fp32 parity at tensor-core speed; bPC entry points only so far)."""
+    bf16 split operands, six products per GEMM: fp32 parity at tensor-core speed)."""
     global _COMPUTE_DTYPE
     if name not in ("f32", "bf16", "f32x3"):
         raise ValueError('compute dtype must be "f32", "bf16" or "f32x3"')
@@ -161,9 +161,7 @@ class _Net:
         scal = _get_param_scalings(model, x, skip_model=skip_model, param_type=param_type, gamma=gamma)
         self.true_dims = list(dims)
         bs = [lin.bias for lin in self.linears] if all(has_bias) else None
-        if _COMPUTE_DTYPE == "f32x3":
-            raise NotImplementedError('compute dtype "f32x3" serves the bPC entry points; PC networks run "f32" or "bf16"')
-        self.padded = _COMPUTE_DTYPE == "bf16" and any(v % 8 for v in dims)
+        self.padded = _COMPUTE_DTYPE != "f32" and any(v % 8 for v in dims)  # (both tensor-core paths)
         if self.padded:
             # The tensor-core path needs every feature dim to be a multiple of 8 (TMA row pitch, 16-byte vectors):
             # zero-pad weights, biases, inputs, targets and activities.  Padded entries are zero and stay zero
@@ -197,7 +195,7 @@ class _Net:
                 d.skip[l] = 1 if skips[l] else 0
                 d.scalings[l] = scal[l]
             d.has_bias = 1 if all(has_bias) else 0
-            d.dtype = _lib.DTYPE_BF16 if _COMPUTE_DTYPE == "bf16" else _lib.DTYPE_F32
+            d.dtype = _lib.DTYPE_IDS[_COMPUTE_DTYPE]
             d.loss = _lib.LOSS_MSE if loss_id == "mse" else _lib.LOSS_CE
             d.output_energy_scaling = lam
             d.activity_decay = float(activity_decay)

@@ -79,11 +79,11 @@ int validate(const jpcb_pc_desc* d, int min_layers = 2) {
   for (int l = 0; l <= d->n_layers; ++l)
     if ((long long)d->batch_local * d->dims[l] >= (1LL << 31)) return fail(JPCB_ENOTIMPL, "batch_local * dims[%d] must be < 2^31 (32-bit element indices)", l);
   if (d->loss != JPCB_LOSS_MSE && d->loss != JPCB_LOSS_CE) return fail(JPCB_EINVAL, "`mse` and `ce` are the only valid losses.");
-  if (d->dtype != JPCB_DTYPE_F32 && d->dtype != JPCB_DTYPE_BF16) return fail(JPCB_EINVAL, "bad dtype %d", d->dtype);
+  if (d->dtype != JPCB_DTYPE_F32 && d->dtype != JPCB_DTYPE_BF16 && d->dtype != JPCB_DTYPE_F32X3) return fail(JPCB_EINVAL, "bad dtype %d", d->dtype);
   if (d->solver != JPCB_SOLVER_EULER && d->solver != JPCB_SOLVER_HEUN) return fail(JPCB_EINVAL, "bad solver %d", d->solver);
   if (d->n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", d->n_steps);
   if (d->free_input && d->scalings[0] != 1.f) return fail(JPCB_EINVAL, "free_input (unsupervised) needs scalings[0] == 1: the reference's branch is unscaled");
-  if (d->dtype == JPCB_DTYPE_BF16) {
+  if (d->dtype != JPCB_DTYPE_F32) {
     if (d->batch_local % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs batch_local %% 8 == 0 (got %d)", d->batch_local);
     for (int l = 0; l <= d->n_layers; ++l)
       if (d->dims[l] % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs every dim %% 8 == 0 (dims[%d]=%d)", l, d->dims[l]);
@@ -109,6 +109,11 @@ struct Bump {
 constexpr int RED_FLOATS = JPCB_MAX_LAYERS + 64;  // [0,L): layer energy sums; then misc accumulators
 constexpr int RED_LOSS = JPCB_MAX_LAYERS + 0;
 constexpr int RED_SUMSQ = JPCB_MAX_LAYERS + 1;
+
+// Operand-copy geometry of the tensor-core paths.  bf16: plain copies [rows, d].  f32x3 (fp32 parity): 3-way split copies
+// [rows, 3 P(d)] = [hi | mid | lo], P(d) = d rounded up to the 64-wide k-block with zero padding (elementwise.cuh).
+inline int x3_part(const jpcb_pc_desc* d, int dd) { return d->dtype == JPCB_DTYPE_F32X3 ? (dd + 63) / 64 * 64 : dd; }
+inline size_t x3_cw(const jpcb_pc_desc* d, int dd) { return d->dtype == JPCB_DTYPE_F32X3 ? 3 * (size_t)x3_part(d, dd) : (size_t)dd; }
 
 struct Ws {
   float* red = nullptr;
@@ -140,8 +145,9 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
   w->G1.assign(L, nullptr);
   w->P1 = b.take<float>(Bl * d->dims[1]);
   if (d->loss == JPCB_LOSS_CE) w->logits = b.take<float>(Bl * d->dims[L]);
-  const bool tc = d->dtype == JPCB_DTYPE_BF16, heun = d->solver == JPCB_SOLVER_HEUN;
-  for (int l = 0; l < L; ++l) w->err[l] = tc ? nullptr : b.take<float>(Bl * d->dims[l + 1]);
+  const bool tc = d->dtype != JPCB_DTYPE_F32, x3 = d->dtype == JPCB_DTYPE_F32X3, heun = d->solver == JPCB_SOLVER_HEUN;
+  // (the split path keeps fp32 errors too: e_l / skip sources of the gradient epilogue, bias gradients)
+  for (int l = 0; l < L; ++l) w->err[l] = (tc && !x3) ? nullptr : b.take<float>(Bl * d->dims[l + 1]);
   const bool fr = d->free_input != 0;
   if (heun) {
     for (int l = 0; l < L - 1; ++l) {
@@ -165,12 +171,11 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
   w->Eb.assign(L, nullptr);
   if (tc) {
     for (int l = 0; l < L; ++l) {
-      const size_t wn = (size_t)d->dims[l] * d->dims[l + 1];
-      w->Wb[l] = b.take<bf16>(wn);
-      if (l >= 1 || fr) w->WTb[l] = b.take<bf16>(wn);
-      w->Hb[l] = b.take<bf16>(Bl * d->dims[l]);
-      if (heun && (l >= 1 || fr)) w->Htb[l] = b.take<bf16>(Bl * d->dims[l]);
-      w->Eb[l] = b.take<bf16>(Bl * d->dims[l + 1]);
+      w->Wb[l] = b.take<bf16>((size_t)d->dims[l + 1] * x3_cw(d, d->dims[l]));
+      if (l >= 1 || fr) w->WTb[l] = b.take<bf16>((size_t)d->dims[l] * x3_cw(d, d->dims[l + 1]));
+      w->Hb[l] = b.take<bf16>(Bl * x3_cw(d, d->dims[l]));
+      if (heun && (l >= 1 || fr)) w->Htb[l] = b.take<bf16>(Bl * x3_cw(d, d->dims[l]));
+      w->Eb[l] = b.take<bf16>(Bl * x3_cw(d, d->dims[l + 1]));
     }
   }
   w->bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
@@ -350,6 +355,7 @@ struct Run {
   int L, Bl;
   float invB;
   bool tc;
+  bool x3 = false;                // JPCB_DTYPE_F32X3: split operand copies, six products per GEMM
   bool fr = false;                // desc->free_input: z_0 is a free activity (unsupervised PC)
   const float* x_stage = nullptr; // free_input: z_0 of the Heun stage state (else the input)
   float* x_out = nullptr;         // free_input: where the next grads() call writes z_0's gradient / new value
@@ -360,7 +366,7 @@ struct Run {
     d = desc; W = W_; b = b_; x = x_; y = y_;
     st = reinterpret_cast<cudaStream_t>(stream);
     L = d->n_layers; Bl = d->batch_local; invB = 1.f / (float)d->batch_global;
-    tc = d->dtype == JPCB_DTYPE_BF16;
+    tc = d->dtype != JPCB_DTYPE_F32; x3 = d->dtype == JPCB_DTYPE_F32X3;
     if (!W || !x) return fail(JPCB_EINVAL, "null weight list or input");
     if (d->has_bias && !b) return fail(JPCB_EINVAL, "has_bias set but no bias list");
     carve(d, wsp, &ws);
@@ -370,6 +376,24 @@ struct Run {
     return JPCB_OK;
   }
   const float* bias(int l) const { return d->has_bias ? b[l] : nullptr; }
+  // split-path geometry of a tensor-core task whose concatenated dimension is `ka` (A) / `kb` (B) wide, and of a bf16 output copy
+  void split_geom(GTask& t, int ka, int kb) const {
+    if (!x3) return;
+    t.split = 6; t.a_ld = (int)x3_cw(d, ka); t.b_ld = (int)x3_cw(d, kb); t.a_part = x3_part(d, ka); t.b_part = x3_part(d, kb);
+  }
+  void set_ob(GTask& t, bf16* p) const { t.e.Ob = p; if (x3 && p) { t.e.ob_ld = (int)x3_cw(d, t.e.N); t.e.ob_part = x3_part(d, t.e.N); } }
+  int split3(const float* src, bf16* dst, int R, int C, int act) {
+    const int P = x3_part(d, C);
+    split3_kernel<<<ew_grid((size_t)R * P, 256), 256, 0, st>>>(src, dst, R, C, P, act); count_launch();
+    return JPCB_OK;
+  }
+  // bf16 operand copy of a [Bl, C] fp32 tensor: plain cast or 3-way split
+  int operand_copy(const float* src, bf16* dst, int C, int act) {
+    if (x3) return split3(src, dst, Bl, C, act);
+    const size_t n = (size_t)Bl * C;
+    cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(src, dst, n, act); count_launch();
+    return JPCB_OK;
+  }
   float eskip(int l) const { return (d->skip[l] && l >= 1 && l <= L - 2) ? 1.f : 0.f; }  // energy-side skip (_energies.py:111-117)
   int launch(const std::vector<GTask>& t) { return tc ? launch_tc(t, st) : launch_simt(t, st); }
 
@@ -381,6 +405,21 @@ struct Run {
       for (int l = fr ? 0 : 1; l < L; ++l) {
         const int R = d->dims[l + 1], C = d->dims[l];
         transpose_f32_kernel<<<ew_grid(((R + 31) / 32) * ((C + 31) / 32), 1), dim3(32, 8), 0, st>>>(W[l], ws.WTf[l], R, C); count_launch();
+      }
+      CK(cudaGetLastError());
+      return JPCB_OK;
+    }
+    if (x3) {
+      for (int l = 0; l < L; ++l) {
+        const int R = d->dims[l + 1], C = d->dims[l], PR = x3_part(d, R);
+        split3(W[l], ws.Wb[l], R, C, ACT_LINEAR);
+        if (l >= 1 || fr) {  // W_l [R, C] -> split3(W_l^T) [C, 3 P(R)]
+          transpose_split3_kernel<<<ew_grid(((PR + 31) / 32) * ((C + 31) / 32), 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C, PR); count_launch();
+        }
+        // copies the epilogues write (valid columns only): their padding columns must read as zero
+        CK(cudaMemsetAsync(ws.Eb[l], 0, (size_t)Bl * x3_cw(d, R) * sizeof(bf16), st));
+        CK(cudaMemsetAsync(ws.Hb[l], 0, (size_t)Bl * x3_cw(d, C) * sizeof(bf16), st));
+        if (ws.Htb[l]) CK(cudaMemsetAsync(ws.Htb[l], 0, (size_t)Bl * x3_cw(d, C) * sizeof(bf16), st));
       }
       CK(cudaGetLastError());
       return JPCB_OK;
@@ -410,13 +449,9 @@ struct Run {
       CK(cudaGetLastError());
       return JPCB_OK;
     }
-    const size_t n0 = (size_t)Bl * d->dims[0];
-    cast_act_bf16_kernel<<<ew_grid(n0 / 4 + 1, 256), 256, 0, st>>>(x, ws.Hb[0], n0, d->act[0]); count_launch();
+    operand_copy(x, ws.Hb[0], d->dims[0], d->act[0]);
     if (S)
-      for (int l = 1; l < L; ++l) {
-        const size_t n = (size_t)Bl * d->dims[l];
-        cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(S[l - 1], ws.Hb[l], n, d->act[l]); count_launch();
-      }
+      for (int l = 1; l < L; ++l) operand_copy(S[l - 1], ws.Hb[l], d->dims[l], d->act[l]);
     CK(cudaGetLastError());
     return JPCB_OK;
   }
@@ -434,6 +469,7 @@ struct Run {
     t.a_smn = d->dims[l]; t.a_sk = 1; t.a_act = ACT_LINEAR;
     t.b_p = W[l]; t.b_smn = d->dims[l]; t.b_sk = 1;
     t.a_b = l == 0 ? (st0 ? ws.Htb[0] : ws.Hb[0]) : H[l]; t.b_b = ws.Wb[l];
+    split_geom(t, d->dims[l], d->dims[l]);
     t.e.alpha = d->scalings[l];
     t.e.bias = bias(l);
   }
@@ -448,7 +484,7 @@ struct Run {
       t.e.U = l == 0 ? x : A_out[l - 1];
       t.e.O = A_out[l];
       if (l == 0 && keep_p1) t.e.O2 = ws.P1;
-      if (l + 1 < L) { t.e.act = d->act[l + 1]; if (tc) t.e.Ob = ws.Hb[l + 1]; else t.e.Oh = ws.Hf[l + 1]; }
+      if (l + 1 < L) { t.e.act = d->act[l + 1]; if (tc) set_ob(t, ws.Hb[l + 1]); else t.e.Oh = ws.Hf[l + 1]; }
       const bool ce = d->loss == JPCB_LOSS_CE;
       if (l == L - 1 && loss_acc && y && !ce) { t.e.red = loss_acc; t.e.Y = y; }
       RET(launch({t}));
@@ -471,8 +507,9 @@ struct Run {
   // one warp per row: cross-entropy error / energy of the output layer from its logits
   int ce_rows(const float* lg, float lam, float* err, bf16* err_b, float* red) {
     const int wpb = 8, blocks = (Bl + wpb - 1) / wpb;
-    ce_rows_kernel<<<blocks < num_sms() * 4 ? blocks : num_sms() * 4, wpb * 32, 0, st>>>(lg, y, Bl, d->dims[L], lam, err, err_b, red);
+    ce_rows_kernel<<<blocks < num_sms() * 4 ? blocks : num_sms() * 4, wpb * 32, 0, st>>>(lg, y, Bl, d->dims[L], lam, err, x3 ? nullptr : err_b, red);
     count_launch();
+    if (x3 && err_b && err) split3(err, err_b, Bl, d->dims[L], ACT_LINEAR);  // (the split copy is made from the fp32 error)
     CK(cudaGetLastError());
     return JPCB_OK;
   }
@@ -497,7 +534,7 @@ struct Run {
       t.e.T = Tl ? Tl[l] : (l == L - 1 ? y : S[l]);
       t.e.escale = esc_all != 0.f ? esc_all : (l == L - 1 ? d->output_energy_scaling : 1.f);
       t.e.O = ws.err[l];
-      t.e.Ob = ws.Eb[l];
+      set_ob(t, ws.Eb[l]);
       if (energy) t.e.red = ws.red + l;
       ts.push_back(t);
     }
@@ -509,7 +546,8 @@ struct Run {
   int error0_from_p1(const float* const* S, bool energy) {
     const size_t n0 = (size_t)Bl * d->dims[1];
     if (n0 % 4 == 0 && (reinterpret_cast<uintptr_t>(S[0]) & 15) == 0) {  // plain streaming pass (the usual case)
-      err0_kernel<<<ew_grid(n0 / 4, 256), 256, 0, st>>>(S[0], ws.P1, ws.err[0], ws.Eb[0], n0 / 4, energy ? ws.red + 0 : nullptr);
+      err0_kernel<<<ew_grid(n0 / 4, 256), 256, 0, st>>>(S[0], ws.P1, ws.err[0], ws.Eb[0], n0 / 4, energy ? ws.red + 0 : nullptr, d->dims[1],
+                                                         x3 ? (int)x3_cw(d, d->dims[1]) : 0, x3 ? x3_part(d, d->dims[1]) : 0);
       count_launch();
       CK(cudaGetLastError());
       return JPCB_OK;
@@ -518,7 +556,7 @@ struct Run {
     t.e.mode = EPI_ERR;
     t.e.M = Bl; t.e.N = d->dims[1]; t.K = 0;
     t.e.alpha = 0.f; t.e.skip = 1.f; t.e.U = ws.P1; t.e.T = S[0];
-    t.e.O = ws.err[0]; t.e.Ob = ws.Eb[0];
+    t.e.O = ws.err[0]; set_ob(t, ws.Eb[0]);
     if (energy) t.e.red = ws.red + 0;
     t.a_p = S[0]; t.b_p = S[0];  // never dereferenced (K == 0)
     return launch_simt({t}, st);
@@ -538,17 +576,19 @@ struct Run {
       t.a_p = ws.err[l]; t.a_smn = d->dims[l + 1]; t.a_sk = 1;
       t.b_p = ws.WTf[l]; t.b_smn = d->dims[l + 1]; t.b_sk = 1;  // B(n,k) = W_l[k][n] = WTf_l[n][k]
       t.a_b = ws.Eb[l]; t.b_b = ws.WTb[l];
+      split_geom(t, d->dims[l + 1], d->dims[l + 1]);
       t.e.alpha = d->scalings[l];
       t.e.skip = eskip(l);
-      t.e.En = ws.err[l]; t.e.Enb = ws.Eb[l];
+      // (split path: the bf16 error copies are 3-part operand copies, not readable as plain bf16 -- fp32 errors instead)
+      t.e.En = ws.err[l]; t.e.Enb = x3 ? nullptr : ws.Eb[l];
       t.e.Z = Z[l - 1];
       if (l == 1 && p1_hoisted) t.e.P = ws.P1;
-      else { t.e.El = ws.err[l - 1]; t.e.Elb = ws.Eb[l - 1]; }
+      else { t.e.El = ws.err[l - 1]; t.e.Elb = x3 ? nullptr : ws.Eb[l - 1]; }
       t.e.c = c; t.e.ad = d->activity_decay; t.e.gscale = 1.f;
       t.e.O = Out[l - 1];
       if (sub == GRAD_HEUN1 || sub == GRAD_HEUN2) t.e.G1 = ws.G1[l - 1];
       if (sub == GRAD_HEUN2) { t.e.Z0 = Z0[l - 1]; t.e.red = err_red; t.e.tol_r = rtol; t.e.tol_a = atol; }
-      if (sub != GRAD_OUT) { if (tc) t.e.Ob = (stage_out ? ws.Htb : ws.Hb)[l]; else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[l]; }
+      if (sub != GRAD_OUT) { if (tc) set_ob(t, (stage_out ? ws.Htb : ws.Hb)[l]); else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[l]; }
       ts.push_back(t);
     }
     if (fr) {
@@ -563,13 +603,14 @@ struct Run {
       t.a_p = ws.err[0]; t.a_smn = d->dims[1]; t.a_sk = 1;
       t.b_p = ws.WTf[0]; t.b_smn = d->dims[1]; t.b_sk = 1;
       t.a_b = ws.Eb[0]; t.b_b = ws.WTb[0];
+      split_geom(t, d->dims[1], d->dims[1]);
       t.e.alpha = d->scalings[0];
       t.e.Z = zx; t.e.P = zx;
       t.e.c = c; t.e.ad = d->activity_decay; t.e.gscale = 1.f;
       t.e.O = x_out;
       if (sub == GRAD_HEUN1 || sub == GRAD_HEUN2) t.e.G1 = ws.G1x;
       if (sub == GRAD_HEUN2) { t.e.Z0 = x; t.e.red = err_red; t.e.tol_r = rtol; t.e.tol_a = atol; }
-      if (sub != GRAD_OUT) { if (tc) t.e.Ob = (stage_out ? ws.Htb : ws.Hb)[0]; else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[0]; }
+      if (sub != GRAD_OUT) { if (tc) set_ob(t, (stage_out ? ws.Htb : ws.Hb)[0]); else t.e.Oh = (stage_out ? ws.Hft : ws.Hf)[0]; }
       ts.push_back(t);
       x_out = nullptr;
     }
@@ -597,7 +638,10 @@ struct Run {
     const bool front = !fr && from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !(tc_flags() & 8);
     if (front) {
       if (tc) {
-        for (int l = (L - 2 - T > 0 ? L - 2 - T : 0); l < L - 1; ++l) CK(cudaMemsetAsync(ws.Eb[l], 0, (size_t)Bl * d->dims[l + 1] * sizeof(bf16), st));
+        for (int l = (L - 2 - T > 0 ? L - 2 - T : 0); l < L - 1; ++l) {
+          CK(cudaMemsetAsync(ws.Eb[l], 0, (size_t)Bl * x3_cw(d, d->dims[l + 1]) * sizeof(bf16), st));
+          if (x3) CK(cudaMemsetAsync(ws.err[l], 0, (size_t)Bl * d->dims[l + 1] * sizeof(float), st));  // (the split path reads fp32 errors)
+        }
       } else {
         CK(cudaMemsetAsync(ws.err[0], 0, (size_t)(reinterpret_cast<char*>(ws.err[L - 1]) - reinterpret_cast<char*>(ws.err[0])), st));
       }
@@ -642,6 +686,7 @@ struct Run {
       t.b_p = l == 0 ? (ws.Hf[0] ? ws.Hf[0] : x) : ws.Hf[l]; t.b_smn = 1; t.b_sk = d->dims[l];  // act already applied
       (void)S;
       t.a_b = ws.Eb[l]; t.b_b = ws.Hb[l]; t.mn_major = tc;
+      split_geom(t, d->dims[l + 1], d->dims[l]);
       t.e.alpha = -d->scalings[l] * invB;
       t.e.O = gW[l];
       ts.push_back(t);
@@ -652,7 +697,7 @@ struct Run {
       for (int l = 0; l < L; ++l) {
         const int N = d->dims[l + 1];
         const float sc = -d->scalings[l] * invB;
-        if (tc) colsum_kernel<bf16><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.Eb[l], gb[l], Bl, N, sc);
+        if (tc && !x3) colsum_kernel<bf16><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.Eb[l], gb[l], Bl, N, sc);
         else colsum_kernel<float><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.err[l], gb[l], Bl, N, sc);
         count_launch();
       }
@@ -881,7 +926,7 @@ void carve_epc(const jpcb_pc_desc* d, void* base, size_t pc_bytes, EpcWs* w) {
   w->Z.assign(L, nullptr);
   w->Rho.assign(L, nullptr);
   for (int l = 0; l + 1 < L; ++l) w->Z[l] = b.take<float>(Bl * d->dims[l + 1]);
-  if (d->dtype == JPCB_DTYPE_BF16)
+  if (d->dtype == JPCB_DTYPE_BF16)  // (the split path keeps fp32 errors in ws.err like the fp32 path)
     for (int l = 0; l < L; ++l) w->Rho[l] = b.take<float>(Bl * d->dims[l + 1]);
   w->bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
 }
@@ -910,7 +955,7 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
   if (workspace_bytes < X.bytes) return fail(JPCB_EWORKSPACE, "workspace too small: need %zu bytes (jpcb_epc_workspace_bytes), got %zu", X.bytes, workspace_bytes);
   const int L = r.L, Bl = r.Bl;
   const bool tc = r.tc, ce = desc->loss == JPCB_LOSS_CE;
-  auto rho = [&](int l) { return tc ? X.Rho[l] : r.ws.err[l]; };  // rho_{l+1}, fp32
+  auto rho = [&](int l) { return (tc && !r.x3) ? X.Rho[l] : r.ws.err[l]; };  // rho_{l+1}, fp32
   RET(r.zero_red());
   RET(r.prep_weights());
   RET(r.prep_inputs(nullptr));
@@ -923,7 +968,7 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
     if (desc->skip[l]) t.e.Gin = l == 0 ? x : X.Z[l - 1];  // any non-None skip below the output layer (:441-442)
     t.e.O = X.Z[l];
     t.e.act = desc->act[l + 1];
-    if (tc) t.e.Ob = r.ws.Hb[l + 1]; else t.e.Oh = r.ws.Hf[l + 1];
+    if (tc) r.set_ob(t, r.ws.Hb[l + 1]); else t.e.Oh = r.ws.Hf[l + 1];
     RET(r.launch({t}));
   }
   {  // output layer: z_L = a f(z_{L-1}) - eps_L; residual rho_L = y - z_L (or the softmax error) and its energy
@@ -938,7 +983,7 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
     } else {
       t.e.mode = EPI_ERR;
       t.e.T = y; t.e.escale = 1.f;
-      t.e.O = rho(L - 1); t.e.Ob = r.ws.Eb[L - 1];
+      t.e.O = rho(L - 1); r.set_ob(t, r.ws.Eb[L - 1]);
       t.e.red = r.ws.red + (L - 1);
       RET(r.launch({t}));
     }
@@ -964,16 +1009,16 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
     t.a_p = rho(l); t.a_smn = desc->dims[l + 1]; t.a_sk = 1;
     t.b_p = r.ws.WTf[l]; t.b_smn = desc->dims[l + 1]; t.b_sk = 1;
     t.a_b = r.ws.Eb[l]; t.b_b = r.ws.WTb[l];
+    r.split_geom(t, desc->dims[l + 1], desc->dims[l + 1]);
     t.e.alpha = desc->scalings[l];
     t.e.skip = (desc->skip[l] && l + 1 < L) ? 1.f : 0.f;  // (the output layer's forward pass has no skip term)
-    t.e.En = rho(l); t.e.Enb = r.ws.Eb[l];
+    t.e.En = rho(l); t.e.Enb = r.x3 ? nullptr : r.ws.Eb[l];
     t.e.Z = X.Z[l - 1]; t.e.P = X.Z[l - 1];
     t.e.c = -1.f; t.e.gscale = 1.f;
     t.e.O = rho(l - 1);
     RET(r.launch({t}));
     if (tc) {
-      const size_t n = (size_t)Bl * desc->dims[l];
-      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, r.st>>>(rho(l - 1), r.ws.Eb[l - 1], n, ACT_LINEAR); count_launch();
+      r.operand_copy(rho(l - 1), r.ws.Eb[l - 1], desc->dims[l], ACT_LINEAR);
       CK(cudaGetLastError());
     }
   }

@@ -86,7 +86,9 @@ int variant_key(const GTask& t) {
     if (e.mode == EPI_GRAD && noextra && e.act == ACT_RELU && e.El) {
       if (e.sub == GRAD_OUT && e.Gin == nullptr) return 17;
       if (e.sub == GRAD_EULER && e.Gin != nullptr) return 18;
+      if (e.sub == GRAD_EULER && e.gscale == 1.f) return 19;
     }
+    if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && plain && e.act == ACT_RELU && !e.El && !e.Elb && e.P) return 6;  // e_l = z - P
     return 0;
   }
   const bool act_ok = e.act == ACT_TANH || e.act == ACT_RELU;
@@ -121,6 +123,7 @@ int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
     case 15: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 2>(g, grid, st);
     case 17: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_RELU, 2, 1>(g, grid, st);
     case 18: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 2>(g, grid, st);
+    case 19: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 1>(g, grid, st);
     default: return launch_variant<CG, -1, -1, -1, -1, 0>(g, grid, st);
   }
 }

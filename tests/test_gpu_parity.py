@@ -1028,8 +1028,6 @@ def test_bpc_f32x3_split_tensor_core_path():
     _check_bpc_infer(*c, TOL32, T=4, dt=0.5)
     c = _bpc_case(24, 200, 3, 40, "silu", 64)
     _check_bpc(*c, TOL32)
-    with pytest.raises(NotImplementedError):   # PC networks: "f32" or "bf16"
-        J.init_activities_with_ffwd(to_gpu_model(c[0]), dev(c[3]))
 
 
 def test_config5_bpc_full_size_f32x3():
@@ -1039,3 +1037,34 @@ def test_config5_bpc_full_size_f32x3():
     c = _bpc_case(10, 1024, 6, 784, "relu", 1024)
     _check_bpc(*c, TOL32)
     _check_bpc_infer(*c, TOL32, T=30, dt=0.5, kink_budget=3)
+
+
+def test_pc_f32x3_split_tensor_core_path():
+    """The PC entry points on the split path at the fp32 tolerance: every-entry-point check, fused Euler / Heun solves and
+    train steps, cross-entropy, unsupervised, ePC, the adaptive solve, hybrid PC's regression."""
+    import jpc_b200 as J
+    J.set_compute_dtype("f32x3")
+    om, sk, x, y = _case(24, 72, 4, 16, "tanh", 16, use_bias=True)
+    _check_all(om, sk, x, y, TOL32)
+    _check_all(om, sk, x, y, TOL32, gamma=2.0, lam=0.7, ad=0.05)
+    _solve_case(om, sk, x, y, "euler", 4.0, 0.5, TOL32, perturbed=True)
+    _solve_case(om, sk, x, y, "heun", 2.0, 0.8 * 16 / 10, TOL32, perturbed=True, ad=0.05)
+    _check_fused(om, sk, x, y, "euler", 5.0, 0.5, TOL32)
+    _check_fused(om, sk, x, y, "heun", 3.0, 0.5, TOL32)
+    om, sk, x, y = _case(10, 130, 6, 10, "relu", 24, param_type="mupc", skips=True)   # padded dims, skips, relu variants
+    _check_all(om, sk, x, y, TOL32, param_type="mupc")
+    _check_fused(om, sk, x, y, "euler", 4.0, 0.3 * 24, TOL32, param_type="mupc")
+    om, sk, x, y = _case(12, 40, 3, 8, "relu", 8, use_bias=True)
+    _check_ce(om, sk, x, y, TOL32)
+    _adaptive_case(om, sk, x, y, 2e-5, 4.0, None)
+    _check_epc(om, sk, x, y, TOL32)
+    om, y2, acts = _unsup_case(16, 40, 3, 8, "tanh", 8, True)
+    _check_unsup(om, y2, acts, TOL32)
+
+
+def test_config_sized_pc_f32x3():
+    """A large fp32 PC network (the shape class of BASELINE config 4, at 1/4 width) at fp32 parity on the tensor cores."""
+    import jpc_b200 as J
+    J.set_compute_dtype("f32x3")
+    om, sk, x, y = _case(512, 512, 6, 512, "relu", 512)
+    _check_fused(om, sk, x, y, "euler", 10.0, 0.1 * 512, TOL32, kink_budget=4)
