@@ -177,8 +177,10 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, uint32_t idx,
 }
 
 // bf16 operand copy of 4 values: plain (row pitch N), or the 3-way split v = hi + mid + lo of the fp32-parity path
+// SPLIT = false: the instantiation never sees split copies (the hot bf16 variants stay free of this code)
+template <bool SPLIT>
 __device__ __forceinline__ void st_ob(const Epi& e, int row, int col, uint32_t idx, int nvalid, bool vec, const float (&v)[4]) {
-  if (e.ob_part == 0) {
+  if (!SPLIT || e.ob_part == 0) {
     st4(e.Ob, idx, nvalid, vec, v);
     return;
   }
@@ -258,6 +260,8 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
                                             const EpiPre& p, bool have_bias4, const float (&bias4)[4]) {
   const uint32_t idx = (uint32_t)row * (uint32_t)e.N + (uint32_t)col;  // M*N < 2^31 (validated on the host)
   static_assert(PLAIN == 0 || MODE != EPI_GRAD || SUB == GRAD_EULER || SUB == GRAD_OUT, "plain GRAD variants exist for OUT / EULER only");
+  // split (fp32-parity) operand copies reach the generic instantiation and the variants marked with ELSRC == 2 only
+  constexpr bool SPLIT = MODE < 0 || ELSRC == 2;
   const int mode = MODE >= 0 ? MODE : e.mode;
   const int sub = SUB >= 0 ? SUB : e.sub;
   const int act = ACT >= 0 ? ACT : e.act;
@@ -298,7 +302,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
       if (e.Ob || e.Oh) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) out[j] = act_fwd<FAST>(act, pred[j]);
-        if (e.Ob) st_ob(e, row, col, idx, nvalid, vec, out);
+        if (e.Ob) st_ob<SPLIT>(e, row, col, idx, nvalid, vec, out);
         if (e.Oh) st4(e.Oh, idx, nvalid, vec, out);
       }
       if (e.red) {
@@ -313,7 +317,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
       out[j] = PLAIN ? d : e.escale * d;
     }
     if (e.O) st4(e.O, idx, nvalid, vec, out);
-    if (e.Ob) st_ob(e, row, col, idx, nvalid, vec, out);
+    if (e.Ob) st_ob<SPLIT>(e, row, col, idx, nvalid, vec, out);
     if (e.red) {  // layer energy (lam/2) sum d^2 -- only the launches that report energies pay for it
       const float half = PLAIN ? 0.5f : (e.escale != 0.f ? 0.5f / e.escale : 0.f);  // out = lam d  =>  lam/2 d^2 = out^2 / (2 lam)
 #pragma unroll
@@ -402,7 +406,7 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
     float h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = act_fwd<FAST>(act, out[j]);
-    if (e.Ob) st_ob(e, row, col, idx, nvalid, vec, h);
+    if (e.Ob) st_ob<SPLIT>(e, row, col, idx, nvalid, vec, h);
     if (e.Oh) st4(e.Oh, idx, nvalid, vec, h);
   }
   return r;

@@ -77,20 +77,21 @@ int variant_key(const GTask& t) {
   if (tc_flags() & 4) return 0;
   const bool noextra = e.skip == 0.f && e.bias == nullptr && e.escale == 1.f && e.ad == 0.f;
   const bool plain = noextra && e.Gin == nullptr && e.gscale == 1.f;
-  if (e.mode == EPI_ERR) return plain ? 1 : 7;  // (no activation in this epilogue: also serves the fp32-parity split path)
   if (e.mode == EPI_SCALE) return 2;
   if (t.split) {
+    if (e.mode == EPI_ERR) return 20;
+
     // fp32-parity path: the specialised variants use fast activation approximations, so only activations that are exact
     // either way (relu, identity) may take them; e_l comes from the fp32 error buffers (ELSRC == 2)
-    if (e.mode == EPI_FFWD && (e.act == ACT_RELU || e.act == ACT_LINEAR)) return e.act == ACT_RELU ? 9 : 10;
+    if (e.mode == EPI_FFWD && (e.act == ACT_RELU || e.act == ACT_LINEAR)) return e.act == ACT_RELU ? 21 : 22;
     if (e.mode == EPI_GRAD && noextra && e.act == ACT_RELU && e.El) {
       if (e.sub == GRAD_OUT && e.Gin == nullptr) return 17;
       if (e.sub == GRAD_EULER && e.Gin != nullptr) return 18;
       if (e.sub == GRAD_EULER && e.gscale == 1.f) return 19;
     }
-    if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && plain && e.act == ACT_RELU && !e.El && !e.Elb && e.P) return 6;  // e_l = z - P
     return 0;
   }
+  if (e.mode == EPI_ERR) return plain ? 1 : 7;
   const bool act_ok = e.act == ACT_TANH || e.act == ACT_RELU;
   if (e.mode == EPI_GRAD && e.sub == GRAD_EULER && plain && act_ok && !e.El && (e.Elb || e.P))
     return 3 + (e.act == ACT_RELU ? 2 : 0) + (e.Elb ? 0 : 1);
@@ -124,6 +125,10 @@ int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
     case 17: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_RELU, 2, 1>(g, grid, st);
     case 18: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 2>(g, grid, st);
     case 19: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 1>(g, grid, st);
+    // split-capable twins of the ERR / FFWD variants (ELSRC == 2 marks "may write 3-way split operand copies")
+    case 20: return launch_variant<CG, EPI_ERR, 0, 0, 2, 0>(g, grid, st);
+    case 21: return launch_variant<CG, EPI_FFWD, 0, ACT_RELU, 2, 0>(g, grid, st);
+    case 22: return launch_variant<CG, EPI_FFWD, 0, ACT_LINEAR, 2, 0>(g, grid, st);
     default: return launch_variant<CG, -1, -1, -1, -1, 0>(g, grid, st);
   }
 }
