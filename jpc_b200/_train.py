@@ -16,6 +16,7 @@ from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities
 from ._errors import _check_param_type
 from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,
                      get_t_max)
+from .nn import tree_unflatten_like
 from .optim import update_and_apply
 from .solvers import ConstantStepSize, Heun, PIDController
 
@@ -26,6 +27,14 @@ def _world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size()
     return 1
+
+
+def _contig_strides(shape):
+    st, acc = [], 1
+    for n in reversed(shape):
+        st.append(acc)
+        acc *= n
+    return tuple(reversed(st))
 
 
 class _Arena:
@@ -51,7 +60,8 @@ class _Arena:
             offs.append(off)
             off += (s + 63) // 64 * 64
         self.flat = torch.empty(off, dtype=torch.float32, device=device)
-        views = [self.flat[o:o + s].view(sh) for o, s, sh in zip(offs, sizes, shapes)]
+        # one as_strided per view (contiguous strides of each shape at its offset): this runs every train step
+        views = [self.flat.as_strided(sh, _contig_strides(sh), o) for o, sh in zip(offs, shapes)]
         self.gW, self.gb = [], ([] if bias_shapes is not None else None)
         i = 0
         for l in range(L):
@@ -176,11 +186,28 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
     arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
     acts = net.out_acts(acts)
-    param_grads = _grads_pytree(net, *net.out_grads(arena.gW, arena.gb))
+    gW, gb = net.out_grads(arena.gW, arena.gb)
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)
-    g_norms = compute_param_norms(param_grads) if grad_norms else (None, None)
+    g_norms = compute_param_norms(_grads_pytree(net, gW, gb)) if grad_norms else (None, None)
     a_norms = compute_activity_norms(acts) if activity_norms else None
-    (model, skip_model), opt_state = update_and_apply(optim, param_grads, opt_state, (model, skip_model))
+    # the update: parameter and gradient leaves are already at hand as flat lists in tree order (per layer: weight, bias;
+    # the skip model has no array leaves), so the fused optimiser kernel is fed without walking the pytrees
+    fused = getattr(optim, "fused_apply_flat", None)
+    res = None
+    if fused is not None:
+        p_leaves, g_leaves = [], []
+        for l, lin in enumerate(net.linears):
+            p_leaves.append(lin.weight)
+            g_leaves.append(gW[l])
+            if lin.bias is not None:
+                p_leaves.append(lin.bias)
+                g_leaves.append(gb[l])
+        res = fused(p_leaves, g_leaves, opt_state)
+    if res is not None:
+        new_leaves, opt_state = res
+        model, skip_model = tree_unflatten_like((model, skip_model), new_leaves)
+    else:
+        (model, skip_model), opt_state = update_and_apply(optim, _grads_pytree(net, gW, gb), opt_state, (model, skip_model))
     if calculate_accuracy and input is None:
         raise ValueError("calculate_accuracy needs an input (the accuracy is that of the feed-forward pass)")
     acc = compute_accuracy(output, init_activities_with_ffwd(model, input, skip_model=skip_model,

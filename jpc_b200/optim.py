@@ -22,6 +22,7 @@ class GradientTransformation(NamedTuple):
     init: callable
     update: callable
     fused_apply: callable = None  # (params_tree, grads_tree, state) -> (new_params_tree, new_state), or None
+    fused_apply_flat: callable = None  # the same on flat leaf lists: (p_leaves, g_leaves, state) -> (new_leaves, new_state) | None
 
 
 def _fusable(leaves) -> bool:
@@ -43,16 +44,19 @@ def sgd(learning_rate: float) -> GradientTransformation:
         new = torch._foreach_mul(leaves, -float(learning_rate)) if leaves else []
         return tree_unflatten_like(updates, list(new)), state
 
-    def fused_apply(params, grads, state):
+    def fused_flat(p, g, state):
         from . import _lib
-        p, g = tree_leaves(params), tree_leaves(grads)
         if len(p) != len(g) or not _fusable(p + g):
             return None
         out = [torch.empty_like(t) for t in p]
         _lib.check(_lib.lib.jpcb_optim_sgd(len(p), _tables(p), _lib.ptr_array(p), _lib.ptr_array(g), float(learning_rate),
                                            _lib.ptr_array(out), torch.cuda.current_stream(p[0].device).cuda_stream))
-        return tree_unflatten_like(params, out), state
-    return GradientTransformation(init, update, fused_apply)
+        return out, state
+
+    def fused_apply(params, grads, state):
+        res = fused_flat(tree_leaves(params), tree_leaves(grads), state)
+        return None if res is None else (tree_unflatten_like(params, res[0]), res[1])
+    return GradientTransformation(init, update, fused_apply, fused_flat)
 
 
 def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> GradientTransformation:
@@ -76,9 +80,8 @@ def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 
         torch._foreach_mul_(step, -float(learning_rate) / (1 - b1 ** count))
         return tree_unflatten_like(updates, list(step)), {"count": count, "mu": list(mu), "nu": list(nu)}
 
-    def fused_apply(params, grads, state):
+    def fused_flat(p, g, state):
         from . import _lib
-        p, g = tree_leaves(params), tree_leaves(grads)
         mu, nu = state["mu"], state["nu"]
         if not (len(p) == len(g) == len(mu) == len(nu)) or not _fusable(p + g + list(mu) + list(nu)):
             return None
@@ -88,8 +91,12 @@ def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 
                                             _lib.ptr_array(nu), float(learning_rate), float(b1), float(b2), float(eps), count,
                                             _lib.ptr_array(out), _lib.ptr_array(mo), _lib.ptr_array(vo),
                                             torch.cuda.current_stream(p[0].device).cuda_stream))
-        return tree_unflatten_like(params, out), {"count": count, "mu": mo, "nu": vo}
-    return GradientTransformation(init, update, fused_apply)
+        return out, {"count": count, "mu": mo, "nu": vo}
+
+    def fused_apply(params, grads, state):
+        res = fused_flat(tree_leaves(params), tree_leaves(grads), state)
+        return None if res is None else (tree_unflatten_like(params, res[0]), res[1])
+    return GradientTransformation(init, update, fused_apply, fused_flat)
 
 
 def apply_updates(model, updates):
