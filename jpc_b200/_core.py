@@ -353,7 +353,7 @@ def pc_energy_fn(params, activities, y, *, x=None, loss="mse", param_type="sp", 
     return F
 
 
-def compute_pc_activity_grad(params, activities, y, *, x=None, loss_id="mse", param_type="sp", weight_decay=0.0,
+def compute_pc_activity_grad(params, activities, y, *, x, loss_id="mse", param_type="sp", weight_decay=0.0,
                              spectral_penalty=0.0, activity_decay=0.0, gamma=None, output_energy_scaling=None):
     """jpc/_core/_grads.py:95-167: (energy, dF/dactivities)."""
     model, skip_model = _unpack_params(params)
