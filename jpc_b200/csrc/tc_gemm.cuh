@@ -44,11 +44,18 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
 #ifndef JPCB_TC_EPI_WARPS
 #define JPCB_TC_EPI_WARPS 8
 #endif
-constexpr int TC_EPI_WARPS = JPCB_TC_EPI_WARPS;                 // 8 or 16 (multiples of the 4 TMEM lane quarters)
-constexpr int TC_EPI_COLS = TC_BLOCK_N / (TC_EPI_WARPS / 4);   // columns of the tile one epilogue warp owns
-constexpr int TC_EPI_PATCHES = TC_EPI_COLS / 16;
-
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_EPI_WARPS = JPCB_TC_EPI_WARPS;  // default number of epilogue warps: 8, 12 or 16 (multiples of the 4 TMEM lane quarters)
+// Epilogue-warp geometry for EW epilogue warps (a kernel template parameter: the launch-bound memory-heavy GRAD variant
+// runs 12, the others 8).  The tile's 16 patches (16 columns each) are dealt to the EW / 4 column parts as evenly as
+// possible: 8 warps 8+8, 12 warps 5+5+6, 16 warps 4x4.
+template <int EW>
+struct TcEpi {
+  static constexpr int PARTS = EW / 4;                  // column parts of the 256-wide tile (one per warp of a lane quarter)
+  static constexpr bool EVEN = (16 % PARTS) == 0;
+  static constexpr int PATCHES = 16 / PARTS;            // patches per part when the split is even
+  static constexpr int THREADS = 64 + 32 * EW;          // TMA warp + MMA warp + epilogue warps
+  __host__ __device__ static constexpr int part_begin(int p) { return (16 * p) / PARTS; }
+};
 constexpr int TC_XPOSE_BYTES = 32 * 16 * 4;  // one 32x16 fp32 patch per epilogue warp
 constexpr int TC_TMEM_COLS = 512;
 
@@ -58,7 +65,7 @@ struct TcCfg {
   static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGES = CG == 2 ? 6 : 4;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + TC_EPI_WARPS * TC_XPOSE_BYTES + 256;
+  static constexpr int smem_bytes(int ew) { return 1024 /*align slack*/ + STAGES * STAGE_BYTES + ew * TC_XPOSE_BYTES + 256; }
 };
 
 struct alignas(64) TcTask {
@@ -339,11 +346,13 @@ __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, in
 #ifndef JPCB_TC_EPI_DEPTH
 #define JPCB_TC_EPI_DEPTH 3
 #endif
-template <int MODE, int SUB, int ACT, int ELSRC, int PLAIN>
+template <int MODE, int SUB, int ACT, int ELSRC, int PLAIN, int EW>
 __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
-                                             uint32_t tphase) {
+                                             uint32_t tphase, int np) {
   float r = 0.f;
-  constexpr int DEPTH = (PLAIN == 1 && JPCB_TC_EPI_DEPTH == 3) ? 3 : 2;
+  // (the 3-deep ring needs a fully unrolled, compile-time patch count: even splits only)
+  constexpr int TC_EPI_PATCHES = TcEpi<EW>::PATCHES;
+  constexpr int DEPTH = (PLAIN == 1 && JPCB_TC_EPI_DEPTH == 3 && TcEpi<EW>::EVEN) ? 3 : 2;
   if constexpr (DEPTH == 3) {
     EpiPre pre[3][4];
     float bias[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -366,13 +375,14 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
     mbar_wait(tfull, tphase);  // accumulator of this tile complete
     tc_fence_after();
 #pragma unroll 1
-    for (int ch = 0; ch < TC_EPI_PATCHES; ch += 2) {
+    for (int ch = 0; ch < np; ch += 2) {   // np: this part's patch count (runtime when the split is uneven)
       const int cb = col0 + ch * 16;  // first column of this 16-wide patch
       if (cb >= e.N) break;           // warp-uniform
-      tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 16, lane, pb, bb);
+      const bool second = ch + 1 < np && cb + 16 < e.N;
+      if (second) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 16, lane, pb, bb);
       r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pa, ba);
-      if (cb + 16 >= e.N) break;
-      if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pa, ba);
+      if (!second) break;
+      if (ch + 2 < np) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pa, ba);
       r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb + 16, lane, t_row + (uint32_t)(ch * 16 + 16), xp, pb, bb);
     }
   }
@@ -385,8 +395,8 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
 // PLAIN (1 / 2): no task of the launch has a skip term, bias or decay (2: each has a partial-gradient input).
 // MNMAJ: both operands are read MN-major, i.e. D = A^T B with A [K, M] and B [K, N] row-major in HBM
 // (weight gradients e^T phi(z), K = batch) -- no transposed operand copies are ever materialised.
-template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false, int EW = TC_EPI_WARPS>
+__global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
   using Cfg = TcCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -394,14 +404,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t xpose_base = smem_base + STAGES * Cfg::STAGE_BYTES;
   float* xpose_ptr = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  const uint32_t bar_base = xpose_base + TC_EPI_WARPS * TC_XPOSE_BYTES;
+  const uint32_t bar_base = xpose_base + EW * TC_XPOSE_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + TC_EPI_WARPS * TC_XPOSE_BYTES + 8 * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + EW * TC_XPOSE_BYTES + 8 * (2 * STAGES + 4));
   const uint32_t tmem_slot_addr = bar_base + 8u * (2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), TC_EPI_WARPS * CG);  // the epilogue warps of both CTAs arrive on the leader's
+      mbar_init(tempty_bar(s), EW * CG);  // the epilogue warps of both CTAs arrive on the leader's
     }
     fence_barrier_init();
   }
@@ -509,9 +519,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
     }
   } else {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
-    const int ew = warp - 2;          // 0..TC_EPI_WARPS-1
+    const int ew = warp - 2;          // 0..EW-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int part = ew >> 2;         // which TC_EPI_COLS columns of the 256-wide tile
+    const int part = ew >> 2;         // which column part of the 256-wide tile
+    const int pc0 = TcEpi<EW>::part_begin(part) * 16, np = TcEpi<EW>::part_begin(part + 1) - TcEpi<EW>::part_begin(part);
     float* xp = xpose_ptr + ew * (TC_XPOSE_BYTES / 4);
     int as = 0;
     uint32_t aphase = 0;
@@ -521,9 +532,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm(const __grid_co
       const Epi e = epi_pin(t.e);  // registers, not runtime-indexed parameter space (see epi_pin)
       const int local = tile - t.tile_begin;
       const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + part * TC_EPI_COLS);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + pc0);
       // (waits for the accumulator inside, after the first patch's loads are in flight)
-      float r = tc_epi_warp<MODE, SUB, ACT, ELSRC, PLAIN>(e, m0 + q * 32, n0 + part * TC_EPI_COLS, lane, t_row, xp, tfull_bar(as), aphase);
+      float r = tc_epi_warp<MODE, SUB, ACT, ELSRC, PLAIN, EW>(e, m0 + q * 32, n0 + pc0, lane, t_row, xp, tfull_bar(as), aphase, np);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): release the stage
       tc_fence_before();
       __syncwarp();
