@@ -1060,6 +1060,17 @@ def test_pc_f32x3_split_tensor_core_path():
     _check_epc(om, sk, x, y, TOL32)
     om, y2, acts = _unsup_case(16, 40, 3, 8, "tanh", 8, True)
     _check_unsup(om, y2, acts, TOL32)
+    # hybrid PC's layer-wise regression
+    gen, amo = _hpc_models(16, 40, 3, 24, "relu", True)
+    xh, yh = data(8, 16, 24, onehot_out=False)
+    fgen, famo = f32_model(gen), f32_model(amo)
+    aa = O.init_activities_with_amort(famo, fgen, yh)
+    eq = [a + 0.3 * torch.randn(a.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64) for a in aa[1:]]
+    for_amort = eq[::-1][1:]
+    ag = O.compute_hpc_param_grads(famo, for_amort, aa, yh, xh)
+    jg = J.compute_hpc_param_grads(to_gpu_model(amo), devs(for_amort), devs(aa), dev(yh), dev(xh))
+    for l in range(3):
+        assert rel(jg[l][1].weight, ag[l]["W"]) < TOL32 and rel(jg[l][1].bias, ag[l]["b"]) < TOL32
 
 
 def test_config_sized_pc_f32x3():
