@@ -276,6 +276,30 @@ def run_bpc(args, w):
                                              "ALGORITHMIC FLOPs counted once, 6x that many are executed; whole step",
                                     "f32": "simt_grouped_gemm<128,128,16,2,2> (fp32 CUDA-core FMA path), whole step"}[dtype]},
             "cpu_baseline": None}
+    if not args.no_cpu_baseline:
+        # the reference's algorithm for this step on the host cores (oracle port: restated bPC energy + reverse-mode AD),
+        # fp32, on a bounded sample of the batch
+        from oracle import pc_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        rows = min(w["B"], max(16, args.cpu_rows // 4))
+        xs, ys = lab_h[:rows].contiguous(), img_h[:rows].contiguous()
+        td_o, bu_o = gen_l, amo_l[::-1]
+
+        def cpu_step():
+            a = O.init_activities_with_ffwd(gen_l, xs)   # one feed-forward sweep (same work as the amortiser sweep of the GPU arm)
+            for _ in range(T):
+                _, g = O.compute_bpc_activity_grad(td_o, bu_o, a, ys, x=xs)
+                a = [p - w["dt"] * q for p, q in zip(a, g)]
+            return O.compute_bpc_param_grads(td_o, bu_o, a, ys, x=xs)
+        cpu_step()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or time.perf_counter() - t0 < 8.0:
+            cpu_step()
+            reps += 1
+        line["cpu_baseline"] = {"value": rows * reps / (time.perf_counter() - t0), "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": f"{reps} steps of {rows} of {w['B']} rows, fp32 torch-CPU autograd "
+                                                           "restatement of the reference's bPC step"}
     print(json.dumps(line), flush=True)
     return 0
 
