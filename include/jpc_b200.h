@@ -167,7 +167,8 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
  * unused dummy slot ([batch, td.dims[H+1]]).  x: [batch, td.dims[0]], y: [batch, td.dims[H+1]].
  * td.skip[j] (1 <= j <= H-1) applies to both directions, td.scalings is ignored (the reference
  * validates param_type but applies no scalings, _energies.py:314).  Supervised mode (x given), Euler
- * steps, fp32 CUDA-core path in this version (td.dtype = JPCB_DTYPE_F32). */
+ * steps; td.dtype selects fp32 CUDA cores, bf16 tensor cores (needs td.act[k+1] == bu_act[k] and dims / batch
+ * multiples of 8) or fp32 parity on tensor cores (JPCB_DTYPE_F32X3, same layout rules). */
 typedef struct jpcb_bpc_desc {
   jpcb_pc_desc td;                 /* top-down model: dims d_0(x) .. d_{H+1}(y); solver fields used */
   int32_t bu_act[JPCB_MAX_LAYERS]; /* activation applied to the input of bottom_up_model[l] */

@@ -84,9 +84,9 @@ int validate(const jpcb_pc_desc* d, int min_layers = 2) {
   if (d->n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", d->n_steps);
   if (d->free_input && d->scalings[0] != 1.f) return fail(JPCB_EINVAL, "free_input (unsupervised) needs scalings[0] == 1: the reference's branch is unscaled");
   if (d->dtype != JPCB_DTYPE_F32) {
-    if (d->batch_local % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs batch_local %% 8 == 0 (got %d)", d->batch_local);
+    if (d->batch_local % 8) return fail(JPCB_ENOTIMPL, "the tensor-core paths (bf16, f32x3) need batch_local %% 8 == 0 (got %d)", d->batch_local);
     for (int l = 0; l <= d->n_layers; ++l)
-      if (d->dims[l] % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs every dim %% 8 == 0 (dims[%d]=%d)", l, d->dims[l]);
+      if (d->dims[l] % 8) return fail(JPCB_ENOTIMPL, "the tensor-core paths (bf16, f32x3) need every dim %% 8 == 0 (dims[%d]=%d)", l, d->dims[l]);
   }
   return JPCB_OK;
 }

@@ -69,9 +69,9 @@ int validate_bpc(const jpcb_bpc_desc* d) {
   }
   if (t.dtype != JPCB_DTYPE_F32 && t.dtype != JPCB_DTYPE_BF16 && t.dtype != JPCB_DTYPE_F32X3) return fail(JPCB_EINVAL, "bad dtype %d", t.dtype);
   if (t.dtype != JPCB_DTYPE_F32) {
-    if (t.batch_local % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs batch_local %% 8 == 0 (got %d)", t.batch_local);
+    if (t.batch_local % 8) return fail(JPCB_ENOTIMPL, "the tensor-core paths (bf16, f32x3) need batch_local %% 8 == 0 (got %d)", t.batch_local);
     for (int l = 0; l <= t.n_layers; ++l)
-      if (t.dims[l] % 8) return fail(JPCB_ENOTIMPL, "bf16 tensor-core path needs every dim %% 8 == 0 (dims[%d]=%d)", l, t.dims[l]);
+      if (t.dims[l] % 8) return fail(JPCB_ENOTIMPL, "the tensor-core paths (bf16, f32x3) need every dim %% 8 == 0 (dims[%d]=%d)", l, t.dims[l]);
     for (int k = 0; k + 1 < t.n_layers; ++k)
       if (t.act[k + 1] != d->bu_act[k])
         return fail(JPCB_ENOTIMPL, "bf16 bPC path needs td.act[%d] == bu_act[%d] (one bf16 operand copy per activity)", k + 1, k);
