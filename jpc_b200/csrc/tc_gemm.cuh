@@ -351,8 +351,13 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
                                              uint32_t tphase, int np) {
   float r = 0.f;
   // (the 3-deep ring needs a fully unrolled, compile-time patch count: even splits only)
-  constexpr int TC_EPI_PATCHES = TcEpi<EW>::PATCHES;
-  constexpr int DEPTH = (PLAIN == 1 && JPCB_TC_EPI_DEPTH == 3 && TcEpi<EW>::EVEN) ? 3 : 2;
+  // patches per part, rounded up when the split is uneven (the loop is fully unrolled for the static ring index and every
+  // iteration is guarded by the part's own count `np`)
+  constexpr int TC_EPI_PATCHES = (16 + TcEpi<EW>::PARTS - 1) / TcEpi<EW>::PARTS;
+#ifndef JPCB_TC_EPI_DEPTH3_UNEVEN
+#define JPCB_TC_EPI_DEPTH3_UNEVEN 0
+#endif
+  constexpr int DEPTH = (PLAIN == 1 && JPCB_TC_EPI_DEPTH == 3 && (TcEpi<EW>::EVEN || JPCB_TC_EPI_DEPTH3_UNEVEN)) ? 3 : 2;
   if constexpr (DEPTH == 3) {
     EpiPre pre[3][4];
     float bias[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -363,8 +368,8 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
 #pragma unroll
     for (int ch = 0; ch < TC_EPI_PATCHES; ++ch) {
       const int cb = col0 + ch * 16;  // first column of this 16-wide patch
-      if (cb < e.N) {                 // warp-uniform
-        if (ch + 2 < TC_EPI_PATCHES) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pre[(ch + 2) % 3], bias[(ch + 2) % 3]);
+      if ((TcEpi<EW>::EVEN || ch < np) && cb < e.N) {      // warp-uniform
+        if (ch + 2 < TC_EPI_PATCHES && (TcEpi<EW>::EVEN || ch + 2 < np)) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pre[(ch + 2) % 3], bias[(ch + 2) % 3]);
         r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pre[ch % 3], bias[ch % 3]);
       }
     }
