@@ -265,15 +265,6 @@ struct BpcRun {
     return launch({a, b});
   }
 
-  // error against a hoisted prediction, e = z - P, as one streaming pass (no GEMM)
-  int hoisted_error(const float* z, const float* pred, float* err, bf16* err_b, int N, float* red_slot) {
-    const size_t n = (size_t)Bl * N;
-    err0_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(z, pred, err, err_b, n / 4, red_slot, N, x3 ? (int)cw(N) : 0, x3 ? P(N) : 0);
-    count_launch();
-    CK(cudaGetLastError());
-    return JPCB_OK;
-  }
-
   // all 2(H+1) prediction errors on state S (+ energy sums when `energy`)
   int errors(const float* const* S, bool energy, bool hoisted) {
     std::vector<GTask> ts, k0;  // k0: the two GEMM-free tasks (always on the CUDA-core kernel)
@@ -310,8 +301,13 @@ struct BpcRun {
     // the two GEMM-free errors: streaming kernel when the layout allows 16-byte vectors, else the CUDA-core kernel's K = 0 path
     if (hoisted && D[1] % 4 == 0 && D[H] % 4 == 0 && (reinterpret_cast<uintptr_t>(S[0]) & 15) == 0 && (reinterpret_cast<uintptr_t>(S[H - 1]) & 15) == 0) {
       RET(launch(ts));
-      RET(hoisted_error(S[0], P0, e[0], Eb[0], D[1], energy ? red + 0 : nullptr));
-      return hoisted_error(S[H - 1], QH, dl[H], Db[H], D[H], energy ? red + H + 1 + H : nullptr);
+      const size_t n0 = (size_t)Bl * D[1] / 4, nH = (size_t)Bl * D[H] / 4;
+      const Err0Job j0{S[0], P0, e[0], Eb[0], n0, energy ? red + 0 : nullptr, D[1], x3 ? (int)cw(D[1]) : 0, x3 ? P(D[1]) : 0};
+      const Err0Job jH{S[H - 1], QH, dl[H], Db[H], nH, energy ? red + H + 1 + H : nullptr, D[H], x3 ? (int)cw(D[H]) : 0, x3 ? P(D[H]) : 0};
+      err0_pair_kernel<<<dim3(ew_grid((n0 > nH ? n0 : nH), 256), 2), 256, 0, st>>>(j0, jH);
+      count_launch();
+      CK(cudaGetLastError());
+      return JPCB_OK;
     }
     if (!tc) { ts.insert(ts.end(), k0.begin(), k0.end()); return launch_simt(ts, st); }
     RET(launch_tc(ts, st));

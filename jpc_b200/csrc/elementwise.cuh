@@ -166,6 +166,38 @@ static __device__ __forceinline__ void split3_store(__nv_bfloat16* dst, size_t b
   dst[base + P] = mid;
   dst[base + 2 * (size_t)P] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
 }
+// Two hoisted-prediction errors in one launch (bPC: e_0 and delta_H); blockIdx.y selects the job.
+struct Err0Job {
+  const float* z; const float* p; float* err; __nv_bfloat16* err_b; size_t n4; float* red; int N, ob_ld, ob_part;
+};
+static __global__ void err0_pair_kernel(const Err0Job a, const Err0Job b) {
+  const Err0Job& j = blockIdx.y == 0 ? a : b;
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < j.n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 u = __ldcs(reinterpret_cast<const float4*>(j.z) + i), v = __ldcs(reinterpret_cast<const float4*>(j.p) + i);
+    const float d[4] = {u.x - v.x, u.y - v.y, u.z - v.z, u.w - v.w};
+    if (j.err) reinterpret_cast<float4*>(j.err)[i] = make_float4(d[0], d[1], d[2], d[3]);
+    if (j.err_b) {
+      if (j.ob_part == 0) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(d[0], d[1]), hi = __floats2bfloat162_rn(d[2], d[3]);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&lo);
+        t.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(j.err_b)[i] = t;
+      } else {
+        const size_t row = (i * 4) / (size_t)j.N, col = (i * 4) % (size_t)j.N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split3_store(j.err_b, row * (size_t)j.ob_ld + col + k, j.ob_part, d[k]);
+      }
+    }
+    acc += 0.5f * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+  }
+  if (j.red) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(j.red, acc);
+  }
+}
+
 static __global__ void split3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int P, int act) {
   const size_t n = (size_t)R * P;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
