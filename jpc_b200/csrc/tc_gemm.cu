@@ -38,14 +38,14 @@ int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   return JPCB_OK;
 }
 
-template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false, int EW = TC_EPI_WARPS>
+template <int CG, int BN, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false, int EW = TC_EPI_WARPS>
 int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
-  using Cfg = TcCfg<CG>;
+  using Cfg = TcCfg<CG, BN>;
   constexpr int SMEM = Cfg::smem_bytes(EW);
   static_assert(SMEM <= 227 * 1024, "shared memory of the tensor-core kernel exceeds the per-CTA limit");
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN, MNMAJ, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    CK(cudaFuncSetAttribute(tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN, MNMAJ, EW, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -65,7 +65,7 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (tc_flags() & 16) ? 1 : 2;
-  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN, MNMAJ, EW>, g));
+  CK(cudaLaunchKernelEx(&cfg, tc_grouped_gemm<CG, MODE, SUB, ACT, ELSRC, PLAIN, MNMAJ, EW, BN>, g));
   count_launch();
   return JPCB_OK;
 }
@@ -106,34 +106,34 @@ int variant_key(const GTask& t) {
   return 0;
 }
 
-template <int CG>
+template <int CG, int BN>
 int launch_group(const TcGroup& g, int key, int grid, cudaStream_t st) {
   switch (key) {
-    case 1: return launch_variant<CG, EPI_ERR, 0, 0, -1, 1>(g, grid, st);
-    case 7: return launch_variant<CG, EPI_ERR, 0, 0, -1, 0>(g, grid, st);
-    case 2: return launch_variant<CG, EPI_SCALE, 0, 0, -1, 0>(g, grid, st);
+    case 1: return launch_variant<CG, BN, EPI_ERR, 0, 0, -1, 1>(g, grid, st);
+    case 7: return launch_variant<CG, BN, EPI_ERR, 0, 0, -1, 0>(g, grid, st);
+    case 2: return launch_variant<CG, BN, EPI_SCALE, 0, 0, -1, 0>(g, grid, st);
     // the Euler update with e_l from the bf16 error copy -- the phase that is bound by its epilogue's memory latency, not by
     // the MMAs -- runs 12 epilogue warps (3 per scheduler instead of 2; 126 registers, 2-deep load ring): 207 -> 198 us on c4
-    case 3: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, 1, false, 12>(g, grid, st);
-    case 4: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 1, 1>(g, grid, st);
-    case 5: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 1, false, 12>(g, grid, st);
-    case 6: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 1, 1>(g, grid, st);
-    case 8: return launch_variant<CG, EPI_FFWD, 0, ACT_TANH, -1, 0>(g, grid, st);
-    case 9: return launch_variant<CG, EPI_FFWD, 0, ACT_RELU, -1, 0>(g, grid, st);
-    case 10: return launch_variant<CG, EPI_FFWD, 0, ACT_LINEAR, -1, 0>(g, grid, st);
-    case 11: return launch_variant<CG, EPI_SCALE, 0, 0, -1, 0, true>(g, grid, st);
-    case 12: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_TANH, 0, 1>(g, grid, st);
-    case 13: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_RELU, 0, 1>(g, grid, st);
-    case 14: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, 2>(g, grid, st);
-    case 15: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 2>(g, grid, st);
-    case 17: return launch_variant<CG, EPI_GRAD, GRAD_OUT, ACT_RELU, 2, 1>(g, grid, st);
-    case 18: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 2>(g, grid, st);
-    case 19: return launch_variant<CG, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 1>(g, grid, st);
+    case 3: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, 1, false, BN == 256 ? 12 : 8>(g, grid, st);
+    case 4: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_TANH, 1, 1>(g, grid, st);
+    case 5: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 1, false, BN == 256 ? 12 : 8>(g, grid, st);
+    case 6: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_RELU, 1, 1>(g, grid, st);
+    case 8: return launch_variant<CG, BN, EPI_FFWD, 0, ACT_TANH, -1, 0>(g, grid, st);
+    case 9: return launch_variant<CG, BN, EPI_FFWD, 0, ACT_RELU, -1, 0>(g, grid, st);
+    case 10: return launch_variant<CG, BN, EPI_FFWD, 0, ACT_LINEAR, -1, 0>(g, grid, st);
+    case 11: return launch_variant<CG, BN, EPI_SCALE, 0, 0, -1, 0, true>(g, grid, st);
+    case 12: return launch_variant<CG, BN, EPI_GRAD, GRAD_OUT, ACT_TANH, 0, 1>(g, grid, st);
+    case 13: return launch_variant<CG, BN, EPI_GRAD, GRAD_OUT, ACT_RELU, 0, 1>(g, grid, st);
+    case 14: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_TANH, 0, 2>(g, grid, st);
+    case 15: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_RELU, 0, 2>(g, grid, st);
+    case 17: return launch_variant<CG, BN, EPI_GRAD, GRAD_OUT, ACT_RELU, 2, 1>(g, grid, st);
+    case 18: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 2>(g, grid, st);
+    case 19: return launch_variant<CG, BN, EPI_GRAD, GRAD_EULER, ACT_RELU, 2, 1>(g, grid, st);
     // split-capable twins of the ERR / FFWD variants (ELSRC == 2 marks "may write 3-way split operand copies")
-    case 20: return launch_variant<CG, EPI_ERR, 0, 0, 2, 0>(g, grid, st);
-    case 21: return launch_variant<CG, EPI_FFWD, 0, ACT_RELU, 2, 0>(g, grid, st);
-    case 22: return launch_variant<CG, EPI_FFWD, 0, ACT_LINEAR, 2, 0>(g, grid, st);
-    default: return launch_variant<CG, -1, -1, -1, -1, 0>(g, grid, st);
+    case 20: return launch_variant<CG, BN, EPI_ERR, 0, 0, 2, 0>(g, grid, st);
+    case 21: return launch_variant<CG, BN, EPI_FFWD, 0, ACT_RELU, 2, 0>(g, grid, st);
+    case 22: return launch_variant<CG, BN, EPI_FFWD, 0, ACT_LINEAR, 2, 0>(g, grid, st);
+    default: return launch_variant<CG, BN, -1, -1, -1, -1, 0>(g, grid, st);
   }
 }
 
@@ -151,6 +151,22 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
   for (size_t first = 0; first < tasks.size(); ++first) {
     if (done[first]) continue;
     const int key = keys[first];
+    // tile width of this group: 256, or 128 when that needs fewer (half-weight) rounds of the persistent grid -- launches
+    // with only one or two waves of 256-wide tiles lose up to half a wave to quantisation
+    const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
+    int BN = TC_BLOCK_N;
+    {
+      long long t256 = 0, t128 = 0;
+      for (size_t j = first; j < tasks.size(); ++j) {
+        if (done[j] || keys[j] != key) continue;
+        const long long tm = (tasks[j].e.M + BM - 1) / BM;
+        t256 += tm * ((tasks[j].e.N + 255) / 256);
+        t128 += tm * ((tasks[j].e.N + 127) / 128);
+      }
+      const long long r256 = 2 * ((t256 + units - 1) / units), r128 = (t128 + units - 1) / units;  // in half-tile rounds
+      static const int allow128 = [] { const char* v = getenv("JPCB_TC_BN128"); return v ? atoi(v) : 1; }();
+      if (allow128 && r128 < r256 && t256 <= 4LL * units) BN = 128;
+    }
     size_t i = first;
     while (i < tasks.size()) {
       TcGroup g;
@@ -169,13 +185,13 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
           RET(make_map(&s.tmB, t.b_b, t.K, t.split ? t.b_ld : t.e.N, 64));
         } else {
           RET(make_map(&s.tmA, t.a_b, t.e.M, t.split ? t.a_ld : t.K, TC_BLOCK_M));
-          RET(make_map(&s.tmB, t.b_b, t.e.N, t.split ? t.b_ld : t.K, Cfg::B_ROWS));
+          RET(make_map(&s.tmB, t.b_b, t.e.N, t.split ? t.b_ld : t.K, BN / CG));
         }
         s.split = t.split; s.a_part = t.a_part; s.b_part = t.b_part;
         s.pad_[0] = s.pad_[1] = 0;
         s.K = t.K;
         s.tile_begin = tiles;
-        s.tiles_n = (t.e.N + TC_BLOCK_N - 1) / TC_BLOCK_N;
+        s.tiles_n = (t.e.N + BN - 1) / BN;
         s.e = t.e;
         tiles += s.tiles_n * ((t.e.M + BM - 1) / BM);
         ++n;
@@ -183,9 +199,9 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
       if (n == 0) break;
       g.ntasks = n;
       g.total_tiles = tiles;
-      const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
       const int grid = CG * (tiles < units ? tiles : units);
-      RET(launch_group<CG>(g, key, grid, st));
+      if (BN == 128) RET((launch_group<CG, 128>(g, key, grid, st)));
+      else RET((launch_group<CG, 256>(g, key, grid, st)));
     }
   }
   return JPCB_OK;

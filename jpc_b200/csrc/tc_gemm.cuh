@@ -48,23 +48,26 @@ constexpr int TC_EPI_WARPS = JPCB_TC_EPI_WARPS;  // default number of epilogue w
 // Epilogue-warp geometry for EW epilogue warps (a kernel template parameter: the launch-bound memory-heavy GRAD variant
 // runs 12, the others 8).  The tile's 16 patches (16 columns each) are dealt to the EW / 4 column parts as evenly as
 // possible: 8 warps 8+8, 12 warps 5+5+6, 16 warps 4x4.
-template <int EW>
+template <int EW, int BN = 256>
 struct TcEpi {
-  static constexpr int PARTS = EW / 4;                  // column parts of the 256-wide tile (one per warp of a lane quarter)
-  static constexpr bool EVEN = (16 % PARTS) == 0;
-  static constexpr int PATCHES = 16 / PARTS;            // patches per part when the split is even
+  static constexpr int NP = BN / 16;                    // 16-column patches across the tile
+  static constexpr int PARTS = EW / 4;                  // column parts of the tile (one per warp of a lane quarter)
+  static constexpr bool EVEN = (NP % PARTS) == 0;
+  static constexpr int PATCHES = NP / PARTS;            // patches per part when the split is even
   static constexpr int THREADS = 64 + 32 * EW;          // TMA warp + MMA warp + epilogue warps
-  __host__ __device__ static constexpr int part_begin(int p) { return (16 * p) / PARTS; }
+  __host__ __device__ static constexpr int part_begin(int p) { return (NP * p) / PARTS; }
 };
 constexpr int TC_XPOSE_BYTES = 32 * 16 * 4;  // one 32x16 fp32 patch per epilogue warp
 constexpr int TC_TMEM_COLS = 512;
 
-template <int CG>
+// BN: tile width.  256 is the default (most operand reuse per staged byte); 128 halves the tile for launches that offer
+// only one or two waves of 256-wide tiles (bPC's gradient halves: 80 tile pairs on 74 CTA pairs), at a deeper ring.
+template <int CG, int BN = TC_BLOCK_N>
 struct TcCfg {
-  static constexpr int B_ROWS = TC_BLOCK_N / CG;           // N-rows of B staged by each CTA
+  static constexpr int B_ROWS = BN / CG;                   // N-rows of B staged by each CTA
   static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int STAGES = CG == 2 ? (BN == 256 ? 6 : 8) : 4;
   static constexpr int smem_bytes(int ew) { return 1024 /*align slack*/ + STAGES * STAGE_BYTES + ew * TC_XPOSE_BYTES + 256; }
 };
 
@@ -346,18 +349,19 @@ __device__ __forceinline__ float tc_epi_patch(const Epi& e, int row0, int cb, in
 #ifndef JPCB_TC_EPI_DEPTH
 #define JPCB_TC_EPI_DEPTH 3
 #endif
-template <int MODE, int SUB, int ACT, int ELSRC, int PLAIN, int EW>
+template <int MODE, int SUB, int ACT, int ELSRC, int PLAIN, int EW, int BN>
 __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, int lane, uint32_t t_row, float* xp, uint32_t tfull,
                                              uint32_t tphase, int np) {
   float r = 0.f;
   // (the 3-deep ring needs a fully unrolled, compile-time patch count: even splits only)
   // patches per part, rounded up when the split is uneven (the loop is fully unrolled for the static ring index and every
   // iteration is guarded by the part's own count `np`)
-  constexpr int TC_EPI_PATCHES = (16 + TcEpi<EW>::PARTS - 1) / TcEpi<EW>::PARTS;
+  using Ep = TcEpi<EW, BN>;
+  constexpr int TC_EPI_PATCHES = (Ep::NP + Ep::PARTS - 1) / Ep::PARTS;
 #ifndef JPCB_TC_EPI_DEPTH3_UNEVEN
 #define JPCB_TC_EPI_DEPTH3_UNEVEN 0
 #endif
-  constexpr int DEPTH = (PLAIN == 1 && JPCB_TC_EPI_DEPTH == 3 && (TcEpi<EW>::EVEN || JPCB_TC_EPI_DEPTH3_UNEVEN)) ? 3 : 2;
+  constexpr int DEPTH = (PLAIN == 1 && JPCB_TC_EPI_DEPTH == 3 && (Ep::EVEN || JPCB_TC_EPI_DEPTH3_UNEVEN)) ? 3 : 2;
   if constexpr (DEPTH == 3) {
     EpiPre pre[3][4];
     float bias[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -368,8 +372,8 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
 #pragma unroll
     for (int ch = 0; ch < TC_EPI_PATCHES; ++ch) {
       const int cb = col0 + ch * 16;  // first column of this 16-wide patch
-      if ((TcEpi<EW>::EVEN || ch < np) && cb < e.N) {      // warp-uniform
-        if (ch + 2 < TC_EPI_PATCHES && (TcEpi<EW>::EVEN || ch + 2 < np)) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pre[(ch + 2) % 3], bias[(ch + 2) % 3]);
+      if ((Ep::EVEN || ch < np) && cb < e.N) {      // warp-uniform
+        if (ch + 2 < TC_EPI_PATCHES && (Ep::EVEN || ch + 2 < np)) tc_epi_loads<MODE, ELSRC, PLAIN>(e, row0, cb + 32, lane, pre[(ch + 2) % 3], bias[(ch + 2) % 3]);
         r += tc_epi_patch<MODE, SUB, ACT, ELSRC, PLAIN>(e, row0, cb, lane, t_row + (uint32_t)(ch * 16), xp, pre[ch % 3], bias[ch % 3]);
       }
     }
@@ -400,9 +404,9 @@ __device__ __forceinline__ float tc_epi_warp(const Epi& e, int row0, int col0, i
 // PLAIN (1 / 2): no task of the launch has a skip term, bias or decay (2: each has a partial-gradient input).
 // MNMAJ: both operands are read MN-major, i.e. D = A^T B with A [K, M] and B [K, N] row-major in HBM
 // (weight gradients e^T phi(z), K = batch) -- no transposed operand copies are ever materialised.
-template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false, int EW = TC_EPI_WARPS>
+template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ = false, int EW = TC_EPI_WARPS, int BN = TC_BLOCK_N>
 __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
-  using Cfg = TcCfg<CG>;
+  using Cfg = TcCfg<CG, BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
       const TcTask& t = g.t[ti];
       const int local = tile - t.tile_begin;
       const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M;
-      const int n0 = (local % t.tiles_n) * TC_BLOCK_N + (int)rank * Cfg::B_ROWS;
+      const int n0 = (local % t.tiles_n) * BN + (int)rank * Cfg::B_ROWS;
       const int nkb = (t.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
       // t.split = number of split products to run (6 = all; 4 drops the two hi*lo terms, 3 also mid*mid): the LAST
       // t.split entries of the smallest-first list
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M * CG, TC_BLOCK_N, MNMAJ);
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M * CG, BN, MNMAJ);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
         const int nkb = ((g.t[ti].K + TC_BLOCK_K - 1) / TC_BLOCK_K) * (g.t[ti].split ? g.t[ti].split : 1);  // k-blocks over all passes
         mbar_wait(tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -527,7 +531,8 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
     const int ew = warp - 2;          // 0..EW-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int part = ew >> 2;         // which column part of the 256-wide tile
-    const int pc0 = TcEpi<EW>::part_begin(part) * 16, np = TcEpi<EW>::part_begin(part + 1) - TcEpi<EW>::part_begin(part);
+    using Ep = TcEpi<EW, BN>;
+    const int pc0 = Ep::part_begin(part) * 16, np = Ep::part_begin(part + 1) - Ep::part_begin(part);
     float* xp = xpose_ptr + ew * (TC_XPOSE_BYTES / 4);
     int as = 0;
     uint32_t aphase = 0;
@@ -536,10 +541,10 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
       const TcTask& t = g.t[ti];
       const Epi e = epi_pin(t.e);  // registers, not runtime-indexed parameter space (see epi_pin)
       const int local = tile - t.tile_begin;
-      const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = (local % t.tiles_n) * TC_BLOCK_N;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BLOCK_N + pc0);
+      const int m0 = (local / t.tiles_n) * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = (local % t.tiles_n) * BN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + pc0);
       // (waits for the accumulator inside, after the first patch's loads are in flight)
-      float r = tc_epi_warp<MODE, SUB, ACT, ELSRC, PLAIN, EW>(e, m0 + q * 32, n0 + pc0, lane, t_row, xp, tfull_bar(as), aphase, np);
+      float r = tc_epi_warp<MODE, SUB, ACT, ELSRC, PLAIN, EW, BN>(e, m0 + q * 32, n0 + pc0, lane, t_row, xp, tfull_bar(as), aphase, np);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): release the stage
       tc_fence_before();
       __syncwarp();
