@@ -408,20 +408,22 @@ template <int CG, int MODE, int SUB, int ACT, int ELSRC, int PLAIN, bool MNMAJ =
 __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const __grid_constant__ TcGroup g) {
   using Cfg = TcCfg<CG, BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC = TC_TMEM_COLS / BN;  // fp32 accumulator stages in TMEM (512 columns): 2 at BN = 256, 4 at BN = 128
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t xpose_base = smem_base + STAGES * Cfg::STAGE_BYTES;
   float* xpose_ptr = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
   const uint32_t bar_base = xpose_base + EW * TC_XPOSE_BYTES;
-  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address
+  // barriers: full[STAGES], empty[STAGES], tmem_full[ACC], tmem_empty[ACC]; then the TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC + s); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + EW * TC_XPOSE_BYTES + 8 * (2 * STAGES + 4));
-  const uint32_t tmem_slot_addr = bar_base + 8u * (2 * STAGES + 4);
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + EW * TC_XPOSE_BYTES + 8 * (2 * STAGES + 2 * ACC));
+  const uint32_t tmem_slot_addr = bar_base + 8u * (2 * STAGES + 2 * ACC);
+  static_assert(8 * (2 * STAGES + 2 * ACC) + 4 <= 256, "barrier block exceeds its slack in TcCfg::smem_bytes");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader CTA of the pair
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
       mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx (covers both CTAs' bytes)
       mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast to both CTAs when CG = 2)
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ACC; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EW * CG);  // the epilogue warps of both CTAs arrive on the leader's
     }
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (++as == ACC) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(TcEpi<EW>::THREADS, 1) tc_grouped_gemm(const _
         r = warp_sum(r);
         if (lane == 0) atomicAdd(e.red, r);
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == ACC) { as = 0; aphase ^= 1u; }
     }
   }
 
