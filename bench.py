@@ -172,13 +172,35 @@ def cpu_reference_step_fn(w, sample_rows):
     return step
 
 
+def cpu_bpc_step_fn(w, sample_rows):
+    """The reference's bPC step (config 5) on the host cores: oracle port -- restated bPC energy + reverse-mode AD, T
+    gradient steps on the activities, then both models' parameter gradients; fp32, `sample_rows` rows."""
+    import torch
+    from oracle import pc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen_l, _, _ = make_inputs(dict(w, d_in=w["d_in"], d_out=w["d_out"]), seed_w=0)
+    amo_l, _, _ = make_inputs(dict(w, d_in=w["d_out"], d_out=w["d_in"]), seed_w=1)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(w["B"], w["d_out"], generator=g)[:sample_rows].contiguous()
+    lab = torch.nn.functional.one_hot(torch.randint(0, w["d_in"], (w["B"],), generator=g), w["d_in"]).float()[:sample_rows].contiguous()
+    td_o, bu_o, T = gen_l, amo_l[::-1], n_steps(w)
+
+    def step():
+        a = O.init_activities_with_ffwd(gen_l, lab)   # one feed-forward sweep (same work as the amortiser sweep of the GPU arm)
+        for _ in range(T):
+            _, gr = O.compute_bpc_activity_grad(td_o, bu_o, a, img, x=lab)
+            a = [p - w["dt"] * q for p, q in zip(a, gr)]
+        return O.compute_bpc_param_grads(td_o, bu_o, a, img, x=lab)
+    return step
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import torch
     rows = min(w["B"], args.cpu_rows)
-    step = cpu_reference_step_fn(w, rows)
+    step = cpu_bpc_step_fn(w, rows) if w.get("bpc") else cpu_reference_step_fn(w, rows)
     for _ in range(max(1, min(args.warmup, 1))):
         step()
     t0 = time.perf_counter()
@@ -279,18 +301,8 @@ def run_bpc(args, w):
     if not args.no_cpu_baseline:
         # the reference's algorithm for this step on the host cores (oracle port: restated bPC energy + reverse-mode AD),
         # fp32, on a bounded sample of the batch
-        from oracle import pc_oracle as O
-        torch.set_num_threads(os.cpu_count() or 1)
         rows = min(w["B"], max(16, args.cpu_rows // 4))
-        xs, ys = lab_h[:rows].contiguous(), img_h[:rows].contiguous()
-        td_o, bu_o = gen_l, amo_l[::-1]
-
-        def cpu_step():
-            a = O.init_activities_with_ffwd(gen_l, xs)   # one feed-forward sweep (same work as the amortiser sweep of the GPU arm)
-            for _ in range(T):
-                _, g = O.compute_bpc_activity_grad(td_o, bu_o, a, ys, x=xs)
-                a = [p - w["dt"] * q for p, q in zip(a, g)]
-            return O.compute_bpc_param_grads(td_o, bu_o, a, ys, x=xs)
+        cpu_step = cpu_bpc_step_fn(w, rows)
         cpu_step()
         t0 = time.perf_counter()
         reps = 0
@@ -323,8 +335,6 @@ def main():
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        if w.get("bpc"):
-            raise SystemExit("--impl reference is implemented for the PC workloads (c1-c4)")
         return run_reference(args, w)
     if w.get("bpc"):
         return run_bpc(args, w)
