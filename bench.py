@@ -209,7 +209,8 @@ def run_reference(args, w):
     dt = time.perf_counter() - t0
     val = rows * args.steps / dt
     cores = torch.get_num_threads()
-    sample = f"{rows} of {w['B']} rows of the workload per step, fp32, torch-CPU autograd restatement of jpc.make_pc_step"
+    what = "the reference's bPC step" if w.get("bpc") else "jpc.make_pc_step"
+    sample = f"{rows} of {w['B']} rows of the workload per step, fp32, torch-CPU autograd restatement of {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
