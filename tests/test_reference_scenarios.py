@@ -366,3 +366,26 @@ def test_evaluation_helpers(jpc, simple_model, x, y_onehot):
                                                              sigma=0.05, ode_solver=jpc.Heun(), max_t1=10,
                                                              stepsize_controller=jpc.PIDController(rtol=1e-3, atol=1e-3))
     assert all(0 <= float(a) <= 100 for a in (amort_acc, hpc_acc, gen_acc)) and tuple(output_preds.shape) == (B, D_OUT)
+
+
+# ---- the reference README's two usage examples (README.md:62-145), batch dimension made explicit ------------------
+def test_readme_quick_example_and_advanced_usage(jpc):
+    x = torch.ones(1, 3).cuda()
+    y = -x
+    model = jpc.make_mlp(0, input_dim=3, width=50, depth=5, output_dim=3, act_fn="relu")
+    optim = jpc.optim.adam(1e-3)
+    opt_state = optim.init((model, None))
+    result = jpc.make_pc_step(model=model, optim=optim, opt_state=opt_state, output=y, input=x)
+    model, opt_state = result["model"], result["opt_state"]
+    assert len(model) == 5 and _finite(result["loss"]) and opt_state["count"] == 1
+    # advanced usage: explicit init -> inference loop -> parameter update (legacy spelling `update_params`)
+    activity_optim = jpc.optim.sgd(0.5)
+    activities = jpc.init_activities_with_ffwd(model=model, input=x)
+    activity_opt_state = activity_optim.init(activities)
+    for _ in range(len(model)):
+        activity_update_result = jpc.update_pc_activities(params=(model, None), activities=activities, optim=activity_optim,
+                                                          opt_state=activity_opt_state, output=y, input=x)
+        activities = activity_update_result["activities"]
+        activity_opt_state = activity_update_result["opt_state"]
+    result = jpc.update_params(params=(model, None), activities=activities, optim=optim, opt_state=opt_state, output=y, input=x)
+    assert len(result["model"]) == 5 and result["opt_state"]["count"] == 2
