@@ -180,22 +180,26 @@ __device__ __forceinline__ void st4(__nv_bfloat16* __restrict__ p, uint32_t idx,
 // SPLIT = false: the instantiation never sees split copies (the hot bf16 variants stay free of this code)
 template <bool SPLIT>
 __device__ __forceinline__ void st_ob(const Epi& e, int row, int col, uint32_t idx, int nvalid, bool vec, const float (&v)[4]) {
-  if (!SPLIT || e.ob_part == 0) {
+  if constexpr (!SPLIT) {
     st4(e.Ob, idx, nvalid, vec, v);
-    return;
-  }
-  float hi[4], mid[4], lo[4];
+  } else {
+    if (e.ob_part == 0) {
+      st4(e.Ob, idx, nvalid, vec, v);
+      return;
+    }
+    float hi[4], mid[4], lo[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-    const float r1 = v[j] - hi[j];
-    mid[j] = __bfloat162float(__float2bfloat16_rn(r1));
-    lo[j] = r1 - mid[j];
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+      const float r1 = v[j] - hi[j];
+      mid[j] = __bfloat162float(__float2bfloat16_rn(r1));
+      lo[j] = r1 - mid[j];
+    }
+    const uint32_t b0 = (uint32_t)row * (uint32_t)e.ob_ld + (uint32_t)col;
+    st4(e.Ob, b0, nvalid, vec, hi);
+    st4(e.Ob, b0 + (uint32_t)e.ob_part, nvalid, vec, mid);
+    st4(e.Ob, b0 + 2u * (uint32_t)e.ob_part, nvalid, vec, lo);
   }
-  const uint32_t b0 = (uint32_t)row * (uint32_t)e.ob_ld + (uint32_t)col;
-  st4(e.Ob, b0, nvalid, vec, hi);
-  st4(e.Ob, b0 + (uint32_t)e.ob_part, nvalid, vec, mid);
-  st4(e.Ob, b0 + 2u * (uint32_t)e.ob_part, nvalid, vec, lo);
 }
 
 // The fused epilogue is split in two so that callers can put many independent global loads in
@@ -309,19 +313,19 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (j < nvalid) { float d = p.a[j] - pred[j]; r += 0.5f * d * d; }
       }
-      return r;
-    }
+    } else {  // EPI_ERR
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float d = j < nvalid ? p.a[j] - pred[j] : 0.f;
-      out[j] = PLAIN ? d : e.escale * d;
-    }
-    if (e.O) st4(e.O, idx, nvalid, vec, out);
-    if (e.Ob) st_ob<SPLIT>(e, row, col, idx, nvalid, vec, out);
-    if (e.red) {  // layer energy (lam/2) sum d^2 -- only the launches that report energies pay for it
-      const float half = PLAIN ? 0.5f : (e.escale != 0.f ? 0.5f / e.escale : 0.f);  // out = lam d  =>  lam/2 d^2 = out^2 / (2 lam)
+      for (int j = 0; j < 4; ++j) {
+        const float d = j < nvalid ? p.a[j] - pred[j] : 0.f;
+        out[j] = PLAIN ? d : e.escale * d;
+      }
+      if (e.O) st4(e.O, idx, nvalid, vec, out);
+      if (e.Ob) st_ob<SPLIT>(e, row, col, idx, nvalid, vec, out);
+      if (e.red) {  // layer energy (lam/2) sum d^2 -- only the launches that report energies pay for it
+        const float half = PLAIN ? 0.5f : (e.escale != 0.f ? 0.5f / e.escale : 0.f);  // out = lam d  =>  lam/2 d^2 = out^2 / (2 lam)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r += half * out[j] * out[j];
+        for (int j = 0; j < 4; ++j) r += half * out[j] * out[j];
+      }
     }
     return r;
   }
