@@ -87,10 +87,10 @@ typedef struct jpcb_pc_desc {
   int32_t free_input;                /* unsupervised PC (`x = None` in the reference, jpc/_core/_energies.py:86,
                                       * 123-124): there is no input; z_0 is a free activity.  Every activity list
                                       * (A, gA, A_new) then has n_layers + 1 entries [z_0, z_1 .. z_{L-1}, dummy]
-                                      * exactly like the reference's, and the `x` argument must be NULL.  The first
-                                      * layer's prediction is used as the reference uses it (scalings[0] must be 1:
-                                      * "sp" is the only parameterisation the reference's unsupervised branch
-                                      * accepts).  jpcb_pc_ffwd_init / jpcb_pc_train_step need an input. */
+                                      * exactly like the reference's, and the `x` argument must be NULL.  scalings[0]
+                                      * is applied as given: the reference's PC branch is unscaled and only runs with
+                                      * "sp" (callers pass 1); its ePC branch scales the first layer like any other.
+                                      * jpcb_pc_ffwd_init / jpcb_pc_train_step need an input. */
 } jpcb_pc_desc;
 
 int jpcb_version(void);
@@ -228,7 +228,9 @@ int jpcb_hpc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const 
  * One call = the forward chain (L dependent GEMMs), and if gradients are requested the backward chain
  * rho_l = act_l'(z_l) . (a_l rho_{l+1} W_l) + s_l rho_{l+1} from rho_L = y - z_L (L-1 dependent GEMMs):
  *   gE[l-1] = (eps_l - rho_l) / B  (l < L),   gE[L-1] = rho_L / B,   gW[l] = -(a_l/B) rho_{l+1}^T act_l(z_l).
- * F, gE, (gW, gb) are each nullable.  Workspace: jpcb_epc_workspace_bytes(desc) (larger than the PC one). */
+ * F, gE, (gW, gb) are each nullable.  Workspace: jpcb_epc_workspace_bytes(desc) (larger than the PC one).
+ * desc->free_input (x = None in the reference): E and gE have L + 1 entries, E[0] plays z_0, x must be NULL, and -- as in
+ * the reference, whose penalty loop still covers the first L - 1 list entries -- z_0 is penalised and eps_{L-1} is not. */
 size_t jpcb_epc_workspace_bytes(const jpcb_pc_desc* desc);
 int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
                    const float* const* E, const float* x, const float* y, float* F, float* const* gE,

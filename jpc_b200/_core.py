@@ -110,6 +110,13 @@ def _get_param_scalings(model, input, *, skip_model=None, param_type="sp", gamma
     return scalings
 
 
+class _Shape:
+    """Stand-in for an array of which only `.shape` is read."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
 _DESC_CACHE: dict = {}
 _WS_CACHE: dict = {}
 
@@ -119,7 +126,7 @@ class _Net:
 
     def __init__(self, model, skip_model, x, y, *, param_type, loss_id, gamma, output_energy_scaling,
                  activity_decay, weight_decay, spectral_penalty, solver=0, n_steps=0, dt=0.0, dt_last=0.0,
-                 batch_global=None):
+                 batch_global=None, scaled_free_input=False):
         _check_param_type(param_type)
         if loss_id not in ("mse", "ce"):
             raise ValueError("`mse` and `ce` are the only valid losses.")
@@ -128,7 +135,7 @@ class _Net:
         self.free = x is None
         if self.free and y is None:
             raise ValueError("unsupervised mode (input=None) needs the target to size the batch")
-        if self.free and param_type != "sp":
+        if self.free and param_type != "sp" and not scaled_free_input:
             raise ValueError("unsupervised mode (input=None) supports param_type='sp' only: the reference's "
                              "`_get_param_scalings` needs the input's width for 'mupc' / 'ntp'")
         L = len(model)
@@ -158,7 +165,9 @@ class _Net:
             raise ValueError("input feature dim does not match the first layer")
         B = y.shape[0] if self.free else x.shape[0]
         skips = _skip_flags(skip_model, L)
-        scal = _get_param_scalings(model, x, skip_model=skip_model, param_type=param_type, gamma=gamma)
+        # (ePC's x=None branch scales the first layer by the width of errors[0] = d_0, jpc/_core/_energies.py:422-427)
+        scal_in = x if x is not None else _Shape((B, dims[0]))
+        scal = _get_param_scalings(model, scal_in, skip_model=skip_model, param_type=param_type, gamma=gamma)
         self.true_dims = list(dims)
         bs = [lin.bias for lin in self.linears] if all(has_bias) else None
         self.padded = _COMPUTE_DTYPE != "f32" and any(v % 8 for v in dims)  # (both tensor-core paths)

@@ -2,7 +2,7 @@
 (jpc/_core/_init.py:163-190), `epc_energy_fn` (jpc/_core/_energies.py:360-458), `compute_epc_error_grad` /
 `compute_epc_param_grads` (jpc/_core/_grads.py:857-949), `update_epc_errors` / `update_epc_params`
 (jpc/_core/_updates.py:785-960).  Every function is one `jpcb_epc_grads` call (forward chain + optional backward
-chain on the device); supervised networks only (the reference's `x=None` branch is not on this path)."""
+chain on the device); supervised, or `x=None` with errors[0] in the role of z_0."""
 from __future__ import annotations
 
 import torch
@@ -23,11 +23,10 @@ def init_epc_errors(layer_sizes, batch_size, mode="supervised", device=None):
 
 
 def _run(params, errors, y, x, loss, param_type, want_energy, want_egrads, want_pgrads):
-    if x is None:
-        raise NotImplementedError("unsupervised ePC (x=None) is not on the B200 path")
     model, skip_model = _unpack_params(params)
+    # x=None: errors[0] plays z_0 and the list has L + 1 entries (jpc/_core/_energies.py:429-432)
     net = _Net(model, skip_model, x, y, param_type=param_type, loss_id=loss, gamma=None, output_energy_scaling=None,
-               activity_decay=0.0, weight_decay=0.0, spectral_penalty=0.0)
+               activity_decay=0.0, weight_decay=0.0, spectral_penalty=0.0, scaled_free_input=True)
     net.check_acts(errors)  # the error list has the shapes of the activity list
     net.ws_bytes = _lib.lib.jpcb_epc_workspace_bytes(net.desc)
     ws = net.workspace()

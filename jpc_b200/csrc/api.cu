@@ -82,7 +82,6 @@ int validate(const jpcb_pc_desc* d, int min_layers = 2) {
   if (d->dtype != JPCB_DTYPE_F32 && d->dtype != JPCB_DTYPE_BF16 && d->dtype != JPCB_DTYPE_F32X3) return fail(JPCB_EINVAL, "bad dtype %d", d->dtype);
   if (d->solver != JPCB_SOLVER_EULER && d->solver != JPCB_SOLVER_HEUN) return fail(JPCB_EINVAL, "bad solver %d", d->solver);
   if (d->n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", d->n_steps);
-  if (d->free_input && d->scalings[0] != 1.f) return fail(JPCB_EINVAL, "free_input (unsupervised) needs scalings[0] == 1: the reference's branch is unscaled");
   if (d->dtype != JPCB_DTYPE_F32) {
     if (d->batch_local % 8) return fail(JPCB_ENOTIMPL, "the tensor-core paths (bf16, f32x3) need batch_local %% 8 == 0 (got %d)", d->batch_local);
     for (int l = 0; l <= d->n_layers; ++l)
@@ -916,6 +915,7 @@ namespace {
 struct EpcWs {
   std::vector<float*> Z;    // [L-1] z_1 .. z_{L-1} of the error-perturbed forward pass
   std::vector<float*> Rho;  // [L]   tensor-core path: fp32 back-propagated signal rho_{l+1} (the fp32 path keeps it in ws.err)
+  float* R0 = nullptr;      // free_input: rho_0 [Bl, d_0], the signal arriving at z_0
   size_t bytes = 0;
 };
 void carve_epc(const jpcb_pc_desc* d, void* base, size_t pc_bytes, EpcWs* w) {
@@ -928,6 +928,7 @@ void carve_epc(const jpcb_pc_desc* d, void* base, size_t pc_bytes, EpcWs* w) {
   for (int l = 0; l + 1 < L; ++l) w->Z[l] = b.take<float>(Bl * d->dims[l + 1]);
   if (d->dtype == JPCB_DTYPE_BF16)  // (the split path keeps fp32 errors in ws.err like the fp32 path)
     for (int l = 0; l < L; ++l) w->Rho[l] = b.take<float>(Bl * d->dims[l + 1]);
+  if (d->free_input) w->R0 = b.take<float>(Bl * d->dims[0]);
   w->bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
 }
 }  // namespace
@@ -944,7 +945,11 @@ size_t jpcb_epc_workspace_bytes(const jpcb_pc_desc* desc) {
 int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* E, const float* x,
                    const float* y, float* F, float* const* gE, float* const* gW, float* const* gb, void* workspace,
                    size_t workspace_bytes, void* stream) {
-  if (desc && desc->free_input) return fail(JPCB_ENOTIMPL, "unsupervised ePC (x = None) is not on the B200 path");
+  // free_input (x = None in the reference, jpc/_core/_energies.py:429-432): errors[0] plays z_0; the lists have L + 1 entries
+  const bool fr = desc && desc->free_input;
+  float* gx = nullptr;
+  if (fr && gE) { gx = gE[0]; gE = gE + 1; }
+  RET(split_free(desc, x, E));
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
   if (!E || !y) return fail(JPCB_EINVAL, "null errors / target");
@@ -988,9 +993,16 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
       RET(r.launch({t}));
     }
   }
-  // ---- energy: (sum_{l<L} 1/2 |eps_l|^2 + output term) / B  (:449-457) ----
+  // ---- energy: (sum of 1/2 |.|^2 over the FIRST L-1 entries of the caller's list + output term) / B  (:449-457).
+  // Supervised: eps_1 .. eps_{L-1}.  x = None: the list starts with z_0, so z_0 and eps_1 .. eps_{L-2} (the reference's
+  // loop bound does not move: eps_{L-1} goes unpenalised -- kept as is) ----
+  const int n_pen = fr ? L - 2 : L - 1;  // penalised entries among E[0..] = eps_1 ..
   if (F) {
-    for (int l = 0; l + 1 < L; ++l) {
+    if (fr) {
+      const size_t n = (size_t)Bl * desc->dims[0];
+      sumsq_kernel<<<ew_grid(n, 1024), 256, 0, r.st>>>(x, n, r.ws.red + RED_SUMSQ); count_launch();
+    }
+    for (int l = 0; l < n_pen; ++l) {
       const size_t n = (size_t)Bl * desc->dims[l + 1];
       sumsq_kernel<<<ew_grid(n, 1024), 256, 0, r.st>>>(E[l], n, r.ws.red + RED_SUMSQ); count_launch();
     }
@@ -1022,13 +1034,35 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
       CK(cudaGetLastError());
     }
   }
+  if (fr && gE) {  // the signal arriving at z_0 = errors[0]: rho_0 = act_0'(z_0) . (a_0 rho_1 W_0) + s_0 rho_1
+    GTask t;
+    t.e.mode = EPI_GRAD; t.e.sub = GRAD_OUT; t.e.act = desc->act[0];
+    t.e.M = Bl; t.e.N = desc->dims[0]; t.K = desc->dims[1];
+    t.a_p = rho(0); t.a_smn = desc->dims[1]; t.a_sk = 1;
+    t.b_p = r.ws.WTf[0]; t.b_smn = desc->dims[1]; t.b_sk = 1;
+    t.a_b = r.ws.Eb[0]; t.b_b = r.ws.WTb[0];
+    r.split_geom(t, desc->dims[1], desc->dims[1]);
+    t.e.alpha = desc->scalings[0];
+    t.e.skip = (desc->skip[0] && L > 1) ? 1.f : 0.f;
+    t.e.En = rho(0); t.e.Enb = r.x3 ? nullptr : r.ws.Eb[0];
+    t.e.Z = x; t.e.P = x;
+    t.e.c = -1.f; t.e.gscale = 1.f;
+    t.e.O = X.R0;
+    RET(r.launch({t}));
+  }
   if (gE) {
+    if (fr) {
+      if (!gx) return fail(JPCB_EINVAL, "null error-gradient buffer 0");
+      const size_t n = (size_t)Bl * desc->dims[0];
+      axpby_kernel<<<ew_grid(n, 256), 256, 0, r.st>>>(x, X.R0, gx, n, r.invB, -r.invB); count_launch();
+    }
     for (int l = 0; l < L; ++l) {
       if (!gE[l]) return fail(JPCB_EINVAL, "null error-gradient buffer %d", l);
       const size_t n = (size_t)Bl * desc->dims[l + 1];
-      // hidden errors: (eps - rho) / B; the output "error" enters z_L with a minus sign and carries no quadratic term: rho_L / B
-      if (l + 1 < L) axpby_kernel<<<ew_grid(n, 256), 256, 0, r.st>>>(E[l], rho(l), gE[l], n, r.invB, -r.invB);
-      else scale_kernel<<<ew_grid(n, 256), 256, 0, r.st>>>(rho(l), gE[l], n, r.invB);
+      // penalised errors: (eps - rho) / B; unpenalised hidden ones (x = None: eps_{L-1}): -rho / B; the output "error"
+      // enters z_L with a minus sign and carries no quadratic term: rho_L / B
+      if (l < n_pen) axpby_kernel<<<ew_grid(n, 256), 256, 0, r.st>>>(E[l], rho(l), gE[l], n, r.invB, -r.invB);
+      else scale_kernel<<<ew_grid(n, 256), 256, 0, r.st>>>(rho(l), gE[l], n, l + 1 < L ? -r.invB : r.invB);
       count_launch();
     }
     CK(cudaGetLastError());

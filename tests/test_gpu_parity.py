@@ -949,8 +949,24 @@ def test_epc_fp32():
     import jpc_b200 as J
     errs = J.init_epc_errors([10, 20, 20, 5], 8)
     assert [tuple(e.shape) for e in errs] == [(8, 20), (8, 20), (8, 5)] and float(sum(e.abs().sum() for e in errs)) == 0.0
-    with pytest.raises(NotImplementedError):
-        J.epc_energy_fn((to_gpu_model(om), None), errs, dev(y), x=None)
+    # x = None: errors[0] plays z_0, L + 1 entries; the reference's penalty covers the first L - 1 list entries (z_0 in,
+    # eps_{L-1} out) and scales the first layer by the width of errors[0]
+    for ptype, skips in (("sp", False), ("mupc", True)):
+        om, sk, x, y = _case(12, 16, 5, 4, "tanh", 6, use_bias=True, param_type=ptype, skips=skips)
+        g = torch.Generator().manual_seed(7)
+        full = [(0.4 * torch.randn(6, w, generator=g, dtype=torch.float64)).float().double() for w in [12, 16, 16, 16, 16, 4]]
+        F, ge = O.compute_epc_error_grad(om, sk, full, y, x=None, param_type=ptype)
+        pg = O.compute_epc_param_grads(om, sk, full, y, x=None, param_type=ptype)
+        P = (to_gpu_model(om), _gpu_skip(sk))
+        gF, gge = J.compute_epc_error_grad(P, devs(full), dev(y), x=None, param_type=ptype)
+        assert abs(float(gF) - float(F)) <= TOL32 * abs(float(F)) and len(gge) == 6
+        gmax = max(float(t.abs().max()) for t in ge)
+        for p, q in zip(gge, ge):
+            assert float((p.double().cpu() - q).abs().max()) <= TOL32 * gmax
+        mg, _ = J.compute_epc_param_grads(P, devs(full), dev(y), x=None, param_type=ptype)
+        wmax = max(float(q["W"].abs().max()) for q in pg)
+        for l, q in enumerate(pg):
+            assert float((mg[l][1].weight.double().cpu() - q["W"]).abs().max()) <= TOL32 * wmax
 
 
 def test_epc_bf16():

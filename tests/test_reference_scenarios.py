@@ -3,7 +3,7 @@ syntax (keyword names, argument order, result keys) -- a user switching `import 
 `optax` -> `jpc.optim`, `diffrax` -> `jpc.{Heun, Euler, PIDController, ConstantStepSize}` keeps their code.
 Scenario list and fixture shapes follow /root/reference/tests/{conftest,test_train,test_infer,test_updates,
 test_init,test_energies,test_grads,test_utils,test_errors,test_test_functions}.py (batch 4, 10-20-20-5, relu,
-no bias); PDM / analytical / unsupervised-ePC scenarios are out of scope.  Like the reference's, these
+no bias); PDM / analytical scenarios are out of scope.  Like the reference's, these
 are smoke-level assertions (keys, shapes, finiteness); numerical parity is tests/test_gpu_parity.py's job."""
 import pytest
 import torch
