@@ -469,6 +469,38 @@ def main():
         e2e_s = float(t)
     e2e_val = B_global * args.steps / e2e_s
 
+    # ---- the same end-to-end loop through jpc_b200.PCTrainer: the train step + SGD update as ONE replayed CUDA graph on
+    # persistent buffers (single process only; an extra, `e2e` above stays the reference-shaped functional API) ----
+    e2e_graph = None
+    if world == 1:
+        try:
+            tr = J.PCTrainer(gm, J.optim.sgd(1e-3 * w["B"]), batch_size=w["B"], skip_model=gsk, param_type=w["ptype"], ode_solver=solver,
+                             max_t1=w["max_t1"], dt=w["dt"], stepsize_controller=J.ConstantStepSize())
+
+            def graph_step(i):
+                xb, yb, ready, consumed = bufs[i % 2]
+                torch.cuda.current_stream(dev).wait_event(ready)
+                stage(i + 1)
+                out = tr.step(yb, xb)
+                consumed.record(torch.cuda.current_stream(dev))
+                return float(out["loss"])
+
+            sync_all()
+            for b in bufs:
+                b[3].record(torch.cuda.current_stream(dev))
+            stage(0)
+            for i in range(2):
+                graph_step(i)
+            sync_all()
+            t0 = time.perf_counter()
+            for i in range(2, 2 + args.steps):
+                graph_step(i)
+            sync_all()
+            e2e_graph = {"value": B_global * args.steps / (time.perf_counter() - t0), "unit": UNIT,
+                         "what": "jpc_b200.PCTrainer.step: H2D of the batch + one CUDA-graph replay (train step + in-place SGD) + loss read-back"}
+        except NotImplementedError:
+            e2e_graph = None
+
     # ---- roofline of the dominant kernel (grouped GEMM of one inference phase) ----
     fl = flops_per_step(w)
     roof = None
@@ -555,6 +587,7 @@ def main():
                                     "(same result; executed < dense FLOPs)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel() * 4,
                     "d2h_bytes_per_step": 4},
+            "e2e_graph": e2e_graph,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "loss": loss_val,
         }

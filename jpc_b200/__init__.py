@@ -26,6 +26,7 @@ from ._epc import (compute_epc_error_grad, compute_epc_param_grads, epc_energy_f
                    update_epc_params)
 from ._hpc import (compute_hpc_param_grads, hpc_energy_fn, init_activities_with_amort, make_hpc_step, test_hpc)
 from ._train import make_pc_step
+from ._graph import PCTrainer
 from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,
                      cross_entropy_loss, get_t_max, mse_loss)
 from .nn import get_act_fn, make_mlp, make_skip_model

@@ -23,6 +23,7 @@ class GradientTransformation(NamedTuple):
     update: callable
     fused_apply: callable = None  # (params_tree, grads_tree, state) -> (new_params_tree, new_state), or None
     fused_apply_flat: callable = None  # the same on flat leaf lists: (p_leaves, g_leaves, state) -> (new_leaves, new_state) | None
+    sgd_learning_rate: float = None    # set by sgd(): lets PCTrainer put the (stateless) update inside its CUDA graph
 
 
 def _fusable(leaves) -> bool:
@@ -56,7 +57,7 @@ def sgd(learning_rate: float) -> GradientTransformation:
     def fused_apply(params, grads, state):
         res = fused_flat(tree_leaves(params), tree_leaves(grads), state)
         return None if res is None else (tree_unflatten_like(params, res[0]), res[1])
-    return GradientTransformation(init, update, fused_apply, fused_flat)
+    return GradientTransformation(init, update, fused_apply, fused_flat, float(learning_rate))
 
 
 def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> GradientTransformation:

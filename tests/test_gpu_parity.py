@@ -1095,3 +1095,35 @@ def test_config_sized_pc_f32x3():
     J.set_compute_dtype("f32x3")
     om, sk, x, y = _case(512, 512, 6, 512, "relu", 512)
     _check_fused(om, sk, x, y, "euler", 10.0, 0.1 * 512, TOL32, kink_budget=4)
+
+
+# ---- PCTrainer: the fixed-step train step as one replayed CUDA graph ---------------------------------------------
+@pytest.mark.parametrize("dtype,opt_name", [("f32", "sgd"), ("f32", "adam"), ("bf16", "sgd"), ("f32x3", "sgd")])
+def test_pc_trainer_graph_matches_make_pc_step(dtype, opt_name):
+    """Three consecutive train steps on three different batches: the graph-replayed trainer and the functional
+    `make_pc_step` must produce the same losses, energies, activities and parameters (same kernels, same order)."""
+    import jpc_b200 as J
+    J.set_compute_dtype(dtype)
+    om, sk, x, y = _case(24, 64, 4, 16, "tanh", 32, use_bias=True, skips=False)
+    gm = to_gpu_model(om)
+    mk = (lambda: J.optim.sgd(0.05)) if opt_name == "sgd" else (lambda: J.optim.adam(1e-2))
+    kw = dict(ode_solver=J.Heun(), max_t1=3, dt=0.5, stepsize_controller=J.ConstantStepSize())
+    tr = J.PCTrainer(gm, mk(), batch_size=32, **kw)
+    opt = mk()
+    model, st = gm, opt.init((gm, None))
+    g = torch.Generator().manual_seed(4)
+    for it in range(3):
+        xb = torch.randn(32, 24, generator=g).cuda()
+        yb = torch.randn(32, 16, generator=g).cuda()
+        ref = J.make_pc_step(model, opt, st, yb, input=xb, **kw)
+        out = tr.step(yb, xb)
+        torch.cuda.synchronize()
+        # (loss / energy sums are accumulated with atomics: equal up to summation order)
+        assert abs(float(out["loss"]) - float(ref["loss"])) <= 1e-6 * abs(float(ref["loss"]))
+        assert rel(out["energies"], ref["energies"].double().cpu()) < 1e-6
+        for p, q in zip(out["activities"], ref["activities"]):
+            assert rel(p, q.double().cpu()) < 1e-6
+        model, st = ref["model"], ref["opt_state"]
+        for a, b in zip(J.nn.tree_leaves(tr.model), J.nn.tree_leaves(model)):
+            assert rel(a, b.double().cpu()) < 1e-6
+    assert rel(gm[0][1].weight, om[0]["W"]) < 1e-7   # the caller's model was not touched
