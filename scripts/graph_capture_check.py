@@ -6,7 +6,7 @@ import bench, jpc_b200 as J
 from jpc_b200 import _lib
 from jpc_b200._core import _Net, _solver_id, _time_grid
 from jpc_b200._train import _Arena
-for wl in ('c1', 'c3', 'c2'):
+for wl in (sys.argv[1:] or ['c1', 'c3', 'c2']):
     w = bench.WORKLOADS[wl]
     J.set_compute_dtype(w['dtype'])
     om, x_h, y_h = bench.make_inputs(w)
