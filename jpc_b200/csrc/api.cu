@@ -131,6 +131,8 @@ struct Ws {
   std::vector<bf16*> Hb;       // [L]   act_l(u_l)  [Bl, d_l]
   std::vector<bf16*> Htb;      // [L]   same for the Heun stage state
   std::vector<bf16*> Eb;       // [L]   err[l] [Bl, d_{l+1}]
+  int* sched = nullptr;        // completion counters of the whole-solve launch: 2 (L-1) tasks x row blocks of 256
+  size_t sched_ints = 0;
   size_t bytes = 0;
 };
 
@@ -175,6 +177,10 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
       w->Hb[l] = b.take<bf16>(Bl * x3_cw(d, d->dims[l]));
       if (heun && (l >= 1 || fr)) w->Htb[l] = b.take<bf16>(Bl * x3_cw(d, d->dims[l]));
       w->Eb[l] = b.take<bf16>(Bl * x3_cw(d, d->dims[l + 1]));
+    }
+    if (!x3) {
+      w->sched_ints = (size_t)2 * L * ((Bl + 255) / 256);
+      w->sched = b.take<int>(w->sched_ints);
     }
   }
   w->bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
@@ -515,7 +521,9 @@ struct Run {
 
   // `Tl` / `esc_all` (layer-wise regression, jpcb_hpc_param_grads): per-layer targets instead of the next
   // activity, and one error weight for every layer instead of lambda on the output layer only
-  int errors(int lo, const float* const* S, bool stage, bool energy, const float* const* Tl = nullptr, float esc_all = 0.f) {
+  // `collect`: hand the tasks back instead of launching them (the whole-solve launch takes them as its schedule)
+  int errors(int lo, const float* const* S, bool stage, bool energy, const float* const* Tl = nullptr, float esc_all = 0.f,
+             std::vector<GTask>* collect = nullptr) {
     std::vector<GTask> ts;
     const bool ce = d->loss == JPCB_LOSS_CE;
     for (int l = lo; l < L; ++l) {
@@ -537,6 +545,7 @@ struct Run {
       if (energy) t.e.red = ws.red + l;
       ts.push_back(t);
     }
+    if (collect) { *collect = ts; return JPCB_OK; }
     RET(launch(ts));
     if (ce) RET(ce_rows(ws.logits, d->output_energy_scaling, ws.err[L - 1], ws.Eb[L - 1], energy ? ws.red + (L - 1) : nullptr));
     return JPCB_OK;
@@ -566,7 +575,8 @@ struct Run {
   // `stage_out`: the updated state is the Heun stage state (operand copies go to Htb / Hft)
   // `err_red` (GRAD_HEUN2 only): accumulates the scaled embedded-error sum of squares of an adaptive trial step
   int grads(int sub, float c, const float* const* Z, const float* const* Z0, float* const* Out, bool stage_out,
-            bool p1_hoisted, int lo = 1, float* err_red = nullptr, float rtol = 0.f, float atol = 0.f) {
+            bool p1_hoisted, int lo = 1, float* err_red = nullptr, float rtol = 0.f, float atol = 0.f,
+            std::vector<GTask>* collect = nullptr) {
     std::vector<GTask> ts;
     for (int l = lo; l < L; ++l) {
       GTask t;
@@ -613,6 +623,7 @@ struct Run {
       ts.push_back(t);
       x_out = nullptr;
     }
+    if (collect) { *collect = ts; return JPCB_OK; }
     return launch(ts);
   }
 
@@ -634,7 +645,9 @@ struct Run {
     const int T = d->n_steps;
     const size_t n_dummy = (size_t)Bl * d->dims[L];
     float* const xw = const_cast<float*>(x);  // free_input: z_0 is updated in place like every other activity
-    const bool front = !fr && from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !(tc_flags() & 8);
+    // (a skip at layer 0 enters the feed-forward init but not the energy, _init.py:69-78 vs _energies.py:111-126: then
+    //  err[0] = x != 0 at the init and there is no wavefront to exploit)
+    const bool front = !fr && from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !d->skip[0] && !(tc_flags() & 8);
     if (front) {
       if (tc) {
         for (int l = (L - 2 - T > 0 ? L - 2 - T : 0); l < L - 1; ++l) {
@@ -644,6 +657,15 @@ struct Run {
       } else {
         CK(cudaMemsetAsync(ws.err[0], 0, (size_t)(reinterpret_cast<char*>(ws.err[L - 1]) - reinterpret_cast<char*>(ws.err[0])), st));
       }
+    }
+    // wide bf16 layers: all T Euler steps as ONE launch of the staged kernel (csrc/tc_staged.cuh: ERR and GRAD tiles of
+    // every step in one dependency-tracked stream); anything it is not compiled for falls through to the phase loop
+    if (tc && !x3 && !fr && T >= 1 && d->solver == JPCB_SOLVER_EULER && d->loss == JPCB_LOSS_MSE && d->activity_decay == 0.f && ws.sched) {
+      std::vector<GTask> es, gs;
+      RET(errors(1, A, false, false, nullptr, 0.f, &es));
+      RET(grads(GRAD_EULER, d->dt * invB, A, nullptr, A, false, true, 1, nullptr, 0.f, 0.f, &gs));
+      const int rc = launch_tc_solve(es, gs, T, d->dt_last * invB, front, ws.sched, ws.sched_ints, st);
+      if (rc != JPCB_SOLVE_NA) return rc;
     }
     for (int s = 0; s < T; ++s) {
       const float h = s == T - 1 ? d->dt_last : d->dt;

@@ -54,5 +54,9 @@ struct GTask {
 // one grouped launch (per <= 16 / 64 tasks) of the tcgen05 / CUDA-core kernel over `tasks`
 int launch_tc(const std::vector<GTask>& tasks, cudaStream_t st);
 int launch_simt(const std::vector<GTask>& tasks, cudaStream_t st);
+// the whole fixed-step Euler solve as one launch (tc_staged.cuh); JPCB_SOLVE_NA: not applicable, enqueue phase by phase
+constexpr int JPCB_SOLVE_NA = -1;
+int launch_tc_solve(const std::vector<GTask>& errs, const std::vector<GTask>& grads, int nsteps, float c_last, bool wave,
+                    int* counters, size_t counter_ints, cudaStream_t st);
 
 }  // namespace jpcb

@@ -41,19 +41,20 @@ int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   return JPCB_OK;
 }
 
-// epilogue slab of the staged kernel (tc_staged.cuh): [rows, cols] row-major fp32 or bf16, box = {32 columns, 128 rows};
-// the swizzle span equals the box's row bytes (128 B fp32 / 64 B bf16) so that row-owner threads read conflict-free
-int make_slab_map(CUtensorMap* m, const void* p, int rows, int cols, bool is_f32) {
+// epilogue slab of the staged kernel (tc_staged.cuh): [rows, cols] row-major fp32 or bf16, box = {box_cols columns, 128 rows};
+// the swizzle span equals the box's row bytes (128 / 64 / 32 B) so that row-owner threads read conflict-free
+int make_slab_map(CUtensorMap* m, const void* p, int rows, int cols, bool is_f32, int box_cols = TS_SLAB_COLS) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const int es = is_f32 ? 4 : 2;
+  const int es = is_f32 ? 4 : 2, row_bytes = box_cols * es;
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  if (row_bytes != 128 && row_bytes != 64 && row_bytes != 32) return fail(JPCB_EINVAL, "internal: slab rows of %d bytes", row_bytes);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * es};
-  cuuint32_t box[2] = {(cuuint32_t)TS_SLAB_COLS, (cuuint32_t)TC_BLOCK_M};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)TC_BLOCK_M};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled (slab) failed (%d) rows=%d cols=%d", (int)r, rows, cols);
   return JPCB_OK;
 }
@@ -106,35 +107,24 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
 }
 
 // ---- staged-epilogue kernel (tc_staged.cuh) ----
-int staged_flags() {  // JPCB_STAGED bit 0: GRAD (Euler, plain) phases, bit 1: ERR (plain) phases
-  static const int f = [] { const char* v = getenv("JPCB_STAGED"); return v ? atoi(v) : 3; }();
-  return f;
+int staged_flags() {  // JPCB_STAGED bit 0: GRAD (Euler, plain) phases, bit 1: ERR (plain) phases, bit 2: whole-solve launch
+  const char* v = getenv("JPCB_STAGED");  // (read per call: tests switch paths inside one process)
+  return v ? atoi(v) : 7;
 }
-// 0: not eligible; else the activation the kernel is compiled for (ERR tasks join either)
-int staged_kind(const GTask& t, int key) {
+// -1: not eligible; else the tile kind.  `solve`: GRAD tasks that take e_l from a hoisted prediction (key 4 / 6) too
+int staged_kind(const GTask& t, int key, bool solve = false) {
   const Epi& e = t.e;
   if (t.split || t.mn_major || e.ob_part != 0 || !e.Ob) return -1;
   if ((key == 3 || key == 5) && (staged_flags() & 1) && e.O && !e.Oh && e.Elb && e.Z) return TS_GRAD;
+  if (solve && (key == 4 || key == 6) && e.O && !e.Oh && e.P && e.Z) return TS_GRAD_P;
   if (key == 1 && (staged_flags() & 2) && !e.O && e.T) return TS_ERR;
   return -1;
 }
-int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
-template <int ACT, int STAGES, int SLOTS>
-int launch_staged_cfg(const TsGroup& g, int grid, cudaStream_t st) {
-  static std::atomic<unsigned long long> attr_done{0};
-  constexpr int SMEM = ts_smem(STAGES, SLOTS);
-  static_assert(SMEM <= 227 * 1024, "staged kernel: shared memory over the per-CTA limit");
-  RET(ensure_dyn_smem(tc_staged_gemm<ACT, STAGES, SLOTS>, SMEM, attr_done));
-  return launch_pair_kernel(tc_staged_gemm<ACT, STAGES, SLOTS>, g, grid, TS_THREADS, SMEM, st, 2);
-}
 template <int ACT>
-int launch_staged_act(TsGroup& g, int grid, cudaStream_t st) {
-  static const int cfg = env_int("JPCB_TS_CFG", 0), pf = env_int("JPCB_TS_PF", 0), hints = env_int("JPCB_TS_HINTS", 0);
-  static const int dbg = env_int("JPCB_TS_DBG", 0);
-  g.pf_dist = pf; g.hints = hints; g.dbg = dbg;
-  if (cfg == 1) return launch_staged_cfg<ACT, 5, 2>(g, grid, st);
-  if (cfg == 2) return launch_staged_cfg<ACT, 3, 5>(g, grid, st);
-  return launch_staged_cfg<ACT, TS_STAGES, TS_SLOTS>(g, grid, st);
+int launch_staged_act(const TsGroup& g, int grid, cudaStream_t st) {
+  static std::atomic<unsigned long long> attr_done{0};
+  RET(ensure_dyn_smem(tc_staged_gemm<ACT>, TS_SMEM, attr_done));
+  return launch_pair_kernel(tc_staged_gemm<ACT>, g, grid, TS_THREADS, TS_SMEM, st, 2);
 }
 int fill_staged_task(TsTask& s, const GTask& t, int kind, int tile_begin) {
   const Epi& e = t.e;
@@ -145,12 +135,18 @@ int fill_staged_task(TsTask& s, const GTask& t, int kind, int tile_begin) {
     RET(make_slab_map(&s.tmI0, e.Z, e.M, e.N, true));
     RET(make_slab_map(&s.tmI1, e.Elb, e.M, e.N, false));
     RET(make_slab_map(&s.tmO0, e.O, e.M, e.N, true));
+    RET(make_slab_map(&s.tmO1, e.Ob, e.M, e.N, false));
+  } else if (kind == TS_GRAD_P) {
+    RET(make_slab_map(&s.tmI0, e.Z, e.M, e.N, true, 16));
+    RET(make_slab_map(&s.tmI1, e.P, e.M, e.N, true, 16));
+    RET(make_slab_map(&s.tmO0, e.O, e.M, e.N, true, 16));
+    RET(make_slab_map(&s.tmO1, e.Ob, e.M, e.N, false, 16));
   } else {
     RET(make_slab_map(&s.tmI0, e.T, e.M, e.N, true));
+    RET(make_slab_map(&s.tmO1, e.Ob, e.M, e.N, false));
   }
-  RET(make_slab_map(&s.tmO1, e.Ob, e.M, e.N, false));
   s.K = t.K; s.tile_begin = tile_begin; s.tiles_n = (e.N + TC_BLOCK_N - 1) / TC_BLOCK_N; s.kind = kind;
-  s.M = e.M; s.N = e.N; s.alpha = e.alpha; s.cg = e.c * e.gscale; s.red = kind == TS_ERR ? e.red : nullptr;
+  s.M = e.M; s.N = e.N; s.alpha = e.alpha; s.cg = s.cg_last = e.c * e.gscale; s.red = kind == TS_ERR ? e.red : nullptr;
   return JPCB_OK;
 }
 
@@ -322,6 +318,69 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
 }
 
 }  // namespace
+
+// The whole fixed-step Euler solve as ONE launch of the staged kernel (tc_staged.cuh, "whole-solve schedule").
+// errs[i] / grads[i]: the ERR / GRAD task of layer i + 1 for one step; returns JPCB_SOLVE_NA when the tasks are not of
+// the kinds the kernel is compiled for (the caller then enqueues the phases one by one).
+int launch_tc_solve(const std::vector<GTask>& errs, const std::vector<GTask>& grads, int nsteps, float c_last, bool wave,
+                    int* counters, size_t counter_ints, cudaStream_t st) {
+  const int L1 = (int)errs.size();
+  if (!(staged_flags() & 4) || (tc_flags() & 6) || L1 < 1 || (int)grads.size() != L1 || 2 * L1 > TS_MAX_TASKS || L1 - 1 > TS_MAX_WARM || nsteps < 1)
+    return JPCB_SOLVE_NA;
+  int act = -1;
+  for (int i = 0; i < L1; ++i) {
+    if (staged_kind(errs[i], variant_key(errs[i]), true) != TS_ERR) return JPCB_SOLVE_NA;
+    const int k = variant_key(grads[i]);
+    const int kind = staged_kind(grads[i], k, true);
+    if (kind != TS_GRAD && kind != TS_GRAD_P) return JPCB_SOLVE_NA;
+    const int a = (k == 5 || k == 6) ? ACT_RELU : ACT_TANH;
+    if (act >= 0 && a != act) return JPCB_SOLVE_NA;
+    act = a;
+    if (errs[i].e.M != errs[0].e.M || grads[i].e.M != errs[0].e.M || errs[i].e.red) return JPCB_SOLVE_NA;
+  }
+  const int M = errs[0].e.M, R = (M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M), units = num_sms() / 2;
+  static thread_local TsGroup g;
+  memset(&g, 0, offsetof(TsGroup, t));
+  long long per_e = 0, per_g = 0;
+  for (int i = 0; i < L1; ++i) {
+    RET(fill_staged_task(g.t[i], errs[i], TS_ERR, 0));
+    RET(fill_staged_task(g.t[L1 + i], grads[i], staged_kind(grads[i], variant_key(grads[i]), true), 0));
+    g.t[L1 + i].cg_last = c_last * grads[i].e.gscale;
+    per_e += g.t[i].tiles_n; per_g += g.t[L1 + i].tiles_n;
+  }
+  // too little work per step to fill the persistent grid for a few rounds: the per-phase path picks narrower tiles
+  const char* vmin = getenv("JPCB_SOLVE_MIN_ROUNDS");  // (tests set 0 to force small problems through this path)
+  if ((long long)R * (per_e + per_g) < (long long)(vmin ? atoi(vmin) : 4) * units) return JPCB_SOLVE_NA;
+  if (counter_ints < (size_t)2 * L1 * R || !counters) return fail(JPCB_EWORKSPACE, "internal: schedule counters");
+  auto a_of = [&](int i) { return wave ? (L1 - 1 - i > 0 ? L1 - 1 - i : 0) : 0; };
+  for (int i = 0; i < L1; ++i) {
+    TsTask& e = g.t[i];
+    TsTask& q = g.t[L1 + i];
+    e.done = counters + (size_t)i * R;
+    q.done = counters + (size_t)(L1 + i) * R;
+    e.dep[0] = TsDep{q.done, q.tiles_n, a_of(i), 0, 0};
+    if (i + 1 < L1) e.dep[1] = TsDep{counters + (size_t)(L1 + i + 1) * R, g.t[L1 + i + 1].tiles_n, a_of(i + 1), 0, 0};
+    q.dep[0] = TsDep{e.done, e.tiles_n, a_of(i), 1, 0};
+    if (i >= 1) q.dep[1] = TsDep{counters + (size_t)(i - 1) * R, g.t[i - 1].tiles_n, a_of(i - 1), 1, 0};
+  }
+  g.ntasks = 2 * L1; g.persist = 1; g.R = R; g.nsteps = nsteps; g.L1 = L1; g.wave = wave ? 1 : 0;
+  g.warm = wave ? (L1 - 1 < nsteps ? L1 - 1 : nsteps) : 0;
+  g.tiles_full = (int)(R * (per_e + per_g));
+  long long tiles = 0;
+  for (int s = 0; s <= g.warm; ++s) {
+    g.warm_begin[s] = (int)tiles;
+    long long per = 0;
+    for (int i = a_of(0) - s > 0 ? a_of(0) - s : 0; i < L1; ++i) per += g.t[i].tiles_n + g.t[L1 + i].tiles_n;
+    tiles += R * per;
+  }
+  tiles = g.warm_begin[g.warm] + (long long)(nsteps - g.warm) * g.tiles_full;
+  if (tiles >= (1LL << 30)) return JPCB_SOLVE_NA;
+  g.total_tiles = (int)tiles;
+  CK(cudaMemsetAsync(counters, 0, (size_t)2 * L1 * R * sizeof(int), st));
+  const int grid = 2 * (int)(tiles < units ? tiles : units);
+  if (act == ACT_RELU) return launch_staged_act<ACT_RELU>(g, grid, st);
+  return launch_staged_act<ACT_TANH>(g, grid, st);
+}
 
 int launch_tc(const std::vector<GTask>& tasks, cudaStream_t st) {
   if (tasks.empty()) return JPCB_OK;

@@ -1127,3 +1127,57 @@ def test_pc_trainer_graph_matches_make_pc_step(dtype, opt_name):
         for a, b in zip(J.nn.tree_leaves(tr.model), J.nn.tree_leaves(model)):
             assert rel(a, b.double().cpu()) < 1e-6
     assert rel(gm[0][1].weight, om[0]["W"]) < 1e-7   # the caller's model was not touched
+
+
+# ---- whole-solve launch of the staged tcgen05 kernel (csrc/tc_staged.cuh): all T Euler steps in one dependency-tracked stream ----
+def _with_env(**kw):
+    import contextlib
+    import os
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kw}
+        os.environ.update({k: str(v) for k, v in kw.items()})
+        try:
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+@pytest.mark.parametrize("shape", [
+    # d_in, width, depth, d_out, act, B, max_t1, dt
+    (72, 200, 3, 40, "relu", 136, 2.0, 0.5),       # ragged tiles, one row block
+    (64, 264, 5, 48, "tanh", 600, 6.0, 0.5 * 600 / 64),  # three row blocks (the last partial), stress step, 12 steps > depth
+    (128, 256, 2, 64, "tanh", 256, 1.0, 0.3),      # two layers: one ERR task + the hoisted-prediction GRAD task; clipped last step
+    (96, 520, 6, 24, "relu", 264, 1.5, 0.5),       # fewer steps (3) than layers: every step inside the wavefront warm-up
+])
+def test_whole_solve_launch_bf16(shape):
+    """The one-launch solve must reproduce the fp64 oracle (2e-2) AND the phase-by-phase launches of the same kernels
+    (same arithmetic, so equal up to the order of the energy atomics), from the feed-forward init (wavefront schedule, fused
+    train step) and from a perturbed state (dense schedule, solve_inference)."""
+    import jpc_b200 as J
+    d_in, width, depth, d_out, act, B, max_t1, dt = shape
+    J.set_compute_dtype("bf16")
+    om, sk, x, y = _case(d_in, width, depth, d_out, act, B, onehot_out=False)
+    with _with_env(JPCB_SOLVE_MIN_ROUNDS=0, JPCB_STAGED=7):
+        n0 = J._lib.lib.jpcb_launch_count()
+        _check_fused(om, sk, x, y, "euler", max_t1, dt, TOLBF)
+        acts1, arena1 = _fused_step_raw(om, sk, x, y, "euler", max_t1, dt)
+        n1 = J._lib.lib.jpcb_launch_count()
+        _solve_case(om, sk, x, y, "euler", max_t1, dt, TOLBF, perturbed=True)
+    with _with_env(JPCB_SOLVE_MIN_ROUNDS=0, JPCB_STAGED=3):
+        n2 = J._lib.lib.jpcb_launch_count()
+        acts2, arena2 = _fused_step_raw(om, sk, x, y, "euler", max_t1, dt)
+        n3 = J._lib.lib.jpcb_launch_count()
+    T = int(math.ceil(max_t1 / dt - 1e-6))
+    assert (n3 - n2) - (n1 - n0) // 2 >= T, "the whole-solve path did not replace the per-phase launches"
+    for p, q in zip(acts1[:-1], acts2[:-1]):
+        assert rel(p, q.double().cpu()) < 1e-5
+    for p, q in zip(arena1.gW, arena2.gW):
+        assert rel(p, q.double().cpu()) < 1e-4   # (bf16 operand copies of nearly equal activities may round apart)
+    assert rel(arena1.E, arena2.E.double().cpu()) < 1e-5
