@@ -41,6 +41,11 @@ int make_map(CUtensorMap* m, const bf16* p, int rows, int cols, int box_rows) {
   return JPCB_OK;
 }
 
+CUtensorMapL2promotion slab_promo() {
+  const char* v = getenv("JPCB_TS_PROMO");
+  const int k = v ? atoi(v) : 256;
+  return k == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (k == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (k == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+}
 // epilogue slab of the staged kernel (tc_staged.cuh): [rows, cols] row-major fp32 or bf16, box = {box_cols columns, 128 rows};
 // the swizzle span equals the box's row bytes (128 / 64 / 32 B) so that row-owner threads read conflict-free
 int make_slab_map(CUtensorMap* m, const void* p, int rows, int cols, bool is_f32, int box_cols = TS_SLAB_COLS) {
@@ -54,7 +59,7 @@ int make_slab_map(CUtensorMap* m, const void* p, int rows, int cols, bool is_f32
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)TC_BLOCK_M};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, slab_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(JPCB_ECUDA, "cuTensorMapEncodeTiled (slab) failed (%d) rows=%d cols=%d", (int)r, rows, cols);
   return JPCB_OK;
 }
