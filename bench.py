@@ -327,6 +327,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = the workload's batch on every rank (default, the driver's contract); strong = the "
                          "workload's batch split over the ranks (SURVEY 8e: 4096 -> 2048/1024/512 rows)")
+    ap.add_argument("--grad-dtype", default="f32", choices=["f32", "bf16"],
+                    help="N > 1: payload of the gradient all-reduce (bf16 halves the NVLink bytes; energies / loss stay fp32)")
     ap.add_argument("--cpu-rows", type=int, default=256, help="rows per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bpc-f32", action="store_true", help="c5: run bPC on the fp32 CUDA-core path (same as --bpc-dtype f32)")
@@ -357,7 +359,7 @@ def main():
     import jpc_b200 as J
     from jpc_b200 import _lib
     from jpc_b200._core import _Net, _solver_id, _time_grid
-    from jpc_b200._train import _Arena
+    from jpc_b200._train import _Arena, dp_param_grads_and_exchange
 
     J.set_compute_dtype(w["dtype"])
     if args.scaling == "strong" and world > 1:
@@ -385,10 +387,18 @@ def main():
     A_ptrs, gW_ptrs = _lib.ptr_array(acts), _lib.ptr_array(arena.gW)
     gb_ptrs = _lib.ptr_array(arena.gb) if arena.gb else None
 
+    if args.grad_dtype != "f32":
+        J.set_grad_allreduce_dtype(args.grad_dtype)
+
     def step():
+        # N = 1: the whole step is one C-ABI call.  N > 1: the same call without the weight gradients, then the gradients
+        # bucket by bucket with each bucket's NCCL all-reduce (SUM of [gW, gb | E_layers, loss]) overlapping the next
+        # bucket's GEMMs -- exactly what jpc_b200.make_pc_step does under torch.distributed
         _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(x), _lib.ptr(y), A_ptrs, _lib.ptr(arena.loss),
-                                               _lib.ptr(arena.E), gW_ptrs, gb_ptrs, _lib.ptr(ws), ws.numel(), stream))
-        arena.all_reduce()  # ONE NCCL all-reduce (SUM) of [gW, gb, E_layers, loss]; no-op at N = 1
+                                               _lib.ptr(arena.E), gW_ptrs if world == 1 else None,
+                                               gb_ptrs if world == 1 else None, _lib.ptr(ws), ws.numel(), stream))
+        if world > 1:
+            dp_param_grads_and_exchange(net, arena)
 
     def sync_all():
         if world > 1:

@@ -153,11 +153,24 @@ int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const f
                         void* stream);
 
 /* make_pc_step up to (excluding) the optimiser  (jpc/_train.py:135-232): ffwd init, loss at the
- * init, T-step inference, per-layer energies at the solution, parameter gradients. */
+ * init, T-step inference, per-layer energies at the solution, parameter gradients.
+ * gW == NULL: everything but the parameter gradients; the prediction errors and operand copies at the
+ * solution stay in `workspace` for jpcb_pc_param_grads_range (data-parallel callers that exchange the
+ * gradients bucket by bucket while the remaining buckets are still being computed). */
 int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
                        const float* x, const float* y, float* const* A_out, float* loss_out,
                        float* E_layers, float* const* gW, float* const* gb, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* compute_pc_param_grads (jpc/_core/_grads.py:487-499) for layers [layer_lo, layer_hi) only, from
+ * the prediction errors / operand copies that the LAST jpcb_pc_train_step or jpcb_pc_param_grads call
+ * with the same descriptor left in `workspace` (nothing else may have used the workspace in between).
+ * gW / gb are the full per-layer pointer lists; only the entries of the range are written.  One
+ * grouped launch per call: a caller records an event after each call and starts that bucket's
+ * all-reduce while the next bucket's GEMMs run. */
+int jpcb_pc_param_grads_range(const jpcb_pc_desc* desc, const float* const* W, const float* const* b,
+                              const float* x, int layer_lo, int layer_hi, float* const* gW,
+                              float* const* gb, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- bidirectional PC (jpc/_core/_energies.py:246-357) ---------------------------------------
  * H = td.n_layers - 1.  Top-down model W_j (j = 0..H): [td.dims[j+1], td.dims[j]], maps u_j (x for

@@ -363,12 +363,14 @@ def pc_energy_fn(params, activities, y, *, x=None, loss="mse", param_type="sp", 
 
 
 def compute_pc_activity_grad(params, activities, y, *, x, loss_id="mse", param_type="sp", weight_decay=0.0,
-                             spectral_penalty=0.0, activity_decay=0.0, gamma=None, output_energy_scaling=None):
-    """jpc/_core/_grads.py:95-167: (energy, dF/dactivities)."""
+                             spectral_penalty=0.0, activity_decay=0.0, gamma=None, output_energy_scaling=None,
+                             batch_global=None):
+    """jpc/_core/_grads.py:95-167: (energy, dF/dactivities).  `batch_global` (not in the reference signature): the 1/B
+    of the energy when `activities` is one rank's shard of a data-parallel batch."""
     model, skip_model = _unpack_params(params)
     net = _Net(model, skip_model, x, y, param_type=param_type, loss_id=loss_id, gamma=gamma,
                output_energy_scaling=output_energy_scaling, activity_decay=activity_decay,
-               weight_decay=weight_decay, spectral_penalty=spectral_penalty)
+               weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=batch_global)
     net.check_acts(activities)
     ws = net.workspace()
     F = torch.empty((), dtype=torch.float32, device=net.dev)
@@ -439,11 +441,18 @@ def _solver_id(solver) -> int:
 MAX_STEPS = 4096  # diffrax.diffeqsolve default
 
 
-def _rms(tensors) -> float:
-    """optimistix.rms_norm over a list of arrays (host read-back of one scalar; controller logic only)."""
-    tot = sum(float(torch.sum(t.double() ** 2)) for t in tensors)
+def _rms(tensors, reduce_over_ranks=False) -> float:
+    """optimistix.rms_norm over a list of arrays (host read-back of one scalar; controller logic only).  With
+    `reduce_over_ranks` the norm is that of the GLOBAL data-parallel batch: sums of squares and element counts are
+    all-reduced, so every rank gets the same number (the controller's decisions must not diverge between ranks)."""
+    tot = sum(torch.sum(t.double() ** 2) for t in tensors)
     n = sum(t.numel() for t in tensors)
-    return math.sqrt(tot / n)
+    if reduce_over_ranks:
+        import torch.distributed as dist
+        buf = torch.stack([tot, torch.tensor(float(n), dtype=torch.float64, device=tot.device)])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        tot, n = buf[0], float(buf[1])
+    return math.sqrt(float(tot) / n)
 
 
 class _SaveAt:
@@ -494,7 +503,11 @@ class _SaveAt:
             self.i += 1
 
     def finish(self, cur):
-        if not self.steps:
+        if self.ts is not None:
+            # diffrax writes the t1 row at the current save index: right after the last `ts` row it filled (the rows
+            # beyond stay inf when a steady-state event ended the solve early; the last row when it ran to t1)
+            self._put(self.i, cur)
+        elif not self.steps:
             self._put(-1, cur)
         return self.ys
 
@@ -529,20 +542,28 @@ def _solve_adaptive(params, activities, output, input, loss_id, param_type, solv
     input, output = net.x, net.y
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    numel = sum(a.numel() for a in activities) * world  # (padding entries are zero: they add nothing to the sums)
+    dp = world > 1
+    # the controller's norms are over the GLOBAL batch: global element count (shards may be uneven; padding
+    # entries are zero and add nothing to the sums), global sums of squares, the gradient's 1/B that of the global batch --
+    # so every rank computes the same step sizes and takes the same accept / reject decisions
+    numel = sum(a.numel() for a in activities)
+    if dp:
+        nbuf = torch.tensor([float(numel)], dtype=torch.float64, device=net.dev)
+        dist.all_reduce(nbuf, op=dist.ReduceOp.SUM)
+        numel = int(nbuf.item())
     if dt0 is None:
         # Hairer / Wanner initial step, as diffrax's PIDController.init does when dt0 is None
         A0 = [a.contiguous() for a in activities]
-        _, g0 = compute_pc_activity_grad(params, A0, kw_out, **kw)
+        _, g0 = compute_pc_activity_grad(params, A0, kw_out, batch_global=net.desc.batch_global, **kw)
         f0 = [-g for g in g0]
         scale = [ctrl.atol + a.abs() * ctrl.rtol for a in A0]
-        d0 = _rms([a / s for a, s in zip(A0, scale)])
-        d1 = _rms([f / s for f, s in zip(f0, scale)])
+        d0 = _rms([a / s for a, s in zip(A0, scale)], dp)
+        d1 = _rms([f / s for f, s in zip(f0, scale)], dp)
         small = d0 < 1e-5 or d1 < 1e-5
         h0 = 1e-6 if small else 0.01 * d0 / d1
         y1 = [a + h0 * f for a, f in zip(A0, f0)]
-        _, g1 = compute_pc_activity_grad(params, y1, kw_out, **kw)
-        d2 = _rms([(-gb - f) / s for gb, f, s in zip(g1, f0, scale)]) / h0
+        _, g1 = compute_pc_activity_grad(params, y1, kw_out, batch_global=net.desc.batch_global, **kw)
+        d2 = _rms([(-gb - f) / s for gb, f, s in zip(g1, f0, scale)], dp) / h0
         max_d = max(d1, d2)
         h1 = max(1e-6, h0 * 1e-3) if max_d <= 1e-15 else (0.01 / max_d) ** (1.0 / order)
         dt = min(100.0 * h0, h1)
@@ -583,9 +604,11 @@ def solve_inference(params, activities, output, *, input=None, loss_id="mse", pa
                     activity_decay=0.0, gamma=None, output_energy_scaling=None, record_iters=False,
                     record_every=None, batch_global=None):
     """jpc/_core/_infer.py:20-133.  Fixed-step solvers (ConstantStepSize): all T steps x L layers run on the
-    device without returning to the host (the reference's steady-state Event, `_infer.py:136-145`, tests the
-    RMS of the ACTIVITIES against ~1e-3 and never fires on real activities; it is not checked inside the fused
-    loop).  PIDController (the default): controller-driven trial steps, see `_solve_adaptive`.  Returns leaves
+    device without returning to the host.  DEVIATION: the reference's steady-state Event (`_infer.py:136-145`) also
+    applies to fixed steps; with ConstantStepSize it falls back to atol = rtol = 1e-3 and stops the solve after a step
+    once rms(ACTIVITIES) < 1e-3 (1 + rms) -- i.e. only for activities that are all ~1e-3 or smaller (zero or tiny
+    initial activities), never for feed-forward-initialised networks.  The fused loop does not evaluate it: such a solve
+    runs all T steps here.  PIDController (the default): controller-driven trial steps, see `_solve_adaptive`.  Returns leaves
     with the reference's leading time axis: (1, B, d) by default (SaveAt(t1=True)), (4096, B, d) inf-padded with
     `record_iters`, (len(ts) + 1, B, d) with `record_every` (see `_SaveAt`).  `batch_global` (not in the reference
     signature) is the 1/B of the energy when `activities` is one rank's shard of a data-parallel batch."""

@@ -69,6 +69,7 @@ SIGNATURES = {
                                      C.c_size_t, _P]),
     "jpcb_pc_param_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _PP, _PP, _P, _P, C.c_size_t, _P]),
     "jpcb_pc_train_step": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _P, _P, _PP, _P, _P, _PP, _PP, _P, C.c_size_t, _P]),
+    "jpcb_pc_param_grads_range": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _P, C.c_int, C.c_int, _PP, _PP, _P, C.c_size_t, _P]),
     "jpcb_bpc_workspace_bytes": (C.c_size_t, [C.POINTER(BpcDesc)]),
     "jpcb_bpc_energy": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
     "jpcb_bpc_activity_grad": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, _PP, _P, C.c_size_t, _P]),

@@ -70,13 +70,119 @@ class _Arena:
                 self.gb.append(views[i]); i += 1
         self.E = views[i]
         self.loss = views[i + 1]
+        self.n_layers = L
+        self.per_layer = 2 if bias_shapes is not None else 1
+        self.offs = offs            # start of every segment in `flat`; offs[per_layer * l] = first element of layer l
+        self.tail_off = offs[-2]    # [E_layers, loss]
 
     def all_reduce(self):
         """The one exchange step of the data-parallel path: SUM over ranks of every rank's partial
         gradients / energies / loss (each already divided by the GLOBAL batch size)."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            _reduce_slices(self, [(0, self.flat.numel())])
+
+    def buckets(self, n_buckets: int):
+        """Contiguous layer groups [(layer_lo, layer_hi, flat_lo, flat_hi)] of roughly equal size covering the whole
+        arena (the tail [E_layers, loss] rides with the last group): the unit of the bucketed exchange."""
+        L = self.n_layers
+        n_buckets = max(1, min(int(n_buckets), L))
+        starts = [self.offs[self.per_layer * l] for l in range(L)] + [self.tail_off]
+        target = self.tail_off / n_buckets
+        out, lo = [], 0
+        for b in range(n_buckets):
+            if b == n_buckets - 1:
+                hi = L
+            else:
+                hi = lo + 1
+                while hi < L - (n_buckets - 1 - b) and starts[hi] < (b + 1) * target:
+                    hi += 1
+            out.append((lo, hi, starts[lo], starts[hi] if hi < L else self.flat.numel()))
+            lo = hi
+            if lo >= L:
+                break
+        return out
+
+
+_GRAD_REDUCE_DTYPE = "f32"
+
+
+def set_grad_allreduce_dtype(name: str) -> None:
+    """Payload of the data-parallel gradient exchange: "f32" (default; the N-rank result equals the single-process one
+    to ~1e-7) or "bf16" (half the NVLink bytes: the weight / bias gradients travel as bf16 and are summed in bf16 -- within
+    the 2e-2 of the bf16 compute path, not within the 1e-5 of the fp32 paths; energies and loss always travel as fp32)."""
+    global _GRAD_REDUCE_DTYPE
+    if name not in ("f32", "bf16"):
+        raise ValueError('gradient all-reduce dtype must be "f32" or "bf16"')
+    _GRAD_REDUCE_DTYPE = name
+
+
+def _reduce_slices(arena, slices):
+    """all-reduce (SUM) of `flat[lo:hi]` for every slice, on the CURRENT stream."""
+    import torch.distributed as dist
+    for lo, hi in slices:
+        if _GRAD_REDUCE_DTYPE == "bf16" and arena.flat.is_cuda:
+            w_hi = min(hi, arena.tail_off)
+            if w_hi > lo:
+                part = arena.flat[lo:w_hi]
+                half = part.to(torch.bfloat16)
+                dist.all_reduce(half, op=dist.ReduceOp.SUM)
+                part.copy_(half)
+            if hi > arena.tail_off:
+                dist.all_reduce(arena.flat[max(lo, arena.tail_off):hi], op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(arena.flat[lo:hi], op=dist.ReduceOp.SUM)
+
+
+_COMM_STREAMS: dict = {}
+DP_BUCKETS = 4   # layer groups of the bucketed exchange (SURVEY 8e)
+
+
+def _comm_stream(dev):
+    st = _COMM_STREAMS.get(dev)
+    if st is None:
+        st = _COMM_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def dp_param_grads_and_exchange(net, arena, n_buckets=None):
+    """The data-parallel tail of a train step whose jpcb_pc_train_step ran with gW = NULL: weight gradients bucket by
+    bucket (one grouped GEMM launch per layer group, jpcb_pc_param_grads_range), each bucket's NCCL all-reduce enqueued on
+    a side stream as soon as its launch is, so it travels over NVLink while the next bucket's GEMMs run; the caller's
+    stream then waits for the last bucket.  (The energies / loss tail rides with the last bucket.)"""
+    main = torch.cuda.current_stream(net.dev)
+    comm = _comm_stream(net.dev)
+    ws = net.workspace()
+    gW_p, gb_p = _lib.ptr_array(arena.gW), (_lib.ptr_array(arena.gb) if arena.gb else None)
+    arena.flat.record_stream(comm)
+    for llo, lhi, flo, fhi in arena.buckets(DP_BUCKETS if n_buckets is None else n_buckets):
+        _lib.check(_lib.lib.jpcb_pc_param_grads_range(net.desc, net.W, net.b, _lib.ptr(net.x), llo, lhi, gW_p, gb_p,
+                                                      _lib.ptr(ws), ws.numel(), main.cuda_stream))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            _reduce_slices(arena, [(flo, fhi)])
+    main.wait_stream(comm)
+
+
+_GLOBAL_ROWS: dict = {}
+
+
+def global_batch(local_rows: int, device) -> int:
+    """Rows of the GLOBAL data-parallel batch: the sum of every rank's local row count (shards need not be equal:
+    `shard_rows` hands out B // N and B // N + 1 rows).  One tiny all-reduce the first time a local row count is seen;
+    afterwards the shard layout is assumed stable for that local count (pass `batch_global=` to make_pc_step to skip it)."""
+    world = _world()
+    if world == 1:
+        return int(local_rows)
+    got = _GLOBAL_ROWS.get(int(local_rows))
+    if got is None:
+        import torch.distributed as dist
+        t = torch.tensor([float(local_rows)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        got = _GLOBAL_ROWS[int(local_rows)] = int(t.item())
+    return got
 
 
 def shard_rows(n_rows: int, rank: int, world: int):
@@ -90,8 +196,9 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
                  max_t1=20, dt=None, stepsize_controller=None, skip_model=None, weight_decay=0.0,
                  spectral_penalty=0.0, activity_decay=0.0, key=None, layer_sizes=None, batch_size=None,
                  sigma=0.05, record_activities=False, record_energies=False, record_every=None,
-                 activity_norms=False, param_norms=False, grad_norms=False, calculate_accuracy=False):
-    """jpc/_train.py:35-267.  Same arguments, same 13-key result dict."""
+                 activity_norms=False, param_norms=False, grad_norms=False, calculate_accuracy=False, batch_global=None):
+    """jpc/_train.py:35-267.  Same arguments, same 13-key result dict.  `batch_global` (an addition): rows of the global
+    batch when `output` / `input` are one rank's shard under torch.distributed (default: the sum of the ranks' row counts)."""
     _check_param_type(param_type)
     if input is None and any(arg is None for arg in (key, layer_sizes, batch_size)):
         raise ValueError("""
@@ -109,9 +216,10 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     world = _world()
     if recording and world > 1:
         raise NotImplementedError("recorded trajectories are per-process: not available under data parallelism")
+    bg = int(batch_global) if batch_global is not None else global_batch(output.shape[0], output.device)
     common = dict(param_type=param_type, loss_id=loss_id, gamma=None, output_energy_scaling=None, activity_decay=activity_decay,
-                  weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=output.shape[0] * world)
-    t_max, sol, rec_energies = 0, None, None
+                  weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=bg)
+    t_max, sol, rec_energies, exchanged = 0, None, None, False
     if input is None and not isinstance(stepsize_controller, (PIDController, ConstantStepSize)):
         raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
     if input is None:
@@ -127,7 +235,7 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         sol = solve_inference((model, skip_model), acts0, output, input=None, loss_id=loss_id, param_type=param_type,
                               solver=ode_solver, max_t1=max_t1, dt=dt, stepsize_controller=stepsize_controller,
                               weight_decay=weight_decay, spectral_penalty=spectral_penalty, activity_decay=activity_decay,
-                              batch_global=output.shape[0] * world, record_iters=record_activities,
+                              batch_global=bg, record_iters=record_activities,
                               record_every=record_every)
         t_max = get_t_max(sol) if record_activities else 0
         acts = net.in_acts([a[t_max].contiguous() for a in sol])
@@ -150,10 +258,14 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         arena = _Arena(net)
         acts = net.new_acts()
         ws = net.workspace()
+        bucketed = world > 1 and net.dev.type == "cuda"
         _lib.check(_lib.lib.jpcb_pc_train_step(
             net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr_array(acts), _lib.ptr(arena.loss),
-            _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
-            _lib.ptr(ws), ws.numel(), net.stream()))
+            _lib.ptr(arena.E), None if bucketed else _lib.ptr_array(arena.gW),
+            None if bucketed or not arena.gb else _lib.ptr_array(arena.gb), _lib.ptr(ws), ws.numel(), net.stream()))
+        if bucketed:   # weight gradients + their exchange, bucket by bucket (the exchange overlaps the remaining GEMMs)
+            dp_param_grads_and_exchange(net, arena)
+            exchanged = True
     elif isinstance(stepsize_controller, (PIDController, ConstantStepSize)):
         # adaptive steps (the reference's default) or a recorded trajectory: init + loss, the solve (controller-driven
         # trial steps / one step per call when rows are saved), then energies + gradients at the selected row
@@ -168,7 +280,7 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         sol = solve_inference((model, skip_model), net.out_acts(acts0), output, input=input, loss_id=loss_id, param_type=param_type,
                               solver=ode_solver, max_t1=max_t1, dt=dt, stepsize_controller=stepsize_controller,
                               weight_decay=weight_decay, spectral_penalty=spectral_penalty, activity_decay=activity_decay,
-                              batch_global=input.shape[0] * world, record_iters=record_activities,
+                              batch_global=bg, record_iters=record_activities,
                               record_every=record_every)
         # jpc/_train.py:183,199-201,223-225: row t_max of a recorded trajectory, row 0 otherwise (with `record_every`
         # alone row 0 is the state at ts[0] = 0, i.e. the initial activities -- the reference does the same)
@@ -184,7 +296,8 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
                                                 _lib.ptr(arena.E), _lib.ptr(ws), ws.numel(), net.stream()))
     else:
         raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
-    arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
+    if not exchanged:
+        arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
     acts = net.out_acts(acts)
     gW, gb = net.out_grads(arena.gW, arena.gb)
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)

@@ -45,13 +45,17 @@ int fail(int code, const char* fmt, ...) {
 void count_launch(int n) { g_launches += (unsigned long long)n; }
 
 int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    return v;
-  }();
-  return n;
+  // per DEVICE (a process may drive several GPUs), cached in a small table; a relaxed race only repeats the query
+  static std::atomic<int> cache[64];
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64) {
+    v = cache[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+  }
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 int tc_flags() {
@@ -429,14 +433,18 @@ struct Run {
       CK(cudaGetLastError());
       return JPCB_OK;
     }
-    for (int l = 0; l < L; ++l) {
-      const size_t n = (size_t)d->dims[l] * d->dims[l + 1];
-      cast_act_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, st>>>(W[l], ws.Wb[l], n, ACT_LINEAR); count_launch();
-      if (l >= 1 || fr) {
-        const int R = d->dims[l + 1], C = d->dims[l];
-        const int tiles = ((R + 31) / 32) * ((C + 31) / 32);
-        transpose_to_bf16_kernel<float><<<ew_grid(tiles, 1), dim3(32, 8), 0, st>>>(W[l], ws.WTb[l], R, C); count_launch();
+    // plain bf16 path: every layer's Wb (and W^T copy) in one grouped launch, each weight read once
+    for (int l0 = 0; l0 < L; l0 += PREP_MAX_JOBS) {
+      PrepJobs jobs;
+      jobs.n = 0; jobs.total = 0;
+      for (int l = l0; l < L && jobs.n < PREP_MAX_JOBS; ++l) {
+        PrepJob& jb = jobs.j[jobs.n++];
+        jb.W = W[l]; jb.Wb = ws.Wb[l]; jb.WTb = (l >= 1 || fr) ? ws.WTb[l] : nullptr;
+        jb.R = d->dims[l + 1]; jb.C = d->dims[l];
+        jb.tile_begin = jobs.total; jb.tiles_c = (jb.C + 63) / 64;
+        jobs.total += jb.tiles_c * ((jb.R + 63) / 64);
       }
+      prep_weights_kernel<<<ew_grid(jobs.total, 1), 256, 0, st>>>(jobs); count_launch();
     }
     CK(cudaGetLastError());
     return JPCB_OK;
@@ -695,11 +703,12 @@ struct Run {
   }
 
   // parameter gradients from err[] (already computed on state S) -- jpc/_core/_grads.py:487-499
-  int wgrads(const float* const* S, float* const* gW, float* const* gb) {
+  int wgrads(const float* const* S, float* const* gW, float* const* gb, int l_lo = 0, int l_hi = -1) {
+    if (l_hi < 0) l_hi = L;
     // tensor-core path: gW_l = -(a_l/B) Eb[l]^T Hb[l] with both operands read MN-major straight from
     // the [batch, d] bf16 copies the inference phases already keep (K = batch runs across their rows)
     std::vector<GTask> ts;
-    for (int l = 0; l < L; ++l) {
+    for (int l = l_lo; l < l_hi; ++l) {
       GTask t;
       t.e.mode = EPI_SCALE;
       t.e.M = d->dims[l + 1]; t.e.N = d->dims[l]; t.K = Bl;
@@ -715,7 +724,7 @@ struct Run {
     RET(launch(ts));
     if (d->has_bias) {
       if (!gb) return fail(JPCB_EINVAL, "has_bias set but no bias-gradient list");
-      for (int l = 0; l < L; ++l) {
+      for (int l = l_lo; l < l_hi; ++l) {
         const int N = d->dims[l + 1];
         const float sc = -d->scalings[l] * invB;
         if (tc && !x3) colsum_kernel<bf16><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.Eb[l], gb[l], Bl, N, sc);
@@ -1101,7 +1110,7 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
                                "unsupervised steps are jpcb_pc_infer + jpcb_pc_param_grads on caller-initialised activities");
   Run r;
   RET(r.init(desc, W, b, x, y, workspace, workspace_bytes, stream));
-  if (!A_out || !y || !gW) return fail(JPCB_EINVAL, "null activities / target / output");
+  if (!A_out || !y) return fail(JPCB_EINVAL, "null activities / target");
   RET(r.zero_red());
   RET(r.prep_weights());
   RET(r.prep_inputs(nullptr));
@@ -1109,8 +1118,18 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
   RET(r.infer_loop(A_out, true));
   RET(r.errors(1, A_out, false, true));           // errors + layer energies at the solution
   RET(r.error0_from_p1(A_out, true));
-  RET(r.wgrads(A_out, gW, gb));
+  if (gW) RET(r.wgrads(A_out, gW, gb));           // (NULL: the caller follows up with jpcb_pc_param_grads_range)
   return r.finalize(E_layers, nullptr, false, loss_out);
+}
+
+int jpcb_pc_param_grads_range(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, int layer_lo,
+                              int layer_hi, float* const* gW, float* const* gb, void* workspace, size_t workspace_bytes, void* stream) {
+  if (desc && desc->free_input) return fail(JPCB_ENOTIMPL, "jpcb_pc_param_grads_range follows jpcb_pc_train_step, which needs an input");
+  Run r;
+  RET(r.init(desc, W, b, x, nullptr, workspace, workspace_bytes, stream));
+  if (!gW) return fail(JPCB_EINVAL, "null gradient list");
+  if (layer_lo < 0 || layer_hi > r.L || layer_lo >= layer_hi) return fail(JPCB_EINVAL, "bad layer range [%d, %d) of %d layers", layer_lo, layer_hi, r.L);
+  return r.wgrads(nullptr, gW, gb, layer_lo, layer_hi);
 }
 
 }  // extern "C"

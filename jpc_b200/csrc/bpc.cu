@@ -213,18 +213,26 @@ struct BpcRun {
   int prep(const float* const* S) {
     if (!tc) return JPCB_OK;
     if (x3) return prep_x3(S);
-    for (int j = 0; j <= H; ++j) {
-      const size_t wn = (size_t)D[j] * D[j + 1];
-      cast_act_bf16_kernel<<<ew_grid(wn / 4 + 1, 256), 256, 0, st>>>(W[j], Wb[j], wn, ACT_LINEAR); count_launch();
-      cast_act_bf16_kernel<<<ew_grid(wn / 4 + 1, 256), 256, 0, st>>>(V[j], Vb[j], wn, ACT_LINEAR); count_launch();
-      if (j >= 1) {  // W_j [D[j+1], D[j]] -> [D[j], D[j+1]]
-        transpose_to_bf16_kernel<float><<<ew_grid(((D[j + 1] + 31) / 32) * ((D[j] + 31) / 32), 1), dim3(32, 8), 0, st>>>(W[j], WTb[j], D[j + 1], D[j]);
-        count_launch();
+    {  // every weight of both models read once: bf16 copy + transposed bf16 copy where a transposed GEMM needs it
+      PrepJobs jobs;
+      jobs.n = 0; jobs.total = 0;
+      auto flush = [&]() {
+        if (jobs.n == 0) return;
+        prep_weights_kernel<<<ew_grid(jobs.total, 1), 256, 0, st>>>(jobs); count_launch();
+        jobs.n = 0; jobs.total = 0;
+      };
+      auto add = [&](const float* Wp, bf16* Wbp, bf16* WTp, int R, int C) {
+        if (jobs.n == PREP_MAX_JOBS) flush();
+        PrepJob& jb = jobs.j[jobs.n++];
+        jb.W = Wp; jb.Wb = Wbp; jb.WTb = WTp; jb.R = R; jb.C = C;
+        jb.tile_begin = jobs.total; jb.tiles_c = (C + 63) / 64;
+        jobs.total += jb.tiles_c * ((R + 63) / 64);
+      };
+      for (int j = 0; j <= H; ++j) {
+        add(W[j], Wb[j], j >= 1 ? WTb[j] : nullptr, D[j + 1], D[j]);      // W_j [D[j+1], D[j]]
+        add(V[j], Vb[j], j <= H - 1 ? VTb[j] : nullptr, D[j], D[j + 1]);  // V_j [D[j], D[j+1]]
       }
-      if (j <= H - 1) {  // V_j [D[j], D[j+1]] -> [D[j+1], D[j]]
-        transpose_to_bf16_kernel<float><<<ew_grid(((D[j] + 31) / 32) * ((D[j + 1] + 31) / 32), 1), dim3(32, 8), 0, st>>>(V[j], VTb[j], D[j], D[j + 1]);
-        count_launch();
-      }
+      flush();
     }
     const size_t nx = (size_t)Bl * D[0], ny = (size_t)Bl * D[H + 1];
     cast_act_bf16_kernel<<<ew_grid(nx / 4 + 1, 256), 256, 0, st>>>(x, Hx, nx, d->td.act[0]); count_launch();

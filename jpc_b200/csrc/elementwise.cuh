@@ -69,6 +69,78 @@ static __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, __n
   }
 }
 
+// bf16 operand copies of ALL layers' weights in one launch (tensor-core path): Wb = bf16(W) [R, C] and, where the layer's
+// transposed GEMM needs it, WTb = bf16(W)^T [C, R] -- each fp32 weight is read ONCE (a cast pass + a transpose pass per layer
+// read it twice and cost 2 launches per layer: 0.33 ms of config 4's step, a constant that does not shrink with the batch
+// shard under data parallelism).  64 x 64 tiles, 256 threads; every global access is a 16-byte (fp32) / 8-byte (bf16) vector.
+struct PrepJob {
+  const float* W;
+  __nv_bfloat16* Wb;
+  __nv_bfloat16* WTb;  // or null
+  int R, C, tile_begin, tiles_c;
+};
+constexpr int PREP_MAX_JOBS = 32;
+struct PrepJobs {
+  int n, total;
+  PrepJob j[PREP_MAX_JOBS];
+};
+static __global__ void __launch_bounds__(256) prep_weights_kernel(const __grid_constant__ PrepJobs jobs) {
+  __shared__ float tile[64][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 columns x 4 rows each
+  for (int t = blockIdx.x; t < jobs.total; t += gridDim.x) {
+    int ji = 0;
+    while (ji + 1 < jobs.n && t >= jobs.j[ji + 1].tile_begin) ++ji;
+    const PrepJob& jb = jobs.j[ji];
+    const int local = t - jb.tile_begin, r0 = (local / jb.tiles_c) * 64, c0 = (local % jb.tiles_c) * 64;
+    const int R = jb.R, C = jb.C;
+    const bool vec = (C % 4 == 0) && (R % 4 == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 16 * i, c = c0 + 4 * tx;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r < R) {
+        if (vec && c + 3 < C) {
+          const float4 q = *reinterpret_cast<const float4*>(jb.W + (size_t)r * C + c);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+          *reinterpret_cast<uint2*>(jb.Wb + (size_t)r * C + c) = o;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c + k < C) { v[k] = jb.W[(size_t)r * C + c + k]; jb.Wb[(size_t)r * C + c + k] = __float2bfloat16_rn(v[k]); }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tile[ty + 16 * i][4 * tx + k] = v[k];
+    }
+    __syncthreads();
+    if (jb.WTb != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 16 * i, r = r0 + 4 * tx;  // output row c of W^T, columns r .. r + 3
+        if (c < C) {
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = tile[4 * tx + k][ty + 16 * i];
+          if (vec && r + 3 < R) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(jb.WTb + (size_t)c * R + r) = o;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (r + k < R) jb.WTb[(size_t)c * R + r + k] = __float2bfloat16_rn(v[k]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // out[n] = scale * sum_m E[m, n]   (bias gradients, jpc/_core/_grads.py:487-499 closed form)
 template <typename TIn>
 static __global__ void colsum_kernel(const TIn* __restrict__ E, float* __restrict__ out, int M, int N, float scale) {

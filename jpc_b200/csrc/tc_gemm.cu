@@ -355,7 +355,7 @@ int launch_tc_solve(const std::vector<GTask>& errs, const std::vector<GTask>& gr
   }
   // too little work per step to fill the persistent grid for a few rounds: the per-phase path picks narrower tiles
   const char* vmin = getenv("JPCB_SOLVE_MIN_ROUNDS");  // (tests set 0 to force small problems through this path)
-  if ((long long)R * (per_e + per_g) < (long long)(vmin ? atoi(vmin) : 4) * units) return JPCB_SOLVE_NA;
+  if ((long long)R * (per_e + per_g) < (long long)(vmin ? atoi(vmin) : 2) * units) return JPCB_SOLVE_NA;
   if (counter_ints < (size_t)2 * L1 * R || !counters) return fail(JPCB_EWORKSPACE, "internal: schedule counters");
   auto a_of = [&](int i) { return wave ? (L1 - 1 - i > 0 ? L1 - 1 - i : 0) : 0; };
   for (int i = 0; i < L1; ++i) {

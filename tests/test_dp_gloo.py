@@ -84,3 +84,25 @@ def test_arena_layout():
     a.flat.zero_()
     a.gW[1].fill_(3.0)
     assert float(a.flat.sum()) == 30.0
+
+
+def test_arena_buckets_cover_the_arena():
+    """The bucketed exchange (jpc_b200._train.dp_param_grads_and_exchange) reduces `flat[lo:hi]` per layer group: the
+    groups must be contiguous, ordered, cover every layer once and the whole flat buffer (tail [E, loss] in the last)."""
+    from jpc_b200._train import _Arena
+    for L, bias in ((8, False), (3, True), (1, False), (13, True)):
+        ws = [(16 + 8 * l, 24 + 4 * l) for l in range(L)]
+        bs = [(16 + 8 * l,) for l in range(L)] if bias else None
+        arena = _Arena(weight_shapes=ws, bias_shapes=bs, device="cpu")
+        for nb in (1, 2, 4, 7, 50):
+            bk = arena.buckets(nb)
+            assert bk[0][0] == 0 and bk[0][2] == 0 and bk[-1][1] == L and bk[-1][3] == arena.flat.numel()
+            assert len(bk) <= min(nb, L)
+            for (a0, a1, f0, f1), (b0, b1, g0, g1) in zip(bk[:-1], bk[1:]):
+                assert a1 == b0 and f1 == g0 and a0 < a1 and f0 < f1
+            # every gradient view lies inside the flat range of its layer's bucket
+            for llo, lhi, flo, fhi in bk:
+                for l in range(llo, lhi):
+                    off = arena.gW[l].storage_offset()
+                    assert flo <= off and off + arena.gW[l].numel() <= fhi
+            assert arena.E.storage_offset() >= bk[-1][2]

@@ -254,7 +254,9 @@ def test_saveat_bookkeeping_matches_oracle_interpolation():
     assert ys[0].shape[0] == 4096 and torch.equal(ys[0][3], traj[-1][1][0]) and bool(torch.isinf(ys[0][4:]).all())
     from jpc_b200._utils import get_t_max
     assert int(get_t_max(ys)) == 3
-    # an early stop leaves the unreached ts rows at inf
+    # an early stop (steady-state event after the first step, t = 0.4): diffrax writes the t1 row at the current save
+    # index -- right after the one `ts` row it filled -- and the rows beyond stay inf
     save = _SaveAt(net, 1.5, False, 0.5)
     save.step(*traj[0], *traj[1])
-    assert bool(torch.isinf(save.finish(traj[1][1])[0][1:3]).all())
+    ys = save.finish(traj[1][1])
+    assert torch.equal(ys[0][1], traj[1][1][0]) and bool(torch.isinf(ys[0][2:]).all()) and bool(torch.isfinite(ys[0][0]).all())
