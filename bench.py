@@ -482,7 +482,7 @@ def main():
     # ---- the same end-to-end loop through jpc_b200.PCTrainer: the train step + SGD update as ONE replayed CUDA graph on
     # persistent buffers (single process only; an extra, `e2e` above stays the reference-shaped functional API) ----
     e2e_graph = None
-    if world == 1:
+    if True:
         try:
             tr = J.PCTrainer(gm, J.optim.sgd(1e-3 * w["B"]), batch_size=w["B"], skip_model=gsk, param_type=w["ptype"], ode_solver=solver,
                              max_t1=w["max_t1"], dt=w["dt"], stepsize_controller=J.ConstantStepSize())
@@ -506,8 +506,14 @@ def main():
             for i in range(2, 2 + args.steps):
                 graph_step(i)
             sync_all()
-            e2e_graph = {"value": B_global * args.steps / (time.perf_counter() - t0), "unit": UNIT,
-                         "what": "jpc_b200.PCTrainer.step: H2D of the batch + one CUDA-graph replay (train step + in-place SGD) + loss read-back"}
+            g_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([g_s], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                g_s = float(t)
+            e2e_graph = {"value": B_global * args.steps / g_s, "unit": UNIT,
+                         "what": "jpc_b200.PCTrainer.step: H2D of the batch + one CUDA-graph replay (train step + "
+                                 + ("captured NCCL all-reduce + " if world > 1 else "") + "in-place SGD) + loss read-back"}
         except NotImplementedError:
             e2e_graph = None
 
@@ -603,7 +609,12 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # (leave without tearing the communicators down: destroying a process group whose collective was captured into a
+        #  still-alive CUDA graph -- PCTrainer under data parallelism -- blocked at exit on this stack; nothing is left to flush)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
     return 0
 
 

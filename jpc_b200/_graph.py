@@ -9,9 +9,14 @@ and never synchronises, so stream capture just works) and every `step()` is a co
 buffers and one graph launch.  Same arithmetic, same kernels, same results as `make_pc_step`
 (tests/test_gpu_parity.py::test_pc_trainer_graph_matches_make_pc_step).
 
+Data parallel (torch.distributed initialised, world_size > 1): every rank builds its trainer collectively; the batch
+arguments are the rank's row shard, the energy is normalised by the GLOBAL batch, and the NCCL all-reduce (SUM) of the
+gradient arena is captured INSIDE the graph, between the gradient kernels and the update.  The captured collective runs on
+a communicator of its own (`dist.new_group`), never used eagerly after the warm-up: interleaving eager collectives with
+graph replays on one communicator is what hung the first attempt at this (round 1).
+
 Restrictions: fixed-step solvers (`ConstantStepSize`), `optim.sgd` inside the graph (other optimisers run after the
-graph through the optax protocol, in place), single process (under data parallelism the all-reduce sits between the
-gradient and the update: use `make_pc_step`)."""
+graph through the optax protocol, in place)."""
 from __future__ import annotations
 
 import torch
@@ -19,7 +24,7 @@ import torch
 from . import _lib
 from ._core import _Net, _solver_id, _time_grid
 from ._errors import _check_param_type
-from ._train import _Arena, _world
+from ._train import _Arena, _world, global_batch
 from .nn import tree_leaves, tree_unflatten_like
 from .solvers import ConstantStepSize, Euler
 
@@ -30,8 +35,11 @@ class PCTrainer:
         _check_param_type(param_type)
         if not isinstance(stepsize_controller, ConstantStepSize):
             raise NotImplementedError("PCTrainer replays a fixed launch sequence: pass stepsize_controller=ConstantStepSize() and dt")
-        if _world() > 1:
-            raise NotImplementedError("PCTrainer is single-process; use make_pc_step under data parallelism")
+        self._world = _world()
+        self._pg = None
+        if self._world > 1:
+            import torch.distributed as dist
+            self._pg = dist.new_group(backend="nccl")  # collective: every rank constructs its trainer at the same point
         ode_solver = Euler() if ode_solver is None else ode_solver
         T, h, h_last = _time_grid(max_t1, dt)
         # persistent parameters: clones of the caller's (the caller's model is left untouched)
@@ -47,7 +55,8 @@ class PCTrainer:
         self.y = torch.zeros(batch_size, d_out, dtype=torch.float32, device=dev)
         self._net = _Net(self.model, self.skip_model, self.x, self.y, param_type=param_type, loss_id=loss_id, gamma=None,
                          output_energy_scaling=None, activity_decay=activity_decay, weight_decay=0.0, spectral_penalty=0.0,
-                         solver=_solver_id(ode_solver), n_steps=T, dt=h, dt_last=h_last)
+                         solver=_solver_id(ode_solver), n_steps=T, dt=h, dt_last=h_last,
+                         batch_global=global_batch(batch_size, dev) if self._world > 1 else None)
         if self._net.padded:
             raise NotImplementedError("PCTrainer needs feature dims that are multiples of 8 on the tensor-core paths "
                                       "(the functional API pads per call; a persistent padded layout is not built)")
@@ -68,6 +77,9 @@ class PCTrainer:
             net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr_array(self._acts), _lib.ptr(arena.loss),
             _lib.ptr(arena.E), _lib.ptr_array(arena.gW), _lib.ptr_array(arena.gb) if arena.gb else None,
             _lib.ptr(ws), ws.numel(), st))
+        if self._pg is not None:  # the one exchange step (captured into the graph like the kernels around it)
+            import torch.distributed as dist
+            dist.all_reduce(arena.flat, op=dist.ReduceOp.SUM, group=self._pg)
         if self._sgd_lr is not None:
             import ctypes as C
             p, g = self._params, []
@@ -81,7 +93,7 @@ class PCTrainer:
 
     def _capture(self):
         with torch.cuda.stream(self._stream):
-            for _ in range(2):  # warm-up outside capture (lazy module loads, function attributes); undone below
+            for _ in range(3 if self._pg is not None else 2):  # warm-up outside capture (lazy module loads, function attributes, NCCL communicator set-up); undone below
                 saved = [p.clone() for p in self._params]
                 self._enqueue()
                 for p, s in zip(self._params, saved):
@@ -94,6 +106,11 @@ class PCTrainer:
             for p, s in zip(self._params, saved):  # (capture does not execute; nothing to undo -- kept for clarity)
                 p.copy_(s)
             self._stream.synchronize()
+
+    def close(self):
+        """Drops the captured graph (and with it the captured collective).  Under data parallelism call this on every rank
+        before `torch.distributed.destroy_process_group()`."""
+        self._graph = None
 
     def step(self, output, input):
         """One train step on (input, output): returns the reference's result dict (views of the trainer's static buffers:

@@ -93,6 +93,39 @@ if rank == 0:
     print(f"bf16 gradient payload vs fp32 payload: updated-weight rel err {err:.2e}", flush=True)
     assert err < 2e-2
 dist.barrier()
+# ---- PCTrainer under data parallelism: train step + captured NCCL all-reduce + SGD update as one replayed CUDA graph ----
+for dtype, tol in (("f32", 1e-5), ("bf16", 2e-2)):
+    J.set_compute_dtype(dtype)
+    B, d = 256, 128
+    g = torch.Generator().manual_seed(3)
+    model = J.make_mlp(3, d, d, 4, d, "tanh", use_bias=True)
+    lo, hi = shard_rows(B, rank, world)
+    kw = dict(ode_solver=J.Euler(), max_t1=4, dt=0.5, stepsize_controller=J.ConstantStepSize())
+    T._GLOBAL_ROWS.clear()
+    tr = J.PCTrainer(model, J.optim.sgd(0.05), batch_size=hi - lo, **kw)
+    opt = J.optim.sgd(0.05)
+    ref_model, ref_st = model, opt.init((model, None))
+    for it in range(3):
+        x = torch.randn(B, d, generator=g).cuda()
+        y = torch.randn(B, d, generator=g).cuda()
+        out = tr.step(y[lo:hi].contiguous(), x[lo:hi].contiguous())
+        dist.barrier()                      # an eager collective on the default communicator between graph replays
+        if rank == 0:
+            saved, real = T._world, T._Arena.all_reduce
+            T._world = lambda: 1
+            T._Arena.all_reduce = lambda self: None
+            try:
+                ref = J.make_pc_step(ref_model, opt, ref_st, y, input=x, **kw)
+            finally:
+                T._world, T._Arena.all_reduce = saved, real
+            ref_model, ref_st = ref["model"], ref["opt_state"]
+            err = max(float((a[1].weight - b[1].weight).abs().max() / b[1].weight.abs().max()) for a, b in zip(tr.model, ref_model))
+            l_err = abs(float(out["loss"]) - float(ref["loss"])) / abs(float(ref["loss"]))
+            print(f"PCTrainer[{dtype}] DP step {it}: weights vs single-process make_pc_step rel err {err:.2e}, loss {l_err:.2e}", flush=True)
+            assert err < tol and l_err < max(tol, 1e-5)
+dist.barrier()
 if rank == 0:
     print("DP NCCL parity OK", flush=True)
-dist.destroy_process_group()
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(0)   # (see bench.py: no communicator teardown while a graph that captured a collective is alive)
