@@ -451,7 +451,13 @@ def main():
             yb.copy_(y_pin, non_blocking=True)
             ready.record(copy_stream)
 
-    def e2e_step(i):
+    # The result (loss) of EVERY step travels device -> host inside the timed region: a non-blocking copy into pinned host
+    # memory, drained (and checked) when the timed region ends -- the way a training loop logs its loss without stalling the
+    # launch queue.  `e2e_blocking_read` is the same loop with the host blocking on every step's loss instead.
+    loss_pin = torch.empty(256, dtype=torch.float32).pin_memory()
+    E2E_WARM = max(args.warmup, 8)  # (the functional API's buffers cycle through a few address sets; launch plans settle)
+
+    def e2e_step(i, blocking=False):
         nonlocal model, skipm, st
         xb, yb, ready, consumed = bufs[i % 2]
         torch.cuda.current_stream(dev).wait_event(ready)
@@ -460,24 +466,36 @@ def main():
                              dt=w["dt"], stepsize_controller=J.ConstantStepSize(), skip_model=skipm)
         consumed.record(torch.cuda.current_stream(dev))
         model, skipm, st = out["model"], out["skip_model"], out["opt_state"]
-        return float(out["loss"])  # device -> host read of the step's result
+        if blocking:
+            return float(out["loss"])
+        loss_pin[i % 256].copy_(out["loss"], non_blocking=True)
+        return None
 
-    for b in bufs:
-        b[3].record(torch.cuda.current_stream(dev))
-    stage(0)
-    for i in range(2):
-        e2e_step(i)
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(2, 2 + args.steps):
-        e2e_step(i)
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t)
+    def e2e_loop(step_fn, blocking):
+        sync_all()
+        for b in bufs:
+            b[3].record(torch.cuda.current_stream(dev))
+        stage(0)
+        for i in range(E2E_WARM):
+            step_fn(i, blocking)
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(E2E_WARM, E2E_WARM + args.steps):
+            step_fn(i, blocking)
+        sync_all()  # (drains the loss copies too)
+        secs = time.perf_counter() - t0
+        if not bool(torch.isfinite(loss_pin[:min(256, E2E_WARM + args.steps)]).all()):
+            raise SystemExit("bench.py: a non-finite loss came back from the end-to-end loop")
+        if world > 1:
+            t = torch.tensor([secs], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t)
+        return secs
+
+    loss_pin.zero_()
+    e2e_s = e2e_loop(e2e_step, False)
     e2e_val = B_global * args.steps / e2e_s
+    e2e_blocking_val = B_global * args.steps / e2e_loop(e2e_step, True)
 
     # ---- the same end-to-end loop through jpc_b200.PCTrainer: the train step + SGD update as ONE replayed CUDA graph on
     # persistent buffers (single process only; an extra, `e2e` above stays the reference-shaped functional API) ----
@@ -487,30 +505,15 @@ def main():
             tr = J.PCTrainer(gm, J.optim.sgd(1e-3 * w["B"]), batch_size=w["B"], skip_model=gsk, param_type=w["ptype"], ode_solver=solver,
                              max_t1=w["max_t1"], dt=w["dt"], stepsize_controller=J.ConstantStepSize())
 
-            def graph_step(i):
+            def graph_step(i, blocking=False):
                 xb, yb, ready, consumed = bufs[i % 2]
                 torch.cuda.current_stream(dev).wait_event(ready)
                 stage(i + 1)
                 out = tr.step(yb, xb)
                 consumed.record(torch.cuda.current_stream(dev))
-                return float(out["loss"])
+                loss_pin[i % 256].copy_(out["loss"], non_blocking=True)
 
-            sync_all()
-            for b in bufs:
-                b[3].record(torch.cuda.current_stream(dev))
-            stage(0)
-            for i in range(2):
-                graph_step(i)
-            sync_all()
-            t0 = time.perf_counter()
-            for i in range(2, 2 + args.steps):
-                graph_step(i)
-            sync_all()
-            g_s = time.perf_counter() - t0
-            if world > 1:
-                t = torch.tensor([g_s], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                g_s = float(t)
+            g_s = e2e_loop(graph_step, False)
             e2e_graph = {"value": B_global * args.steps / g_s, "unit": UNIT,
                          "what": "jpc_b200.PCTrainer.step: H2D of the batch + one CUDA-graph replay (train step + "
                                  + ("captured NCCL all-reduce + " if world > 1 else "") + "in-place SGD) + loss read-back"}
@@ -613,7 +616,11 @@ def main():
                        "wavefront": "from the feed-forward init only layers the error wavefront has reached are evaluated "
                                     "(same result; executed < dense FLOPs)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel() * 4,
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4,
+                    "d2h": "non-blocking copy of the step's loss into pinned host memory every step, drained at the end of the "
+                           "timed region", "warmup": E2E_WARM},
+            "e2e_blocking_read": {"value": e2e_blocking_val, "unit": UNIT,
+                                  "what": "the same loop with the host blocking on every step's loss (float(loss))"},
             "e2e_graph": e2e_graph,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "loss": loss_val,

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JPCB_VERSION 100
+#define JPCB_VERSION 101
 #define JPCB_MAX_LAYERS 256
 
 /* error codes */
@@ -65,8 +65,11 @@ extern "C" {
 #define JPCB_SOLVER_EULER 0 /* diffrax.Euler  + ConstantStepSize */
 #define JPCB_SOLVER_HEUN 1  /* diffrax.Heun   + ConstantStepSize */
 
-/* Descriptor of one PC network in the reference's make_mlp layer form
- * f_l(u) = W_l act_l(u) + b_l  (jpc/_utils.py:87-106), l = 0..n_layers-1. */
+/* Descriptor of one PC network of dense layers, l = 0..n_layers-1:
+ *   f_l(u) = post_act_l( W_l act_l(u) + b_l ).
+ * The reference's make_mlp builds Form A, `Sequential([Lambda(act), Linear])`: post_act = identity
+ * (jpc/_utils.py:87-106); its hand-built example networks are Form B, `Sequential([Linear, Lambda(act)])`: act = identity
+ * (examples/jpc_from_scratch.ipynb cell 12, examples/discriminative_pc.ipynb cell 8). */
 typedef struct jpcb_pc_desc {
   int32_t n_layers;                  /* L = len(model) >= 2 */
   int32_t batch_local;               /* rows held by this rank */
@@ -91,6 +94,11 @@ typedef struct jpcb_pc_desc {
                                       * is applied as given: the reference's PC branch is unscaled and only runs with
                                       * "sp" (callers pass 1); its ePC branch scales the first layer like any other.
                                       * jpcb_pc_ffwd_init / jpcb_pc_train_step need an input. */
+  int32_t post_act[JPCB_MAX_LAYERS]; /* activation applied to the OUTPUT of layer l's linear map (Form B); 0 = none.
+                                      * With pre = W_l act_l(u_l) + b_l:  e_{l+1} = t - a_l post(pre) - s_l u_l, and the
+                                      * error that travels through W_l (activity and weight gradients) is post'(pre) . e_{l+1}
+                                      * (SURVEY A.2 "Form B").  Supervised PC entry points only (not free_input, bPC, hybrid
+                                      * PC, ePC); a cross-entropy output layer must have post_act = 0. */
 } jpcb_pc_desc;
 
 int jpcb_version(void);
@@ -268,6 +276,23 @@ int jpcb_optim_adam(int n_tensors, const long long* numel, const float* const* p
                     const float* const* grads, const float* const* mu, const float* const* nu,
                     double learning_rate, double b1, double b2, double eps, int step,
                     float* const* params_out, float* const* mu_out, float* const* nu_out, void* stream);
+
+/* ---- launch plans ("build once, replay") ---------------------------------------------
+ * Every compute entry point above only ENQUEUES, and a call with identical arguments -- descriptor, every pointer
+ * (including the contents of the pointer lists), workspace, stream, device -- enqueues an identical kernel sequence.
+ * The reference pays the corresponding cost once, when `eqx.filter_jit` traces `make_pc_step` (jpc/_train.py:34); here
+ * the library keeps a small cache of instantiated CUDA graphs: the `min_calls`-th time an identical call is seen its
+ * sequence is captured on a library-owned stream and from then on the call is one cudaGraphLaunch on the caller's
+ * stream (the functional host API allocates its outputs from a caching allocator, so its pointer sets repeat with a
+ * short period).  Results are identical; jpcb_launch_count() keeps counting the kernels inside replayed graphs.
+ * Calls made while the caller is itself capturing `stream` bypass the cache.  Planned entry points: jpcb_pc_ffwd_init,
+ * jpcb_pc_energy, jpcb_pc_activity_grad, jpcb_pc_infer (sumsq_out == NULL), jpcb_pc_param_grads, jpcb_pc_train_step,
+ * jpcb_bpc_energy, jpcb_bpc_activity_grad, jpcb_bpc_infer, jpcb_bpc_param_grads, jpcb_bpc_train_step.
+ * Defaults: 16 plans, min_calls 2 (environment: JPCB_PLAN=0 disables, JPCB_PLAN=n plans, JPCB_PLAN_MIN=m). */
+int jpcb_plan_cache_configure(int max_plans /* 0: disable and drop all plans */, int min_calls);
+int jpcb_plan_cache_clear(void);
+void jpcb_plan_cache_stats(unsigned long long* replays, unsigned long long* captures,
+                           unsigned long long* bypassed);
 
 #ifdef __cplusplus
 }

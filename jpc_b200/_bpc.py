@@ -37,6 +37,8 @@ class _BpcNet:
         H = n - 1
         td = [_layer_parts(l) for l in top_down_model]
         bu = [_layer_parts(l) for l in bottom_up_model]
+        if any(q[2] != "linear" for q in td + bu):
+            raise NotImplementedError("bPC: layers of the form Sequential([Linear, Lambda(act)]) are not on the B200 path")
         self.td_lin, self.bu_lin = [p[1] for p in td], [p[1] for p in bu]
         self.top_down_model, self.bottom_up_model = top_down_model, bottom_up_model
         Ws, Vs = [l.weight for l in self.td_lin], [l.weight for l in self.bu_lin]

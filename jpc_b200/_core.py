@@ -23,7 +23,7 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from . import _lib
+from . import _flat, _lib
 from ._errors import _check_param_type
 from .nn import Identity, Lambda, Linear, Sequential, tree_unflatten_like
 from .optim import update_and_apply
@@ -59,20 +59,45 @@ _TORCH_ACT_NAMES = {torch.tanh: "tanh", _F.tanh: "tanh", torch.relu: "relu", _F.
                     _F.leaky_relu: "leaky_relu", torch.selu: "selu", _F.selu: "selu", _F.silu: "silu"}
 
 
-def _layer_parts(layer) -> Tuple[str, Linear]:
-    """(activation id, Linear) of one layer in the make_mlp form Sequential([Lambda(act), Linear])
-    (jpc/_utils.py:102-106).  Anything else is outside the B200 path (no CPU fallback)."""
+def _act_name(obj):
+    """Activation id of a `Lambda(fn)` (or bare callable) in a layer, or None."""
+    fn = getattr(obj, "fn", obj)
+    name = getattr(fn, "name", None)
+    if name is None:
+        try:
+            name = _TORCH_ACT_NAMES.get(fn)
+        except TypeError:
+            name = None
+    return name if name in _lib.ACT_IDS else None
+
+
+def _layer_parts(layer) -> Tuple[str, Linear, str]:
+    """(input activation id, Linear, output activation id) of one layer.  Two layer forms are on the B200 path:
+      Form A  Sequential([Lambda(act), Linear])   f(u) = W act(u) + b    -- what jpc.make_mlp builds (jpc/_utils.py:102-106)
+      Form B  Sequential([Linear, Lambda(act)])   f(u) = act(W u + b)    -- the hand-built networks of the reference's
+              examples (examples/jpc_from_scratch.ipynb cell 12, examples/discriminative_pc.ipynb cell 8)
+    plus a bare Linear (either form with the identity) and Sequential([Lambda, Linear, Lambda]).  Anything else (conv,
+    attention, arbitrary callables) has no B200 path, and there is no CPU fallback."""
+    if type(layer) is Sequential:  # exact-type fast path: this runs for every layer of every call
+        subs = layer.layers
+        if len(subs) == 2 and type(subs[1]) is Linear and type(subs[0]) is Lambda:
+            name = getattr(subs[0].fn, "name", None)
+            if name in _lib.ACT_IDS:
+                return name, subs[1], "linear"
     if isinstance(layer, Linear) or (hasattr(layer, "weight") and not hasattr(layer, "layers")):
-        return "linear", layer
+        return "linear", layer, "linear"
     subs = getattr(layer, "layers", None)
-    if subs is not None and len(subs) == 2 and hasattr(subs[1], "weight"):
-        fn = getattr(subs[0], "fn", subs[0])
-        name = getattr(fn, "name", None) or _TORCH_ACT_NAMES.get(fn)
-        if name in _lib.ACT_IDS:
-            return name, subs[1]
+    if subs is not None and 1 <= len(subs) <= 3:
+        lin_at = [i for i, m in enumerate(subs) if hasattr(m, "weight")]
+        if len(lin_at) == 1:
+            i = lin_at[0]
+            pre = _act_name(subs[i - 1]) if i >= 1 else "linear"
+            post = _act_name(subs[i + 1]) if i + 1 < len(subs) else "linear"
+            if pre is not None and post is not None and i <= 1 and len(subs) - i <= 2:
+                return pre, subs[i], post
     raise NotImplementedError(
-        "jpc_b200 accelerates MLP layers of the form Sequential([Lambda(act_fn), Linear]) "
-        "(jpc.make_mlp); other layer types have no B200 path and there is no CPU fallback.")
+        "jpc_b200 accelerates MLP layers of the forms Sequential([Lambda(act_fn), Linear]) (jpc.make_mlp), "
+        "Sequential([Linear, Lambda(act_fn)]) and bare Linear; other layer types have no B200 path and there is no CPU fallback.")
 
 
 def _skip_flags(skip_model, L: int):
@@ -145,31 +170,47 @@ class _Net:
             raise NotImplementedError("weight_decay / spectral_penalty on bare Linear layers are not on the B200 path")
         # (for make_mlp models those two regularisers are no-ops in the reference as well: the
         #  layers are Sequential objects without a `.weight`, jpc/_core/_energies.py:128-143)
-        self.linears = [p[1] for p in parts]
+        self.linears = linears = [p[1] for p in parts]
         self.model, self.skip_model = model, skip_model
-        Ws = [lin.weight for lin in self.linears]
-        dev = Ws[0].device
+        dev = linears[0].weight.device
         if dev.type != "cuda":
             raise RuntimeError("jpc_b200 has no CPU path: model weights must be CUDA tensors")
-        for t in Ws + ([x] if x is not None else []) + ([y] if y is not None else []):
-            if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+        f32 = torch.float32
+        Ws, bs, dims = [], [], [linears[0].weight.shape[1]]
+        for l, lin in enumerate(linears):  # one pass per layer: this runs every call of the functional API
+            w, b_ = lin.weight, lin.bias
+            if w.dtype is not f32 or not w.is_contiguous() or w.device != dev:
                 raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
-        has_bias = [lin.bias is not None for lin in self.linears]
-        if any(has_bias) and not all(has_bias):
+            if b_ is not None:
+                if b_.dtype is not f32 or not b_.is_contiguous() or b_.device != dev:
+                    raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
+                bs.append(b_)
+            d_out, d_in = w.shape
+            if d_in != dims[l]:
+                raise ValueError(f"layer {l}: weight shape {tuple(w.shape)} does not chain from {dims[l]}")
+            dims.append(d_out)
+            Ws.append(w)
+        for t in ([x] if x is not None else []) + ([y] if y is not None else []):
+            if t.dtype is not f32 or not t.is_contiguous() or t.device != dev:
+                raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
+        if bs and len(bs) != L:
             raise NotImplementedError("mixed bias / no-bias layers are not on the B200 path")
-        dims = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
-        for l in range(L):
-            if Ws[l].shape[1] != dims[l]:
-                raise ValueError(f"layer {l}: weight shape {tuple(Ws[l].shape)} does not chain from {dims[l]}")
+        has_bias = [bool(bs)] * L
         if x is not None and x.shape[1] != dims[0]:
             raise ValueError("input feature dim does not match the first layer")
+        posts = tuple(p[2] for p in parts)
+        self.form_b = any(q != "linear" for q in posts)
+        if self.form_b and param_type != "sp":
+            # (the reference's _get_param_scalings reads model[0][1].weight, jpc/_core/_energies.py:915: an activation
+            #  object for a Sequential([Linear, Lambda]) layer -- it only runs "sp" with that form)
+            raise NotImplementedError("layers of the form Sequential([Linear, Lambda(act)]) support param_type='sp' only")
         B = y.shape[0] if self.free else x.shape[0]
         skips = _skip_flags(skip_model, L)
         # (ePC's x=None branch scales the first layer by the width of errors[0] = d_0, jpc/_core/_energies.py:422-427)
         scal_in = x if x is not None else _Shape((B, dims[0]))
         scal = _get_param_scalings(model, scal_in, skip_model=skip_model, param_type=param_type, gamma=gamma)
         self.true_dims = list(dims)
-        bs = [lin.bias for lin in self.linears] if all(has_bias) else None
+        bs = bs if bs else None
         self.padded = _COMPUTE_DTYPE != "f32" and any(v % 8 for v in dims)  # (both tensor-core paths)
         if self.padded:
             # The tensor-core path needs every feature dim to be a multiple of 8 (TMA row pitch, 16-byte vectors):
@@ -191,7 +232,7 @@ class _Net:
             dims = pd
         lam = 1.0 if output_energy_scaling is None else float(output_energy_scaling)
         bg = B if batch_global is None else int(batch_global)
-        key = (L, B, bg, tuple(dims), tuple(p[0] for p in parts), all(has_bias), tuple(skips), tuple(scal),
+        key = (L, B, bg, tuple(dims), tuple(p[0] for p in parts), posts, all(has_bias), tuple(skips), tuple(scal),
                _COMPUTE_DTYPE, loss_id, lam, float(activity_decay), solver, n_steps, float(dt), float(dt_last), self.free)
         cached = _DESC_CACHE.get(key)
         if cached is None:
@@ -201,6 +242,7 @@ class _Net:
                 d.dims[i] = v
             for l in range(L):
                 d.act[l] = _lib.ACT_IDS[parts[l][0]]
+                d.post_act[l] = _lib.ACT_IDS[posts[l]]
                 d.skip[l] = 1 if skips[l] else 0
                 d.scalings[l] = scal[l]
             d.has_bias = 1 if all(has_bias) else 0
@@ -223,8 +265,10 @@ class _Net:
         self.adims = dims[0 if self.free else 1:]
         self.true_adims = self.true_dims[0 if self.free else 1:]
         self.has_bias = all(has_bias)
-        self.W = _lib.ptr_array(Ws)
-        self.b = _lib.ptr_array(bs) if self.has_bias else None
+        self.w_ptrs = [w.data_ptr() for w in Ws]
+        self.b_ptrs = [b_.data_ptr() for b_ in bs] if self.has_bias else None
+        self.W = _lib.ptr_array_from_ints(self.w_ptrs)
+        self.b = _lib.ptr_array_from_ints(self.b_ptrs) if self.has_bias else None
         self._keep = (Ws, bs)  # keep tensors alive while pointer arrays exist
         self.x, self.y = x, y   # (zero-padded copies when self.padded)
         self.w_shapes = [tuple(w.shape) for w in Ws]
@@ -258,9 +302,10 @@ class _Net:
             if a.device != self.dev or a.dtype != torch.float32 or not a.is_contiguous():
                 raise ValueError("activities must be contiguous fp32 CUDA tensors")
 
-    def new_acts(self):
-        """Output buffers in the layout the library sees (padded feature dims when self.padded)."""
-        return [torch.empty(self.B, w, dtype=torch.float32, device=self.dev) for w in self.adims]
+    def new_acts(self, lead=()):
+        """Output buffers in the layout the library sees (padded feature dims when self.padded): one allocation, carved."""
+        lay = _flat.layout([(self.B, w) for w in self.adims])
+        return lay.carve(torch.empty(lay.total, dtype=torch.float32, device=self.dev), lead)
 
     def in_acts(self, activities, clone=False):
         """User activities -> the layout the library sees."""

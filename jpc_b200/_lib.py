@@ -39,6 +39,7 @@ class PcDesc(C.Structure):
         ("dt", C.c_float),
         ("dt_last", C.c_float),
         ("free_input", C.c_int32),
+        ("post_act", C.c_int32 * MAX_LAYERS),
     ]
 
 
@@ -78,6 +79,9 @@ SIGNATURES = {
     "jpcb_hpc_param_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
     "jpcb_epc_workspace_bytes": (C.c_size_t, [C.POINTER(PcDesc)]),
     "jpcb_epc_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _PP, _PP, _PP, _P, C.c_size_t, _P]),
+    "jpcb_plan_cache_configure": (C.c_int, [C.c_int, C.c_int]),
+    "jpcb_plan_cache_clear": (C.c_int, []),
+    "jpcb_plan_cache_stats": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "jpcb_optim_sgd": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), _PP, _PP, C.c_double, _PP, _P]),
     "jpcb_optim_adam": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), _PP, _PP, _PP, _PP, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int, _PP, _PP, _PP, _P]),
@@ -127,11 +131,29 @@ def check(code: int) -> None:
 
 def ptr_array(tensors) -> "C.Array":
     """Host array of device pointers from a list of tensors (None -> NULL)."""
-    arr = (C.c_void_p * max(1, len(tensors)))()
-    for i, t in enumerate(tensors):
-        arr[i] = None if t is None else t.data_ptr()
-    return arr
+    return (C.c_void_p * max(1, len(tensors)))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def ptr_array_from_ints(addrs) -> "C.Array":
+    """Host array of device pointers from integer addresses."""
+    return (C.c_void_p * max(1, len(addrs)))(*addrs)
 
 
 def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def plan_cache_configure(max_plans: int = 16, min_calls: int = 2) -> None:
+    """Launch plans of the library (include/jpc_b200.h, csrc/plan.cu): identical calls are captured into a CUDA graph the
+    `min_calls`-th time they are seen and replayed from then on.  `max_plans=0` disables (every call enqueues its kernels)."""
+    check(lib.jpcb_plan_cache_configure(int(max_plans), int(min_calls)))
+
+
+def plan_cache_clear() -> None:
+    check(lib.jpcb_plan_cache_clear())
+
+
+def plan_cache_stats() -> dict:
+    a, b, c = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+    lib.jpcb_plan_cache_stats(C.byref(a), C.byref(b), C.byref(c))
+    return {"replays": a.value, "captures": b.value, "bypassed": c.value}

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _flat, _lib
 from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_from_normal, init_activities_with_ffwd,
                     solve_inference)
 from ._errors import _check_param_type
@@ -54,14 +54,10 @@ class _Arena:
             if bias_shapes is not None:
                 shapes.append(bias_shapes[l])
         shapes += [(L,), ()]
-        sizes = [int(torch.Size(sh).numel()) for sh in shapes]
-        offs, off = [], 0
-        for s in sizes:
-            offs.append(off)
-            off += (s + 63) // 64 * 64
-        self.flat = torch.empty(off, dtype=torch.float32, device=device)
-        # one as_strided per view (contiguous strides of each shape at its offset): this runs every train step
-        views = [self.flat.as_strided(sh, _contig_strides(sh), o) for o, sh in zip(offs, shapes)]
+        lay = _flat.layout(shapes)  # (cached per shape list; views carved run by run: this runs every train step)
+        offs = lay.offs
+        self.flat = torch.empty(lay.total, dtype=torch.float32, device=device)
+        views = lay.carve(self.flat)
         self.gW, self.gb = [], ([] if bias_shapes is not None else None)
         i = 0
         for l in range(L):
@@ -166,6 +162,59 @@ def dp_param_grads_and_exchange(net, arena, n_buckets=None):
     main.wait_stream(comm)
 
 
+def _fused_param_update(net, arena, optim, opt_state):
+    """`optim.update` + `eqx.apply_updates` (jpc/_train.py:234-242) through the library's update kernel, fed from what this
+    step already holds: the parameter addresses `_Net` gathered (and validated), the gradient addresses inside the arena,
+    and ONE fresh flat buffer per output family carved into the new leaves.  (new leaves, new state), or None when the
+    optimiser is not one of the two the kernel implements."""
+    spec = getattr(optim, "fused_spec", None)
+    if spec is None or (spec[0] == "adam" and not (isinstance(opt_state, dict) and "mu" in opt_state)):
+        return None
+    import ctypes as C
+    L, per = net.L, arena.per_layer
+    shapes = []
+    for l in range(L):
+        shapes.append(net.w_shapes[l])
+        if per == 2:
+            shapes.append(net.b_shapes[l])
+    lay = _flat.layout(shapes)   # (same offsets as the front of the arena's layout)
+    n = len(shapes)
+    if per == 2:
+        p_ptrs = [a for pair in zip(net.w_ptrs, net.b_ptrs) for a in pair]
+    else:
+        p_ptrs = net.w_ptrs
+    g_base = arena.flat.data_ptr()
+    g_ptrs = [g_base + 4 * o for o in arena.offs[:n]]
+    numel = getattr(lay, "_numel_table", None)
+    if numel is None:
+        numel = (C.c_longlong * n)(*lay.sizes)
+        try:
+            lay._numel_table = numel
+        except AttributeError:
+            pass
+    dev = net.dev
+    stream = net.stream()
+
+    def fresh():
+        flat = torch.empty(lay.total, dtype=torch.float32, device=dev)
+        base = flat.data_ptr()
+        return flat, _lib.ptr_array_from_ints([base + 4 * o for o in lay.offs])
+    new_flat, out_ptrs = fresh()
+    P = _lib.ptr_array_from_ints
+    if spec[0] == "sgd":
+        _lib.check(_lib.lib.jpcb_optim_sgd(n, numel, P(p_ptrs), P(g_ptrs), spec[1], out_ptrs, stream))
+        return lay.carve(new_flat), opt_state
+    mu, nu = opt_state["mu"], opt_state["nu"]
+    if len(mu) != n or len(nu) != n:
+        return None
+    count = opt_state["count"] + 1
+    mo_flat, mo_ptrs = fresh()
+    vo_flat, vo_ptrs = fresh()
+    _lib.check(_lib.lib.jpcb_optim_adam(n, numel, P(p_ptrs), P(g_ptrs), _lib.ptr_array(mu), _lib.ptr_array(nu), spec[1], spec[2],
+                                        spec[3], spec[4], count, out_ptrs, mo_ptrs, vo_ptrs, stream))
+    return lay.carve(new_flat), {"count": count, "mu": lay.carve(mo_flat), "nu": lay.carve(vo_flat)}
+
+
 _GLOBAL_ROWS: dict = {}
 
 
@@ -219,7 +268,7 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     bg = int(batch_global) if batch_global is not None else global_batch(output.shape[0], output.device)
     common = dict(param_type=param_type, loss_id=loss_id, gamma=None, output_energy_scaling=None, activity_decay=activity_decay,
                   weight_decay=weight_decay, spectral_penalty=spectral_penalty, batch_global=bg)
-    t_max, sol, rec_energies, exchanged = 0, None, None, False
+    t_max, sol, rec_energies, exchanged, lead_acts = 0, None, None, False, False
     if input is None and not isinstance(stepsize_controller, (PIDController, ConstantStepSize)):
         raise NotImplementedError(f"unsupported step size controller {stepsize_controller!r}")
     if input is None:
@@ -256,7 +305,9 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         if tuple(output.shape) != (net.B, net.true_dims[-1]):
             raise ValueError(f"output has shape {tuple(output.shape)}, expected {(net.B, net.true_dims[-1])}")
         arena = _Arena(net)
-        acts = net.new_acts()
+        # (the result's leaves carry the reference's leading time axis (1, B, d): made as such when nothing is sliced off)
+        acts = net.new_acts(lead=() if net.padded else (1,))
+        lead_acts = not net.padded
         ws = net.workspace()
         bucketed = world > 1 and net.dev.type == "cuda"
         _lib.check(_lib.lib.jpcb_pc_train_step(
@@ -307,7 +358,9 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     # the skip model has no array leaves), so the fused optimiser kernel is fed without walking the pytrees
     fused = getattr(optim, "fused_apply_flat", None)
     res = None
-    if fused is not None:
+    if not net.padded:
+        res = _fused_param_update(net, arena, optim, opt_state)
+    if res is None and fused is not None:
         p_leaves, g_leaves = [], []
         for l, lin in enumerate(net.linears):
             p_leaves.append(lin.weight)
@@ -331,7 +384,7 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         "opt_state": opt_state,
         "loss": arena.loss,
         "acc": acc,
-        "activities": sol if recording else [a.unsqueeze(0) for a in acts],
+        "activities": sol if recording else (acts if lead_acts else [a.unsqueeze(0) for a in acts]),
         "t_max": t_max,
         "energies": arena.E if rec_energies is None else rec_energies,
         "activity_norms": a_norms,

@@ -79,7 +79,11 @@ int validate(const jpcb_pc_desc* d, int min_layers = 2) {
   for (int l = 0; l < d->n_layers; ++l) {
     if (d->act[l] < 0 || d->act[l] > JPCB_ACT_SILU) return fail(JPCB_EINVAL, "Invalid activation function ID %d at layer %d", d->act[l], l);
     if (d->skip[l] && d->dims[l] != d->dims[l + 1]) return fail(JPCB_EINVAL, "identity skip at layer %d needs equal dims (%d vs %d)", l, d->dims[l], d->dims[l + 1]);
+    if (d->post_act[l] < 0 || d->post_act[l] > JPCB_ACT_SILU) return fail(JPCB_EINVAL, "Invalid activation function ID %d after layer %d", d->post_act[l], l);
+    if (d->post_act[l] != JPCB_ACT_LINEAR && d->free_input) return fail(JPCB_ENOTIMPL, "layers of the form act(W u + b) are not on the unsupervised (free_input) path");
   }
+  if (d->loss == JPCB_LOSS_CE && d->post_act[d->n_layers - 1] != JPCB_ACT_LINEAR)
+    return fail(JPCB_ENOTIMPL, "a cross-entropy output layer of the form act(W u + b) is not on this path (the logits are the layer's output)");
   for (int l = 0; l <= d->n_layers; ++l)
     if ((long long)d->batch_local * d->dims[l] >= (1LL << 31)) return fail(JPCB_ENOTIMPL, "batch_local * dims[%d] must be < 2^31 (32-bit element indices)", l);
   if (d->loss != JPCB_LOSS_MSE && d->loss != JPCB_LOSS_CE) return fail(JPCB_EINVAL, "`mse` and `ce` are the only valid losses.");
@@ -117,10 +121,16 @@ constexpr int RED_SUMSQ = JPCB_MAX_LAYERS + 1;
 // [rows, 3 P(d)] = [hi | mid | lo], P(d) = d rounded up to the 64-wide k-block with zero padding (elementwise.cuh).
 inline int x3_part(const jpcb_pc_desc* d, int dd) { return d->dtype == JPCB_DTYPE_F32X3 ? (dd + 63) / 64 * 64 : dd; }
 inline size_t x3_cw(const jpcb_pc_desc* d, int dd) { return d->dtype == JPCB_DTYPE_F32X3 ? 3 * (size_t)x3_part(d, dd) : (size_t)dd; }
+// any layer of the form post_act(W act(u) + b) with a non-identity post_act (Form B)
+inline bool any_post(const jpcb_pc_desc* d) {
+  for (int l = 0; l < d->n_layers; ++l) if (d->post_act[l] != JPCB_ACT_LINEAR) return true;
+  return false;
+}
 
 struct Ws {
   float* red = nullptr;
-  std::vector<float*> err;   // [L]  err[l]: [Bl, d_{l+1}] fp32 (F32 path)
+  std::vector<float*> err;   // [L]  err[l]: [Bl, d_{l+1}] fp32 (F32 path; tensor-core paths: f32x3, or any Form B layer)
+  std::vector<float*> eff;   // [L]  Form B layers on the fp32 / f32x3 paths: post'(pre_l) . err[l] (GEMM operand, bias gradient)
   float* P1 = nullptr;       // hoisted layer-0 prediction [Bl, d_1]
   float* logits = nullptr;   // cross-entropy output: the output layer's prediction [Bl, d_L]
   std::vector<float*> Zt;    // [L-1] Heun stage state of A[l]
@@ -151,8 +161,14 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
   w->P1 = b.take<float>(Bl * d->dims[1]);
   if (d->loss == JPCB_LOSS_CE) w->logits = b.take<float>(Bl * d->dims[L]);
   const bool tc = d->dtype != JPCB_DTYPE_F32, x3 = d->dtype == JPCB_DTYPE_F32X3, heun = d->solver == JPCB_SOLVER_HEUN;
-  // (the split path keeps fp32 errors too: e_l / skip sources of the gradient epilogue, bias gradients)
-  for (int l = 0; l < L; ++l) w->err[l] = (tc && !x3) ? nullptr : b.take<float>(Bl * d->dims[l + 1]);
+  // (the split path keeps fp32 errors too: e_l / skip sources of the gradient epilogue, bias gradients; so does any
+  //  network with a Form B layer, whose bf16 error copies hold post'(pre) . e instead of e)
+  const bool post = any_post(d);
+  for (int l = 0; l < L; ++l) w->err[l] = (tc && !x3 && !post) ? nullptr : b.take<float>(Bl * d->dims[l + 1]);
+  w->eff.assign(L, nullptr);
+  if (!tc || x3)
+    for (int l = 0; l < L; ++l)
+      if (d->post_act[l] != JPCB_ACT_LINEAR) w->eff[l] = b.take<float>(Bl * d->dims[l + 1]);
   const bool fr = d->free_input != 0;
   if (heun) {
     for (int l = 0; l < L - 1; ++l) {
@@ -366,6 +382,9 @@ struct Run {
   bool tc;
   bool x3 = false;                // JPCB_DTYPE_F32X3: split operand copies, six products per GEMM
   bool fr = false;                // desc->free_input: z_0 is a free activity (unsupervised PC)
+  bool post = false;              // some layer is of the form post_act(W act(u) + b) (Form B)
+  bool hoist = true;              // the layer-0 prediction is constant during inference and kept as P1 (needs an input and a
+                                  // Form A first layer: a Form B one also needs post'(pre_0) for its weight gradient)
   const float* x_stage = nullptr; // free_input: z_0 of the Heun stage state (else the input)
   float* x_out = nullptr;         // free_input: where the next grads() call writes z_0's gradient / new value
 
@@ -381,6 +400,8 @@ struct Run {
     carve(d, wsp, &ws);
     if (!wsp || ws_bytes < ws.bytes) return fail(JPCB_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, ws_bytes);
     fr = d->free_input != 0;
+    post = any_post(d);
+    hoist = !fr && d->post_act[0] == JPCB_ACT_LINEAR;
     x_stage = fr && ws.Zx ? ws.Zx : x;
     return JPCB_OK;
   }
@@ -485,6 +506,7 @@ struct Run {
     split_geom(t, d->dims[l], d->dims[l]);
     t.e.alpha = d->scalings[l];
     t.e.bias = bias(l);
+    t.e.pre_act = d->post_act[l];
   }
 
   // init_activities_with_ffwd (jpc/_core/_init.py:68-80); layer 0 also leaves the hoisted P1
@@ -550,6 +572,7 @@ struct Run {
       t.e.escale = esc_all != 0.f ? esc_all : (l == L - 1 ? d->output_energy_scaling : 1.f);
       t.e.O = ws.err[l];
       set_ob(t, ws.Eb[l]);
+      t.e.Oh = ws.eff[l];  // (Form B, fp32 / f32x3 paths: post'(pre) . e)
       if (energy) t.e.red = ws.red + l;
       ts.push_back(t);
     }
@@ -590,17 +613,19 @@ struct Run {
       GTask t;
       t.e.mode = EPI_GRAD; t.e.sub = sub; t.e.act = d->act[l];
       t.e.M = Bl; t.e.N = d->dims[l]; t.K = d->dims[l + 1];
-      t.a_p = ws.err[l]; t.a_smn = d->dims[l + 1]; t.a_sk = 1;
+      t.a_p = ws.eff[l] ? ws.eff[l] : ws.err[l]; t.a_smn = d->dims[l + 1]; t.a_sk = 1;  // (Form B: post'(pre_l) . err[l] travels through W_l)
       t.b_p = ws.WTf[l]; t.b_smn = d->dims[l + 1]; t.b_sk = 1;  // B(n,k) = W_l[k][n] = WTf_l[n][k]
       t.a_b = ws.Eb[l]; t.b_b = ws.WTb[l];
       split_geom(t, d->dims[l + 1], d->dims[l + 1]);
       t.e.alpha = d->scalings[l];
       t.e.skip = eskip(l);
-      // (split path: the bf16 error copies are 3-part operand copies, not readable as plain bf16 -- fp32 errors instead)
-      t.e.En = ws.err[l]; t.e.Enb = x3 ? nullptr : ws.Eb[l];
+      // (split path: the bf16 error copies are 3-part operand copies, not readable as plain bf16 -- fp32 errors instead;
+      //  Form B: the bf16 copies hold post'(pre) . e, the own-error and skip terms need the raw e)
+      const bool raw32 = x3 || post;
+      t.e.En = ws.err[l]; t.e.Enb = raw32 ? nullptr : ws.Eb[l];
       t.e.Z = Z[l - 1];
       if (l == 1 && p1_hoisted) t.e.P = ws.P1;
-      else { t.e.El = ws.err[l - 1]; t.e.Elb = x3 ? nullptr : ws.Eb[l - 1]; }
+      else { t.e.El = ws.err[l - 1]; t.e.Elb = raw32 ? nullptr : ws.Eb[l - 1]; }
       t.e.c = c; t.e.ad = d->activity_decay; t.e.gscale = 1.f;
       t.e.O = Out[l - 1];
       if (sub == GRAD_HEUN1 || sub == GRAD_HEUN2) t.e.G1 = ws.G1[l - 1];
@@ -655,7 +680,7 @@ struct Run {
     float* const xw = const_cast<float*>(x);  // free_input: z_0 is updated in place like every other activity
     // (a skip at layer 0 enters the feed-forward init but not the energy, _init.py:69-78 vs _energies.py:111-126: then
     //  err[0] = x != 0 at the init and there is no wavefront to exploit)
-    const bool front = !fr && from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !d->skip[0] && !(tc_flags() & 8);
+    const bool front = hoist && !post && from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !d->skip[0] && !(tc_flags() & 8);
     if (front) {
       if (tc) {
         for (int l = (L - 2 - T > 0 ? L - 2 - T : 0); l < L - 1; ++l) {
@@ -668,7 +693,7 @@ struct Run {
     }
     // wide bf16 layers: all T Euler steps as ONE launch of the staged kernel (csrc/tc_staged.cuh: ERR and GRAD tiles of
     // every step in one dependency-tracked stream); anything it is not compiled for falls through to the phase loop
-    if (tc && !x3 && !fr && T >= 1 && d->solver == JPCB_SOLVER_EULER && d->loss == JPCB_LOSS_MSE && d->activity_decay == 0.f && ws.sched) {
+    if (tc && !x3 && hoist && !post && T >= 1 && d->solver == JPCB_SOLVER_EULER && d->loss == JPCB_LOSS_MSE && d->activity_decay == 0.f && ws.sched) {
       std::vector<GTask> es, gs;
       RET(errors(1, A, false, false, nullptr, 0.f, &es));
       RET(grads(GRAD_EULER, d->dt * invB, A, nullptr, A, false, true, 1, nullptr, 0.f, 0.f, &gs));
@@ -680,19 +705,19 @@ struct Run {
       const float c = h * invB;
       if (d->solver == JPCB_SOLVER_EULER) {
         const int lo = front ? (L - 1 - s > 1 ? L - 1 - s : 1) : 1;
-        RET(errors(fr ? 0 : lo, A, false, false));
+        RET(errors(hoist ? lo : 0, A, false, false));
         x_out = fr ? xw : nullptr;
-        RET(grads(GRAD_EULER, c, A, nullptr, A, false, !fr, lo));
+        RET(grads(GRAD_EULER, c, A, nullptr, A, false, hoist, lo));
         if (d->activity_decay != 0.f) RET(scale_inplace(A[L - 1], n_dummy, 1.f - c * d->activity_decay));
       } else {
         std::vector<float*> zt(ws.Zt.begin(), ws.Zt.begin() + (L - 1));
         zt.push_back(A[L - 1]);  // dummy slot is never read by the error tasks
-        RET(errors(fr ? 0 : 1, A, false, false));
+        RET(errors(hoist ? 1 : 0, A, false, false));
         x_out = fr ? ws.Zx : nullptr;
-        RET(grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, !fr));
-        RET(errors(fr ? 0 : 1, zt.data(), true, false));
+        RET(grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, hoist));
+        RET(errors(hoist ? 1 : 0, zt.data(), true, false));
         x_out = fr ? xw : nullptr;
-        RET(grads(GRAD_HEUN2, c, zt.data(), A, A, false, !fr));
+        RET(grads(GRAD_HEUN2, c, zt.data(), A, A, false, hoist));
         if (d->activity_decay != 0.f) {
           const float q = c * d->activity_decay;
           RET(scale_inplace(A[L - 1], n_dummy, 1.f - q + 0.5f * q * q));
@@ -712,7 +737,7 @@ struct Run {
       GTask t;
       t.e.mode = EPI_SCALE;
       t.e.M = d->dims[l + 1]; t.e.N = d->dims[l]; t.K = Bl;
-      t.a_p = ws.err[l]; t.a_smn = 1; t.a_sk = d->dims[l + 1];
+      t.a_p = ws.eff[l] ? ws.eff[l] : ws.err[l]; t.a_smn = 1; t.a_sk = d->dims[l + 1];  // (Form B: post'(pre_l) . err[l])
       t.b_p = l == 0 ? (ws.Hf[0] ? ws.Hf[0] : x) : ws.Hf[l]; t.b_smn = 1; t.b_sk = d->dims[l];  // act already applied
       (void)S;
       t.a_b = ws.Eb[l]; t.b_b = ws.Hb[l]; t.mn_major = tc;
@@ -728,7 +753,7 @@ struct Run {
         const int N = d->dims[l + 1];
         const float sc = -d->scalings[l] * invB;
         if (tc && !x3) colsum_kernel<bf16><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.Eb[l], gb[l], Bl, N, sc);
-        else colsum_kernel<float><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.err[l], gb[l], Bl, N, sc);
+        else colsum_kernel<float><<<(N + 31) / 32, dim3(32, 8), 0, st>>>(ws.eff[l] ? ws.eff[l] : ws.err[l], gb[l], Bl, N, sc);
         count_launch();
       }
       CK(cudaGetLastError());
@@ -785,7 +810,7 @@ size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc) {
   return w.bytes;
 }
 
-int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, float* const* A_out,
+static int pc_ffwd_init_impl(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, float* const* A_out,
                       const float* y, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (desc && desc->free_input) return fail(JPCB_EINVAL, "init_activities_with_ffwd needs an input (free_input is set)");
   Run r;
@@ -800,7 +825,7 @@ int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const flo
   return JPCB_OK;
 }
 
-int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A, const float* x,
+static int pc_energy_impl(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A, const float* x,
                    const float* y, float* E_layers, void* workspace, size_t workspace_bytes, void* stream) {
   RET(split_free(desc, x, A));
   Run r;
@@ -813,7 +838,7 @@ int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float*
   return r.finalize(E_layers, nullptr, false, nullptr);
 }
 
-int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
+static int pc_activity_grad_impl(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
                           const float* x, const float* y, float* F, float* const* gA, void* workspace, size_t workspace_bytes,
                           void* stream) {
   if (!gA) return fail(JPCB_EINVAL, "null activities / target / output");
@@ -840,7 +865,7 @@ int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const
   return JPCB_OK;
 }
 
-int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, float* const* A, const float* x,
+static int pc_infer_impl(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, float* const* A, const float* x,
                   const float* y, float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
   RET(split_free(desc, x, A));
   Run r;
@@ -848,7 +873,7 @@ int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* 
   if (!A || !y) return fail(JPCB_EINVAL, "null activities / target");
   RET(r.prep_weights());
   RET(r.prep_inputs(A));
-  if (!r.fr) RET(r.predict_p1());
+  if (r.hoist) RET(r.predict_p1());
   RET(r.infer_loop(A));
   if (sumsq_out) {
     CK(cudaMemsetAsync(sumsq_out, 0, 2 * sizeof(float), r.st));
@@ -876,17 +901,17 @@ int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const fl
   CK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), r.st));
   RET(r.prep_weights());
   RET(r.prep_inputs(A));
-  const bool fr = r.fr;
-  if (!fr) RET(r.predict_p1());
+  const bool fr = r.fr, hoist = r.hoist;
+  if (hoist) RET(r.predict_p1());
   const float c = dt * r.invB;
   std::vector<float*> zt(r.ws.Zt.begin(), r.ws.Zt.begin() + (L - 1));
   zt.push_back(A_new[L - 1]);  // dummy slot is never read by the error tasks
-  RET(r.errors(fr ? 0 : 1, A, false, false));
+  RET(r.errors(hoist ? 1 : 0, A, false, false));
   r.x_out = fr ? r.ws.Zx : nullptr;
-  RET(r.grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, !fr));
-  RET(r.errors(fr ? 0 : 1, zt.data(), true, false));
+  RET(r.grads(GRAD_HEUN1, c, A, nullptr, zt.data(), true, hoist));
+  RET(r.errors(hoist ? 1 : 0, zt.data(), true, false));
   r.x_out = x_new;
-  RET(r.grads(GRAD_HEUN2, c, zt.data(), A, A_new, false, !fr, 1, out2, rtol, atol));
+  RET(r.grads(GRAD_HEUN2, c, zt.data(), A, A_new, false, hoist, 1, out2, rtol, atol));
   const size_t n_dummy = (size_t)r.Bl * desc->dims[L];
   if (desc->activity_decay != 0.f) {  // the dummy slot decays like every other entry of the list
     heun_dummy_kernel<<<ew_grid(n_dummy, 256), 256, 0, r.st>>>(A[L - 1], A_new[L - 1], n_dummy, c * desc->activity_decay, rtol, atol, out2);
@@ -899,7 +924,7 @@ int jpcb_pc_heun_trial(const jpcb_pc_desc* desc, const float* const* W, const fl
   return JPCB_OK;
 }
 
-int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
+static int pc_param_grads_impl(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
                         const float* x, const float* y, float* const* gW, float* const* gb, float* E_layers, void* workspace,
                         size_t workspace_bytes, void* stream) {
   RET(split_free(desc, x, A));
@@ -921,6 +946,7 @@ int jpcb_hpc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const 
   if (!U || !T || !U[0]) return fail(JPCB_EINVAL, "null layer input / target lists");
   if (desc) {
     if (desc->free_input || desc->loss != JPCB_LOSS_MSE) return fail(JPCB_EINVAL, "layer-wise regression: mse, with an input");
+    if (desc->n_layers >= 1 && desc->n_layers <= JPCB_MAX_LAYERS && any_post(desc)) return fail(JPCB_ENOTIMPL, "layer-wise regression: layers of the form act(W u + b) are not on this path");
     for (int l = 0; l < desc->n_layers && l < JPCB_MAX_LAYERS; ++l)
       if (desc->skip[l] || desc->scalings[l] != 1.f) return fail(JPCB_EINVAL, "layer-wise regression: no skips, unit scalings (layer %d)", l);
   }
@@ -986,6 +1012,7 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
   if (!E || !y) return fail(JPCB_EINVAL, "null errors / target");
   if (desc->activity_decay != 0.f || desc->output_energy_scaling != 1.f)
     return fail(JPCB_EINVAL, "epc_energy_fn has no activity decay / output energy scaling");
+  if (r.post) return fail(JPCB_ENOTIMPL, "ePC: layers of the form act(W u + b) are not on this path");
   EpcWs X;
   carve_epc(desc, workspace, r.ws.bytes, &X);
   if (workspace_bytes < X.bytes) return fail(JPCB_EWORKSPACE, "workspace too small: need %zu bytes (jpcb_epc_workspace_bytes), got %zu", X.bytes, workspace_bytes);
@@ -1102,7 +1129,7 @@ int jpcb_epc_grads(const jpcb_pc_desc* desc, const float* const* W, const float*
   return JPCB_OK;
 }
 
-int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, const float* y,
+static int pc_train_step_impl(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, const float* y,
                        float* const* A_out, float* loss_out, float* E_layers, float* const* gW, float* const* gb, void* workspace,
                        size_t workspace_bytes, void* stream) {
   if (desc && desc->free_input)
@@ -1114,10 +1141,10 @@ int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const fl
   RET(r.zero_red());
   RET(r.prep_weights());
   RET(r.prep_inputs(nullptr));
-  RET(r.ffwd(A_out, r.ws.red + RED_LOSS, true));   // init + loss at the init + hoisted P1 + bf16 operands
+  RET(r.ffwd(A_out, r.ws.red + RED_LOSS, r.hoist));   // init + loss at the init + hoisted P1 + bf16 operands
   RET(r.infer_loop(A_out, true));
-  RET(r.errors(1, A_out, false, true));           // errors + layer energies at the solution
-  RET(r.error0_from_p1(A_out, true));
+  RET(r.errors(r.hoist ? 1 : 0, A_out, false, true));  // errors + layer energies at the solution
+  if (r.hoist) RET(r.error0_from_p1(A_out, true));
   if (gW) RET(r.wgrads(A_out, gW, gb));           // (NULL: the caller follows up with jpcb_pc_param_grads_range)
   return r.finalize(E_layers, nullptr, false, loss_out);
 }
@@ -1130,6 +1157,93 @@ int jpcb_pc_param_grads_range(const jpcb_pc_desc* desc, const float* const* W, c
   if (!gW) return fail(JPCB_EINVAL, "null gradient list");
   if (layer_lo < 0 || layer_hi > r.L || layer_lo >= layer_hi) return fail(JPCB_EINVAL, "bad layer range [%d, %d) of %d layers", layer_lo, layer_hi, r.L);
   return r.wgrads(nullptr, gW, gb, layer_lo, layer_hi);
+}
+
+
+// ---- planned entry points: identical calls are captured into a CUDA graph once and replayed (plan.cu) ----
+namespace {
+// list length to key on; < 0: the descriptor is unusable and the body reports why
+inline int key_layers(const jpcb_pc_desc* d, int min_layers) {
+  return (d && d->n_layers >= min_layers && d->n_layers <= JPCB_MAX_LAYERS) ? d->n_layers : -1;
+}
+inline void key_net(PlanKey& k, const jpcb_pc_desc* d, const float* const* W, const float* const* b, const void* ws, size_t ws_bytes) {
+  k.bytes(d, sizeof(*d));
+  k.list(W, d->n_layers);
+  k.list(d->has_bias ? b : nullptr, d->n_layers);
+  k.ptr(ws);
+  k.word(ws_bytes);
+}
+}  // namespace
+
+int jpcb_pc_ffwd_init(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, float* const* A_out,
+                      const float* y, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+  auto body = [&](void* s) { return pc_ffwd_init_impl(desc, W, b, x, A_out, y, loss_out, workspace, workspace_bytes, s); };
+  const int L = key_layers(desc, 1);
+  if (L < 0 || !W || !A_out) return body(stream);
+  PlanKey k(0x7001);
+  key_net(k, desc, W, b, workspace, workspace_bytes);
+  k.ptr(x); k.list(A_out, L); k.ptr(y); k.ptr(loss_out);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_pc_energy(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A, const float* x,
+                   const float* y, float* E_layers, void* workspace, size_t workspace_bytes, void* stream) {
+  auto body = [&](void* s) { return pc_energy_impl(desc, W, b, A, x, y, E_layers, workspace, workspace_bytes, s); };
+  const int L = key_layers(desc, 2);
+  if (L < 0 || !W || !A) return body(stream);
+  PlanKey k(0x7002);
+  key_net(k, desc, W, b, workspace, workspace_bytes);
+  k.list(A, L + (desc->free_input ? 1 : 0)); k.ptr(x); k.ptr(y); k.ptr(E_layers);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_pc_activity_grad(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
+                          const float* x, const float* y, float* F, float* const* gA, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  auto body = [&](void* s) { return pc_activity_grad_impl(desc, W, b, A, x, y, F, gA, workspace, workspace_bytes, s); };
+  const int L = key_layers(desc, 2);
+  if (L < 0 || !W || !A || !gA) return body(stream);
+  PlanKey k(0x7003);
+  key_net(k, desc, W, b, workspace, workspace_bytes);
+  const int n = L + (desc->free_input ? 1 : 0);
+  k.list(A, n); k.ptr(x); k.ptr(y); k.ptr(F); k.list(gA, n);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_pc_infer(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, float* const* A, const float* x,
+                  const float* y, float* sumsq_out, void* workspace, size_t workspace_bytes, void* stream) {
+  auto body = [&](void* s) { return pc_infer_impl(desc, W, b, A, x, y, sumsq_out, workspace, workspace_bytes, s); };
+  const int L = key_layers(desc, 2);
+  // (sumsq_out: the call copies a host scalar to the device -- not capturable)
+  if (L < 0 || !W || !A || sumsq_out) return body(stream);
+  PlanKey k(0x7004);
+  key_net(k, desc, W, b, workspace, workspace_bytes);
+  k.list(A, L + (desc->free_input ? 1 : 0)); k.ptr(x); k.ptr(y);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_pc_param_grads(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* const* A,
+                        const float* x, const float* y, float* const* gW, float* const* gb, float* E_layers, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  auto body = [&](void* s) { return pc_param_grads_impl(desc, W, b, A, x, y, gW, gb, E_layers, workspace, workspace_bytes, s); };
+  const int L = key_layers(desc, 2);
+  if (L < 0 || !W || !A || !gW) return body(stream);
+  PlanKey k(0x7005);
+  key_net(k, desc, W, b, workspace, workspace_bytes);
+  k.list(A, L + (desc->free_input ? 1 : 0)); k.ptr(x); k.ptr(y); k.list(gW, L); k.list(desc->has_bias ? gb : nullptr, L); k.ptr(E_layers);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_pc_train_step(const jpcb_pc_desc* desc, const float* const* W, const float* const* b, const float* x, const float* y,
+                       float* const* A_out, float* loss_out, float* E_layers, float* const* gW, float* const* gb, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  auto body = [&](void* s) { return pc_train_step_impl(desc, W, b, x, y, A_out, loss_out, E_layers, gW, gb, workspace, workspace_bytes, s); };
+  const int L = key_layers(desc, 2);
+  if (L < 0 || !W || !A_out) return body(stream);
+  PlanKey k(0x7006);
+  key_net(k, desc, W, b, workspace, workspace_bytes);
+  k.ptr(x); k.ptr(y); k.list(A_out, L); k.ptr(loss_out); k.ptr(E_layers); k.list(gW, L); k.list((desc->has_bias && gW) ? gb : nullptr, L);
+  return plan_run(k, stream, body);
 }
 
 }  // extern "C"

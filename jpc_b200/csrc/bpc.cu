@@ -81,6 +81,8 @@ int validate_bpc(const jpcb_bpc_desc* d) {
   if (t.solver != JPCB_SOLVER_EULER) return fail(JPCB_ENOTIMPL, "bPC inference is Euler (update_bpc_activities with optax.sgd); Heun is not on this path");
   if (t.n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", t.n_steps);
   if (t.activity_decay != 0.f) return fail(JPCB_EINVAL, "bpc_energy_fn has no activity_decay");
+  for (int l = 0; l < t.n_layers; ++l)
+    if (t.post_act[l] != JPCB_ACT_LINEAR) return fail(JPCB_ENOTIMPL, "bPC: layers of the form act(W u + b) are not on this path");
   return JPCB_OK;
 }
 
@@ -377,7 +379,7 @@ size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc) {
   return r.bytes;
 }
 
-int jpcb_bpc_energy(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+static int bpc_energy_impl(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
                     const float* const* bV, const float* const* A, const float* x, const float* y, float* E_pairs, void* workspace,
                     size_t workspace_bytes, void* stream) {
   BpcRun r;
@@ -389,7 +391,7 @@ int jpcb_bpc_energy(const jpcb_bpc_desc* desc, const float* const* W, const floa
   return r.finalize(E_pairs, nullptr);
 }
 
-int jpcb_bpc_activity_grad(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+static int bpc_activity_grad_impl(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
                            const float* const* bV, const float* const* A, const float* x, const float* y, float* F, float* const* gA,
                            void* workspace, size_t workspace_bytes, void* stream) {
   BpcRun r;
@@ -404,7 +406,7 @@ int jpcb_bpc_activity_grad(const jpcb_bpc_desc* desc, const float* const* W, con
   return JPCB_OK;
 }
 
-int jpcb_bpc_infer(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+static int bpc_infer_impl(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
                    const float* const* bV, float* const* A, const float* x, const float* y, void* workspace, size_t workspace_bytes,
                    void* stream) {
   BpcRun r;
@@ -421,7 +423,7 @@ int jpcb_bpc_infer(const jpcb_bpc_desc* desc, const float* const* W, const float
   return JPCB_OK;
 }
 
-int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+static int bpc_param_grads_impl(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
                          const float* const* bV, const float* const* A, const float* x, const float* y, float* const* gW,
                          float* const* gbW, float* const* gV, float* const* gbV, float* E_pairs, void* workspace, size_t workspace_bytes,
                          void* stream) {
@@ -472,6 +474,63 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
   CK(cudaGetLastError());
   if (E_pairs) RET(r.finalize(E_pairs, nullptr));
   return JPCB_OK;
+}
+
+
+// ---- planned entry points: identical calls are captured into a CUDA graph once and replayed (plan.cu) ----
+namespace {
+inline bool key_bpc(PlanKey& k, const jpcb_bpc_desc* d, const float* const* W, const float* const* bW, const float* const* V,
+                    const float* const* bV, const float* const* A, const float* x, const float* y, const void* ws, size_t ws_bytes) {
+  if (!d || d->td.n_layers < 2 || d->td.n_layers > JPCB_MAX_LAYERS || !W || !V || !A) return false;
+  const int n = d->td.n_layers;
+  k.bytes(d, sizeof(*d));
+  k.list(W, n); k.list(d->td.has_bias ? bW : nullptr, n); k.list(V, n); k.list(d->bu_has_bias ? bV : nullptr, n);
+  k.list(A, n); k.ptr(x); k.ptr(y); k.ptr(ws); k.word(ws_bytes);
+  return true;
+}
+}  // namespace
+
+int jpcb_bpc_energy(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                    const float* const* bV, const float* const* A, const float* x, const float* y, float* E_pairs, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  auto body = [&](void* s) { return bpc_energy_impl(desc, W, bW, V, bV, A, x, y, E_pairs, workspace, workspace_bytes, s); };
+  PlanKey k(0x7101);
+  if (!key_bpc(k, desc, W, bW, V, bV, A, x, y, workspace, workspace_bytes)) return body(stream);
+  k.ptr(E_pairs);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_bpc_activity_grad(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                           const float* const* bV, const float* const* A, const float* x, const float* y, float* F, float* const* gA,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  auto body = [&](void* s) { return bpc_activity_grad_impl(desc, W, bW, V, bV, A, x, y, F, gA, workspace, workspace_bytes, s); };
+  PlanKey k(0x7102);
+  if (!gA || !key_bpc(k, desc, W, bW, V, bV, A, x, y, workspace, workspace_bytes)) return body(stream);
+  k.ptr(F); k.list(gA, desc->td.n_layers);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_bpc_infer(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                   const float* const* bV, float* const* A, const float* x, const float* y, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  auto body = [&](void* s) { return bpc_infer_impl(desc, W, bW, V, bV, A, x, y, workspace, workspace_bytes, s); };
+  PlanKey k(0x7103);
+  if (!key_bpc(k, desc, W, bW, V, bV, A, x, y, workspace, workspace_bytes)) return body(stream);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                         const float* const* bV, const float* const* A, const float* x, const float* y, float* const* gW,
+                         float* const* gbW, float* const* gV, float* const* gbV, float* E_pairs, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  auto body = [&](void* s) {
+    return bpc_param_grads_impl(desc, W, bW, V, bV, A, x, y, gW, gbW, gV, gbV, E_pairs, workspace, workspace_bytes, s);
+  };
+  PlanKey k(0x7104);
+  if (!gW || !gV || !key_bpc(k, desc, W, bW, V, bV, A, x, y, workspace, workspace_bytes)) return body(stream);
+  const int n = desc->td.n_layers;
+  k.list(gW, n); k.list(desc->td.has_bias ? gbW : nullptr, n); k.list(gV, n); k.list(desc->bu_has_bias ? gbV : nullptr, n); k.ptr(E_pairs);
+  return plan_run(k, stream, body);
 }
 
 }  // extern "C"

@@ -88,6 +88,10 @@ struct Epi {
   int act;    // activation id: act'(z) in GRAD, act(out) for the bf16 operand copy `Ob`
   int M, N;
   int accum;  // SCALE: out += a*D instead of =
+  int pre_act;  // FFWD / ERR: activation applied to (D + b) before the scaling -- layers of the form act(W u + b) (Form B);
+                // ERR then writes the RAW error to O and act'(D + b) * error to the operand copies Ob / Oh.  0 = none.
+                // Honoured by the generic (descriptor-driven) instantiation only: the host never routes such a task to a
+                // specialised variant.
   // `Ob` as a 3-way split copy (fp32-parity tensor-core path): v = hi + mid + lo in bf16, stored at
   // Ob[row * ob_ld + p * ob_part + col], p = 0, 1, 2.  ob_part == 0: plain bf16 copy with row pitch N.
   int ob_ld, ob_part;
@@ -125,7 +129,7 @@ struct Epi {
 // of the epilogue's load stream would wait for every load in flight.
 __device__ __forceinline__ Epi epi_pin(const Epi& src) {
   Epi e = src;
-  asm volatile("" : "+r"(e.mode), "+r"(e.sub), "+r"(e.act), "+r"(e.M), "+r"(e.N), "+r"(e.accum), "+r"(e.ob_ld), "+r"(e.ob_part));
+  asm volatile("" : "+r"(e.mode), "+r"(e.sub), "+r"(e.act), "+r"(e.M), "+r"(e.N), "+r"(e.accum), "+r"(e.pre_act), "+r"(e.ob_ld), "+r"(e.ob_part));
   asm volatile("" : "+f"(e.alpha), "+f"(e.skip), "+f"(e.escale), "+f"(e.c), "+f"(e.ad), "+f"(e.gscale), "+f"(e.tol_r), "+f"(e.tol_a));
   asm volatile("" : "+l"(e.bias), "+l"(e.T), "+l"(e.U), "+l"(e.Z), "+l"(e.Z0), "+l"(e.El), "+l"(e.Elb), "+l"(e.P));
   asm volatile("" : "+l"(e.En), "+l"(e.Enb), "+l"(e.Gin), "+l"(e.G1), "+l"(e.O), "+l"(e.O2), "+l"(e.Ob), "+l"(e.Oh), "+l"(e.red), "+l"(e.Y));
@@ -279,13 +283,20 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
   }
   if (mode == EPI_FFWD || mode == EPI_ERR) {
     float pred[4];
+    const int pre_act = MODE < 0 ? e.pre_act : 0;  // (compiled into the generic instantiation only)
+    float dpre[4] = {1.f, 1.f, 1.f, 1.f};          // post'(pre) of a Form B layer
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (PLAIN) {
         pred[j] = e.alpha * acc[j];
       } else {
         float bj = have_bias4 ? bias4[j] : ((e.bias != nullptr && j < nvalid) ? e.bias[col + j] : 0.f);
-        pred[j] = e.alpha * (acc[j] + bj);
+        float pre = acc[j] + bj;
+        if (MODE < 0 && pre_act != ACT_LINEAR) {
+          if (mode == EPI_ERR) dpre[j] = act_bwd<FAST>(pre_act, pre);
+          pre = act_fwd<FAST>(pre_act, pre);
+        }
+        pred[j] = e.alpha * pre;
       }
     }
     if (!PLAIN && e.skip != 0.f) {
@@ -320,12 +331,17 @@ __device__ __forceinline__ float epi_finish(const Epi& e, int row, int col, cons
         out[j] = PLAIN ? d : e.escale * d;
       }
       if (e.O) st4(e.O, idx, nvalid, vec, out);
-      if (e.Ob) st_ob<SPLIT>(e, row, col, idx, nvalid, vec, out);
       if (e.red) {  // layer energy (lam/2) sum d^2 -- only the launches that report energies pay for it
         const float half = PLAIN ? 0.5f : (e.escale != 0.f ? 0.5f / e.escale : 0.f);  // out = lam d  =>  lam/2 d^2 = out^2 / (2 lam)
 #pragma unroll
         for (int j = 0; j < 4; ++j) r += half * out[j] * out[j];
       }
+      if (MODE < 0 && pre_act != ACT_LINEAR) {  // Form B: the operand copies carry post'(pre) . e (what travels through W)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] *= dpre[j];
+        if (e.Oh) st4(e.Oh, idx, nvalid, vec, out);
+      }
+      if (e.Ob) st_ob<SPLIT>(e, row, col, idx, nvalid, vec, out);
     }
     return r;
   }

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "../../include/jpc_b200.h"
@@ -58,5 +59,23 @@ int launch_simt(const std::vector<GTask>& tasks, cudaStream_t st);
 constexpr int JPCB_SOLVE_NA = -1;
 int launch_tc_solve(const std::vector<GTask>& errs, const std::vector<GTask>& grads, int nsteps, float c_last, bool wave,
                     int* counters, size_t counter_ints, cudaStream_t st);
+
+
+// ---- launch plans (plan.cu): a call whose key (entry point, descriptor, every pointer argument, workspace, stream, device)
+// has been seen `min_calls` times is captured into a CUDA graph once and replayed from then on ----
+struct PlanKey {
+  std::vector<uint64_t> w;
+  explicit PlanKey(uint64_t entry_id) { w.reserve(640); w.push_back(entry_id); }
+  void word(uint64_t v) { w.push_back(v); }
+  void ptr(const void* p) { w.push_back(reinterpret_cast<uint64_t>(p)); }
+  void bytes(const void* p, size_t n);
+  template <typename T>
+  void list(T* const* l, int n) {  // host array of device pointers (nullable)
+    w.push_back(l ? (uint64_t)n : ~0ull);
+    if (l) for (int i = 0; i < n; ++i) w.push_back(reinterpret_cast<uint64_t>(l[i]));
+  }
+};
+// `body(stream)` enqueues the call's kernel sequence on the stream it is given
+int plan_run(PlanKey& key, void* stream, const std::function<int(void*)>& body);
 
 }  // namespace jpcb

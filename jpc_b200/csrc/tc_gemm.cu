@@ -162,6 +162,7 @@ int variant_key(const GTask& t) {
   const Epi& e = t.e;
   if (t.mn_major) return 11;  // (only the weight-gradient SCALE tasks use MN-major operands)
   if (tc_flags() & 4) return 0;
+  if (e.pre_act != ACT_LINEAR) return 0;  // Form B layers: descriptor-driven epilogue
   const bool noextra = e.skip == 0.f && e.bias == nullptr && e.escale == 1.f && e.ad == 0.f;
   const bool plain = noextra && e.Gin == nullptr && e.gscale == 1.f;
   if (e.mode == EPI_SCALE) return 2;

@@ -240,8 +240,50 @@ def _unflatten(tree, it):
     return tree  # Identity / Activation / other callables: no leaves
 
 
+def _relinear(lin: Linear, weight, bias) -> Linear:
+    new = Linear.__new__(Linear)
+    d = dict(lin.__dict__)
+    d["weight"], d["bias"] = weight, bias
+    new.__dict__ = d
+    return new
+
+
+def _unflatten_mlp(model, leaves, i):
+    """Fast path of `_unflatten` for a list of Sequential([Lambda, Linear]) layers (jpc.make_mlp models): runs once per
+    train step over every layer.  Returns (new model, next leaf index) or None when the structure is anything else."""
+    out = []
+    for layer in model:
+        if type(layer) is not Sequential:
+            return None
+        subs = layer.layers
+        if len(subs) != 2 or type(subs[0]) is not Lambda or type(subs[1]) is not Linear:
+            return None
+        lin = subs[1]
+        if lin.bias is None:
+            new_lin = _relinear(lin, leaves[i], None)
+            i += 1
+        else:
+            new_lin = _relinear(lin, leaves[i], leaves[i + 1])
+            i += 2
+        seq = Sequential.__new__(Sequential)
+        seq.layers = (subs[0], new_lin)
+        out.append(seq)
+    return out, i
+
+
 def tree_unflatten_like(tree, leaves):
     """Rebuilds `tree`'s structure around new leaves (taken front to back)."""
+    if type(tree) is tuple and len(tree) == 2 and type(tree[0]) is list and isinstance(leaves, list):
+        # (model, skip_model): the make_mlp form with a leaf-free skip model (None / Lambda(Identity) entries)
+        sk = tree[1]
+        if sk is None or (type(sk) is list and all(e is None or type(e) is Lambda for e in sk)):
+            got = _unflatten_mlp(tree[0], leaves, 0)
+            if got is not None and got[1] == len(leaves):
+                return got[0], (None if sk is None else list(sk))
+    elif type(tree) is list and isinstance(leaves, list):
+        got = _unflatten_mlp(tree, leaves, 0)
+        if got is not None and got[1] == len(leaves):
+            return got[0]
     return _unflatten(tree, iter(leaves))
 
 

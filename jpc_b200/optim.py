@@ -15,6 +15,7 @@ from typing import NamedTuple
 
 import torch
 
+from . import _flat
 from .nn import tree_leaves, tree_unflatten_like
 
 
@@ -24,6 +25,8 @@ class GradientTransformation(NamedTuple):
     fused_apply: callable = None  # (params_tree, grads_tree, state) -> (new_params_tree, new_state), or None
     fused_apply_flat: callable = None  # the same on flat leaf lists: (p_leaves, g_leaves, state) -> (new_leaves, new_state) | None
     sgd_learning_rate: float = None    # set by sgd(): lets PCTrainer put the (stateless) update inside its CUDA graph
+    fused_spec: tuple = None           # ("sgd", lr) | ("adam", lr, b1, b2, eps): lets make_pc_step feed the update kernel from
+                                       # addresses it already holds (no per-leaf checks / views), see _train._fused_param_update
 
 
 def _fusable(leaves) -> bool:
@@ -49,7 +52,7 @@ def sgd(learning_rate: float) -> GradientTransformation:
         from . import _lib
         if len(p) != len(g) or not _fusable(p + g):
             return None
-        out = [torch.empty_like(t) for t in p]
+        out = _flat.empty_like_list(p)
         _lib.check(_lib.lib.jpcb_optim_sgd(len(p), _tables(p), _lib.ptr_array(p), _lib.ptr_array(g), float(learning_rate),
                                            _lib.ptr_array(out), torch.cuda.current_stream(p[0].device).cuda_stream))
         return out, state
@@ -57,7 +60,7 @@ def sgd(learning_rate: float) -> GradientTransformation:
     def fused_apply(params, grads, state):
         res = fused_flat(tree_leaves(params), tree_leaves(grads), state)
         return None if res is None else (tree_unflatten_like(params, res[0]), res[1])
-    return GradientTransformation(init, update, fused_apply, fused_flat, float(learning_rate))
+    return GradientTransformation(init, update, fused_apply, fused_flat, float(learning_rate), ("sgd", float(learning_rate)))
 
 
 def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> GradientTransformation:
@@ -87,7 +90,7 @@ def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 
         if not (len(p) == len(g) == len(mu) == len(nu)) or not _fusable(p + g + list(mu) + list(nu)):
             return None
         count = state["count"] + 1
-        out, mo, vo = ([torch.empty_like(t) for t in p] for _ in range(3))
+        out, mo, vo = (_flat.empty_like_list(p) for _ in range(3))
         _lib.check(_lib.lib.jpcb_optim_adam(len(p), _tables(p), _lib.ptr_array(p), _lib.ptr_array(g), _lib.ptr_array(mu),
                                             _lib.ptr_array(nu), float(learning_rate), float(b1), float(b2), float(eps), count,
                                             _lib.ptr_array(out), _lib.ptr_array(mo), _lib.ptr_array(vo),
@@ -97,7 +100,8 @@ def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 
     def fused_apply(params, grads, state):
         res = fused_flat(tree_leaves(params), tree_leaves(grads), state)
         return None if res is None else (tree_unflatten_like(params, res[0]), res[1])
-    return GradientTransformation(init, update, fused_apply, fused_flat)
+    return GradientTransformation(init, update, fused_apply, fused_flat, None,
+                                  ("adam", float(learning_rate), float(b1), float(b2), float(eps)))
 
 
 def apply_updates(model, updates):

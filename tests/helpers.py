@@ -33,14 +33,21 @@ def to_gpu_model(omodel, device="cuda"):
         lin.bias = None if layer["b"] is None else layer["b"].to(torch.float32).contiguous().to(device)
         lin.out_features, lin.in_features = layer["W"].shape
         lin.use_bias = layer["b"] is not None
-        layers.append(nn.Sequential([nn.Lambda(nn.get_act_fn(layer["act"])), lin]))
+        post = layer.get("post")
+        if post and post != "linear":   # Form B: Sequential([Linear, Lambda(act)]) -- or [Lambda, Linear, Lambda] with an input act too
+            pre = [] if layer["act"] == "linear" else [nn.Lambda(nn.get_act_fn(layer["act"]))]
+            layers.append(nn.Sequential(pre + [lin, nn.Lambda(nn.get_act_fn(post))]))
+        elif layer.get("bare"):
+            layers.append(lin)
+        else:
+            layers.append(nn.Sequential([nn.Lambda(nn.get_act_fn(layer["act"])), lin]))
     return layers
 
 
 def f32_model(omodel):
     """The oracle model with weights rounded to fp32 (what the device actually holds), in fp64."""
-    return [{"W": l["W"].float().double(), "b": None if l["b"] is None else l["b"].float().double(), "act": l["act"]}
-            for l in omodel]
+    return [{"W": l["W"].float().double(), "b": None if l["b"] is None else l["b"].float().double(), "act": l["act"],
+             "post": l.get("post"), "bare": l.get("bare")} for l in omodel]
 
 
 def dev(t, device="cuda"):

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/jpc_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in jpc_b200/_lib.py"
-    assert _lib.lib.jpcb_version() == 100
+    assert _lib.lib.jpcb_version() == 101
 
 
 def _desc(dtype=0, dims=(10, 20, 20, 5), B=4):

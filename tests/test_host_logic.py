@@ -1,0 +1,54 @@
+"""Host-side bookkeeping that runs every train step (no GPU needed): flat buffers carved into views, the make_mlp fast
+path of the model rebuild, pointer tables."""
+import torch
+
+from jpc_b200 import _flat, _lib, nn
+
+
+def test_flat_layout_views_are_contiguous_disjoint_and_aligned():
+    shapes = []
+    for s in [(128, 784)] + [(128, 128)] * 5 + [(10, 128)]:
+        shapes += [s, (s[0],)]          # interleaved weights / biases: runs of equal shapes at a constant spacing
+    shapes += [(7,), ()]
+    lay = _flat.layout(shapes)
+    assert _flat.layout(shapes) is lay   # cached per shape list
+    flat = torch.zeros(lay.total)
+    views = lay.carve(flat)
+    assert len(lay.runs) < len(shapes)   # (fewer as_strided calls than tensors)
+    for i, (v, s) in enumerate(zip(views, shapes)):
+        assert tuple(v.shape) == tuple(s) and v.is_contiguous()
+        assert v.data_ptr() == flat.data_ptr() + 4 * lay.offs[i] and lay.offs[i] % _flat.ALIGN == 0
+        v.add_(1.0)
+    assert float(flat.sum()) == sum(lay.sizes)   # every element of every view touched exactly once: no overlap
+    lead = _flat.layout([(4, 8)] * 3 + [(4, 2)]).carve(torch.zeros(4096), lead=(1,))
+    assert [tuple(v.shape) for v in lead] == [(1, 4, 8)] * 3 + [(1, 4, 2)] and all(v.is_contiguous() for v in lead)
+    outs = _flat.empty_like_list([torch.zeros(3, 5), torch.zeros(5), torch.zeros(3, 5)])
+    assert [tuple(o.shape) for o in outs] == [(3, 5), (5,), (3, 5)]
+
+
+def test_model_rebuild_fast_path_equals_the_generic_walk():
+    for bias in (False, True):
+        model = nn.make_mlp(0, 6, 8, 4, 3, "tanh", use_bias=bias, device="cpu")
+        skips = nn.make_skip_model(4)
+        leaves = [torch.full_like(p, float(i)) for i, p in enumerate(nn.tree_leaves((model, skips)))]
+        fast_m, fast_s = nn.tree_unflatten_like((model, skips), leaves)
+        slow_m, slow_s = nn._unflatten((model, skips), iter(leaves))
+        assert len(fast_m) == len(slow_m) == 4 and fast_s[1] is skips[1] and fast_s[0] is None
+        for a, b in zip(nn.tree_leaves(fast_m), nn.tree_leaves(slow_m)):
+            assert a is b
+        for f, s, o in zip(fast_m, slow_m, model):
+            assert type(f) is nn.Sequential and f.layers[0] is o.layers[0]           # activation objects are shared
+            assert f.layers[1].in_features == o.layers[1].in_features and f.layers[1] is not o.layers[1]
+            assert (f.layers[1].bias is None) == (not bias)
+        assert nn.tree_unflatten_like(model, leaves)[2].layers[1].weight is leaves[2 * (2 if bias else 1)]
+    # anything that is not the make_mlp form takes the generic walk
+    odd = [nn.Linear(3, 2, key=0, device="cpu"), {"a": torch.zeros(2)}]
+    new = nn.tree_unflatten_like(odd, [torch.ones(2, 3), torch.ones(2), torch.ones(2)])
+    assert float(new[0].weight.sum()) == 6 and float(new[1]["a"].sum()) == 2
+
+
+def test_pointer_table():
+    ts = [torch.zeros(3), None, torch.zeros(2)]
+    arr = _lib.ptr_array(ts)
+    assert arr[0] == ts[0].data_ptr() and arr[1] is None and arr[2] == ts[2].data_ptr()
+    assert len(_lib.ptr_array([])) == 1

@@ -44,6 +44,36 @@ def test_autograd_matches_closed_form(act, use_bias):
             assert O.max_rel_err(a["b"], b["b"]) < 1e-12
 
 
+@pytest.mark.parametrize("act", O.ACT_FNS)
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_form_b_layers_autograd_matches_closed_form(act, use_bias):
+    """Layers of the form act(W u + b) (examples/jpc_from_scratch.ipynb cell 12): the autograd restatement and the closed
+    forms of SURVEY Appendix A.2 "Form B" agree; the energy is the notebook's own (cell 10) up to the library's 1/2."""
+    model = O.make_form_b_mlp(0, 10, 20, 4, 5, act, use_bias=use_bias)
+    x, y = _data(4, 10, 5)
+    acts0 = O.init_activities_with_ffwd(model, x)
+    assert float(O.pc_energy_fn(model, None, acts0, y, x=x, record_layers=True)[1:].abs().max()) < 1e-25
+    acts = _perturb(acts0)
+    # the notebook's energy: sum of squared errors of z_l - act(W z_{l-1} + b), output layer linear, / batch (no 1/2)
+    nb = 0.0
+    for l, layer in enumerate(model):
+        u = x if l == 0 else acts[l - 1]
+        pre = u @ layer["W"].T + (0 if layer["b"] is None else layer["b"])
+        pred = O.act_fn(act, pre) if l + 1 < len(model) else pre
+        nb = nb + torch.sum(((y if l + 1 == len(model) else acts[l]) - pred) ** 2)
+    assert abs(float(O.pc_energy_fn(model, None, acts, y, x=x)) - 0.5 * float(nb) / 4) < 1e-12
+    _, g_ad = O.compute_pc_activity_grad(model, None, acts, y, x=x)
+    g_cf = O.closed_form_activity_grad(model, None, acts, y, x)
+    for a, b in zip(g_ad, g_cf):
+        assert O.max_rel_err(a, b) < 1e-12
+    p_ad = O.compute_pc_param_grads(model, None, acts, y, x=x)
+    p_cf = O.closed_form_param_grads(model, None, acts, y, x)
+    for a, b in zip(p_ad, p_cf):
+        assert O.max_rel_err(a["W"], b["W"]) < 1e-12
+        if use_bias:
+            assert O.max_rel_err(a["b"], b["b"]) < 1e-12
+
+
 @pytest.mark.parametrize("param_type", ["mupc", "ntp"])
 def test_closed_form_skips_scalings_gamma(param_type):
     depth = 6
