@@ -268,6 +268,9 @@ def run_bpc(args, w):
     ms = e0.elapsed_time(e1)
     launches = _lib.lib.jpcb_launch_count() - l0
     clocks = sampler.stop()
+    for _ in range(8):  # (the functional API's buffers cycle through a few address sets; the library's launch plans settle)
+        step(lab_p.to(dev, non_blocking=True), img_p.to(dev, non_blocking=True))
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         gr = step(lab_p.to(dev, non_blocking=True), img_p.to(dev, non_blocking=True))
@@ -329,6 +332,7 @@ def main():
                          "workload's batch split over the ranks (SURVEY 8e: 4096 -> 2048/1024/512 rows)")
     ap.add_argument("--grad-dtype", default="f32", choices=["f32", "bf16"],
                     help="N > 1: payload of the gradient all-reduce (bf16 halves the NVLink bytes; energies / loss stay fp32)")
+    ap.add_argument("--dp-buckets", type=int, default=0, help="N > 1: layer groups of the bucketed gradient exchange (0: automatic)")
     ap.add_argument("--cpu-rows", type=int, default=256, help="rows per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bpc-f32", action="store_true", help="c5: run bPC on the fp32 CUDA-core path (same as --bpc-dtype f32)")
@@ -389,6 +393,8 @@ def main():
 
     if args.grad_dtype != "f32":
         J.set_grad_allreduce_dtype(args.grad_dtype)
+    if args.dp_buckets > 0:
+        J.set_dp_buckets(args.dp_buckets)
 
     def step():
         # N = 1: the whole step is one C-ABI call.  N > 1: the same call without the weight gradients, then the gradients

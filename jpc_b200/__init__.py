@@ -26,7 +26,7 @@ from ._eval import test_discriminative_pc, test_generative_pc
 from ._epc import (compute_epc_error_grad, compute_epc_param_grads, epc_energy_fn, init_epc_errors, update_epc_errors,
                    update_epc_params)
 from ._hpc import (compute_hpc_param_grads, hpc_energy_fn, init_activities_with_amort, make_hpc_step, test_hpc)
-from ._train import make_pc_step, set_grad_allreduce_dtype
+from ._train import make_pc_step, set_dp_buckets, set_grad_allreduce_dtype
 from ._graph import PCTrainer
 from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,
                      cross_entropy_loss, get_t_max, mse_loss)

@@ -45,6 +45,7 @@ struct PlanCache {
   cudaStream_t cap[64] = {};
   int max_plans = 16, min_calls = 2;
   unsigned long long hits = 0, captures = 0, bypass = 0;
+  unsigned long long b_hits = 0, b_caps = 0;  // the capture budget's own counters (reset by clear / configure)
   PlanCache() {
     if (const char* v = getenv("JPCB_PLAN")) max_plans = atoi(v) > 0 ? (atoi(v) == 1 ? 16 : atoi(v)) : 0;
     if (const char* v = getenv("JPCB_PLAN_MIN")) min_calls = atoi(v) > 1 ? atoi(v) : 1;
@@ -72,6 +73,16 @@ uint64_t hash_words(const std::vector<uint64_t>& w) {
   return h;
 }
 
+// experiment / test switches that are read from the environment on every call and change the kernel sequence: part of the key
+uint64_t env_signature() {
+  uint64_t h = 0;
+  for (const char* name : {"JPCB_STAGED", "JPCB_TS_STG", "JPCB_SOLVE_MIN_ROUNDS", "JPCB_TS_PROMO"}) {
+    const char* v = getenv(name);
+    h = h * 1000003ull + (v ? (uint64_t)atoll(v) + 1ull : 0ull);
+  }
+  return h;
+}
+
 }  // namespace
 
 void PlanKey::bytes(const void* p, size_t n) {
@@ -96,6 +107,7 @@ int plan_run(PlanKey& key, void* stream, const std::function<int(void*)>& body) 
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return body(stream);
   key.ptr(stream);
   key.word((uint64_t)dev);
+  key.word(env_signature());
   const uint64_t h = hash_words(key.w);
 
   std::unique_lock<std::mutex> lock(C.mu);
@@ -118,11 +130,14 @@ int plan_run(PlanKey& key, void* stream, const std::function<int(void*)>& body) 
     if (le != cudaSuccess) return fail(JPCB_ECUDA, "cudaGraphLaunch (launch plan) -> %s", cudaGetErrorString(le));
     cudaEventRecord(e.last, st);
     count_launch((int)e.nodes);
-    ++C.hits;
+    ++C.hits; ++C.b_hits;
     C.lru.splice(C.lru.begin(), C.lru, e.lru);
     return JPCB_OK;
   }
   if (++e.seen < C.min_calls) { lock.unlock(); return body(stream); }
+  // capture budget: a caller whose pointer sets repeat once or twice and then move on would pay for captures that are
+  // never replayed -- new plans are only built while replays keep up with captures (existing plans keep replaying)
+  if (C.b_caps >= 16 && C.b_hits < 4 * C.b_caps) { lock.unlock(); return body(stream); }
   // ---- capture (under the lock: one capture stream per device) ----
   if (!C.cap[dev] && cudaStreamCreateWithFlags(&C.cap[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); e.bad = true; lock.unlock(); return body(stream); }
   if (cudaStreamBeginCapture(C.cap[dev], cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); e.bad = true; lock.unlock(); return body(stream); }
@@ -158,7 +173,7 @@ int plan_run(PlanKey& key, void* stream, const std::function<int(void*)>& body) 
   }
   e.exec = exec; e.last = ev; e.nodes = nodes;
   C.lru.push_front(h); e.lru = C.lru.begin(); e.in_lru = true;
-  ++C.captures;
+  ++C.captures; ++C.b_caps;
   const cudaError_t le = cudaGraphLaunch(exec, st);
   if (le != cudaSuccess) return fail(JPCB_ECUDA, "cudaGraphLaunch (launch plan) -> %s", cudaGetErrorString(le));
   cudaEventRecord(ev, st);
@@ -176,6 +191,7 @@ int jpcb_plan_cache_configure(int max_plans, int min_calls) {
   std::lock_guard<std::mutex> lock(C.mu);
   C.max_plans = max_plans < 0 ? 0 : max_plans;
   C.min_calls = min_calls < 1 ? 1 : min_calls;
+  C.b_hits = C.b_caps = 0;
   if (C.max_plans == 0) {
     for (auto& m : C.map) C.drop_graph(m.second);
     C.map.clear();
@@ -191,6 +207,7 @@ int jpcb_plan_cache_clear(void) {
   for (auto& m : C.map) C.drop_graph(m.second);
   C.map.clear();
   C.sweep();
+  C.b_hits = C.b_caps = 0;
   return JPCB_OK;
 }
 

@@ -112,6 +112,10 @@ int launch_variant(const TcGroup& g, int grid, cudaStream_t st) {
 }
 
 // ---- staged-epilogue kernel (tc_staged.cuh) ----
+int staged_stg() {  // JPCB_TS_STG=1: the storer's LSU path (read per call: tests and A/B runs switch it inside one process)
+  const char* v = getenv("JPCB_TS_STG");
+  return v ? atoi(v) : 0;
+}
 int staged_flags() {  // JPCB_STAGED bit 0: GRAD (Euler, plain) phases, bit 1: ERR (plain) phases, bit 2: whole-solve launch
   const char* v = getenv("JPCB_STAGED");  // (read per call: tests switch paths inside one process)
   return v ? atoi(v) : 7;
@@ -152,6 +156,7 @@ int fill_staged_task(TsTask& s, const GTask& t, int kind, int tile_begin) {
   }
   s.K = t.K; s.tile_begin = tile_begin; s.tiles_n = (e.N + TC_BLOCK_N - 1) / TC_BLOCK_N; s.kind = kind;
   s.M = e.M; s.N = e.N; s.alpha = e.alpha; s.cg = s.cg_last = e.c * e.gscale; s.red = kind == TS_ERR ? e.red : nullptr;
+  s.o0 = kind == TS_ERR ? nullptr : e.O; s.o1 = e.Ob;
   return JPCB_OK;
 }
 
@@ -277,6 +282,7 @@ int launch_tc_cg(const std::vector<GTask>& tasks, cudaStream_t st) {
           if (n == 0) break;
           sg.ntasks = n;
           sg.total_tiles = tiles;
+          sg.stg = staged_stg();
           const int grid = CG * (tiles < units ? tiles : units);
           if (key == 5) RET(launch_staged_act<ACT_RELU>(sg, grid, st));
           else RET(launch_staged_act<ACT_TANH>(sg, grid, st));
@@ -369,6 +375,7 @@ int launch_tc_solve(const std::vector<GTask>& errs, const std::vector<GTask>& gr
     q.dep[0] = TsDep{e.done, e.tiles_n, a_of(i), 1, 0};
     if (i >= 1) q.dep[1] = TsDep{counters + (size_t)(i - 1) * R, g.t[i - 1].tiles_n, a_of(i - 1), 1, 0};
   }
+  g.stg = staged_stg();
   g.ntasks = 2 * L1; g.persist = 1; g.R = R; g.nsteps = nsteps; g.L1 = L1; g.wave = wave ? 1 : 0;
   g.warm = wave ? (L1 - 1 < nsteps ? L1 - 1 : nsteps) : 0;
   g.tiles_full = (int)(R * (per_e + per_g));

@@ -76,6 +76,8 @@ struct alignas(64) TsTask {
   int pad0_;
   float* red;     // ERR: layer-energy accumulator or null
   int* done;      // whole-solve schedule: completion counters of this task, one per row block
+  float* o0;            // the tensors behind tmO0 / tmO1 (the storer's LSU path, TsGroup::stg)
+  __nv_bfloat16* o1;
   TsDep dep[2];
 };
 
@@ -92,8 +94,9 @@ struct alignas(64) TsGroup {
   int wave;        // error wavefront: at step s only layer tasks i >= max(0, L1 - 1 - s) are active
   int warm;        // steps with fewer active layers than L1 (0 without wavefront)
   int tiles_full;  // tiles of a step with every layer active
+  int stg;         // storer writes finished slabs with coalesced st.global (LSU) instead of TMA stores
   int warm_begin[TS_MAX_WARM + 1];  // first tile of warm-up step s; warm_begin[warm] = first tile of the first full step
-  int pad_[6];
+  int pad_[5];
   TsTask t[TS_MAX_TASKS];
 };
 
@@ -306,6 +309,23 @@ __device__ __forceinline__ float ts_slab_err(const uint32_t (&acc)[32], uint32_t
   return r;
 }
 
+// Storer, LSU path: one warp copies a finished slab (this CTA's 128 rows) from its slot to global memory with 16-byte
+// accesses -- a row of the slab is `CH` 16-byte chunks, 32 / CH rows per instruction, chunk c of row r sits at c ^ swz(r).
+template <int CH>
+__device__ __forceinline__ void ts_stg_region(uint32_t src, uint8_t* gbase, size_t row_pitch_bytes, int rows_valid, int bytes_valid,
+                                              int lane) {
+  constexpr int RPI = 32 / CH;  // rows per instruction
+  const int c = lane % CH, rl = lane / CH;
+#pragma unroll 4
+  for (int it = 0; it < TC_BLOCK_M / RPI; ++it) {
+    const int r = it * RPI + rl;
+    const uint32_t sw = CH == 8 ? (uint32_t)(r & 7) : (CH == 4 ? (uint32_t)((r >> 1) & 3) : (uint32_t)((r >> 2) & 1));
+    const float4 v = lds128(src + (uint32_t)r * (16u * CH) + (((uint32_t)c ^ sw) << 4));
+    if (r < rows_valid && 16 * c < bytes_valid)   // (widths are multiples of 8 elements: a chunk is inside or outside as a whole)
+      __stcg(reinterpret_cast<float4*>(gbase + (size_t)r * row_pitch_bytes + 16 * c), v);
+  }
+}
+
 template <int ACT, int STAGES = TS_STAGES, int SLOTS = TS_SLOTS>
 __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_constant__ TsGroup g) {
   constexpr int CG = 2, BN = TC_BLOCK_N;
@@ -442,6 +462,41 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_con
       __threadfence();
       red_release_gpu_add(pend, 1);
     };
+    if (g.stg) {
+      // LSU path: slabs leave through coalesced st.global issued by this warp; the slot is free as soon as it has been read,
+      // and a tile is published with an ordinary fence + release (no bulk-group bookkeeping)
+      for (int tile = unit; tile < g.total_tiles; tile += nunits) {
+        const TsTile ti = ts_decode(g, tile);
+        const TsTask& t = g.t[ti.ti];
+        const int m0 = ti.r * (TC_BLOCK_M * CG) + (int)rank * TC_BLOCK_M, n0 = ti.n0;
+        const int nsl = ts_num_slabs(t, n0), sc = ts_slab_cols(t.kind), kind = t.kind;
+        const int rows_valid = t.M - m0;
+        for (int s = 0; s < nsl; ++s, ++j) {
+          const int slot = (int)(j % SLOTS);
+          mbar_wait(sready_bar(slot), (j / SLOTS) & 1u);
+          const uint32_t src = slot_base + slot * TS_SLOT_BYTES;
+          const int c0 = n0 + s * sc, cols_valid = t.N - c0;
+          uint8_t* g0 = reinterpret_cast<uint8_t*>(t.o0) + ((size_t)m0 * t.N + c0) * 4;
+          uint8_t* g1 = reinterpret_cast<uint8_t*>(t.o1) + ((size_t)m0 * t.N + c0) * 2;
+          if (kind == TS_GRAD) {
+            ts_stg_region<8>(src, g0, (size_t)t.N * 4, rows_valid, cols_valid * 4, lane);
+            ts_stg_region<4>(src + TS_SLAB_F32, g1, (size_t)t.N * 2, rows_valid, cols_valid * 2, lane);
+          } else if (kind == TS_GRAD_P) {
+            ts_stg_region<4>(src, g0, (size_t)t.N * 4, rows_valid, cols_valid * 4, lane);
+            ts_stg_region<2>(src + TS_SLAB_F32, g1, (size_t)t.N * 2, rows_valid, cols_valid * 2, lane);
+          } else {
+            ts_stg_region<4>(src + TS_SLAB_F32, g1, (size_t)t.N * 2, rows_valid, cols_valid * 2, lane);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sfree_bar(slot));
+        }
+        if (persist) {
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) red_release_gpu_add(t.done + ti.r, 1);
+        }
+      }
+    } else
     for (int tile = unit; tile < g.total_tiles; tile += nunits) {
       const TsTile ti = ts_decode(g, tile);
       const TsTask& t = g.t[ti.ti];

@@ -2,6 +2,7 @@
 the fp64 oracle on the same seeded inputs.  Tolerances are north_star's: 1e-5 max-norm relative
 error in fp32, 2e-2 in bf16 (SURVEY 8d 'parity gates')."""
 import math
+import os
 
 import pytest
 import torch
@@ -1224,6 +1225,16 @@ def test_whole_solve_launch_bf16(shape):
     for p, q in zip(arena1.gW, arena2.gW):
         assert rel(p, q.double().cpu()) < 1e-4   # (bf16 operand copies of nearly equal activities may round apart)
     assert rel(arena1.E, arena2.E.double().cpu()) < 1e-5
+    # the storer's other way out of shared memory (coalesced st.global instead of TMA stores): same numbers
+    with _with_env(JPCB_SOLVE_MIN_ROUNDS=0, JPCB_STAGED=7, JPCB_TS_STG=0 if os.environ.get("JPCB_TS_STG", "0") != "0" else 1):
+        acts3, arena3 = _fused_step_raw(om, sk, x, y, "euler", max_t1, dt)
+        _solve_case(om, sk, x, y, "euler", max_t1, dt, TOLBF, perturbed=True)
+    with _with_env(JPCB_SOLVE_MIN_ROUNDS=0, JPCB_STAGED=3, JPCB_TS_STG=0 if os.environ.get("JPCB_TS_STG", "0") != "0" else 1):
+        acts4, _ = _fused_step_raw(om, sk, x, y, "euler", max_t1, dt)
+    for p, q, r4 in zip(acts1[:-1], acts3[:-1], acts4[:-1]):
+        assert rel(p, q.double().cpu()) < 1e-6 and rel(p, r4.double().cpu()) < 1e-5
+    for p, q in zip(arena1.gW, arena3.gW):
+        assert rel(p, q.double().cpu()) < 1e-5
 
 
 # ---- the reference's own numeric known answers, run THROUGH the CUDA path (reference tests/test_analytical.py) ----------
