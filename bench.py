@@ -250,8 +250,8 @@ def run_bpc(args, w):
 
     def step(x_lab, y_img):
         acts = J.init_activities_with_ffwd(amort, y_img)          # (reference order: amortiser sweep, image side first)
-        acts = J.solve_bpc_inference(td, bu, acts, y_img, input=x_lab, n_steps=T, dt=w["dt"])
-        return J.compute_bpc_param_grads(td, bu, acts, y_img, x=x_lab)
+        _, g_td, g_bu, _ = J.bpc_train_step(td, bu, acts, y_img, input=x_lab, n_steps=T, dt=w["dt"])  # T Euler steps + both gradients
+        return g_td, g_bu
 
     for _ in range(max(3, args.warmup)):
         step(lab, img)
@@ -295,7 +295,7 @@ def run_bpc(args, w):
                        "l2": "working set fits L2; no flush", "algorithmic_gflop_per_step": total / 1e9},
             "e2e": {"value": w["B"] * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * (img_p.numel() + lab_p.numel()),
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "launch_plans": J.plan_cache_stats(),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                          "kernel": {"bf16": "tc_grouped_gemm (bPC phases: errors / forward half / backward half + update), whole step",
                                     "f32x3": "tc_grouped_gemm on 3-way bf16 split operands (six products per GEMM, fp32 parity): "
@@ -628,7 +628,8 @@ def main():
             "e2e_blocking_read": {"value": e2e_blocking_val, "unit": UNIT,
                                   "what": "the same loop with the host blocking on every step's loss (float(loss))"},
             "e2e_graph": e2e_graph,
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "launch_plans": J.plan_cache_stats(), "roofline": roof,
+            "cpu_baseline": cpu,
             "loss": loss_val,
         }
         print(json.dumps(line), flush=True)

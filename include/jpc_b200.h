@@ -226,6 +226,16 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
                          float* const* gV, float* const* gbV, float* E_pairs, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* The bPC train step of the reference's example loop (examples/bidirectional_pc.ipynb cell 8) after the activity
+ * initialisation: td.n_steps Euler steps in place on A (== jpcb_bpc_infer), then both models' parameter gradients and the
+ * energy pairs at the solution (== jpcb_bpc_param_grads) -- as ONE call: the operands are prepared once and the operand
+ * copies the last Euler step's epilogues wrote feed the weight-gradient GEMMs. */
+int jpcb_bpc_train_step(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW,
+                        const float* const* V, const float* const* bV, float* const* A, const float* x,
+                        const float* y, float* const* gW, float* const* gbW, float* const* gV,
+                        float* const* gbV, float* E_pairs, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* ---- hybrid PC: the amortiser's layer-wise regression -------------------------------
  * hpc_energy_fn (jpc/_core/_energies.py:161-243) and compute_hpc_param_grads (jpc/_core/_grads.py:502-541):
  * for every layer l of the amortiser `desc` describes (unit scalings, no skips, mse),

@@ -19,7 +19,7 @@ from ._core import (
     update_pc_activities,
     update_pc_params,
 )
-from ._bpc import (bpc_energy_fn, compute_bpc_activity_grad, compute_bpc_param_grads, solve_bpc_inference,
+from ._bpc import (bpc_energy_fn, bpc_train_step, compute_bpc_activity_grad, compute_bpc_param_grads, solve_bpc_inference,
                    update_bpc_activities, update_bpc_params)
 from ._errors import _check_param_type
 from ._eval import test_discriminative_pc, test_generative_pc

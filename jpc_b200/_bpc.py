@@ -183,7 +183,9 @@ def compute_bpc_activity_grad(top_down_model, bottom_up_model, activities, y, *,
     return F, net.unpad_acts(g[:-1], activities[:-1]) + [torch.zeros_like(activities[-1])]
 
 
-def _param_grads(net, activities, want_energies=False):
+def _param_grads(net, activities, want_energies=False, fused_steps=False):
+    """jpcb_bpc_param_grads on `activities` -- or, with `fused_steps`, jpcb_bpc_train_step: the descriptor's Euler steps in
+    place on the (library-layout) `activities`, then the gradients at the solution."""
     D, n = net.dims, net.H + 1
     f32 = dict(dtype=torch.float32, device=net.dev)
     gW = [torch.empty(D[j + 1], D[j], **f32) for j in range(n)]
@@ -192,10 +194,11 @@ def _param_grads(net, activities, want_energies=False):
     gbV = [torch.empty(D[j], **f32) for j in range(n)] if net.bu_bias else None
     E = torch.empty(2 * (net.H + 1), dtype=torch.float32, device=net.dev) if want_energies else None
     ws = net.workspace()
-    _lib.check(_lib.lib.jpcb_bpc_param_grads(*net.args(), _lib.ptr_array(net.pad_acts(activities)), _lib.ptr(net.x), _lib.ptr(net.y),
-                                             _lib.ptr_array(gW), _lib.ptr_array(gbW) if gbW else None, _lib.ptr_array(gV),
-                                             _lib.ptr_array(gbV) if gbV else None, _lib.ptr(E), _lib.ptr(ws), ws.numel(),
-                                             net.stream()))
+    fn = _lib.lib.jpcb_bpc_train_step if fused_steps else _lib.lib.jpcb_bpc_param_grads
+    acts = activities if fused_steps else net.pad_acts(activities)
+    _lib.check(fn(*net.args(), _lib.ptr_array(acts), _lib.ptr(net.x), _lib.ptr(net.y),
+                  _lib.ptr_array(gW), _lib.ptr_array(gbW) if gbW else None, _lib.ptr_array(gV),
+                  _lib.ptr_array(gbV) if gbV else None, _lib.ptr(E), _lib.ptr(ws), ws.numel(), net.stream()))
 
     if net.bf16:  # slice the zero-padded rows / columns off again
         T = net.true_dims
@@ -259,3 +262,18 @@ def solve_bpc_inference(top_down_model, bottom_up_model, activities, output, *, 
     _lib.check(_lib.lib.jpcb_bpc_infer(*net.args(), _lib.ptr_array(A), _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr(ws),
                                        ws.numel(), net.stream()))
     return net.unpad_acts(A, activities)
+
+
+def bpc_train_step(top_down_model, bottom_up_model, activities, output, *, input=None, n_steps=1, dt=0.5, skip_model=None,
+                   param_type="sp", backward_energy_weight=1.0, forward_energy_weight=1.0, record_energies=False):
+    """`solve_bpc_inference` followed by `compute_bpc_param_grads` at the solution, as ONE library call
+    (jpcb_bpc_train_step): the inference loop and the learning step of the reference's bPC example
+    (examples/bidirectional_pc.ipynb cell 8: `update_bpc_activities` x T, then the gradients `update_bpc_params` applies)
+    without returning to the host and without preparing the operands twice.  Returns
+    (activities, top_down_grads, bottom_up_grads, energy pairs or None)."""
+    net = _net(top_down_model, bottom_up_model, input, output, skip_model, param_type, backward_energy_weight,
+               forward_energy_weight, n_steps=n_steps, dt=dt)
+    net.check_acts(activities)
+    A = net.pad_acts(activities, clone=True)   # functional API: inputs are never mutated
+    td, bu, E = _param_grads(net, A, want_energies=record_energies, fused_steps=True)
+    return net.unpad_acts(A, activities), td, bu, E

@@ -76,6 +76,7 @@ SIGNATURES = {
     "jpcb_bpc_activity_grad": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, _PP, _P, C.c_size_t, _P]),
     "jpcb_bpc_infer": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _P, C.c_size_t, _P]),
     "jpcb_bpc_param_grads": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
+    "jpcb_bpc_train_step": (C.c_int, [C.POINTER(BpcDesc), _PP, _PP, _PP, _PP, _PP, _P, _P, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
     "jpcb_hpc_param_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
     "jpcb_epc_workspace_bytes": (C.c_size_t, [C.POINTER(PcDesc)]),
     "jpcb_epc_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _PP, _PP, _PP, _P, C.c_size_t, _P]),

@@ -357,6 +357,48 @@ struct BpcRun {
     return launch(b);
   }
 
+  // both models' parameter gradients from the errors of the last errors() call on state A (jpc/_core/_grads.py:544-612)
+  int wgrads(const float* const* A, float* const* gW, float* const* gbW, float* const* gV, float* const* gbV) {
+    std::vector<GTask> ts;
+    for (int j = 0; j <= H; ++j) {
+      GTask t;  // gW_j = -(alpha_f/B) e_j^T phi_j(u_j)
+      t.e.mode = EPI_SCALE; t.e.M = D[j + 1]; t.e.N = D[j]; t.K = Bl;
+      t.a_p = e[j]; t.a_smn = 1; t.a_sk = D[j + 1];
+      t.b_p = j == 0 ? x : A[j - 1]; t.b_smn = 1; t.b_sk = D[j]; t.b_act = d->td.act[j];
+      t.a_b = Eb[j]; t.b_b = j == 0 ? Hx : Hz[j - 1]; t.mn_major = tc;  // both read MN-major: no transposes
+      split_geom(t, D[j + 1], D[j]);
+      t.e.alpha = -af * invB; t.e.O = gW[j];
+      ts.push_back(t);
+      GTask u;  // gV_j = -(alpha_b/B) delta_j^T psi_j(v_j)
+      u.e.mode = EPI_SCALE; u.e.M = D[j]; u.e.N = D[j + 1]; u.K = Bl;
+      u.a_p = dl[j]; u.a_smn = 1; u.a_sk = D[j];
+      u.b_p = j == H ? y : A[j]; u.b_smn = 1; u.b_sk = D[j + 1]; u.b_act = d->bu_act[j];
+      u.a_b = Db[j]; u.b_b = j == H ? Hy : Hz[j]; u.mn_major = tc;
+      split_geom(u, D[j], D[j + 1]);
+      u.e.alpha = -ab * invB; u.e.O = gV[j];
+      ts.push_back(u);
+    }
+    RET(launch(ts));
+    if (d->td.has_bias) {
+      if (!gbW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias-gradient list");
+      for (int j = 0; j <= H; ++j) {
+        if (tc && !x3) colsum_kernel<bf16><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, st>>>(Eb[j], gbW[j], Bl, D[j + 1], -af * invB);
+        else colsum_kernel<float><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, st>>>(e[j], gbW[j], Bl, D[j + 1], -af * invB);
+        count_launch();
+      }
+    }
+    if (d->bu_has_bias) {
+      if (!gbV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias-gradient list");
+      for (int j = 0; j <= H; ++j) {
+        if (tc && !x3) colsum_kernel<bf16><<<(D[j] + 31) / 32, dim3(32, 8), 0, st>>>(Db[j], gbV[j], Bl, D[j], -ab * invB);
+        else colsum_kernel<float><<<(D[j] + 31) / 32, dim3(32, 8), 0, st>>>(dl[j], gbV[j], Bl, D[j], -ab * invB);
+        count_launch();
+      }
+    }
+    CK(cudaGetLastError());
+    return JPCB_OK;
+  }
+
   int finalize(float* E_pairs, float* F) {
     bpc_finalize_kernel<<<1, 32, 0, st>>>(red, H, invB, af, ab, E_pairs, F);
     count_launch();
@@ -433,49 +475,36 @@ static int bpc_param_grads_impl(const jpcb_bpc_desc* desc, const float* const* W
   RET(r.zero_red());
   RET(r.prep(A));
   RET(r.errors(A, E_pairs != nullptr, false));
-  const int H = r.H, Bl = r.Bl;
-  const int32_t* D = r.D;
-  std::vector<GTask> ts;
-  for (int j = 0; j <= H; ++j) {
-    GTask t;  // gW_j = -(alpha_f/B) e_j^T phi_j(u_j)
-    t.e.mode = EPI_SCALE; t.e.M = D[j + 1]; t.e.N = D[j]; t.K = Bl;
-    t.a_p = r.e[j]; t.a_smn = 1; t.a_sk = D[j + 1];
-    t.b_p = j == 0 ? x : A[j - 1]; t.b_smn = 1; t.b_sk = D[j]; t.b_act = desc->td.act[j];
-    t.a_b = r.Eb[j]; t.b_b = j == 0 ? r.Hx : r.Hz[j - 1]; t.mn_major = r.tc;  // both read MN-major: no transposes
-    r.split_geom(t, D[j + 1], D[j]);
-    t.e.alpha = -r.af * r.invB; t.e.O = gW[j];
-    ts.push_back(t);
-    GTask u;  // gV_j = -(alpha_b/B) delta_j^T psi_j(v_j)
-    u.e.mode = EPI_SCALE; u.e.M = D[j]; u.e.N = D[j + 1]; u.K = Bl;
-    u.a_p = r.dl[j]; u.a_smn = 1; u.a_sk = D[j];
-    u.b_p = j == H ? y : A[j]; u.b_smn = 1; u.b_sk = D[j + 1]; u.b_act = desc->bu_act[j];
-    u.a_b = r.Db[j]; u.b_b = j == H ? r.Hy : r.Hz[j]; u.mn_major = r.tc;
-    r.split_geom(u, D[j], D[j + 1]);
-    u.e.alpha = -r.ab * r.invB; u.e.O = gV[j];
-    ts.push_back(u);
-  }
-  RET(r.launch(ts));
-  if (desc->td.has_bias) {
-    if (!gbW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias-gradient list");
-    for (int j = 0; j <= H; ++j) {
-      if (r.tc && !r.x3) colsum_kernel<bf16><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Eb[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
-      else colsum_kernel<float><<<(D[j + 1] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.e[j], gbW[j], Bl, D[j + 1], -r.af * r.invB);
-      count_launch();
-    }
-  }
-  if (desc->bu_has_bias) {
-    if (!gbV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias-gradient list");
-    for (int j = 0; j <= H; ++j) {
-      if (r.tc && !r.x3) colsum_kernel<bf16><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.Db[j], gbV[j], Bl, D[j], -r.ab * r.invB);
-      else colsum_kernel<float><<<(D[j] + 31) / 32, dim3(32, 8), 0, r.st>>>(r.dl[j], gbV[j], Bl, D[j], -r.ab * r.invB);
-      count_launch();
-    }
-  }
+  RET(r.wgrads(A, gW, gbW, gV, gbV));
   CK(cudaGetLastError());
   if (E_pairs) RET(r.finalize(E_pairs, nullptr));
   return JPCB_OK;
 }
 
+
+// solve + parameter gradients in one call: operand preparation once, the activities' operand copies written by the last
+// Euler step's epilogues are the weight-gradient GEMMs' operands
+static int bpc_train_step_impl(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                               const float* const* bV, float* const* A, const float* x, const float* y, float* const* gW,
+                               float* const* gbW, float* const* gV, float* const* gbV, float* E_pairs, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  BpcRun r;
+  RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
+  if (!A || !gW || !gV) return fail(JPCB_EINVAL, "null activities / outputs");
+  RET(r.zero_red());
+  RET(r.prep(A));
+  RET(r.hoist());
+  const int T = desc->td.n_steps;
+  for (int s = 0; s < T; ++s) {
+    const float h = s == T - 1 ? desc->td.dt_last : desc->td.dt;
+    RET(r.errors(A, false, true));
+    RET(r.grads(GRAD_EULER, h * r.invB, A, A));
+  }
+  RET(r.errors(A, E_pairs != nullptr, true));   // errors (+ energies) at the solution; the two clamped-side ones without a GEMM
+  RET(r.wgrads(A, gW, gbW, gV, gbV));
+  if (E_pairs) RET(r.finalize(E_pairs, nullptr));
+  return JPCB_OK;
+}
 
 // ---- planned entry points: identical calls are captured into a CUDA graph once and replayed (plan.cu) ----
 namespace {
@@ -527,6 +556,20 @@ int jpcb_bpc_param_grads(const jpcb_bpc_desc* desc, const float* const* W, const
     return bpc_param_grads_impl(desc, W, bW, V, bV, A, x, y, gW, gbW, gV, gbV, E_pairs, workspace, workspace_bytes, s);
   };
   PlanKey k(0x7104);
+  if (!gW || !gV || !key_bpc(k, desc, W, bW, V, bV, A, x, y, workspace, workspace_bytes)) return body(stream);
+  const int n = desc->td.n_layers;
+  k.list(gW, n); k.list(desc->td.has_bias ? gbW : nullptr, n); k.list(gV, n); k.list(desc->bu_has_bias ? gbV : nullptr, n); k.ptr(E_pairs);
+  return plan_run(k, stream, body);
+}
+
+int jpcb_bpc_train_step(const jpcb_bpc_desc* desc, const float* const* W, const float* const* bW, const float* const* V,
+                        const float* const* bV, float* const* A, const float* x, const float* y, float* const* gW,
+                        float* const* gbW, float* const* gV, float* const* gbV, float* E_pairs, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  auto body = [&](void* s) {
+    return bpc_train_step_impl(desc, W, bW, V, bV, A, x, y, gW, gbW, gV, gbV, E_pairs, workspace, workspace_bytes, s);
+  };
+  PlanKey k(0x7105);
   if (!gW || !gV || !key_bpc(k, desc, W, bW, V, bV, A, x, y, workspace, workspace_bytes)) return body(stream);
   const int n = desc->td.n_layers;
   k.list(gW, n); k.list(desc->td.has_bias ? gbW : nullptr, n); k.list(gV, n); k.list(desc->bu_has_bias ? gbV : nullptr, n); k.ptr(E_pairs);

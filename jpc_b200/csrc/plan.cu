@@ -137,7 +137,7 @@ int plan_run(PlanKey& key, void* stream, const std::function<int(void*)>& body) 
   if (++e.seen < C.min_calls) { lock.unlock(); return body(stream); }
   // capture budget: a caller whose pointer sets repeat once or twice and then move on would pay for captures that are
   // never replayed -- new plans are only built while replays keep up with captures (existing plans keep replaying)
-  if (C.b_caps >= 16 && C.b_hits < 4 * C.b_caps) { lock.unlock(); return body(stream); }
+  if (C.b_caps >= 4 && C.b_hits < 2 * C.b_caps) { lock.unlock(); return body(stream); }
   // ---- capture (under the lock: one capture stream per device) ----
   if (!C.cap[dev] && cudaStreamCreateWithFlags(&C.cap[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); e.bad = true; lock.unlock(); return body(stream); }
   if (cudaStreamBeginCapture(C.cap[dev], cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); e.bad = true; lock.unlock(); return body(stream); }

@@ -382,6 +382,40 @@ def test_bpc_two_layer_minimum():
     _check_bpc(*_bpc_case(5, 8, 2, 4, "silu", 4), TOL32)
 
 
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f32x3"])
+def test_bpc_fused_train_step_equals_solve_then_param_grads(dtype):
+    """jpcb_bpc_train_step (T Euler steps + both models' gradients + energy pairs, one call) against the two calls it
+    fuses, and -- on the fp32 paths -- against the oracle's loop (examples/bidirectional_pc.ipynb cell 8)."""
+    import jpc_b200 as J
+    J.set_compute_dtype(dtype)
+    tol = TOLBF if dtype == "bf16" else TOL32
+    td, bu, sk, x, y, acts = _bpc_case(16, 64, 4, 24, "tanh", 32, use_bias=True) if dtype != "f32" else _bpc_case(6, 12, 4, 9, "tanh", 5, use_bias=True)
+    gtd, gbu = to_gpu_model(td), to_gpu_model(bu)
+    gx, gy, T, dt = dev(x), dev(y), 5, 0.6
+    A1 = J.solve_bpc_inference(gtd, gbu, devs(acts), gy, input=gx, n_steps=T, dt=dt)
+    td1, bu1 = J.compute_bpc_param_grads(gtd, gbu, A1, gy, x=gx)
+    E1 = J.bpc_energy_fn(gtd, gbu, A1, gy, x=gx, record_layers=True)
+    A2, td2, bu2, E2 = J.bpc_train_step(gtd, gbu, devs(acts), gy, input=gx, n_steps=T, dt=dt, record_energies=True)
+    same = 1e-6 if dtype != "bf16" else 1e-2   # (bf16: the two-call form re-rounds the activities' operand copies)
+    for p, q in zip(A2[:-1], A1[:-1]):
+        assert rel(p, q.double().cpu()) < 1e-6
+    assert rel(E2, E1.double().cpu()) < same
+    for got, want in ((td2, td1), (bu2, bu1)):
+        for l in range(len(want)):
+            assert rel(got[l][1].weight, want[l][1].weight.double().cpu()) < same
+            assert rel(got[l][1].bias, want[l][1].bias.double().cpu()) < same
+    a = [t.clone() for t in acts]
+    for _ in range(T):
+        _, g = O.compute_bpc_activity_grad(td, bu, a, y, x=x, skips=sk)
+        a = [p - dt * q for p, q in zip(a, g)]
+    tdg, bug = O.compute_bpc_param_grads(td, bu, a, y, x=x, skips=sk)
+    for got, want in ((td2, tdg), (bu2, bug)):
+        for l, q in enumerate(want):
+            assert rel(got[l][1].weight, q["W"]) < tol
+            assert rel(got[l][1].bias, q["b"]) < tol
+    assert rel(E2, O.bpc_energy_fn(td, bu, a, y, x=x, skips=sk, record_layers=True)) < tol
+
+
 def test_bpc_update_params_keys():
     import jpc_b200 as J
     td, bu, sk, x, y, acts = _bpc_case(6, 12, 3, 9, "relu", 4)
