@@ -290,7 +290,7 @@ int jpcb_optim_adam(int n_tensors, const long long* numel, const float* const* p
 /* ---- launch plans ("build once, replay") ---------------------------------------------
  * Every compute entry point above only ENQUEUES, and a call with identical arguments -- descriptor, every pointer
  * (including the contents of the pointer lists), workspace, stream, device -- enqueues an identical kernel sequence.
- * The reference pays the corresponding cost once, when `eqx.filter_jit` traces `make_pc_step` (jpc/_train.py:34); here
+ * The reference pays the corresponding cost once, when `eqx.filter_jit` traces `make_pc_step` (jpc/_train.py:35); here
  * the library keeps a small cache of instantiated CUDA graphs: the `min_calls`-th time an identical call is seen its
  * sequence is captured on a library-owned stream and from then on the call is one cudaGraphLaunch on the caller's
  * stream (the functional host API allocates its outputs from a caching allocator, so its pointer sets repeat with a
