@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "chain_ffwd.cuh"
 #include "elementwise.cuh"
 #include "host.cuh"
 #include "simt_gemm.cuh"
@@ -431,11 +432,22 @@ struct Run {
 
   // ---- bf16 operand preparation ----
   int prep_weights() {
-    if (!tc) {
+    if (!tc) {  // W_l^T copies for the transposed GEMMs of the gradient phases: every layer in one grouped launch
+      static thread_local TrJobs jobs;
+      jobs.n = 0; jobs.total = 0;
+      auto flush = [&]() {
+        if (jobs.n == 0) return;
+        transpose_f32_group_kernel<<<ew_grid(jobs.total, 1), dim3(32, 8), 0, st>>>(jobs); count_launch();
+        jobs.n = 0; jobs.total = 0;
+      };
       for (int l = fr ? 0 : 1; l < L; ++l) {
-        const int R = d->dims[l + 1], C = d->dims[l];
-        transpose_f32_kernel<<<ew_grid(((R + 31) / 32) * ((C + 31) / 32), 1), dim3(32, 8), 0, st>>>(W[l], ws.WTf[l], R, C); count_launch();
+        if (jobs.n == TR_MAX_JOBS) flush();
+        TrJob& jb = jobs.j[jobs.n++];
+        jb.src = W[l]; jb.dst = ws.WTf[l]; jb.R = d->dims[l + 1]; jb.C = d->dims[l];
+        jb.tile_begin = jobs.total; jb.tiles_c = (jb.C + 31) / 32;
+        jobs.total += jb.tiles_c * ((jb.R + 31) / 32);
       }
+      flush();
       CK(cudaGetLastError());
       return JPCB_OK;
     }
@@ -509,8 +521,81 @@ struct Run {
     t.e.pre_act = d->post_act[l];
   }
 
+  // The error wavefront (infer_loop): from the feed-forward init every hidden error is exactly zero and Euler steps move it
+  // one layer per step.  (a skip at layer 0 enters the feed-forward init but not the energy, _init.py:69-78 vs
+  // _energies.py:111-126: then err[0] = x != 0 at the init and there is no wavefront to exploit)
+  bool wavefront_ok() const {
+    return hoist && !post && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !d->skip[0] && !(tc_flags() & 8);
+  }
+
+  // deep narrow networks on the fp32 path: the whole feed-forward chain as ONE launch in which a CTA owns a few batch rows
+  // and walks all layers for them (chain_ffwd.cuh).  Worth it when the chain is long and every CTA can afford to stream
+  // every weight from L2: L launches of a few microseconds each against (sum of weights) / (~32 B/clk) per CTA.
+  bool chain_ffwd_pays() const {
+    const char* v = getenv("JPCB_CHAIN_FFWD");  // 0: never, 2: whenever legal (read per call: tests compare both paths)
+    const int mode = v ? atoi(v) : 1;
+    if (tc || mode == 0 || L > CF_MAX_LAYERS) return false;
+    double wbytes = 0.0;
+    for (int l = 0; l < L; ++l) {
+      if (d->dims[l] > 1024 || d->dims[l + 1] > 1024) return false;   // (shared memory: 4 x R rows of the widest layer)
+      wbytes += 4.0 * d->dims[l] * d->dims[l + 1];
+    }
+    if (mode == 2) return true;
+    return L >= 6 && wbytes / 60e3 < 3.0 * L;  // microseconds: ~60 GB/s-per-SM streaming vs ~3 us per dependent launch
+  }
+  int chain_ffwd(float* const* A_out, float* loss_acc, bool keep_p1) {
+    static thread_local CfArgs a;
+    a.L = L; a.B = Bl; a.x = x;
+    const bool ce = d->loss == JPCB_LOSS_CE;
+    const bool want_loss = loss_acc && y && !ce;
+    a.Y = want_loss ? y : nullptr; a.loss = want_loss ? loss_acc : nullptr;
+    int kmax = 0;
+    for (int l = 0; l < L; ++l) {
+      CfLayer& c = a.l[l];
+      c.W = W[l]; c.bias = bias(l); c.O = A_out[l];
+      c.O2 = (l == 0 && keep_p1) ? ws.P1 : nullptr;
+      c.Oh = l + 1 < L ? ws.Hf[l + 1] : nullptr;
+      c.K = d->dims[l]; c.N = d->dims[l + 1];
+      c.act_in = d->act[l]; c.act_post = d->post_act[l]; c.act_next = l + 1 < L ? d->act[l + 1] : ACT_LINEAR;
+      c.alpha = d->scalings[l]; c.skip = d->skip[l] ? 1.f : 0.f;  // the init honours any non-None skip (_init.py:69-78)
+      kmax = c.K > kmax ? c.K : kmax;
+    }
+    for (int l = 0; l < L; ++l) kmax = d->dims[l + 1] > kmax ? d->dims[l + 1] : kmax;
+    const int kpad = (kmax + 7) / 4 * 4;
+    constexpr int R = 4;
+    const size_t smem = (size_t)4 * R * kpad * sizeof(float);  // raw + act, double-buffered
+    {  // (per-device function attribute, as for the tensor-core kernels)
+      static std::atomic<unsigned long long> done{0};
+      int dev = 0;
+      CK(cudaGetDevice(&dev));
+      const unsigned long long bit = dev < 64 ? (1ull << dev) : 0ull;
+      if (!bit || !(done.load(std::memory_order_relaxed) & bit)) {
+        CK(cudaFuncSetAttribute(chain_ffwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * R * 1032 * (int)sizeof(float)));
+        if (bit) done.fetch_or(bit, std::memory_order_relaxed);
+      }
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((Bl + R - 1) / R);
+    cfg.blockDim = dim3(CF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // the kernel starts with griddepcontrol.wait
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, chain_ffwd_kernel<R>, a, kpad));
+    count_launch();
+    if (loss_acc && y && ce) RET(ce_rows(A_out[L - 1], 1.f, nullptr, nullptr, loss_acc));
+    return JPCB_OK;
+  }
+
   // init_activities_with_ffwd (jpc/_core/_init.py:68-80); layer 0 also leaves the hoisted P1
-  int ffwd(float* const* A_out, float* loss_acc, bool keep_p1) {
+  // `chain_ok`: the caller does not rely on a later error pass reproducing these activities BIT for bit (the chain kernel
+  // sums in another order than the error kernels: "z_l - prediction" of an untouched layer is then ~1e-9 instead of 0)
+  int ffwd(float* const* A_out, float* loss_acc, bool keep_p1, bool chain_ok) {
+    if (chain_ok && chain_ffwd_pays()) return chain_ffwd(A_out, loss_acc, keep_p1);
     for (int l = 0; l < L; ++l) {
       GTask t;
       fwd_operands(t, l, A_out, false);
@@ -680,7 +765,7 @@ struct Run {
     float* const xw = const_cast<float*>(x);  // free_input: z_0 is updated in place like every other activity
     // (a skip at layer 0 enters the feed-forward init but not the energy, _init.py:69-78 vs _energies.py:111-126: then
     //  err[0] = x != 0 at the init and there is no wavefront to exploit)
-    const bool front = hoist && !post && from_ffwd && d->solver == JPCB_SOLVER_EULER && d->activity_decay == 0.f && L > 2 && !d->skip[0] && !(tc_flags() & 8);
+    const bool front = from_ffwd && wavefront_ok();
     if (front) {
       if (tc) {
         for (int l = (L - 2 - T > 0 ? L - 2 - T : 0); l < L - 1; ++l) {
@@ -820,7 +905,7 @@ static int pc_ffwd_init_impl(const jpcb_pc_desc* desc, const float* const* W, co
   RET(r.prep_weights());
   RET(r.prep_inputs(nullptr));
   const bool want_loss = loss_out && y;
-  RET(r.ffwd(A_out, want_loss ? r.ws.red + RED_LOSS : nullptr, false));
+  RET(r.ffwd(A_out, want_loss ? r.ws.red + RED_LOSS : nullptr, false, true));
   if (want_loss) RET(r.finalize(nullptr, nullptr, false, loss_out));
   return JPCB_OK;
 }
@@ -1141,10 +1226,15 @@ static int pc_train_step_impl(const jpcb_pc_desc* desc, const float* const* W, c
   RET(r.zero_red());
   RET(r.prep_weights());
   RET(r.prep_inputs(nullptr));
-  RET(r.ffwd(A_out, r.ws.red + RED_LOSS, r.hoist));   // init + loss at the init + hoisted P1 + bf16 operands
+  // With the wavefront schedule the layers the front has not reached after T steps keep EXACTLY zero errors (their buffers
+  // were zeroed and are never written): on the fp32 path the error pass at the solution skips them too -- zero energies and
+  // zero gradients by construction, whatever order the feed-forward kernel summed in (so the chain kernel may be used).
+  const bool wave = r.wavefront_ok(), wave_tail = wave && !r.tc;
+  RET(r.ffwd(A_out, r.ws.red + RED_LOSS, r.hoist, wave_tail));   // init + loss at the init + hoisted P1 + operand copies
   RET(r.infer_loop(A_out, true));
-  RET(r.errors(r.hoist ? 1 : 0, A_out, false, true));  // errors + layer energies at the solution
-  if (r.hoist) RET(r.error0_from_p1(A_out, true));
+  const int reach = r.L - 1 - desc->n_steps;  // lowest layer whose error can be non-zero at the solution
+  RET(r.errors(r.hoist ? (wave_tail && reach > 1 ? reach : 1) : 0, A_out, false, true));  // errors + layer energies at the solution
+  if (r.hoist && !(wave_tail && reach > 0)) RET(r.error0_from_p1(A_out, true));
   if (gW) RET(r.wgrads(A_out, gW, gb));           // (NULL: the caller follows up with jpcb_pc_param_grads_range)
   return r.finalize(E_layers, nullptr, false, loss_out);
 }

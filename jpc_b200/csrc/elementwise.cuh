@@ -44,6 +44,42 @@ static __global__ void transpose_f32_kernel(const float* __restrict__ src, float
   }
 }
 
+// The same for a LIST of matrices in one launch (the fp32 path transposes every layer's weights once per call: one launch
+// instead of L -- 127 of config 3's 301 launches per train step were these).
+struct TrJob {
+  const float* src;
+  float* dst;
+  int R, C, tile_begin, tiles_c;
+};
+constexpr int TR_MAX_JOBS = 128;
+struct TrJobs {
+  int n, total;
+  TrJob j[TR_MAX_JOBS];
+};
+static __global__ void transpose_f32_group_kernel(const __grid_constant__ TrJobs jobs) {
+  __shared__ float tile[32][33];
+  for (int t = blockIdx.x; t < jobs.total; t += gridDim.x) {
+    int lo = 0, hi = jobs.n - 1;  // last job with tile_begin <= t
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs.j[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+    }
+    const TrJob& jb = jobs.j[lo];
+    const int local = t - jb.tile_begin, R = jb.R, C = jb.C;
+    const int r0 = (local / jb.tiles_c) * 32, c0 = (local % jb.tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      tile[i][threadIdx.x] = (r < R && c < C) ? jb.src[(size_t)r * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) jb.dst[(size_t)c * R + r] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
 // dst[c][r] = bf16(src[r][c]); src is [R, C] row-major (fp32 or bf16), dst [C, R] row-major.
 template <typename TIn>
 static __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {

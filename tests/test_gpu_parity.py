@@ -1271,6 +1271,38 @@ def test_whole_solve_launch_bf16(shape):
         assert rel(p, q.double().cpu()) < 1e-5
 
 
+# ---- feed-forward chain of a deep narrow network as one launch (csrc/chain_ffwd.cuh) ----------------------------------
+@pytest.mark.parametrize("shape", [
+    # d_in, width, depth, d_out, act, B, bias, param_type, skips
+    (12, 16, 8, 3, "relu", 5, True, "mupc", True),        # skips + scalings + biases, one partial CTA
+    (33, 65, 7, 10, "tanh", 37, True, "sp", False),       # ragged dims (no 16-byte rows), several CTAs
+    (784, 128, 12, 10, "gelu", 128, False, "ntp", True),  # config-3-shaped, shallower
+])
+def test_chain_ffwd_equals_layer_by_layer(shape):
+    """The one-launch chain must give the oracle's feed-forward init (fp32 gate) and what the layer-by-layer launches give,
+    including the loss and -- through the fused train step -- everything downstream of the operand copies it leaves."""
+    import jpc_b200 as J
+    d_in, width, depth, d_out, act, B, bias, ptype, skips = shape
+    om, sk, x, y = _case(d_in, width, depth, d_out, act, B, use_bias=bias, param_type=ptype, skips=skips)
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    ref = O.init_activities_with_ffwd(om, x, skips=sk, param_type=ptype)
+    outs = {}
+    for mode in (2, 0):
+        with _with_env(JPCB_CHAIN_FFWD=mode):
+            n0 = J._lib.lib.jpcb_launch_count()
+            outs[mode] = J.init_activities_with_ffwd(gm, dev(x), skip_model=gsk, param_type=ptype)
+            outs[mode, "n"] = J._lib.lib.jpcb_launch_count() - n0
+            outs[mode, "step"] = _fused_step_raw(om, sk, x, y, "euler", 2.0, 0.5, param_type=ptype)
+    assert outs[0, "n"] - outs[2, "n"] == depth - 1, (outs[0, "n"], outs[2, "n"])   # L launches became one
+    for p, q, r in zip(outs[2], outs[0], ref):
+        assert rel(p, r) < TOL32 and rel(p, q.double().cpu()) < 1e-5
+    (a2, ar2), (a0, ar0) = outs[2, "step"], outs[0, "step"]
+    assert abs(float(ar2.loss) - float(ar0.loss)) <= 1e-5 * abs(float(ar0.loss))
+    for p, q in zip(a2[:-1], a0[:-1]):
+        assert rel(p, q.double().cpu()) < 1e-5
+    gate_all(ar2.gW, [g.double().cpu() for g in ar0.gW], 1e-4, "chain_ffwd.gW")
+
+
 # ---- the reference's own numeric known answers, run THROUGH the CUDA path (reference tests/test_analytical.py) ----------
 @pytest.mark.parametrize("dtype,B", [("f32", 2), ("f32x3", 8)])
 def test_reference_kat_linear_equilibrium_through_cuda(dtype, B):
