@@ -25,7 +25,7 @@ import torch
 
 from . import _flat, _lib
 from ._errors import _check_param_type
-from .nn import Identity, Lambda, Linear, Sequential, tree_unflatten_like
+from .nn import Identity, Lambda, Linear, ModelList, Sequential, tree_unflatten_like
 from .optim import update_and_apply
 from .solvers import ConstantStepSize, Euler, Heun, PIDController
 
@@ -146,6 +146,27 @@ _DESC_CACHE: dict = {}
 _WS_CACHE: dict = {}
 
 
+def _make_lowering(layers, parts, linears, Ws, bs, dims, dev, w_ptrs, b_ptrs):
+    return {"layers": layers, "parts": parts, "linears": linears, "Ws": Ws, "bs": bs,
+            "bs_or_none": bs if bs else [None] * len(Ws), "dims": dims, "dev": dev, "w_ptrs": w_ptrs, "b_ptrs": b_ptrs,
+            "bare": any(isinstance(l, Linear) for l in layers),
+            "acts_t": tuple(p[0] for p in parts), "posts_t": tuple(p[2] for p in parts)}
+
+
+def relower(net, new_model, new_leaves, addrs):
+    """Attaches to `new_model` (a `ModelList` of make_mlp-form layers built by `tree_unflatten_like` from `net`'s model) the
+    lowering `make_pc_step` already knows: same layer forms and dims, parameter leaves `new_leaves` (tree order: weight, bias
+    per layer) at device addresses `addrs`."""
+    if type(new_model) is not ModelList:
+        return
+    low = net._low
+    per = 2 if low["bs"] else 1
+    linears = [layer.layers[1] for layer in new_model]
+    new_model._jpcb = _make_lowering(list(new_model), [(p[0], lin, p[2]) for p, lin in zip(low["parts"], linears)], linears,
+                                     list(new_leaves[0::per]), list(new_leaves[1::per]) if per == 2 else [], low["dims"],
+                                     low["dev"], list(addrs[0::per]), list(addrs[1::per]) if per == 2 else [])
+
+
 class _Net:
     """A model lowered to C-ABI arguments: descriptor + weight/bias pointer arrays."""
 
@@ -164,32 +185,16 @@ class _Net:
             raise ValueError("unsupervised mode (input=None) supports param_type='sp' only: the reference's "
                              "`_get_param_scalings` needs the input's width for 'mupc' / 'ntp'")
         L = len(model)
-        parts = [_layer_parts(l) for l in model]
-        bare = any(isinstance(l, Linear) for l in model)
-        if bare and (float(weight_decay) != 0.0 or float(spectral_penalty) != 0.0):
+        low = self._lowering(model)
+        parts, linears, Ws, bs, dims, dev = low["parts"], low["linears"], low["Ws"], list(low["bs"]), list(low["dims"]), low["dev"]
+        if low["bare"] and (float(weight_decay) != 0.0 or float(spectral_penalty) != 0.0):
             raise NotImplementedError("weight_decay / spectral_penalty on bare Linear layers are not on the B200 path")
         # (for make_mlp models those two regularisers are no-ops in the reference as well: the
         #  layers are Sequential objects without a `.weight`, jpc/_core/_energies.py:128-143)
-        self.linears = linears = [p[1] for p in parts]
+        self.linears = linears
         self.model, self.skip_model = model, skip_model
-        dev = linears[0].weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("jpc_b200 has no CPU path: model weights must be CUDA tensors")
+        self._low = low
         f32 = torch.float32
-        Ws, bs, dims = [], [], [linears[0].weight.shape[1]]
-        for l, lin in enumerate(linears):  # one pass per layer: this runs every call of the functional API
-            w, b_ = lin.weight, lin.bias
-            if w.dtype is not f32 or not w.is_contiguous() or w.device != dev:
-                raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
-            if b_ is not None:
-                if b_.dtype is not f32 or not b_.is_contiguous() or b_.device != dev:
-                    raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
-                bs.append(b_)
-            d_out, d_in = w.shape
-            if d_in != dims[l]:
-                raise ValueError(f"layer {l}: weight shape {tuple(w.shape)} does not chain from {dims[l]}")
-            dims.append(d_out)
-            Ws.append(w)
         for t in ([x] if x is not None else []) + ([y] if y is not None else []):
             if t.dtype is not f32 or not t.is_contiguous() or t.device != dev:
                 raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
@@ -198,7 +203,7 @@ class _Net:
         has_bias = [bool(bs)] * L
         if x is not None and x.shape[1] != dims[0]:
             raise ValueError("input feature dim does not match the first layer")
-        posts = tuple(p[2] for p in parts)
+        posts = low["posts_t"]
         self.form_b = any(q != "linear" for q in posts)
         if self.form_b and param_type != "sp":
             # (the reference's _get_param_scalings reads model[0][1].weight, jpc/_core/_energies.py:915: an activation
@@ -232,7 +237,7 @@ class _Net:
             dims = pd
         lam = 1.0 if output_energy_scaling is None else float(output_energy_scaling)
         bg = B if batch_global is None else int(batch_global)
-        key = (L, B, bg, tuple(dims), tuple(p[0] for p in parts), posts, all(has_bias), tuple(skips), tuple(scal),
+        key = (L, B, bg, tuple(dims), low["acts_t"], posts, all(has_bias), tuple(skips), tuple(scal),
                _COMPUTE_DTYPE, loss_id, lam, float(activity_decay), solver, n_steps, float(dt), float(dt_last), self.free)
         cached = _DESC_CACHE.get(key)
         if cached is None:
@@ -265,14 +270,56 @@ class _Net:
         self.adims = dims[0 if self.free else 1:]
         self.true_adims = self.true_dims[0 if self.free else 1:]
         self.has_bias = all(has_bias)
-        self.w_ptrs = [w.data_ptr() for w in Ws]
-        self.b_ptrs = [b_.data_ptr() for b_ in bs] if self.has_bias else None
+        if self.padded:
+            self.w_ptrs = [w.data_ptr() for w in Ws]
+            self.b_ptrs = [b_.data_ptr() for b_ in bs] if self.has_bias else None
+        else:
+            self.w_ptrs, self.b_ptrs = low["w_ptrs"], (low["b_ptrs"] if self.has_bias else None)
         self.W = _lib.ptr_array_from_ints(self.w_ptrs)
         self.b = _lib.ptr_array_from_ints(self.b_ptrs) if self.has_bias else None
         self._keep = (Ws, bs)  # keep tensors alive while pointer arrays exist
         self.x, self.y = x, y   # (zero-padded copies when self.padded)
         self.w_shapes = [tuple(w.shape) for w in Ws]
         self.b_shapes = [tuple(b_.shape) for b_ in bs] if bs is not None else None
+
+    @staticmethod
+    def _lowering(model):
+        """What `_Net` derives from the model alone -- layer forms, Linear objects, parameter tensors and their device
+        addresses, dims -- validated once.  A `ModelList` (what `make_pc_step` returns) carries it to the next call; it is
+        trusted only while every layer object and every parameter tensor is still the very object it was made from."""
+        low = getattr(model, "_jpcb", None) if type(model) is ModelList else None
+        if low is not None and len(low["layers"]) == len(model):
+            ok = True
+            for layer, ref, lin, w, b_ in zip(model, low["layers"], low["linears"], low["Ws"], low["bs_or_none"]):
+                if layer is not ref or lin.weight is not w or lin.bias is not b_:
+                    ok = False
+                    break
+            if ok:
+                return low
+        parts = [_layer_parts(l) for l in model]
+        linears = [p[1] for p in parts]
+        dev = linears[0].weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("jpc_b200 has no CPU path: model weights must be CUDA tensors")
+        f32 = torch.float32
+        Ws, bs, dims = [], [], [linears[0].weight.shape[1]]
+        for l, lin in enumerate(linears):  # one pass per layer
+            w, b_ = lin.weight, lin.bias
+            if w.dtype is not f32 or not w.is_contiguous() or w.device != dev:
+                raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
+            if b_ is not None:
+                if b_.dtype is not f32 or not b_.is_contiguous() or b_.device != dev:
+                    raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
+                bs.append(b_)
+            d_out, d_in = w.shape
+            if d_in != dims[l]:
+                raise ValueError(f"layer {l}: weight shape {tuple(w.shape)} does not chain from {dims[l]}")
+            dims.append(d_out)
+            Ws.append(w)
+        low = _make_lowering(list(model), parts, linears, Ws, bs, dims, dev, [w.data_ptr() for w in Ws], [b_.data_ptr() for b_ in bs])
+        if type(model) is ModelList:
+            model._jpcb = low
+        return low
 
     def workspace(self) -> torch.Tensor:
         k = (self.dev, self.stream())  # one per stream: calls on different streams may overlap on the device

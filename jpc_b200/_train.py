@@ -12,7 +12,7 @@ import torch
 
 from . import _flat, _lib
 from ._core import (_Net, _grads_pytree, _solver_id, _time_grid, init_activities_from_normal, init_activities_with_ffwd,
-                    solve_inference)
+                    relower, solve_inference)
 from ._errors import _check_param_type
 from ._utils import (compute_accuracy, compute_activity_norms, compute_infer_energies, compute_param_norms,
                      get_t_max)
@@ -57,19 +57,32 @@ class _Arena:
         lay = _flat.layout(shapes)  # (cached per shape list; views carved run by run: this runs every train step)
         offs = lay.offs
         self.flat = torch.empty(lay.total, dtype=torch.float32, device=device)
-        views = lay.carve(self.flat)
-        self.gW, self.gb = [], ([] if bias_shapes is not None else None)
-        i = 0
-        for l in range(L):
-            self.gW.append(views[i]); i += 1
-            if bias_shapes is not None:
-                self.gb.append(views[i]); i += 1
-        self.E = views[i]
-        self.loss = views[i + 1]
+        self._lay = lay
+        self._has_bias = bias_shapes is not None
+        # [E_layers, loss] are always handed out; the per-parameter gradient views only when somebody asks (`gW` / `gb`):
+        # the fused train step and the fused update work from `flat` + `offs`
+        self.E = self.flat.as_strided((L,), (1,), offs[-2])
+        self.loss = self.flat.as_strided((), (), offs[-1])
         self.n_layers = L
         self.per_layer = 2 if bias_shapes is not None else 1
         self.offs = offs            # start of every segment in `flat`; offs[per_layer * l] = first element of layer l
         self.tail_off = offs[-2]    # [E_layers, loss]
+
+    def grad_ptr_arrays(self):
+        """(gW, gb) host arrays of device pointers into `flat`, from the layout's offsets (no tensor views needed)."""
+        base, per, L = self.flat.data_ptr(), self.per_layer, self.n_layers
+        gW = _lib.ptr_array_from_ints([base + 4 * self.offs[per * l] for l in range(L)])
+        gb = _lib.ptr_array_from_ints([base + 4 * self.offs[per * l + 1] for l in range(L)]) if self._has_bias else None
+        return gW, gb
+
+    def __getattr__(self, name):  # (only reached when the attribute is not set yet)
+        if name in ("gW", "gb"):
+            views = self._lay.carve(self.flat)
+            L, per = self.n_layers, self.per_layer
+            self.gW = views[0:per * L:per]
+            self.gb = views[1:per * L:per] if self._has_bias else None
+            return self.__dict__[name]
+        raise AttributeError(name)
 
     def all_reduce(self):
         """The one exchange step of the data-parallel path: SUM over ranks of every rank's partial
@@ -214,21 +227,22 @@ def _fused_param_update(net, arena, optim, opt_state):
     def fresh():
         flat = torch.empty(lay.total, dtype=torch.float32, device=dev)
         base = flat.data_ptr()
-        return flat, _lib.ptr_array_from_ints([base + 4 * o for o in lay.offs])
-    new_flat, out_ptrs = fresh()
+        addrs = [base + 4 * o for o in lay.offs]
+        return flat, _lib.ptr_array_from_ints(addrs), addrs
+    new_flat, out_ptrs, out_addrs = fresh()
     P = _lib.ptr_array_from_ints
     if spec[0] == "sgd":
         _lib.check(_lib.lib.jpcb_optim_sgd(n, numel, P(p_ptrs), P(g_ptrs), spec[1], out_ptrs, stream))
-        return lay.carve(new_flat), opt_state
+        return lay.carve(new_flat), opt_state, out_addrs
     mu, nu = opt_state["mu"], opt_state["nu"]
     if len(mu) != n or len(nu) != n:
         return None
     count = opt_state["count"] + 1
-    mo_flat, mo_ptrs = fresh()
-    vo_flat, vo_ptrs = fresh()
+    mo_flat, mo_ptrs, _ = fresh()
+    vo_flat, vo_ptrs, _ = fresh()
     _lib.check(_lib.lib.jpcb_optim_adam(n, numel, P(p_ptrs), P(g_ptrs), _lib.ptr_array(mu), _lib.ptr_array(nu), spec[1], spec[2],
                                         spec[3], spec[4], count, out_ptrs, mo_ptrs, vo_ptrs, stream))
-    return lay.carve(new_flat), {"count": count, "mu": lay.carve(mo_flat), "nu": lay.carve(vo_flat)}
+    return lay.carve(new_flat), {"count": count, "mu": lay.carve(mo_flat), "nu": lay.carve(vo_flat)}, out_addrs
 
 
 _GLOBAL_ROWS: dict = {}
@@ -326,10 +340,10 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         lead_acts = not net.padded
         ws = net.workspace()
         bucketed = world > 1 and net.dev.type == "cuda"
+        gW_p, gb_p = (None, None) if bucketed else arena.grad_ptr_arrays()
         _lib.check(_lib.lib.jpcb_pc_train_step(
             net.desc, net.W, net.b, _lib.ptr(net.x), _lib.ptr(net.y), _lib.ptr_array(acts), _lib.ptr(arena.loss),
-            _lib.ptr(arena.E), None if bucketed else _lib.ptr_array(arena.gW),
-            None if bucketed or not arena.gb else _lib.ptr_array(arena.gb), _lib.ptr(ws), ws.numel(), net.stream()))
+            _lib.ptr(arena.E), gW_p, gb_p, _lib.ptr(ws), ws.numel(), net.stream()))
         if bucketed:   # weight gradients + their exchange, bucket by bucket (the exchange overlaps the remaining GEMMs)
             dp_param_grads_and_exchange(net, arena)
             exchanged = True
@@ -366,16 +380,19 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     if not exchanged:
         arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
     acts = net.out_acts(acts)
-    gW, gb = net.out_grads(arena.gW, arena.gb)
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)
-    g_norms = compute_param_norms(_grads_pytree(net, gW, gb)) if grad_norms else (None, None)
+    g_norms = compute_param_norms(_grads_pytree(net, *net.out_grads(arena.gW, arena.gb))) if grad_norms else (None, None)
     a_norms = compute_activity_norms(acts) if activity_norms else None
     # the update: parameter and gradient leaves are already at hand as flat lists in tree order (per layer: weight, bias;
     # the skip model has no array leaves), so the fused optimiser kernel is fed without walking the pytrees
     fused = getattr(optim, "fused_apply_flat", None)
-    res = None
+    res, addrs = None, None
     if not net.padded:
         res = _fused_param_update(net, arena, optim, opt_state)
+        if res is not None:
+            res, addrs = res[:2], res[2]
+    if res is None:
+        gW, gb = net.out_grads(arena.gW, arena.gb)   # (gradient views are only carved on this, slower, path)
     if res is None and fused is not None:
         p_leaves, g_leaves = [], []
         for l, lin in enumerate(net.linears):
@@ -388,6 +405,8 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     if res is not None:
         new_leaves, opt_state = res
         model, skip_model = tree_unflatten_like((model, skip_model), new_leaves)
+        if addrs is not None:
+            relower(net, model, new_leaves, addrs)   # (the next step starts from what this one already knows about its model)
     else:
         (model, skip_model), opt_state = update_and_apply(optim, _grads_pytree(net, gW, gb), opt_state, (model, skip_model))
     if calculate_accuracy and input is None:

@@ -240,6 +240,17 @@ def _unflatten(tree, it):
     return tree  # Identity / Activation / other callables: no leaves
 
 
+class ModelList(list):
+    """A plain list of layers (what the reference's `make_mlp` returns) that can carry the lowering `_Net` made of it
+    (`_jpcb`): `make_pc_step` returns its updated model as one, so the next step does not re-derive layer forms, dims and
+    parameter addresses from scratch.  Behaves exactly like a list; slicing / copying gives a plain list again."""
+    __slots__ = ("_jpcb",)
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self._jpcb = None
+
+
 def _relinear(lin: Linear, weight, bias) -> Linear:
     new = Linear.__new__(Linear)
     d = dict(lin.__dict__)
@@ -251,7 +262,7 @@ def _relinear(lin: Linear, weight, bias) -> Linear:
 def _unflatten_mlp(model, leaves, i):
     """Fast path of `_unflatten` for a list of Sequential([Lambda, Linear]) layers (jpc.make_mlp models): runs once per
     train step over every layer.  Returns (new model, next leaf index) or None when the structure is anything else."""
-    out = []
+    out = ModelList()
     for layer in model:
         if type(layer) is not Sequential:
             return None
@@ -273,14 +284,14 @@ def _unflatten_mlp(model, leaves, i):
 
 def tree_unflatten_like(tree, leaves):
     """Rebuilds `tree`'s structure around new leaves (taken front to back)."""
-    if type(tree) is tuple and len(tree) == 2 and type(tree[0]) is list and isinstance(leaves, list):
+    if type(tree) is tuple and len(tree) == 2 and type(tree[0]) in (list, ModelList) and isinstance(leaves, list):
         # (model, skip_model): the make_mlp form with a leaf-free skip model (None / Lambda(Identity) entries)
         sk = tree[1]
         if sk is None or (type(sk) is list and all(e is None or type(e) is Lambda for e in sk)):
             got = _unflatten_mlp(tree[0], leaves, 0)
             if got is not None and got[1] == len(leaves):
                 return got[0], (None if sk is None else list(sk))
-    elif type(tree) is list and isinstance(leaves, list):
+    elif type(tree) in (list, ModelList) and isinstance(leaves, list):
         got = _unflatten_mlp(tree, leaves, 0)
         if got is not None and got[1] == len(leaves):
             return got[0]

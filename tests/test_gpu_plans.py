@@ -98,3 +98,24 @@ def test_calls_under_the_callers_own_capture_bypass_the_plans():
     torch.cuda.synchronize()
     assert J.plan_cache_stats()["bypassed"] > s0["bypassed"]
     assert float(out["loss"]) > 0
+
+
+def test_returned_model_carries_its_lowering_and_loses_it_when_touched():
+    """`make_pc_step` returns its model as a list that remembers how it was lowered (layer forms, dims, parameter
+    addresses): the next call trusts that only while every layer and parameter object is untouched."""
+    J, om, gm, x, y, _, _ = _setup("f32", (20, 32, 5, 6), 16)
+    kw = dict(input=x, ode_solver=J.Euler(), max_t1=2, dt=0.5, stepsize_controller=J.ConstantStepSize())
+    opt = J.optim.adam(1e-2)
+    out = J.make_pc_step(gm, opt, opt.init((gm, None)), y, **kw)
+    m = out["model"]
+    assert isinstance(m, list) and getattr(m, "_jpcb", None) is not None and len(m) == 5
+    acts = J.init_activities_with_ffwd(m, x)
+    e_memo = J.pc_energy_fn((m, None), acts, y, x=x)
+    e_full = J.pc_energy_fn((list(m), None), acts, y, x=x)          # a plain copy: derived from scratch
+    assert abs(float(e_memo) - float(e_full)) <= 1e-6 * abs(float(e_full))   # (energy sums use atomics: equal up to summation order)
+    m[2].layers[1].weight = m[2].layers[1].weight * 2.0              # touch one parameter: the remembered lowering must not be used
+    e_new = J.pc_energy_fn((m, None), acts, y, x=x)
+    e_ref = J.pc_energy_fn((list(m), None), acts, y, x=x)
+    assert abs(float(e_new) - float(e_ref)) <= 1e-6 * abs(float(e_ref)) and abs(float(e_new) - float(e_memo)) > 1e-3 * abs(float(e_memo))
+    out2 = J.make_pc_step(out["model"], opt, out["opt_state"], y, **kw)   # and training simply goes on from the touched model
+    assert float(out2["loss"]) > 0 and out2["model"]._jpcb is not None

@@ -32,6 +32,9 @@ def test_model_rebuild_fast_path_equals_the_generic_walk():
         skips = nn.make_skip_model(4)
         leaves = [torch.full_like(p, float(i)) for i, p in enumerate(nn.tree_leaves((model, skips)))]
         fast_m, fast_s = nn.tree_unflatten_like((model, skips), leaves)
+        assert type(fast_m) is nn.ModelList and isinstance(fast_m, list) and fast_m._jpcb is None
+        again, _ = nn.tree_unflatten_like((fast_m, skips), leaves)        # a returned model goes back in: still the fast path
+        assert type(again) is nn.ModelList and again[0].layers[1].weight is leaves[0]
         slow_m, slow_s = nn._unflatten((model, skips), iter(leaves))
         assert len(fast_m) == len(slow_m) == 4 and fast_s[1] is skips[1] and fast_s[0] is None
         for a, b in zip(nn.tree_leaves(fast_m), nn.tree_leaves(slow_m)):
