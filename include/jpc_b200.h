@@ -287,6 +287,19 @@ int jpcb_optim_adam(int n_tensors, const long long* numel, const float* const* p
                     double learning_rate, double b1, double b2, double eps, int step,
                     float* const* params_out, float* const* mu_out, float* const* nu_out, void* stream);
 
+/* ---- weight regularisers of pc_energy_fn (jpc/_core/_energies.py:127-143) ------------------------------------------
+ * The reference applies `weight_decay` and `spectral_penalty` to the layers that expose `.weight` directly -- bare
+ * nn.Linear layers (the last layer of its hand-built example networks); for make_mlp models both are no-ops:
+ *   F_reg       = weight_decay/2 sum_i |W_i|^2 + spectral_penalty/2 sum_i |W_i^T W_i - I|^2     (not divided by the batch)
+ *   dF_reg/dW_i = weight_decay W_i + 2 spectral_penalty W_i (W_i^T W_i - I)
+ * n tensors W[i]: [rows[i], cols[i]] (host arrays).  F_inout (device float, nullable) receives F_reg, or has it added when
+ * accumulate_F != 0; gW_inout (nullable list; entries nullable) is ACCUMULATED into.  In data-parallel runs the caller adds
+ * these terms once, after the gradient exchange. */
+size_t jpcb_pc_weight_reg_workspace_bytes(int n, const int* rows, const int* cols);
+int jpcb_pc_weight_reg(int n, const float* const* W, const int* rows, const int* cols, float weight_decay,
+                       float spectral_penalty, float* F_inout, int accumulate_F, float* const* gW_inout,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- launch plans ("build once, replay") ---------------------------------------------
  * Every compute entry point above only ENQUEUES, and a call with identical arguments -- descriptor, every pointer
  * (including the contents of the pointer lists), workspace, stream, device -- enqueues an identical kernel sequence.

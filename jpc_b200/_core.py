@@ -187,10 +187,13 @@ class _Net:
         L = len(model)
         low = self._lowering(model)
         parts, linears, Ws, bs, dims, dev = low["parts"], low["linears"], low["Ws"], list(low["bs"]), list(low["dims"]), low["dev"]
-        if low["bare"] and (float(weight_decay) != 0.0 or float(spectral_penalty) != 0.0):
-            raise NotImplementedError("weight_decay / spectral_penalty on bare Linear layers are not on the B200 path")
-        # (for make_mlp models those two regularisers are no-ops in the reference as well: the
-        #  layers are Sequential objects without a `.weight`, jpc/_core/_energies.py:128-143)
+        # weight_decay / spectral_penalty apply to layers that expose `.weight` directly -- bare Linear layers
+        # (jpc/_core/_energies.py:127-143; `> 0` as there); for make_mlp models (Sequential layers) they are no-ops in the
+        # reference as well
+        self.reg = None
+        if low["bare"] and (float(weight_decay) > 0.0 or float(spectral_penalty) > 0.0):
+            idx = [i for i, l in enumerate(model) if hasattr(l, "weight") and not hasattr(l, "layers")]
+            self.reg = (max(float(weight_decay), 0.0), max(float(spectral_penalty), 0.0), idx)
         self.linears = linears
         self.model, self.skip_model = model, skip_model
         self._low = low
@@ -320,6 +323,29 @@ class _Net:
         if type(model) is ModelList:
             model._jpcb = low
         return low
+
+    def weight_reg(self, F=None, gW=None):
+        """Adds the weight regularisers of the bare Linear layers (jpc/_core/_energies.py:127-143) to the device scalar `F`
+        and / or accumulates their gradients into `gW` (per-layer list in the USER's shapes): one library call on the
+        layers' own (unpadded) weights.  No-op when the model has none or both coefficients are zero."""
+        if self.reg is None:
+            return
+        import ctypes as C
+        wd, sp, idx = self.reg
+        Ws = [self.linears[i].weight for i in idx]
+        n = len(Ws)
+        rows = (C.c_int * n)(*[w.shape[0] for w in Ws])
+        cols = (C.c_int * n)(*[w.shape[1] for w in Ws])
+        need = _lib.lib.jpcb_pc_weight_reg_workspace_bytes(n, rows, cols)
+        ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        g = None
+        if gW is not None:
+            for i in idx:
+                if not gW[i].is_contiguous():
+                    raise ValueError("weight regularisers: gradient buffers must be contiguous")
+            g = _lib.ptr_array([gW[i] for i in idx])
+        _lib.check(_lib.lib.jpcb_pc_weight_reg(n, _lib.ptr_array(Ws), rows, cols, wd, sp, _lib.ptr(F), 1, g, _lib.ptr(ws), need,
+                                               self.stream()))
 
     def workspace(self) -> torch.Tensor:
         k = (self.dev, self.stream())  # one per stream: calls on different streams may overlap on the device
@@ -451,6 +477,7 @@ def pc_energy_fn(params, activities, y, *, x=None, loss="mse", param_type="sp", 
     g = net.new_acts()
     _lib.check(_lib.lib.jpcb_pc_activity_grad(net.desc, net.W, net.b, _lib.ptr_array(net.in_acts(activities)), _lib.ptr(net.x),
                                               _lib.ptr(net.y), _lib.ptr(F), _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
+    net.weight_reg(F=F)
     return F
 
 
@@ -469,6 +496,7 @@ def compute_pc_activity_grad(params, activities, y, *, x, loss_id="mse", param_t
     g = net.new_acts()
     _lib.check(_lib.lib.jpcb_pc_activity_grad(net.desc, net.W, net.b, _lib.ptr_array(net.in_acts(activities)), _lib.ptr(net.x),
                                               _lib.ptr(net.y), _lib.ptr(F), _lib.ptr_array(g), _lib.ptr(ws), ws.numel(), net.stream()))
+    net.weight_reg(F=F)   # (the energy value includes the weight regularisers; the activity gradients do not depend on them)
     return F, net.out_acts(g)
 
 
@@ -494,6 +522,7 @@ def _param_grads_raw(net: _Net, activities, want_energies=False, arena=None):
                                             _lib.ptr(net.y), _lib.ptr_array(gW), _lib.ptr_array(gb) if gb else None, _lib.ptr(E),
                                             _lib.ptr(ws), ws.numel(), net.stream()))
     gW, gb = net.out_grads(gW, gb)
+    net.weight_reg(gW=gW)
     return gW, gb, E
 
 

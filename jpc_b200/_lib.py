@@ -80,6 +80,9 @@ SIGNATURES = {
     "jpcb_hpc_param_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _PP, _PP, _PP, _P, _P, C.c_size_t, _P]),
     "jpcb_epc_workspace_bytes": (C.c_size_t, [C.POINTER(PcDesc)]),
     "jpcb_epc_grads": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _PP, _PP, _PP, _P, C.c_size_t, _P]),
+    "jpcb_pc_weight_reg_workspace_bytes": (C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "jpcb_pc_weight_reg": (C.c_int, [C.c_int, _PP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.c_float, _P, C.c_int, _PP, _P,
+                                     C.c_size_t, _P]),
     "jpcb_plan_cache_configure": (C.c_int, [C.c_int, C.c_int]),
     "jpcb_plan_cache_clear": (C.c_int, []),
     "jpcb_plan_cache_stats": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),

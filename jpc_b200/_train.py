@@ -380,8 +380,14 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
     if not exchanged:
         arena.all_reduce()  # the one exchange step of the data-parallel path (no-op when not distributed)
     acts = net.out_acts(acts)
+    gW = gb = None
+    if net.reg is not None or grad_norms or net.padded:
+        # user-shaped gradient tensors are needed: views of the arena (slices of it on a padded tensor-core layout).  The
+        # weight regularisers of bare Linear layers are added here -- once, after the exchange -- on the layers' own weights
+        gW, gb = net.out_grads(arena.gW, arena.gb)
+        net.weight_reg(gW=gW)
     p_norms = compute_param_norms((model, skip_model)) if param_norms else (None, None)
-    g_norms = compute_param_norms(_grads_pytree(net, *net.out_grads(arena.gW, arena.gb))) if grad_norms else (None, None)
+    g_norms = compute_param_norms(_grads_pytree(net, gW, gb)) if grad_norms else (None, None)
     a_norms = compute_activity_norms(acts) if activity_norms else None
     # the update: parameter and gradient leaves are already at hand as flat lists in tree order (per layer: weight, bias;
     # the skip model has no array leaves), so the fused optimiser kernel is fed without walking the pytrees
@@ -391,7 +397,7 @@ def make_pc_step(model, optim, opt_state, output, *, input=None, loss_id="mse", 
         res = _fused_param_update(net, arena, optim, opt_state)
         if res is not None:
             res, addrs = res[:2], res[2]
-    if res is None:
+    if res is None and gW is None:
         gW, gb = net.out_grads(arena.gW, arena.gb)   # (gradient views are only carved on this, slower, path)
     if res is None and fused is not None:
         p_leaves, g_leaves = [], []

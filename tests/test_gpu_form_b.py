@@ -170,3 +170,57 @@ def test_form_b_limits_are_reported():
         J.pc_energy_fn((gm, None), acts, gy, x=None)
     with pytest.raises(NotImplementedError):   # bPC
         J.bpc_energy_fn(gm, gm, acts[1:], gy, x=gx)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_weight_decay_and_spectral_penalty_on_bare_linear_layers(dtype):
+    """The reference applies both regularisers to layers that expose `.weight` directly (jpc/_core/_energies.py:127-143):
+    the bare last Linear of the notebook networks, or every layer of a network built from bare Linears.  Energy value,
+    parameter gradients and the update inside `make_pc_step` against the oracle's autograd; make_mlp models are untouched."""
+    import jpc_b200 as J
+    J.set_compute_dtype(dtype)
+    tol = TOL[dtype]
+    wd, sp = 0.3, 0.05
+    dims, B = ((64, 128, 3, 24), 32) if dtype == "bf16" else ((10, 12, 3, 5), 4)
+    cases = []
+    om, x, y = _case("tanh", dims=dims, B=B)
+    cases.append((om, x, y))
+    lin = f32_model(O.make_mlp(3, dims[0], dims[1], dims[2], dims[3], "linear", use_bias=True))   # a network of bare Linears
+    for layer in lin:
+        layer["bare"] = True
+    cases.append((lin, x, y))
+    for om, x, y in cases:
+        gm, gx, gy = to_gpu_model(om), dev(x), dev(y)
+        acts = [a.float().double() for a in perturb(O.init_activities_with_ffwd(om, x))]
+        if dtype == "bf16":
+            acts = [_bf16(a) for a in acts]
+        gacts = devs(acts)
+        kw = dict(weight_decay=wd, spectral_penalty=sp)
+        F = O.pc_energy_fn(om, None, acts, y, x=x, **kw)
+        assert abs(float(J.pc_energy_fn((gm, None), gacts, gy, x=gx, **kw)) - float(F)) <= tol * abs(float(F))
+        gF, _ = J.compute_pc_activity_grad((gm, None), gacts, gy, x=gx, **kw)
+        assert abs(float(gF) - float(F)) <= tol * abs(float(F))
+        assert abs(float(F) - float(O.pc_energy_fn(om, None, acts, y, x=x))) > 1e-3 * abs(float(F))   # (the terms are not negligible here)
+        pg = O.compute_pc_param_grads(om, None, acts, y, x=x, **kw)
+        gpg, _ = J.compute_pc_param_grads((gm, None), gacts, gy, x=gx, **kw)
+        for l, q in enumerate(pg):
+            assert _close(_lin(gpg[l]).weight, q["W"], tol, float(q["W"].abs().max())), l
+            assert _close(_lin(gpg[l]).bias, q["b"], tol, float(q["b"].abs().max())), l
+        # inside make_pc_step: sgd(1.0) moves every parameter by exactly its (regularised) gradient at the solution
+        sol, _ = O.solve_inference(om, None, O.init_activities_with_ffwd(om, x), y, x=x, solver="euler", max_t1=1.0, dt=0.5,
+                                   event_atol=0.0, event_rtol=0.0)
+        ref = O.compute_pc_param_grads(om, None, sol, y, x=x, **kw)
+        opt = J.optim.sgd(1.0)
+        out = J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx, ode_solver=J.Euler(), max_t1=1.0, dt=0.5,
+                             stepsize_controller=J.ConstantStepSize(), grad_norms=True, **kw)
+        for l, g in enumerate(ref):
+            ulp = 1.2e-7 * float(_lin(gm[l]).weight.abs().max())
+            got = (_lin(gm[l]).weight.double() - _lin(out["model"][l]).weight.double()).cpu()
+            assert float((got - g["W"]).abs().max()) <= tol * float(g["W"].abs().max()) + ulp, l
+        assert out["model_grad_norms"] is not None
+    # make_mlp layers are Sequential objects without `.weight`: both regularisers are no-ops, as in the reference
+    mm = f32_model(O.make_mlp(0, dims[0], dims[1], dims[2], dims[3], "tanh"))
+    gm, gx, gy = to_gpu_model(mm), dev(x), dev(y)
+    ga = J.init_activities_with_ffwd(gm, gx)
+    assert float(J.pc_energy_fn((gm, None), ga, gy, x=gx, weight_decay=wd, spectral_penalty=sp)) == pytest.approx(
+        float(J.pc_energy_fn((gm, None), ga, gy, x=gx)), rel=1e-6)

@@ -290,3 +290,26 @@ def test_saveat_bookkeeping_matches_oracle_interpolation():
     save.step(*traj[0], *traj[1])
     ys = save.finish(traj[1][1])
     assert torch.equal(ys[0][1], traj[1][1][0]) and bool(torch.isinf(ys[0][2:]).all()) and bool(torch.isfinite(ys[0][0]).all())
+
+
+def test_weight_regularisers_apply_to_bare_linear_layers_only():
+    """jpc/_core/_energies.py:127-143: weight_decay / spectral_penalty see only layers that expose `.weight` (bare Linear);
+    their gradient is wd W + 2 sp W (W^T W - I); make_mlp models are untouched."""
+    model = O.make_form_b_mlp(0, 10, 12, 3, 5, "tanh", use_bias=True)
+    model[-1]["bare"] = True
+    x, y = _data(4, 10, 5)
+    acts = _perturb(O.init_activities_with_ffwd(model, x))
+    wd, sp = 0.3, 0.05
+    F0 = O.pc_energy_fn(model, None, acts, y, x=x)
+    F1 = O.pc_energy_fn(model, None, acts, y, x=x, weight_decay=wd, spectral_penalty=sp)
+    W = model[-1]["W"]
+    S = W.T @ W - torch.eye(W.shape[1], dtype=W.dtype)
+    assert abs(float(F1 - F0) - float(0.5 * wd * (W ** 2).sum() + 0.5 * sp * (S ** 2).sum())) < 1e-12
+    g0 = O.compute_pc_param_grads(model, None, acts, y, x=x)
+    g1 = O.compute_pc_param_grads(model, None, acts, y, x=x, weight_decay=wd, spectral_penalty=sp)
+    assert O.max_rel_err(g1[-1]["W"] - g0[-1]["W"], wd * W + 2 * sp * W @ S) < 1e-12
+    for a, b in zip(g0[:-1], g1[:-1]):
+        assert torch.equal(a["W"], b["W"])
+    mlp = O.make_mlp(0, 10, 12, 3, 5, "tanh")
+    a2 = _perturb(O.init_activities_with_ffwd(mlp, x))
+    assert float(O.pc_energy_fn(mlp, None, a2, y, x=x, weight_decay=wd, spectral_penalty=sp)) == float(O.pc_energy_fn(mlp, None, a2, y, x=x))
