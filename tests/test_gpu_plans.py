@@ -119,3 +119,42 @@ def test_returned_model_carries_its_lowering_and_loses_it_when_touched():
     assert abs(float(e_new) - float(e_ref)) <= 1e-6 * abs(float(e_ref)) and abs(float(e_new) - float(e_memo)) > 1e-3 * abs(float(e_memo))
     out2 = J.make_pc_step(out["model"], opt, out["opt_state"], y, **kw)   # and training simply goes on from the touched model
     assert float(out2["loss"]) > 0 and out2["model"]._jpcb is not None
+
+
+def test_plan_eviction_and_capture_budget_keep_results_right():
+    """Two plans of room, three call signatures used round-robin: plans are evicted (and their graphs destroyed only after
+    their last launch completed) and re-captured; past the capture budget the calls simply enqueue their kernels.  Every call
+    must still give the same numbers as with plans off."""
+    from jpc_b200 import _lib
+    from jpc_b200._core import _Net
+    from jpc_b200._train import _Arena
+    J, om, gm, x, y, _, _ = _setup("f32", (24, 48, 4, 8), 16)
+    net = _Net(gm, None, x, y, param_type="sp", loss_id="mse", gamma=None, output_energy_scaling=None, activity_decay=0.0,
+               weight_decay=0.0, spectral_penalty=0.0, solver=_lib.SOLVER_EULER, n_steps=3, dt=0.5, dt_last=0.5)
+    ws = net.workspace()
+    sets = [(_Arena(net), net.new_acts()) for _ in range(3)]
+
+    def call(k):
+        arena, acts = sets[k]
+        arena.flat.zero_()
+        _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(x), _lib.ptr(y), _lib.ptr_array(acts),
+                                               _lib.ptr(arena.loss), _lib.ptr(arena.E), _lib.ptr_array(arena.gW),
+                                               _lib.ptr_array(arena.gb), _lib.ptr(ws), ws.numel(), net.stream()))
+        torch.cuda.synchronize()
+        return arena.flat.clone()
+    try:
+        J.plan_cache_clear()
+        J.plan_cache_configure(0, 2)
+        want = call(0)
+        J.plan_cache_configure(2, 2)
+        s0 = J.plan_cache_stats()
+        for it in range(30):
+            got = call(it % 3)
+            assert rel(got, want.double().cpu()) < 1e-6, it
+        s1 = J.plan_cache_stats()
+    finally:
+        J.plan_cache_clear()
+        J.plan_cache_configure(16, 2)
+    print("eviction run:", {k: s1[k] - s0[k] for k in s1})
+    assert s1["captures"] - s0["captures"] >= 3          # more signatures than room: something was captured again
+    assert s1["captures"] - s0["captures"] <= 12         # ... but the budget stopped the thrashing
