@@ -76,7 +76,7 @@ uint64_t hash_words(const std::vector<uint64_t>& w) {
 // experiment / test switches that are read from the environment on every call and change the kernel sequence: part of the key
 uint64_t env_signature() {
   uint64_t h = 0;
-  for (const char* name : {"JPCB_STAGED", "JPCB_TS_STG", "JPCB_SOLVE_MIN_ROUNDS", "JPCB_TS_PROMO", "JPCB_CHAIN_FFWD"}) {
+  for (const char* name : {"JPCB_STAGED", "JPCB_TS_STG", "JPCB_SOLVE_MIN_ROUNDS", "JPCB_TS_PROMO", "JPCB_CHAIN_FFWD", "JPCB_TS_HINTS"}) {
     const char* v = getenv(name);
     h = h * 1000003ull + (v ? (uint64_t)atoll(v) + 1ull : 0ull);
   }

@@ -96,7 +96,8 @@ struct alignas(64) TsGroup {
   int tiles_full;  // tiles of a step with every layer active
   int stg;         // storer writes finished slabs with coalesced st.global (LSU) instead of TMA stores
   int warm_begin[TS_MAX_WARM + 1];  // first tile of warm-up step s; warm_begin[warm] = first tile of the first full step
-  int pad_[5];
+  int hints;       // L2 eviction-priority hints: bit 0 weights (B operand) evict_last, bit 1 slab loads evict_first, bit 2 slab stores evict_first
+  int pad_[4];
   TsTask t[TS_MAX_TASKS];
 };
 
@@ -157,6 +158,37 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :
                : "l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+// L2 eviction-priority policies and the hinted forms of the TMA instructions
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_cg2_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t src, int c_inner, int c_outer, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c_inner), "r"(c_outer), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -371,6 +403,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_con
     // ===================== mainloop TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
+    const uint64_t pol_last = l2_policy_evict_last();
     for (int tile = unit; tile < g.total_tiles; tile += nunits) {
       const TsTile ti = ts_decode(g, tile);
       const TsTask& t = g.t[ti.ti];
@@ -385,7 +418,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_con
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CG);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           tma_load_2d<CG>(sa, &t.tmA, fb, kb * TC_BLOCK_K, m0);
-          tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0);
+          if (g.hints & 1) tma_load_2d_cg2_hint(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0, pol_last);
+          else tma_load_2d<CG>(sa + TC_A_BYTES, &t.tmB, fb, kb * TC_BLOCK_K, n0);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -423,6 +457,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_con
   } else if (warp == 2) {
     // ===================== epilogue loader: slab inputs of this CTA's 128 rows, in tile order =====================
     uint32_t j = 0;  // running slab counter: slot = j % SLOTS, use parity = (j / SLOTS) & 1
+    const uint64_t pol_first = l2_policy_evict_first();
     for (int tile = unit; tile < g.total_tiles; tile += nunits) {
       const TsTile ti = ts_decode(g, tile);
       const TsTask& t = g.t[ti.ti];
@@ -434,14 +469,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_con
         mbar_wait(sfree_bar(slot), ((j / SLOTS) & 1u) ^ 1u);
         if (elect_one()) {
           const uint32_t dst = slot_base + slot * TS_SLOT_BYTES, bar = sfull_bar(slot);
+          const bool hf = (g.hints & 2) != 0;
+          auto ld = [&](uint32_t d_, const CUtensorMap* mp) {
+            if (hf) tma_load_2d_hint(d_, mp, bar, n0 + s * sc, m0, pol_first);
+            else tma_load_2d<1>(d_, mp, bar, n0 + s * sc, m0);
+          };
           if (kind == TS_GRAD_P) {
             mbar_arrive_expect_tx(bar, 16384);
-            tma_load_2d<1>(dst, &t.tmI0, bar, n0 + s * sc, m0);
-            tma_load_2d<1>(dst + 8192, &t.tmI1, bar, n0 + s * sc, m0);
+            ld(dst, &t.tmI0);
+            ld(dst + 8192, &t.tmI1);
           } else {
             mbar_arrive_expect_tx(bar, kind == TS_GRAD ? TS_SLOT_BYTES : TS_SLAB_F32);
-            tma_load_2d<1>(dst, &t.tmI0, bar, n0 + s * sc, m0);
-            if (kind == TS_GRAD) tma_load_2d<1>(dst + TS_SLAB_F32, &t.tmI1, bar, n0 + s * sc, m0);
+            ld(dst, &t.tmI0);
+            if (kind == TS_GRAD) ld(dst + TS_SLAB_F32, &t.tmI1);
           }
         }
         __syncwarp();
@@ -520,8 +560,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_con
         mbar_wait(sready_bar(slot), (j / SLOTS) & 1u);
         if (lane == 0) {  // (one fixed lane: bulk async-groups are per thread)
           const uint32_t src = slot_base + slot * TS_SLOT_BYTES;
-          if (kind != TS_ERR) tma_store_2d(&t.tmO0, src, n0 + s * sc, m0);
-          tma_store_2d(&t.tmO1, src + TS_SLAB_F32, n0 + s * sc, m0);
+          if (g.hints & 4) {
+            const uint64_t pf = l2_policy_evict_first();
+            if (kind != TS_ERR) tma_store_2d_hint(&t.tmO0, src, n0 + s * sc, m0, pf);
+            tma_store_2d_hint(&t.tmO1, src + TS_SLAB_F32, n0 + s * sc, m0, pf);
+          } else {
+            if (kind != TS_ERR) tma_store_2d(&t.tmO0, src, n0 + s * sc, m0);
+            tma_store_2d(&t.tmO1, src + TS_SLAB_F32, n0 + s * sc, m0);
+          }
           bulk_commit();
           if (prev_slot >= 0) {
             bulk_wait_read<1>();  // everything but the group just committed has been read out of shared memory
