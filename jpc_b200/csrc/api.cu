@@ -1230,7 +1230,11 @@ static int pc_train_step_impl(const jpcb_pc_desc* desc, const float* const* W, c
   // were zeroed and are never written): on the fp32 path the error pass at the solution skips them too -- zero energies and
   // zero gradients by construction, whatever order the feed-forward kernel summed in (so the chain kernel may be used).
   const bool wave = r.wavefront_ok(), wave_tail = wave && !r.tc;
-  RET(r.ffwd(A_out, r.ws.red + RED_LOSS, r.hoist, wave_tail));   // init + loss at the init + hoisted P1 + operand copies
+  // (the hoisted first-layer prediction P1 is the ENERGY's: no skip term at layer 0, jpc/_core/_energies.py:111-126; the init
+  //  honours a skip there, _init.py:69-78 -- with one, z_1 is not P1 and P1 takes its own GEMM)
+  const bool p1_from_init = r.hoist && !desc->skip[0];
+  RET(r.ffwd(A_out, r.ws.red + RED_LOSS, p1_from_init, wave_tail));   // init + loss at the init + hoisted P1 + operand copies
+  if (r.hoist && !p1_from_init) RET(r.predict_p1());
   RET(r.infer_loop(A_out, true));
   const int reach = r.L - 1 - desc->n_steps;  // lowest layer whose error can be non-zero at the solution
   RET(r.errors(r.hoist ? (wave_tail && reach > 1 ? reach : 1) : 0, A_out, false, true));  // errors + layer energies at the solution

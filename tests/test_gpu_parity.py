@@ -1271,6 +1271,32 @@ def test_whole_solve_launch_bf16(shape):
         assert rel(p, q.double().cpu()) < 1e-5
 
 
+def test_user_skip_at_layer_0_disables_the_wavefront_shortcut():
+    """A skip at layer 0 enters the feed-forward init (jpc/_core/_init.py:69-78 honours any non-None skip) but not the energy
+    (jpc/_core/_energies.py:111-126 only layers 1..L-2): err[0] = x != 0 at the init, so the hidden errors are NOT all zero
+    there and the fused train step must evaluate every layer from the first step on."""
+    import jpc_b200 as J
+    d, depth, B = 16, 5, 8
+    om = f32_model(O.make_mlp(0, d, d, depth, 6, "tanh", use_bias=True))
+    sk = [True, True, True, True, False]
+    x, y = data(B, d, 6, onehot_out=False)
+    x, y = x.float().double(), y.float().double()
+    ref = O.pc_train_step(om, sk, x, y, solver="euler", max_t1=2.0, dt=0.5)
+    assert float(ref["energies"][-1]) > 1e-3          # (the first layer's error is large from the start)
+    gm = to_gpu_model(om)
+    gsk = [J.nn.Lambda(J.nn.Identity()) if f else None for f in sk]
+    opt = J.optim.sgd(1.0)
+    for dtype, tol in (("f32", TOL32), ("bf16", TOLBF)):
+        J.set_compute_dtype(dtype)
+        out = J.make_pc_step(gm, opt, opt.init((gm, gsk)), dev(y), input=dev(x), skip_model=gsk, ode_solver=J.Euler(), max_t1=2.0,
+                             dt=0.5, stepsize_controller=J.ConstantStepSize())
+        assert abs(float(out["loss"]) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+        assert rel(out["energies"], ref["energies"]) < tol
+        for p, q in zip(out["activities"][:-1], ref["activities"][:-1]):
+            assert rel(p[0], q) < tol
+    J.set_compute_dtype("f32")
+
+
 # ---- feed-forward chain of a deep narrow network as one launch (csrc/chain_ffwd.cuh) ----------------------------------
 @pytest.mark.parametrize("shape", [
     # d_in, width, depth, d_out, act, B, bias, param_type, skips
