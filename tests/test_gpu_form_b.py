@@ -224,3 +224,45 @@ def test_weight_decay_and_spectral_penalty_on_bare_linear_layers(dtype):
     ga = J.init_activities_with_ffwd(gm, gx)
     assert float(J.pc_energy_fn((gm, None), ga, gy, x=gx, weight_decay=wd, spectral_penalty=sp)) == pytest.approx(
         float(J.pc_energy_fn((gm, None), ga, gy, x=gx)), rel=1e-6)
+
+
+def test_form_b_deep_network_through_the_chain_feed_forward():
+    """Eight Form B layers: the one-launch feed-forward chain (csrc/chain_ffwd.cuh) applies the post-activation too, and
+    the fused train step after it matches the oracle."""
+    import jpc_b200 as J
+    from tests.test_gpu_parity import _with_env
+    om, x, y = _case("tanh", dims=(12, 24, 8, 5), B=6)
+    gm, gx, gy = to_gpu_model(om), dev(x), dev(y)
+    a0 = O.init_activities_with_ffwd(om, x)
+    for mode in (2, 0):
+        with _with_env(JPCB_CHAIN_FFWD=mode):
+            for p, q in zip(J.init_activities_with_ffwd(gm, gx), a0):
+                assert rel(p, q) < TOL["f32"], mode
+    ref = O.pc_train_step(om, None, x, y, solver="euler", max_t1=2.0, dt=0.5)
+    opt = J.optim.sgd(1.0)
+    out = J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx, ode_solver=J.Euler(), max_t1=2.0, dt=0.5,
+                         stepsize_controller=J.ConstantStepSize())
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= TOL["f32"] * abs(float(ref["loss"]))
+    assert rel(out["energies"], ref["energies"]) < TOL["f32"]
+    for p, q in zip(out["activities"][:-1], ref["activities"][:-1]):
+        assert rel(p[0], q) < TOL["f32"]
+
+
+def test_form_b_fused_train_step_f32x3():
+    import jpc_b200 as J
+    J.set_compute_dtype("f32x3")
+    om, x, y = _case("tanh", dims=(64, 128, 4, 32), B=64)
+    gm, gx, gy = to_gpu_model(om), dev(x), dev(y)
+    ref = O.pc_train_step(om, None, x, y, solver="heun", max_t1=2.0, dt=0.5)
+    opt = J.optim.sgd(1.0)
+    out = J.make_pc_step(gm, opt, opt.init((gm, None)), gy, input=gx, ode_solver=J.Heun(), max_t1=2.0, dt=0.5,
+                         stepsize_controller=J.ConstantStepSize())
+    tol = TOL["f32x3"]
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+    assert rel(out["energies"], ref["energies"]) < tol
+    for p, q in zip(out["activities"][:-1], ref["activities"][:-1]):
+        assert rel(p[0], q) < tol
+    for l, g in enumerate(ref["grads"]):
+        ulp = 1.2e-7 * float(_lin(gm[l]).weight.abs().max())
+        got = (_lin(gm[l]).weight.double() - _lin(out["model"][l]).weight.double()).cpu()
+        assert float((got - g["W"]).abs().max()) <= tol * float(g["W"].abs().max()) + ulp, l

@@ -1271,6 +1271,42 @@ def test_whole_solve_launch_bf16(shape):
         assert rel(p, q.double().cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("dtype,tol", [("f32", TOL32), ("bf16", TOLBF), ("f32x3", TOL32)])
+def test_fused_train_step_heun_cross_entropy_skips_biases(dtype, tol):
+    """A corner of the fused train step the configs do not visit: Heun steps, cross-entropy output, identity skips, biases,
+    in all three arithmetic modes -- loss, energies, activities and every parameter gradient against the oracle."""
+    import jpc_b200 as J
+    J.set_compute_dtype(dtype)
+    d_in, width, depth, d_out, B = (64, 64, 5, 16, 32) if dtype != "f32" else (12, 12, 5, 6, 7)
+    om = f32_model(O.make_mlp(0, d_in, width, depth, d_out, "tanh", use_bias=True))
+    sk = O.make_skip_model(depth)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, d_in, generator=g, dtype=torch.float64).float().double()
+    y = torch.nn.functional.one_hot(torch.randint(0, d_out, (B,), generator=g), d_out).double()
+    ref = O.pc_train_step(om, sk, x, y, solver="heun", max_t1=2.0, dt=0.5, loss_id="ce")
+    gm, gsk = to_gpu_model(om), _gpu_skip(sk)
+    opt = J.optim.sgd(1.0)
+    out = J.make_pc_step(gm, opt, opt.init((gm, gsk)), dev(y), input=dev(x), loss_id="ce", skip_model=gsk, ode_solver=J.Heun(),
+                         max_t1=2.0, dt=0.5, stepsize_controller=J.ConstantStepSize())
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+    assert rel(out["energies"], ref["energies"]) < tol
+    for p, q in zip(out["activities"][:-1], ref["activities"][:-1]):
+        assert rel(p[0], q) < tol
+    gmax = max(float(gr["W"].abs().max()) for gr in ref["grads"])
+    # The hidden layers sit near equilibrium after the feed-forward init: their errors e = z - prediction are 1e-3 of z, so a
+    # 1e-7 (fp32) or 4e-3 (bf16 operands) relative rounding of the prediction is 1e-4 / several times e itself, and their
+    # gradients (1e-2 of the output layer's) cannot carry the tolerance on their own scale in ANY arithmetic of that
+    # precision -- gated relative to the gradient list's scale (the group arm of tests/helpers.py:gate_all)
+    floor = lambda own: gmax
+    for l, gr in enumerate(ref["grads"]):   # sgd(1.0): the parameter moved by exactly its gradient
+        ulp = 1.2e-7 * float(gm[l][1].weight.abs().max())
+        got = (gm[l][1].weight.double() - out["model"][l][1].weight.double()).cpu()
+        assert float((got - gr["W"]).abs().max()) <= tol * floor(float(gr["W"].abs().max())) + ulp, l
+        gotb = (gm[l][1].bias.double() - out["model"][l][1].bias.double()).cpu()
+        assert float((gotb - gr["b"]).abs().max()) <= tol * floor(float(gr["b"].abs().max())) + ulp, l
+    J.set_compute_dtype("f32")
+
+
 def test_user_skip_at_layer_0_disables_the_wavefront_shortcut():
     """A skip at layer 0 enters the feed-forward init (jpc/_core/_init.py:69-78 honours any non-None skip) but not the energy
     (jpc/_core/_energies.py:111-126 only layers 1..L-2): err[0] = x != 0 at the init, so the hidden errors are NOT all zero
