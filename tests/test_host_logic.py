@@ -55,3 +55,35 @@ def test_pointer_table():
     arr = _lib.ptr_array(ts)
     assert arr[0] == ts[0].data_ptr() and arr[1] is None and arr[2] == ts[2].data_ptr()
     assert len(_lib.ptr_array([])) == 1
+
+
+def test_gradient_arena_layout_buckets_and_lazy_views():
+    """The data-parallel exchange's flat arena (jpc_b200/_train.py:_Arena): segments aligned and disjoint, [E_layers, loss]
+    at the tail, layer buckets contiguous and covering everything, per-parameter views only made on demand."""
+    from jpc_b200._train import _Arena
+    for bias in (False, True):
+        ws = [(20, 12)] + [(20, 20)] * 5 + [(7, 20)]
+        bs = [(s[0],) for s in ws] if bias else None
+        arena = _Arena(weight_shapes=ws, bias_shapes=bs, device="cpu")
+        assert "gW" not in arena.__dict__ and tuple(arena.E.shape) == (7,) and arena.loss.ndim == 0
+        arena.flat.zero_()
+        for n in (1, 2, 4, 7, 50):
+            bk = arena.buckets(n)
+            assert bk[0][0] == 0 and bk[0][2] == 0 and bk[-1][1] == 7 and bk[-1][3] == arena.flat.numel()
+            for (l0, l1, f0, f1), (m0, m1, g0, g1) in zip(bk, bk[1:]):
+                assert l1 == m0 and f1 == g0 and l0 < l1 and f0 < f1       # contiguous in layers and in the buffer
+            assert len(bk) == min(n, 7)
+        gW, gb = arena.gW, arena.gb                                          # carved now
+        assert len(gW) == 7 and (gb is None) == (not bias)
+        for l, g in enumerate(gW):
+            assert tuple(g.shape) == ws[l] and g.data_ptr() == arena.flat.data_ptr() + 4 * arena.offs[arena.per_layer * l]
+            g.add_(1.0)
+        if bias:
+            for g in gb:
+                g.add_(1.0)
+        arena.E.add_(1.0)
+        arena.loss.add_(1.0)
+        n_el = sum(a * b for a, b in ws) + (sum(s[0] for s in bs) if bias else 0) + 7 + 1
+        assert float(arena.flat.sum()) == n_el                                # every element of every view exactly once
+        pW, pb = arena.grad_ptr_arrays()
+        assert pW[3] == gW[3].data_ptr() and ((pb is None) if not bias else pb[3] == gb[3].data_ptr())
