@@ -23,6 +23,9 @@ from .nn import tree_unflatten_like
 from .optim import update_and_apply
 
 
+_BPC_DESC_CACHE: dict = {}
+
+
 class _BpcNet:
     """(top_down, bottom_up) lowered to a jpcb_bpc_desc + pointer arrays."""
 
@@ -73,35 +76,44 @@ class _BpcNet:
             # activations; zero weight rows and columns), so energies and the un-padded parts of every result are
             # unchanged; results are sliced back.  (Data layout only -- no arithmetic happens here.)
             pd = [(v + 7) // 8 * 8 for v in dims]
-            P = torch.nn.functional.pad
-            Ws = [P(Ws[j], (0, pd[j] - dims[j], 0, pd[j + 1] - dims[j + 1])).contiguous() for j in range(n)]
-            Vs = [P(Vs[j], (0, pd[j + 1] - dims[j + 1], 0, pd[j] - dims[j])).contiguous() for j in range(n)]
+
+            def P(t, pads):  # (only the tensors that actually need padding are copied: this runs every call)
+                return torch.nn.functional.pad(t, pads).contiguous() if any(pads) else t
+            Ws = [P(Ws[j], (0, pd[j] - dims[j], 0, pd[j + 1] - dims[j + 1])) for j in range(n)]
+            Vs = [P(Vs[j], (0, pd[j + 1] - dims[j + 1], 0, pd[j] - dims[j])) for j in range(n)]
             if bWs is not None:
-                bWs = [P(bWs[j], (0, pd[j + 1] - dims[j + 1])).contiguous() for j in range(n)]
+                bWs = [P(bWs[j], (0, pd[j + 1] - dims[j + 1])) for j in range(n)]
             if bVs is not None:
-                bVs = [P(bVs[j], (0, pd[j] - dims[j])).contiguous() for j in range(n)]
-            x = P(x, (0, pd[0] - dims[0])).contiguous()
-            y = P(y, (0, pd[-1] - dims[-1])).contiguous()
+                bVs = [P(bVs[j], (0, pd[j] - dims[j])) for j in range(n)]
+            x = P(x, (0, pd[0] - dims[0]))
+            y = P(y, (0, pd[-1] - dims[-1]))
             dims = pd
-        d = _lib.BpcDesc()
-        d.td.n_layers, d.td.batch_local = n, B
-        d.td.batch_global = B if batch_global is None else int(batch_global)
-        for i, v in enumerate(dims):
-            d.td.dims[i] = v
-        for j in range(n):
-            d.td.act[j] = _lib.ACT_IDS[td[j][0]]
-            d.bu_act[j] = _lib.ACT_IDS[bu[j][0]]
-            d.td.skip[j] = 1 if skips[j] else 0
-            d.td.scalings[j] = 1.0
-        d.td.has_bias, d.bu_has_bias = int(all(td_bias)), int(all(bu_bias))
-        d.td.dtype, d.td.loss = _lib.DTYPE_IDS[self.dtype], _lib.LOSS_MSE
-        d.td.output_energy_scaling, d.td.activity_decay = 1.0, 0.0
-        d.td.solver, d.td.n_steps, d.td.dt, d.td.dt_last = _lib.SOLVER_EULER, int(n_steps), float(dt), float(dt)
-        d.forward_energy_weight, d.backward_energy_weight = float(forward_energy_weight), float(backward_energy_weight)
-        self.desc = d
-        self.ws_bytes = _lib.lib.jpcb_bpc_workspace_bytes(d)
-        if self.ws_bytes == 0:
-            _lib.check(_lib.lib.jpcb_bpc_energy(d, None, None, None, None, None, None, None, None, None, 0, None) or _lib.EINVAL)
+        bg = B if batch_global is None else int(batch_global)
+        key = (n, B, bg, tuple(dims), tuple(p[0] for p in td), tuple(p[0] for p in bu), tuple(skips), all(td_bias), all(bu_bias),
+               self.dtype, int(n_steps), float(dt), float(forward_energy_weight), float(backward_energy_weight))
+        cached = _BPC_DESC_CACHE.get(key)
+        if cached is None:
+            d = _lib.BpcDesc()
+            d.td.n_layers, d.td.batch_local, d.td.batch_global = n, B, bg
+            for i, v in enumerate(dims):
+                d.td.dims[i] = v
+            for j in range(n):
+                d.td.act[j] = _lib.ACT_IDS[td[j][0]]
+                d.bu_act[j] = _lib.ACT_IDS[bu[j][0]]
+                d.td.skip[j] = 1 if skips[j] else 0
+                d.td.scalings[j] = 1.0
+            d.td.has_bias, d.bu_has_bias = int(all(td_bias)), int(all(bu_bias))
+            d.td.dtype, d.td.loss = _lib.DTYPE_IDS[self.dtype], _lib.LOSS_MSE
+            d.td.output_energy_scaling, d.td.activity_decay = 1.0, 0.0
+            d.td.solver, d.td.n_steps, d.td.dt, d.td.dt_last = _lib.SOLVER_EULER, int(n_steps), float(dt), float(dt)
+            d.forward_energy_weight, d.backward_energy_weight = float(forward_energy_weight), float(backward_energy_weight)
+            ws_bytes = _lib.lib.jpcb_bpc_workspace_bytes(d)
+            if ws_bytes == 0:
+                _lib.check(_lib.lib.jpcb_bpc_energy(d, None, None, None, None, None, None, None, None, None, 0, None) or _lib.EINVAL)
+            if len(_BPC_DESC_CACHE) > 128:
+                _BPC_DESC_CACHE.clear()
+            cached = _BPC_DESC_CACHE[key] = (d, ws_bytes)
+        self.desc, self.ws_bytes = cached
         self.H, self.B, self.dims, self.dev = H, B, dims, dev
         self.td_bias, self.bu_bias = all(td_bias), all(bu_bias)
         self.W, self.V = _lib.ptr_array(Ws), _lib.ptr_array(Vs)
@@ -138,7 +150,8 @@ class _BpcNet:
         if not self.bf16:
             return [a.clone() for a in activities] if clone else list(activities)
         P = torch.nn.functional.pad
-        out = [P(a, (0, self.dims[k + 1] - a.shape[1])).contiguous() for k, a in enumerate(activities[:-1])]
+        out = [P(a, (0, self.dims[k + 1] - a.shape[1])).contiguous() if self.dims[k + 1] != a.shape[1] else (a.clone() if clone else a)
+               for k, a in enumerate(activities[:-1])]
         out.append(torch.zeros(self.B, self.dims[-1], dtype=torch.float32, device=self.dev))
         return out
 
