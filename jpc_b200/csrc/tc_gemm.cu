@@ -130,7 +130,8 @@ int staged_kind(const GTask& t, int key, bool solve = false) {
   if (t.split || t.mn_major || e.ob_part != 0 || !e.Ob) return -1;
   if ((key == 3 || key == 5) && (staged_flags() & 1) && e.O && !e.Oh && e.Elb && e.Z) return TS_GRAD;
   if (solve && (key == 4 || key == 6) && e.O && !e.Oh && e.P && e.Z) return TS_GRAD_P;
-  if (key == 1 && (staged_flags() & 2) && !e.O && e.T) return TS_ERR;
+  // (ERR with a bias as its only extra -- networks built with use_bias=True -- is the plain tile + one vector load per 8 columns)
+  if ((key == 1 || (key == 7 && e.skip == 0.f && e.escale == 1.f)) && (staged_flags() & 2) && !e.O && e.T) return TS_ERR;
   return -1;
 }
 template <int ACT>
@@ -161,6 +162,7 @@ int fill_staged_task(TsTask& s, const GTask& t, int kind, int tile_begin) {
   s.K = t.K; s.tile_begin = tile_begin; s.tiles_n = (e.N + TC_BLOCK_N - 1) / TC_BLOCK_N; s.kind = kind;
   s.M = e.M; s.N = e.N; s.alpha = e.alpha; s.cg = s.cg_last = e.c * e.gscale; s.red = kind == TS_ERR ? e.red : nullptr;
   s.o0 = kind == TS_ERR ? nullptr : e.O; s.o1 = e.Ob;
+  s.bias = kind == TS_ERR ? e.bias : nullptr;
   return JPCB_OK;
 }
 

@@ -78,6 +78,7 @@ struct alignas(64) TsTask {
   int* done;      // whole-solve schedule: completion counters of this task, one per row block
   float* o0;            // the tensors behind tmO0 / tmO1 (the storer's LSU path, TsGroup::stg)
   __nv_bfloat16* o1;
+  const float* bias;    // ERR: per-column bias of the layer (e = T - a (D + b)) or null
   TsDep dep[2];
 };
 
@@ -322,16 +323,24 @@ __device__ __forceinline__ void ts_slab_grad_p(const uint32_t (&acc)[16], uint32
 }
 
 // ERR slab: e = T - a D -> bf16; returns 1/2 sum e^2 over the row's VALID columns (`ncols` of the slab are inside the matrix)
-__device__ __forceinline__ float ts_slab_err(const uint32_t (&acc)[32], uint32_t sb, uint32_t row, float alpha, bool want_red, int ncols) {
+// `bias`: the layer's bias at the slab's first column, or null (widths are multiples of 8: a group of 8 columns is inside or
+// outside the matrix as a whole)
+__device__ __forceinline__ float ts_slab_err(const uint32_t (&acc)[32], uint32_t sb, uint32_t row, float alpha, bool want_red, int ncols,
+                                             const float* __restrict__ bias) {
   const uint32_t sz = sb + row * 128u, se = sb + TS_SLAB_F32 + row * 64u, xz = row & 7u, xe = (row >> 1) & 3u;
   float r = 0.f;
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
     const float4 t0 = lds128(sz + (((uint32_t)(2 * h) ^ xz) << 4)), t1 = lds128(sz + (((uint32_t)(2 * h + 1) ^ xz) << 4));
     const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (bias != nullptr && 8 * h < ncols) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * h)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * h + 4));
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+    }
     float e[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) e[k] = fmaf(-alpha, __uint_as_float(acc[8 * h + k]), t[k]);
+    for (int k = 0; k < 8; ++k) e[k] = fmaf(-alpha, __uint_as_float(acc[8 * h + k]) + b[k], t[k]);
     if (want_red) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) r += (8 * h + k < ncols) ? 0.5f * e[k] * e[k] : 0.f;
@@ -630,7 +639,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_staged_gemm(const __grid_con
           tmem_ld_wait();
           if (kind == TS_GRAD) ts_slab_grad<ACT>(acc, sb, row, alpha, cg);
           else {
-            const float rr = ts_slab_err(acc, sb, row, alpha, red != nullptr, ncol_tile - s * TS_SLAB_COLS);
+            const float rr = ts_slab_err(acc, sb, row, alpha, red != nullptr, ncol_tile - s * TS_SLAB_COLS,
+                                         t.bias ? t.bias + n0 + s * TS_SLAB_COLS : nullptr);
             r += row_ok ? rr : 0.f;
           }
         }

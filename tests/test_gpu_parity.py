@@ -1234,14 +1234,15 @@ def _with_env(**kw):
     (128, 256, 2, 64, "tanh", 256, 1.0, 0.3),      # two layers: one ERR task + the hoisted-prediction GRAD task; clipped last step
     (96, 520, 6, 24, "relu", 264, 1.5, 0.5),       # fewer steps (3) than layers: every step inside the wavefront warm-up
 ])
-def test_whole_solve_launch_bf16(shape):
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_whole_solve_launch_bf16(shape, use_bias):
     """The one-launch solve must reproduce the fp64 oracle (2e-2) AND the phase-by-phase launches of the same kernels
     (same arithmetic, so equal up to the order of the energy atomics), from the feed-forward init (wavefront schedule, fused
     train step) and from a perturbed state (dense schedule, solve_inference)."""
     import jpc_b200 as J
     d_in, width, depth, d_out, act, B, max_t1, dt = shape
     J.set_compute_dtype("bf16")
-    om, sk, x, y = _case(d_in, width, depth, d_out, act, B, onehot_out=False)
+    om, sk, x, y = _case(d_in, width, depth, d_out, act, B, use_bias=use_bias, onehot_out=False)   # (biases: the staged ERR tile adds them)
     with _with_env(JPCB_SOLVE_MIN_ROUNDS=0, JPCB_STAGED=7):
         n0 = J._lib.lib.jpcb_launch_count()
         _check_fused(om, sk, x, y, "euler", max_t1, dt, TOLBF)
