@@ -106,6 +106,13 @@ const char* jpcb_last_error(void);
 /* Number of CUDA kernels this library has enqueued in this process (bench.py's gpu_launches). */
 unsigned long long jpcb_launch_count(void);
 
+/* Energies and losses of the PC entry points (mse) by FIXED-ORDER sums over the stored errors instead of the fused
+ * epilogues' floating-point atomics: the values then depend on the data only (bit-for-bit reproducible run to run; the
+ * default accumulation differs at 1e-7 with the order blocks happen to finish in).  Costs two small launches per energy
+ * evaluation; on the plain bf16 path the sums read the bf16 error copies.  Cross-entropy energies, the adaptive
+ * controller's norms and the bPC energies keep the atomics.  Process-wide; default off. */
+int jpcb_set_reproducible(int on);
+
 /* Bytes of caller-provided device workspace any entry point below may use for `desc`. */
 size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc);
 

@@ -4,7 +4,7 @@ everything is computed by libjpc_b200.so through the C-ABI in include/jpc_b200.h
 package loads (and if needed builds) that library and raises if it cannot: there is no fallback.
 """
 from . import _lib  # noqa: F401  (loads libjpc_b200.so or raises)
-from ._lib import plan_cache_clear, plan_cache_configure, plan_cache_stats
+from ._lib import plan_cache_clear, plan_cache_configure, plan_cache_stats, set_reproducible
 from ._core import (
     _get_param_scalings,
     compute_pc_activity_grad,

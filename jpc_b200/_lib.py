@@ -61,6 +61,7 @@ SIGNATURES = {
     "jpcb_version": (C.c_int, []),
     "jpcb_last_error": (C.c_char_p, []),
     "jpcb_launch_count": (C.c_ulonglong, []),
+    "jpcb_set_reproducible": (C.c_int, [C.c_int]),
     "jpcb_pc_workspace_bytes": (C.c_size_t, [C.POINTER(PcDesc)]),
     "jpcb_pc_ffwd_init": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _P, _PP, _P, _P, _P, C.c_size_t, _P]),
     "jpcb_pc_energy": (C.c_int, [C.POINTER(PcDesc), _PP, _PP, _PP, _P, _P, _P, _P, C.c_size_t, _P]),
@@ -161,3 +162,9 @@ def plan_cache_stats() -> dict:
     a, b, c = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
     lib.jpcb_plan_cache_stats(C.byref(a), C.byref(b), C.byref(c))
     return {"replays": a.value, "captures": b.value, "bypassed": c.value}
+
+
+def set_reproducible(on: bool = True) -> None:
+    """Energies and losses by fixed-order sums instead of floating-point atomics (include/jpc_b200.h): bit-for-bit
+    reproducible run to run, two small extra launches per energy evaluation.  Process-wide, default off."""
+    check(lib.jpcb_set_reproducible(1 if on else 0))

@@ -29,6 +29,7 @@ typedef __nv_bfloat16 bf16;
 namespace {
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};  // kernels enqueued by this library (jpcb_launch_count)
+std::atomic<int> g_reproducible{0};             // jpcb_set_reproducible
 }  // namespace
 
 namespace jpcb {
@@ -58,6 +59,8 @@ int num_sms() {
   if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
   return v;
 }
+
+bool reproducible() { return g_reproducible.load(std::memory_order_relaxed) != 0; }
 
 int tc_flags() {
   static const int f = [] { const char* v = getenv("JPCB_TC_FLAGS"); return v ? atoi(v) : 0; }();
@@ -146,6 +149,7 @@ struct Ws {
   std::vector<bf16*> Hb;       // [L]   act_l(u_l)  [Bl, d_l]
   std::vector<bf16*> Htb;      // [L]   same for the Heun stage state
   std::vector<bf16*> Eb;       // [L]   err[l] [Bl, d_{l+1}]
+  float* fix_part = nullptr;   // partial sums of the fixed-order reductions (jpcb_set_reproducible): (L + 2) jobs x FIX_BLOCKS
   int* sched = nullptr;        // completion counters of the whole-solve launch: 2 (L-1) tasks x row blocks of 256
   size_t sched_ints = 0;
   size_t bytes = 0;
@@ -156,6 +160,7 @@ void carve(const jpcb_pc_desc* d, void* base, Ws* w) {
   const size_t Bl = (size_t)d->batch_local;
   Bump b{reinterpret_cast<char*>(base)};
   w->red = b.take<float>(RED_FLOATS);
+  w->fix_part = b.take<float>((size_t)(L + 2) * FIX_BLOCKS);
   w->err.resize(L);
   w->Zt.assign(L, nullptr);
   w->G1.assign(L, nullptr);
@@ -430,6 +435,27 @@ struct Run {
 
   int zero_red() { CK(cudaMemsetAsync(ws.red, 0, RED_FLOATS * sizeof(float), st)); return JPCB_OK; }
 
+  // fixed-order sums into ws.red (jpcb_set_reproducible): the prediction-error energy of layer l from its stored errors,
+  // out = lam d  =>  lam/2 sum d^2 = sum out^2 / (2 lam); the mse loss of the init from the network output and the target
+  std::vector<FixJob> fix;
+  void fix_energy(int l, float escale) {
+    const bool b16 = ws.err[l] == nullptr;   // (plain bf16 path: only the bf16 error copies exist)
+    fix.push_back(FixJob{b16 ? (const void*)ws.Eb[l] : (const void*)ws.err[l], nullptr, (unsigned long long)Bl * d->dims[l + 1],
+                         escale != 0.f ? 0.5f / escale : 0.f, b16 ? 1 : 0, l, 0});
+  }
+  int fix_flush() {
+    if (fix.empty()) return JPCB_OK;
+    if (fix.size() > (size_t)(L + 2) || fix.size() > FIX_MAX_JOBS) return fail(JPCB_EINVAL, "internal: %zu fixed-order sums", fix.size());
+    static thread_local FixJobs jobs;
+    jobs.n = (int)fix.size(); jobs.pad_ = 0;
+    for (size_t i = 0; i < fix.size(); ++i) jobs.j[i] = fix[i];
+    fix_partial_kernel<<<dim3(FIX_BLOCKS, jobs.n), 256, 0, st>>>(jobs, ws.fix_part); count_launch();
+    fix_final_kernel<<<1, 256, 0, st>>>(jobs, ws.fix_part, ws.red); count_launch();
+    CK(cudaGetLastError());
+    fix.clear();
+    return JPCB_OK;
+  }
+
   // ---- bf16 operand preparation ----
   int prep_weights() {
     if (!tc) {  // W_l^T copies for the transposed GEMMs of the gradient phases: every layer in one grouped launch
@@ -547,7 +573,8 @@ struct Run {
     static thread_local CfArgs a;
     a.L = L; a.B = Bl; a.x = x;
     const bool ce = d->loss == JPCB_LOSS_CE;
-    const bool want_loss = loss_acc && y && !ce;
+    const bool fix_loss = loss_acc && y && !ce && reproducible() && loss_acc == ws.red + RED_LOSS;
+    const bool want_loss = loss_acc && y && !ce && !fix_loss;
     a.Y = want_loss ? y : nullptr; a.loss = want_loss ? loss_acc : nullptr;
     int kmax = 0;
     for (int l = 0; l < L; ++l) {
@@ -587,6 +614,10 @@ struct Run {
     cfg.numAttrs = 1;
     CK(cudaLaunchKernelEx(&cfg, chain_ffwd_kernel<R>, a, kpad));
     count_launch();
+    if (fix_loss) {
+      fix.push_back(FixJob{A_out[L - 1], y, (unsigned long long)Bl * d->dims[L], 0.5f, 0, RED_LOSS, 0});
+      RET(fix_flush());
+    }
     if (loss_acc && y && ce) RET(ce_rows(A_out[L - 1], 1.f, nullptr, nullptr, loss_acc));
     return JPCB_OK;
   }
@@ -606,8 +637,13 @@ struct Run {
       if (l == 0 && keep_p1) t.e.O2 = ws.P1;
       if (l + 1 < L) { t.e.act = d->act[l + 1]; if (tc) set_ob(t, ws.Hb[l + 1]); else t.e.Oh = ws.Hf[l + 1]; }
       const bool ce = d->loss == JPCB_LOSS_CE;
-      if (l == L - 1 && loss_acc && y && !ce) { t.e.red = loss_acc; t.e.Y = y; }
+      const bool fix_loss = l == L - 1 && loss_acc && y && !ce && reproducible() && loss_acc == ws.red + RED_LOSS;
+      if (l == L - 1 && loss_acc && y && !ce && !fix_loss) { t.e.red = loss_acc; t.e.Y = y; }
       RET(launch({t}));
+      if (fix_loss) {
+        fix.push_back(FixJob{A_out[L - 1], y, (unsigned long long)Bl * d->dims[L], 0.5f, 0, RED_LOSS, 0});
+        RET(fix_flush());
+      }
       // cross_entropy_loss(logits = network output, y)  (jpc/_utils.py:133-136)
       if (l == L - 1 && loss_acc && y && ce) RET(ce_rows(A_out[L - 1], 1.f, nullptr, nullptr, loss_acc));
     }
@@ -658,11 +694,13 @@ struct Run {
       t.e.O = ws.err[l];
       set_ob(t, ws.Eb[l]);
       t.e.Oh = ws.eff[l];  // (Form B, fp32 / f32x3 paths: post'(pre) . e)
-      if (energy) t.e.red = ws.red + l;
+      if (energy && reproducible() && !collect) fix_energy(l, t.e.escale);   // summed after the launch, in a fixed order
+      else if (energy) t.e.red = ws.red + l;
       ts.push_back(t);
     }
     if (collect) { *collect = ts; return JPCB_OK; }
     RET(launch(ts));
+    RET(fix_flush());
     if (ce) RET(ce_rows(ws.logits, d->output_energy_scaling, ws.err[L - 1], ws.Eb[L - 1], energy ? ws.red + (L - 1) : nullptr));
     return JPCB_OK;
   }
@@ -670,10 +708,12 @@ struct Run {
   int error0_from_p1(const float* const* S, bool energy) {
     const size_t n0 = (size_t)Bl * d->dims[1];
     if (n0 % 4 == 0 && (reinterpret_cast<uintptr_t>(S[0]) & 15) == 0) {  // plain streaming pass (the usual case)
-      err0_kernel<<<ew_grid(n0 / 4, 256), 256, 0, st>>>(S[0], ws.P1, ws.err[0], ws.Eb[0], n0 / 4, energy ? ws.red + 0 : nullptr, d->dims[1],
+      const bool fixed = energy && reproducible() && (ws.err[0] || !x3);
+      err0_kernel<<<ew_grid(n0 / 4, 256), 256, 0, st>>>(S[0], ws.P1, ws.err[0], ws.Eb[0], n0 / 4, energy && !fixed ? ws.red + 0 : nullptr, d->dims[1],
                                                          x3 ? (int)x3_cw(d, d->dims[1]) : 0, x3 ? x3_part(d, d->dims[1]) : 0);
       count_launch();
       CK(cudaGetLastError());
+      if (fixed) { fix_energy(0, 1.f); RET(fix_flush()); }
       return JPCB_OK;
     }
     GTask t;
@@ -681,9 +721,12 @@ struct Run {
     t.e.M = Bl; t.e.N = d->dims[1]; t.K = 0;
     t.e.alpha = 0.f; t.e.skip = 1.f; t.e.U = ws.P1; t.e.T = S[0];
     t.e.O = ws.err[0]; set_ob(t, ws.Eb[0]);
-    if (energy) t.e.red = ws.red + 0;
+    const bool fixed = energy && reproducible();
+    if (energy && !fixed) t.e.red = ws.red + 0;
     t.a_p = S[0]; t.b_p = S[0];  // never dereferenced (K == 0)
-    return launch_simt({t}, st);
+    RET(launch_simt({t}, st));
+    if (fixed) { fix_energy(0, 1.f); RET(fix_flush()); }
+    return JPCB_OK;
   }
 
   // gradient/update of A[l-1], l = 1..L-1.  Z: state where act' is evaluated; p1_hoisted: err[0]
@@ -887,6 +930,7 @@ extern "C" {
 int jpcb_version(void) { return JPCB_VERSION; }
 const char* jpcb_last_error(void) { return g_err.c_str(); }
 unsigned long long jpcb_launch_count(void) { return g_launches.load(); }
+int jpcb_set_reproducible(int on) { g_reproducible.store(on ? 1 : 0); return JPCB_OK; }
 
 size_t jpcb_pc_workspace_bytes(const jpcb_pc_desc* desc) {
   if (validate(desc, 1) != JPCB_OK) return 0;  // (a single layer is enough for jpcb_pc_ffwd_init)

@@ -412,4 +412,50 @@ static __global__ void finalize_kernel(const float* __restrict__ acc, int L, flo
   }
 }
 
+// ---- fixed-order sums (jpcb_set_reproducible): energies and losses without floating-point atomics ------------------------
+// Job j: out[dst_j] = scale_j * sum_i (a_j[i] - b_j[i])^2 (b may be null; a may be bf16).  Pass 1: FIX_BLOCKS blocks per job
+// each sum ONE fixed contiguous chunk (thread t takes elements t, t + 256, ... of it; lanes, warps and blocks are combined
+// in index order) into partials[j][block]; pass 2: one thread per job adds its partials in order.  The result depends on
+// the data only, not on which block ran first -- unlike the atomicAdd accumulation of the fused epilogues (1e-7 run to run).
+constexpr int FIX_BLOCKS = 64, FIX_MAX_JOBS = 264;
+struct FixJob {
+  const void* a;
+  const float* b;
+  unsigned long long n;
+  float scale;
+  int a_bf16, dst, pad_;
+};
+struct FixJobs {
+  int n, pad_;
+  FixJob j[FIX_MAX_JOBS];
+};
+static __global__ void __launch_bounds__(256) fix_partial_kernel(const __grid_constant__ FixJobs jobs, float* __restrict__ partials) {
+  __shared__ float red_s[8];
+  const FixJob& jb = jobs.j[blockIdx.y];
+  const unsigned long long per = (jb.n + FIX_BLOCKS - 1) / FIX_BLOCKS, lo = per * blockIdx.x;
+  const unsigned long long hi = lo + per < jb.n ? lo + per : jb.n;
+  float s = 0.f;
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += 256) {
+    float v = jb.a_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(jb.a)[i]) : reinterpret_cast<const float*>(jb.a)[i];
+    if (jb.b) v -= jb.b[i];
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red_s[w];
+    partials[(size_t)blockIdx.y * FIX_BLOCKS + blockIdx.x] = t;
+  }
+}
+static __global__ void fix_final_kernel(const __grid_constant__ FixJobs jobs, const float* __restrict__ partials, float* __restrict__ out) {
+  for (int j = (int)(blockIdx.x * blockDim.x + threadIdx.x); j < jobs.n; j += (int)(gridDim.x * blockDim.x)) {
+    float t = 0.f;
+    for (int b = 0; b < FIX_BLOCKS; ++b) t += partials[(size_t)j * FIX_BLOCKS + b];
+    out[jobs.j[j].dst] = jobs.j[j].scale * t;
+  }
+}
+
 }  // namespace jpcb

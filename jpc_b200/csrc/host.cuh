@@ -20,6 +20,8 @@ int fail(int code, const char* fmt, ...);
 // one more kernel enqueued by this library (jpcb_launch_count)
 void count_launch(int n = 1);
 int num_sms();
+// jpcb_set_reproducible: energies / losses by fixed-order sums instead of atomics
+bool reproducible();
 // experiment switches from the environment variable JPCB_TC_FLAGS (bit 1: 1-CTA tensor-core kernel)
 int tc_flags();
 

@@ -108,6 +108,7 @@ int plan_run(PlanKey& key, void* stream, const std::function<int(void*)>& body) 
   key.ptr(stream);
   key.word((uint64_t)dev);
   key.word(env_signature());
+  key.word(reproducible() ? 1u : 0u);
   const uint64_t h = hash_words(key.w);
 
   std::unique_lock<std::mutex> lock(C.mu);

@@ -158,3 +158,42 @@ def test_plan_eviction_and_capture_budget_keep_results_right():
     print("eviction run:", {k: s1[k] - s0[k] for k in s1})
     assert s1["captures"] - s0["captures"] >= 3          # more signatures than room: something was captured again
     assert s1["captures"] - s0["captures"] <= 12         # ... but the budget stopped the thrashing
+
+
+@pytest.mark.parametrize("dtype,tol,dims,B", [("f32", 1e-5, (64, 256, 4, 32), 512), ("bf16", 2e-2, (128, 256, 4, 64), 512),
+                                              ("f32", 1e-5, (33, 65, 7, 9), 37)])
+def test_reproducible_sums_are_bitwise_stable_and_right(dtype, tol, dims, B):
+    """jpcb_set_reproducible: loss and energies of the fused train step by fixed-order sums over the stored errors -- the same
+    bits every run, the oracle's values, and (within summation-order noise) what the default atomics give."""
+    from jpc_b200 import _lib
+    from jpc_b200._core import _Net
+    from jpc_b200._train import _Arena
+    J, om, gm, x, y, xd, yd = _setup(dtype, dims, B)
+    ref = O.pc_train_step(om, None, xd, yd, solver="euler", max_t1=2.0, dt=0.5)
+    net = _Net(gm, None, x, y, param_type="sp", loss_id="mse", gamma=None, output_energy_scaling=None, activity_decay=0.0,
+               weight_decay=0.0, spectral_penalty=0.0, solver=_lib.SOLVER_EULER, n_steps=4, dt=0.5, dt_last=0.5)
+
+    def run():
+        arena, acts, ws = _Arena(net), net.new_acts(), net.workspace()
+        arena.flat.zero_()
+        gW, gb = arena.grad_ptr_arrays()
+        _lib.check(_lib.lib.jpcb_pc_train_step(net.desc, net.W, net.b, _lib.ptr(x), _lib.ptr(y), _lib.ptr_array(acts),
+                                               _lib.ptr(arena.loss), _lib.ptr(arena.E), gW, gb, _lib.ptr(ws), ws.numel(), net.stream()))
+        torch.cuda.synchronize()
+        return arena.E.clone(), arena.loss.clone()
+    try:
+        J.plan_cache_configure(0, 2)       # (every call enqueues its kernels: block scheduling is free to differ)
+        J.set_reproducible(True)
+        runs = [run() for _ in range(4)]
+        J.set_reproducible(False)
+        E_at, loss_at = run()
+    finally:
+        J.set_reproducible(False)
+        J.plan_cache_configure(16, 2)
+    for E, loss in runs[1:]:
+        assert torch.equal(E, runs[0][0]) and torch.equal(loss, runs[0][1])
+    E, loss = runs[0]
+    assert abs(float(loss) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+    assert rel(E, ref["energies"]) < tol
+    assert rel(E, E_at.double().cpu()) < (1e-5 if dtype == "f32" else 5e-3)   # (bf16 path: the fixed-order sums read bf16 error copies)
+    assert abs(float(loss) - float(loss_at)) <= 1e-5 * abs(float(loss_at))
