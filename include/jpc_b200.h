@@ -194,7 +194,9 @@ int jpcb_pc_param_grads_range(const jpcb_pc_desc* desc, const float* const* W, c
  * else z_{j-1}).  Activities A[0..H-1] = z_0..z_{H-1} with z_k of width td.dims[k+1]; A[H] is the
  * unused dummy slot ([batch, td.dims[H+1]]).  x: [batch, td.dims[0]], y: [batch, td.dims[H+1]].
  * td.skip[j] (1 <= j <= H-1) applies to both directions, td.scalings is ignored (the reference
- * validates param_type but applies no scalings, _energies.py:314).  Supervised mode (x given), Euler
+ * validates param_type but applies no scalings, _energies.py:314).  td.free_input = 1 is the reference's
+ * `x = None` (x_eff = activities[0], _energies.py:324): pass x = NULL, A[0] is both the input of W_0 and the
+ * target of V_0 (needs td.dims[0] == td.dims[1]) and its gradient gains the two extra terms.  Euler
  * steps; td.dtype selects fp32 CUDA cores, bf16 tensor cores (needs td.act[k+1] == bu_act[k] and dims / batch
  * multiples of 8) or fp32 parity on tensor cores (JPCB_DTYPE_F32X3, same layout rules). */
 typedef struct jpcb_bpc_desc {

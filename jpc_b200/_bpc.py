@@ -32,8 +32,8 @@ class _BpcNet:
     def __init__(self, top_down_model, bottom_up_model, x, y, *, skip_model, param_type, backward_energy_weight,
                  forward_energy_weight, n_steps=0, dt=0.0, batch_global=None):
         _check_param_type(param_type)  # validated; bpc_energy_fn applies no scalings (_energies.py:314)
-        if x is None:
-            raise NotImplementedError("bPC with an unclamped input (x=None) is not on the B200 path yet")
+        # x = None (jpc/_core/_energies.py:324): activities[0] stands in for the input -- desc.td.free_input, `x` pointer NULL.
+        self.free = x is None
         if len(top_down_model) != len(bottom_up_model):
             raise ValueError("top_down_model and bottom_up_model must have the same number of layers")
         n = len(top_down_model)
@@ -48,7 +48,7 @@ class _BpcNet:
         dev = Ws[0].device
         if dev.type != "cuda":
             raise RuntimeError("jpc_b200 has no CPU path: model weights must be CUDA tensors")
-        for t in Ws + Vs + [x, y]:
+        for t in Ws + Vs + ([y] if self.free else [x, y]):
             if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("all tensors must be contiguous fp32 on the same CUDA device")
         dims = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
@@ -58,14 +58,19 @@ class _BpcNet:
                 raise ValueError(f"top-down layer {j}: weight shape {tuple(Ws[j].shape)} does not chain from {dims[j]}")
             if tuple(Vs[j].shape) != (dims[j], dims[j + 1]):
                 raise ValueError(f"bottom-up layer {j}: weight shape {tuple(Vs[j].shape)}, expected {(dims[j], dims[j + 1])}")
-        if x.shape[1] != dims[0] or y.shape[1] != dims[-1] or x.shape[0] != y.shape[0]:
+        if self.free:
+            if dims[0] != dims[1]:
+                raise ValueError(f"bPC with x=None feeds activities[0] (width {dims[1]}) to top_down_model[0] (expects {dims[0]})")
+            if y.shape[1] != dims[-1]:
+                raise ValueError("output shape does not match the models")
+        elif x.shape[1] != dims[0] or y.shape[1] != dims[-1] or x.shape[0] != y.shape[0]:
             raise ValueError("input / output shapes do not match the models")
         td_bias = [l.bias is not None for l in self.td_lin]
         bu_bias = [l.bias is not None for l in self.bu_lin]
         if (any(td_bias) and not all(td_bias)) or (any(bu_bias) and not all(bu_bias)):
             raise NotImplementedError("mixed bias / no-bias layers are not on the B200 path")
         skips = _skip_flags(skip_model, n)
-        B = x.shape[0]
+        B = y.shape[0]
         self.dtype = _core.get_compute_dtype()
         self.bf16 = self.dtype != "f32"  # either tensor-core path: same layout rules (dims / batch multiples of 8)
         bWs = [l.bias for l in self.td_lin] if all(td_bias) else None
@@ -85,12 +90,13 @@ class _BpcNet:
                 bWs = [P(bWs[j], (0, pd[j + 1] - dims[j + 1])) for j in range(n)]
             if bVs is not None:
                 bVs = [P(bVs[j], (0, pd[j] - dims[j])) for j in range(n)]
-            x = P(x, (0, pd[0] - dims[0]))
+            if not self.free:
+                x = P(x, (0, pd[0] - dims[0]))
             y = P(y, (0, pd[-1] - dims[-1]))
             dims = pd
         bg = B if batch_global is None else int(batch_global)
         key = (n, B, bg, tuple(dims), tuple(p[0] for p in td), tuple(p[0] for p in bu), tuple(skips), all(td_bias), all(bu_bias),
-               self.dtype, int(n_steps), float(dt), float(forward_energy_weight), float(backward_energy_weight))
+               self.dtype, int(n_steps), float(dt), float(forward_energy_weight), float(backward_energy_weight), self.free)
         cached = _BPC_DESC_CACHE.get(key)
         if cached is None:
             d = _lib.BpcDesc()
@@ -105,6 +111,7 @@ class _BpcNet:
             d.td.has_bias, d.bu_has_bias = int(all(td_bias)), int(all(bu_bias))
             d.td.dtype, d.td.loss = _lib.DTYPE_IDS[self.dtype], _lib.LOSS_MSE
             d.td.output_energy_scaling, d.td.activity_decay = 1.0, 0.0
+            d.td.free_input = int(self.free)
             d.td.solver, d.td.n_steps, d.td.dt, d.td.dt_last = _lib.SOLVER_EULER, int(n_steps), float(dt), float(dt)
             d.forward_energy_weight, d.backward_energy_weight = float(forward_energy_weight), float(backward_energy_weight)
             ws_bytes = _lib.lib.jpcb_bpc_workspace_bytes(d)

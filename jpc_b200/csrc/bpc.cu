@@ -54,6 +54,17 @@ __global__ void bpc_finalize_kernel(const float* __restrict__ acc, int H, float 
   }
 }
 
+// x = None (jpc/_core/_energies.py:324: x_eff = activities[0]): z_0 is also the INPUT of top-down layer 0 and the TARGET of
+// bottom-up layer 0, which adds  -alpha_f phi_0'(z_0) (e_0 W_0) + alpha_b delta_0  to its gradient.  Gf0 already holds the
+// forward-direction half; Gx the first extra term (its own GEMM); delta_0 comes as fp32 or as the bf16 error copy.
+__global__ void bpc_free_x_combine_kernel(float* __restrict__ Gf0, const float* __restrict__ Gx, const float* __restrict__ d0,
+                                          const __nv_bfloat16* __restrict__ d0b, size_t n, float ab) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float dv = d0 ? d0[i] : __bfloat162float(d0b[i]);
+    Gf0[i] += Gx[i] + ab * dv;
+  }
+}
+
 int validate_bpc(const jpcb_bpc_desc* d) {
   if (!d) return fail(JPCB_EINVAL, "null descriptor");
   const jpcb_pc_desc& t = d->td;
@@ -81,6 +92,9 @@ int validate_bpc(const jpcb_bpc_desc* d) {
   if (t.solver != JPCB_SOLVER_EULER) return fail(JPCB_ENOTIMPL, "bPC inference is Euler (update_bpc_activities with optax.sgd); Heun is not on this path");
   if (t.n_steps < 0) return fail(JPCB_EINVAL, "n_steps=%d", t.n_steps);
   if (t.activity_decay != 0.f) return fail(JPCB_EINVAL, "bpc_energy_fn has no activity_decay");
+  if (t.free_input && t.dims[0] != t.dims[1])
+    return fail(JPCB_EINVAL, "bPC with x = None uses activities[0] as the input of top_down_model[0] and the target of bottom_up_model[0]: "
+                             "needs dims[0] == dims[1] (got %d vs %d)", t.dims[0], t.dims[1]);
   for (int l = 0; l < t.n_layers; ++l)
     if (t.post_act[l] != JPCB_ACT_LINEAR) return fail(JPCB_ENOTIMPL, "bPC: layers of the form act(W u + b) are not on this path");
   return JPCB_OK;
@@ -110,6 +124,8 @@ struct BpcRun {
   // workspace
   float* red = nullptr;             // [2(H+1)] energy sums
   std::vector<float*> e, dl, Gf;    // e_j [Bl, D[j+1]], delta_j [Bl, D[j]], forward half of dF/dz_k [Bl, D[k+1]]
+  bool fx = false;                  // td.free_input: x = None, x_eff = activities[0] (set by the entry points: x = A[0])
+  float* Gx = nullptr;              // fx: -alpha_f phi_0'(z_0) (e_0 W_0)   [Bl, D[0]]
   float* P0 = nullptr;              // W_0 phi_0(x) + b_0        [Bl, D[1]]
   float* QH = nullptr;              // V_H psi_H(y) + c_H        [Bl, D[H]]
   // bf16 operand copies (tensor-core paths).  x3: the fp32-parity path -- every copy is a 3-way split [rows, 3 P(d)]
@@ -145,7 +161,7 @@ struct BpcRun {
     if (tc) {
       for (int j = 0; j <= H; ++j) {
         Wb[j] = b.take<bf16>((size_t)D[j + 1] * cw(D[j])); Vb[j] = b.take<bf16>((size_t)D[j] * cw(D[j + 1]));
-        if (j >= 1) WTb[j] = b.take<bf16>((size_t)D[j] * cw(D[j + 1]));
+        if (j >= 1 || fx) WTb[j] = b.take<bf16>((size_t)D[j] * cw(D[j + 1]));
         if (j <= H - 1) VTb[j] = b.take<bf16>((size_t)D[j + 1] * cw(D[j]));
         Eb[j] = b.take<bf16>((size_t)Bl * cw(D[j + 1]));
         Db[j] = b.take<bf16>((size_t)Bl * cw(D[j]));
@@ -155,6 +171,7 @@ struct BpcRun {
       Hy = b.take<bf16>((size_t)Bl * cw(D[H + 1]));
     }
     for (int k = 0; k < H; ++k) Gf[k] = b.take<float>((size_t)Bl * D[k + 1]);
+    if (fx) Gx = b.take<float>((size_t)Bl * D[0]);
     P0 = b.take<float>((size_t)Bl * D[1]);
     QH = b.take<float>((size_t)Bl * D[H]);
     bytes = ((b.off + 1023) & ~(size_t)1023) + 1024;
@@ -168,7 +185,9 @@ struct BpcRun {
     H = d->td.n_layers - 1; Bl = d->td.batch_local; D = d->td.dims;
     invB = 1.f / (float)d->td.batch_global; af = d->forward_energy_weight; ab = d->backward_energy_weight;
     set_dtype(d->td.dtype);
-    if (!W || !V || !x || !y) return fail(JPCB_EINVAL, "null weight lists / input / target");
+    fx = d->td.free_input != 0;
+    if (fx && x) return fail(JPCB_EINVAL, "free_input (x = None): `x` must be NULL, activities[0] takes its place");
+    if (!W || !V || (!x && !fx) || !y) return fail(JPCB_EINVAL, "null weight lists / input / target");
     if (d->td.has_bias && !bW) return fail(JPCB_EINVAL, "top-down has_bias set but no bias list");
     if (d->bu_has_bias && !bV) return fail(JPCB_EINVAL, "bottom-up has_bias set but no bias list");
     carve(ws);
@@ -199,7 +218,7 @@ struct BpcRun {
     for (int j = 0; j <= H; ++j) {
       split3(W[j], Wb[j], D[j + 1], D[j], ACT_LINEAR);
       split3(V[j], Vb[j], D[j], D[j + 1], ACT_LINEAR);
-      if (j >= 1) tsplit3(W[j], WTb[j], D[j + 1], D[j]);
+      if (j >= 1 || fx) tsplit3(W[j], WTb[j], D[j + 1], D[j]);
       if (j <= H - 1) tsplit3(V[j], VTb[j], D[j], D[j + 1]);
       // error copies are written by the epilogues (valid columns only): their padding columns must read as zero
       CK(cudaMemsetAsync(Eb[j], 0, (size_t)Bl * cw(D[j + 1]) * sizeof(bf16), st));
@@ -231,7 +250,7 @@ struct BpcRun {
         jobs.total += jb.tiles_c * ((R + 63) / 64);
       };
       for (int j = 0; j <= H; ++j) {
-        add(W[j], Wb[j], j >= 1 ? WTb[j] : nullptr, D[j + 1], D[j]);      // W_j [D[j+1], D[j]]
+        add(W[j], Wb[j], (j >= 1 || fx) ? WTb[j] : nullptr, D[j + 1], D[j]);      // W_j [D[j+1], D[j]]
         add(V[j], Vb[j], j <= H - 1 ? VTb[j] : nullptr, D[j], D[j + 1]);  // V_j [D[j], D[j+1]]
       }
       flush();
@@ -281,7 +300,7 @@ struct BpcRun {
     for (int j = 0; j <= H; ++j) {
       GTask t;
       t.e.mode = EPI_ERR; t.e.escale = 1.f;
-      if (j == 0 && hoisted) {  // e_0 = z_0 - P0 without a GEMM
+      if (j == 0 && hoisted && !fx) {  // e_0 = z_0 - P0 without a GEMM
         t.e.M = Bl; t.e.N = D[1]; t.K = 0; t.e.alpha = 0.f; t.e.skip = 1.f; t.e.U = P0;
         t.a_p = S[0]; t.b_p = S[0];
       } else {
@@ -309,7 +328,7 @@ struct BpcRun {
       (t.K == 0 ? k0 : ts).push_back(t);
     }
     // the two GEMM-free errors: streaming kernel when the layout allows 16-byte vectors, else the CUDA-core kernel's K = 0 path
-    if (hoisted && D[1] % 4 == 0 && D[H] % 4 == 0 && (reinterpret_cast<uintptr_t>(S[0]) & 15) == 0 && (reinterpret_cast<uintptr_t>(S[H - 1]) & 15) == 0) {
+    if (hoisted && !fx && D[1] % 4 == 0 && D[H] % 4 == 0 && (reinterpret_cast<uintptr_t>(S[0]) & 15) == 0 && (reinterpret_cast<uintptr_t>(S[H - 1]) & 15) == 0) {
       RET(launch(ts));
       const size_t n0 = (size_t)Bl * D[1] / 4, nH = (size_t)Bl * D[H] / 4;
       const Err0Job j0{S[0], P0, e[0], Eb[0], n0, energy ? red + 0 : nullptr, D[1], x3 ? (int)cw(D[1]) : 0, x3 ? P(D[1]) : 0};
@@ -353,8 +372,35 @@ struct BpcRun {
       if (tc && sub != GRAD_OUT) set_ob(u, Hz[k]);  // act(z_new): the next evaluation's operand (both directions)
       b.push_back(u);
     }
+    if (fx) {  // x = None: the term z_0 receives as the INPUT of top-down layer 0 (own GEMM), see bpc_free_x_combine_kernel
+      GTask t;
+      t.e.mode = EPI_GRAD; t.e.sub = GRAD_OUT; t.e.act = d->td.act[0];
+      t.e.M = Bl; t.e.N = D[0]; t.K = D[1];
+      t.a_p = e[0]; t.a_smn = D[1]; t.a_sk = 1;
+      t.b_p = W[0]; t.b_smn = 1; t.b_sk = D[0];           // B(n,k') = W_0[k'][n]
+      t.a_b = Eb[0]; t.b_b = WTb[0];
+      split_geom(t, D[1], D[1]);
+      t.e.alpha = 1.f; t.e.Z = Z[0]; t.e.P = Z[0];         // "own error" zero: e = Z - P
+      t.e.gscale = af; t.e.c = 1.f; t.e.O = Gx;
+      f.push_back(t);
+    }
     RET(launch(f));
-    return launch(b);
+    if (fx) {
+      const size_t n0 = (size_t)Bl * D[0];
+      bpc_free_x_combine_kernel<<<ew_grid(n0, 256), 256, 0, st>>>(Gf[0], Gx, dl[0], dl[0] ? nullptr : Db[0], n0, ab);
+      count_launch();
+      CK(cudaGetLastError());
+    }
+    RET(launch(b));
+    if (fx && tc && sub != GRAD_OUT) {  // z_0 moved: refresh the operand copy phi_0(z_0) that top-down layer 0 reads
+      if (x3) split3(Z[0], Hx, Bl, D[0], d->td.act[0]);
+      else {
+        const size_t nx = (size_t)Bl * D[0];
+        cast_act_bf16_kernel<<<ew_grid(nx / 4 + 1, 256), 256, 0, st>>>(Z[0], Hx, nx, d->td.act[0]); count_launch();
+      }
+      CK(cudaGetLastError());
+    }
+    return JPCB_OK;
   }
 
   // both models' parameter gradients from the errors of the last errors() call on state A (jpc/_core/_grads.py:544-612)
@@ -417,6 +463,7 @@ size_t jpcb_bpc_workspace_bytes(const jpcb_bpc_desc* desc) {
   BpcRun r;
   r.d = desc; r.H = desc->td.n_layers - 1; r.Bl = desc->td.batch_local; r.D = desc->td.dims;
   r.set_dtype(desc->td.dtype);
+  r.fx = desc->td.free_input != 0;
   r.carve(nullptr);
   return r.bytes;
 }
@@ -427,6 +474,7 @@ static int bpc_energy_impl(const jpcb_bpc_desc* desc, const float* const* W, con
   BpcRun r;
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A || !E_pairs) return fail(JPCB_EINVAL, "null activities / output");
+  if (r.fx) r.x = A[0];
   RET(r.zero_red());
   RET(r.prep(A));
   RET(r.errors(A, true, false));
@@ -439,6 +487,7 @@ static int bpc_activity_grad_impl(const jpcb_bpc_desc* desc, const float* const*
   BpcRun r;
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A || !gA) return fail(JPCB_EINVAL, "null activities / output");
+  if (r.fx) r.x = A[0];
   RET(r.zero_red());
   RET(r.prep(A));
   RET(r.errors(A, true, false));
@@ -454,12 +503,13 @@ static int bpc_infer_impl(const jpcb_bpc_desc* desc, const float* const* W, cons
   BpcRun r;
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A) return fail(JPCB_EINVAL, "null activities");
+  if (r.fx) r.x = A[0];
   RET(r.prep(A));
-  RET(r.hoist());
+  if (!r.fx) RET(r.hoist());   // (x = None: neither clamped-side prediction is hoisted -- P0 is not constant)
   const int T = desc->td.n_steps;
   for (int s = 0; s < T; ++s) {
     const float h = s == T - 1 ? desc->td.dt_last : desc->td.dt;
-    RET(r.errors(A, false, true));
+    RET(r.errors(A, false, !r.fx));
     RET(r.grads(GRAD_EULER, h * r.invB, A, A));
   }
   return JPCB_OK;
@@ -472,6 +522,7 @@ static int bpc_param_grads_impl(const jpcb_bpc_desc* desc, const float* const* W
   BpcRun r;
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A || !gW || !gV) return fail(JPCB_EINVAL, "null activities / outputs");
+  if (r.fx) r.x = A[0];
   RET(r.zero_red());
   RET(r.prep(A));
   RET(r.errors(A, E_pairs != nullptr, false));
@@ -491,16 +542,17 @@ static int bpc_train_step_impl(const jpcb_bpc_desc* desc, const float* const* W,
   BpcRun r;
   RET(r.init(desc, W, bW, V, bV, x, y, workspace, workspace_bytes, stream));
   if (!A || !gW || !gV) return fail(JPCB_EINVAL, "null activities / outputs");
+  if (r.fx) r.x = A[0];
   RET(r.zero_red());
   RET(r.prep(A));
-  RET(r.hoist());
+  if (!r.fx) RET(r.hoist());
   const int T = desc->td.n_steps;
   for (int s = 0; s < T; ++s) {
     const float h = s == T - 1 ? desc->td.dt_last : desc->td.dt;
-    RET(r.errors(A, false, true));
+    RET(r.errors(A, false, !r.fx));
     RET(r.grads(GRAD_EULER, h * r.invB, A, A));
   }
-  RET(r.errors(A, E_pairs != nullptr, true));   // errors (+ energies) at the solution; the two clamped-side ones without a GEMM
+  RET(r.errors(A, E_pairs != nullptr, !r.fx));   // errors (+ energies) at the solution; the two clamped-side ones without a GEMM
   RET(r.wgrads(A, gW, gbW, gV, gbV));
   if (E_pairs) RET(r.finalize(E_pairs, nullptr));
   return JPCB_OK;

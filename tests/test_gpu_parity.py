@@ -318,7 +318,7 @@ def _bpc_case(d_x, width, depth, d_y, act, B, use_bias=False, skips=False, seed=
 def _check_bpc(td, bu, sk, x, y, acts, tol, af=1.0, ab=1.0):
     import jpc_b200 as J
     gtd, gbu, gsk = to_gpu_model(td), to_gpu_model(bu), _gpu_skip(sk)
-    gx, gy, gacts = dev(x), dev(y), devs(acts)
+    gx, gy, gacts = (None if x is None else dev(x)), dev(y), devs(acts)
     kw = dict(forward_energy_weight=af, backward_energy_weight=ab)
     E = O.bpc_energy_fn(td, bu, acts, y, x=x, skips=sk, record_layers=True, **kw)
     gE = J.bpc_energy_fn(gtd, gbu, gacts, gy, x=gx, skip_model=gsk, record_layers=True, **kw)
@@ -349,7 +349,8 @@ def _check_bpc_infer(td, bu, sk, x, y, acts, tol, T, dt, af=1.0, ab=1.0, kink_bu
         _, g = O.compute_bpc_activity_grad(td, bu, a, y, x=x, skips=sk, **kw)
         a = [p - dt * q for p, q in zip(a, g)]
     gtd, gbu, gsk = to_gpu_model(td), to_gpu_model(bu), _gpu_skip(sk)
-    ga = J.solve_bpc_inference(gtd, gbu, devs(acts), dev(y), input=dev(x), n_steps=T, dt=dt, skip_model=gsk, **kw)
+    gx = None if x is None else dev(x)
+    ga = J.solve_bpc_inference(gtd, gbu, devs(acts), dev(y), input=gx, n_steps=T, dt=dt, skip_model=gsk, **kw)
     for p, q in zip(ga[:-1], a[:-1]):
         bad = int(((p.double().cpu() - q).abs() > tol * float(q.abs().max())).sum())
         assert bad <= kink_budget and rel(p, q) < (100 if kink_budget else 1) * tol
@@ -357,7 +358,7 @@ def _check_bpc_infer(td, bu, sk, x, y, acts, tol, T, dt, af=1.0, ab=1.0, kink_bu
     opt = J.optim.sgd(dt)
     b, st = devs(acts), opt.init(devs(acts))
     for _ in range(T):
-        r = J.update_bpc_activities(gtd, gbu, b, opt, st, dev(y), input=dev(x), skip_model=gsk, **kw)
+        r = J.update_bpc_activities(gtd, gbu, b, opt, st, dev(y), input=gx, skip_model=gsk, **kw)
         assert set(r) == {"energy", "activities", "grads", "opt_state"}
         b, st = r["activities"], r["opt_state"]
     for p, q in zip(b[:-1], ga[:-1]):
@@ -414,6 +415,47 @@ def test_bpc_fused_train_step_equals_solve_then_param_grads(dtype):
             assert rel(got[l][1].weight, q["W"]) < tol
             assert rel(got[l][1].bias, q["b"]) < tol
     assert rel(E2, O.bpc_energy_fn(td, bu, a, y, x=x, skips=sk, record_layers=True)) < tol
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f32x3"])
+def test_bpc_unclamped_input(dtype):
+    """x = None (jpc/_core/_energies.py:324): activities[0] is the input of top_down_model[0] AND the target of
+    bottom_up_model[0], so its gradient has two more terms than in the clamped case and the operand copy phi_0(z_0) moves with
+    every Euler step.  Energies, activity gradients, both models' parameter gradients, T fused steps and the fused train step
+    against the oracle."""
+    import jpc_b200 as J
+    J.set_compute_dtype(dtype)
+    tol = TOLBF if dtype == "bf16" else TOL32
+    if dtype == "f32":
+        cases = [_bpc_case(12, 12, 4, 9, "tanh", 5, use_bias=True), _bpc_case(13, 13, 5, 3, "silu", 3, skips=True)]
+    else:
+        cases = [_bpc_case(64, 64, 4, 24, "tanh", 32, use_bias=True), _bpc_case(72, 72, 5, 20, "tanh", 136, skips=True)]
+    for td, bu, sk, x, y, acts in cases:
+        B = y.shape[0]
+        _check_bpc(td, bu, sk, None, y, acts, tol)
+        _check_bpc(td, bu, sk, None, y, acts, tol, af=0.5, ab=0.7)
+        _check_bpc_infer(td, bu, sk, None, y, acts, tol, T=5, dt=0.4)
+        _check_bpc_infer(td, bu, sk, None, y, acts, tol, T=3, dt=0.05 * B, af=0.3)
+        # the fused train step: T steps + gradients + energies at the solution
+        T, dt = 4, 0.3
+        a = [t.clone() for t in acts]
+        for _ in range(T):
+            _, g = O.compute_bpc_activity_grad(td, bu, a, y, x=None, skips=sk)
+            a = [p - dt * q for p, q in zip(a, g)]
+        tdg, bug = O.compute_bpc_param_grads(td, bu, a, y, x=None, skips=sk)
+        gtd, gbu, gsk = to_gpu_model(td), to_gpu_model(bu), _gpu_skip(sk)
+        A2, td2, bu2, E2 = J.bpc_train_step(gtd, gbu, devs(acts), dev(y), input=None, n_steps=T, dt=dt, skip_model=gsk, record_energies=True)
+        gate_all(A2[:-1], a[:-1], tol, "bpc_free.train_step.activities")
+        for got, want in ((td2, tdg), (bu2, bug)):
+            for l, q in enumerate(want):
+                assert rel(got[l][1].weight, q["W"]) < tol
+                if q["b"] is not None:
+                    assert rel(got[l][1].bias, q["b"]) < tol
+        assert rel(E2, O.bpc_energy_fn(td, bu, a, y, x=None, skips=sk, record_layers=True)) < tol
+    # limits: activities[0] must fit top_down_model[0]'s input
+    td, bu, sk, x, y, acts = _bpc_case(6, 12, 3, 9, "tanh", 4)
+    with pytest.raises(ValueError):
+        J.bpc_energy_fn(to_gpu_model(td), to_gpu_model(bu), devs(acts), dev(y), x=None)
 
 
 def test_bpc_update_params_keys():
