@@ -234,6 +234,32 @@ def test_bpc_energy_and_grads():
     assert all(float(gi["W"].abs().max()) > 0 for gi in gtd + gbu)
 
 
+def test_bpc_unclamped_input_matches_hand_derivative():
+    """x = None (jpc/_core/_energies.py:324): z_0 is also the input of top_down[0] and the target of bottom_up[0].  The oracle's
+    autograd gradient of z_0 against the four terms written out by hand (what the CUDA path assembles)."""
+    H, d, af, ab = 3, 7, 0.7, 1.3
+    td = O.make_mlp(0, d, d, H + 1, 4, "tanh", use_bias=True)
+    bu = O.make_mlp(1, 4, d, H + 1, d, "tanh", use_bias=True)[::-1]
+    td[0]["act"] = "tanh"   # (make_mlp leaves the first layer's input linear: give phi_0' something to do)
+    x, _ = _data(5, d, d)
+    _, y = _data(5, 4, 4, seed=3, onehot_out=False)
+    acts = _perturb(O.init_activities_with_ffwd(td, x))
+    kw = dict(forward_energy_weight=af, backward_energy_weight=ab)
+    F, g = O.compute_bpc_activity_grad(td, bu, acts, y, x=None, **kw)
+    Fc, gc = O.compute_bpc_activity_grad(td, bu, acts, y, x=acts[0], **kw)   # same energy, z_0's two extra roles frozen
+    assert abs(float(F) - float(Fc)) < 1e-12
+    B = y.shape[0]
+    z0 = acts[0]
+    e0 = z0 - (O.act_fn(td[0]["act"], z0) @ td[0]["W"].T + td[0]["b"])
+    d0 = z0 - (O.act_fn(bu[0]["act"], z0) @ bu[0]["W"].T + bu[0]["b"])
+    h = O.act_deriv(td[0]["act"], z0)                                        # phi_0'(z_0), elementwise
+    extra = (-af * h * (e0 @ td[0]["W"]) + ab * d0) / B
+    assert float((g[0] - (gc[0] + extra)).abs().max()) < 1e-12
+    for a, b in zip(g[1:], gc[1:]):
+        assert float((a - b).abs().max()) < 1e-14
+    assert float(extra.abs().max()) > 1e-3
+
+
 def test_errors():
     with pytest.raises(ValueError):
         O.check_param_type("bogus")
