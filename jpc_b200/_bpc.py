@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from . import _core
+from . import _core, _flat
 from ._core import _layer_parts, _skip_flags, _WS_CACHE
 from ._errors import _check_param_type
 from .nn import tree_unflatten_like
@@ -203,22 +203,45 @@ def compute_bpc_activity_grad(top_down_model, bottom_up_model, activities, y, *,
     return F, net.unpad_acts(g[:-1], activities[:-1]) + [torch.zeros_like(activities[-1])]
 
 
-def _param_grads(net, activities, want_energies=False, fused_steps=False):
-    """jpcb_bpc_param_grads on `activities` -- or, with `fused_steps`, jpcb_bpc_train_step: the descriptor's Euler steps in
-    place on the (library-layout) `activities`, then the gradients at the solution."""
+def _grad_arena(net, want_energies, zero=False):
+    """Both models' gradients (+ the energy pairs) as views of ONE flat buffer: one allocation per call (addresses repeat
+    from step to step, so the library replays its launch plan) and ONE all-reduce under data parallelism."""
     D, n = net.dims, net.H + 1
-    f32 = dict(dtype=torch.float32, device=net.dev)
-    gW = [torch.empty(D[j + 1], D[j], **f32) for j in range(n)]
-    gV = [torch.empty(D[j], D[j + 1], **f32) for j in range(n)]
-    gbW = [torch.empty(D[j + 1], **f32) for j in range(n)] if net.td_bias else None
-    gbV = [torch.empty(D[j], **f32) for j in range(n)] if net.bu_bias else None
-    E = torch.empty(2 * (net.H + 1), dtype=torch.float32, device=net.dev) if want_energies else None
+    shapes = [(D[j + 1], D[j]) for j in range(n)] + [(D[j], D[j + 1]) for j in range(n)]
+    shapes += [(D[j + 1],) for j in range(n)] if net.td_bias else []
+    shapes += [(D[j],) for j in range(n)] if net.bu_bias else []
+    shapes += [(2 * n,)] if want_energies else []
+    lay = _flat.layout(shapes)
+    flat = (torch.zeros if zero else torch.empty)(lay.total, dtype=torch.float32, device=net.dev)
+    v = lay.carve(flat)
+    gW, gV, k = v[:n], v[n:2 * n], 2 * n
+    gbW = gbV = E = None
+    if net.td_bias:
+        gbW, k = v[k:k + n], k + n
+    if net.bu_bias:
+        gbV, k = v[k:k + n], k + n
+    if want_energies:
+        E = v[k]
+    return flat, gW, gbW, gV, gbV, E
+
+
+def _param_grads(net, activities, want_energies=False, fused_steps=False, exchange=False):
+    """jpcb_bpc_param_grads on `activities` -- or, with `fused_steps`, jpcb_bpc_train_step: the descriptor's Euler steps in
+    place on the (library-layout) `activities`, then the gradients at the solution.  `exchange`: data parallel -- every rank
+    holds a row shard and a descriptor with the GLOBAL batch in its 1/B, so the sums over ranks of gradients and energy pairs
+    are the full-batch values: one all-reduce of the flat buffer (the reference has no collective)."""
+    flat, gW, gbW, gV, gbV, E = _grad_arena(net, want_energies or exchange, zero=exchange)
     ws = net.workspace()
     fn = _lib.lib.jpcb_bpc_train_step if fused_steps else _lib.lib.jpcb_bpc_param_grads
     acts = activities if fused_steps else net.pad_acts(activities)
     _lib.check(fn(*net.args(), _lib.ptr_array(acts), _lib.ptr(net.x), _lib.ptr(net.y),
                   _lib.ptr_array(gW), _lib.ptr_array(gbW) if gbW else None, _lib.ptr_array(gV),
                   _lib.ptr_array(gbV) if gbV else None, _lib.ptr(E), _lib.ptr(ws), ws.numel(), net.stream()))
+    if exchange:
+        import torch.distributed as dist
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if not want_energies:
+        E = None
 
     if net.bf16:  # slice the zero-padded rows / columns off again
         T = net.true_dims
@@ -238,9 +261,12 @@ def _param_grads(net, activities, want_energies=False, fused_steps=False):
 
 
 def compute_bpc_param_grads(top_down_model, bottom_up_model, activities, y, *, x=None, skip_model=None, param_type="sp",
-                            backward_energy_weight=1.0, forward_energy_weight=1.0):
-    """jpc/_core/_grads.py:544-612: (top_down_grads, bottom_up_grads) with the models' structure."""
-    net = _net(top_down_model, bottom_up_model, x, y, skip_model, param_type, backward_energy_weight, forward_energy_weight)
+                            backward_energy_weight=1.0, forward_energy_weight=1.0, batch_global=None):
+    """jpc/_core/_grads.py:544-612: (top_down_grads, bottom_up_grads) with the models' structure.  `batch_global` (not in the
+    reference signature): the B of the 1/B normalisation when this process holds a row shard; the result is then this shard's
+    PART of the gradient (no collective here -- `bpc_train_step` is the data-parallel entry point)."""
+    net = _net(top_down_model, bottom_up_model, x, y, skip_model, param_type, backward_energy_weight, forward_energy_weight,
+               batch_global=batch_global)
     net.check_acts(activities)
     td, bu, _ = _param_grads(net, activities)
     return td, bu
@@ -271,11 +297,12 @@ def update_bpc_params(top_down_model, bottom_up_model, activities, top_down_opti
 
 
 def solve_bpc_inference(top_down_model, bottom_up_model, activities, output, *, input=None, n_steps=1, dt=0.5,
-                        skip_model=None, param_type="sp", backward_energy_weight=1.0, forward_energy_weight=1.0):
+                        skip_model=None, param_type="sp", backward_energy_weight=1.0, forward_energy_weight=1.0,
+                        batch_global=None):
     """n_steps fused Euler steps of size dt on the bPC energy == n_steps x update_bpc_activities with
     optax.sgd(dt) (the reference's inference loop), without returning to the host in between."""
     net = _net(top_down_model, bottom_up_model, input, output, skip_model, param_type, backward_energy_weight,
-               forward_energy_weight, n_steps=n_steps, dt=dt)
+               forward_energy_weight, n_steps=n_steps, dt=dt, batch_global=batch_global)
     net.check_acts(activities)
     A = net.pad_acts(activities, clone=True)
     ws = net.workspace()
@@ -285,15 +312,24 @@ def solve_bpc_inference(top_down_model, bottom_up_model, activities, output, *, 
 
 
 def bpc_train_step(top_down_model, bottom_up_model, activities, output, *, input=None, n_steps=1, dt=0.5, skip_model=None,
-                   param_type="sp", backward_energy_weight=1.0, forward_energy_weight=1.0, record_energies=False):
+                   param_type="sp", backward_energy_weight=1.0, forward_energy_weight=1.0, record_energies=False,
+                   batch_global=None):
     """`solve_bpc_inference` followed by `compute_bpc_param_grads` at the solution, as ONE library call
     (jpcb_bpc_train_step): the inference loop and the learning step of the reference's bPC example
     (examples/bidirectional_pc.ipynb cell 8: `update_bpc_activities` x T, then the gradients `update_bpc_params` applies)
     without returning to the host and without preparing the operands twice.  Returns
-    (activities, top_down_grads, bottom_up_grads, energy pairs or None)."""
+    (activities, top_down_grads, bottom_up_grads, energy pairs or None).
+
+    Data parallel (torch.distributed initialised, one process per GPU, each holding a contiguous row shard of the batch --
+    `shard_rows`): samples are independent through the inference loop once every rank normalises by the GLOBAL batch
+    (`batch_global`, default: the sum of the ranks' row counts), so the activities stay local and the only exchange is ONE
+    all-reduce of both models' gradients and the energy pairs after the call; every rank returns the full-batch gradients."""
+    from ._train import _world, global_batch
+    world = _world()
+    bg = int(batch_global) if batch_global is not None else global_batch(output.shape[0], output.device)
     net = _net(top_down_model, bottom_up_model, input, output, skip_model, param_type, backward_energy_weight,
-               forward_energy_weight, n_steps=n_steps, dt=dt)
+               forward_energy_weight, n_steps=n_steps, dt=dt, batch_global=bg)
     net.check_acts(activities)
     A = net.pad_acts(activities, clone=True)   # functional API: inputs are never mutated
-    td, bu, E = _param_grads(net, A, want_energies=record_energies, fused_steps=True)
+    td, bu, E = _param_grads(net, A, want_energies=record_energies, fused_steps=True, exchange=world > 1)
     return net.unpad_acts(A, activities), td, bu, E

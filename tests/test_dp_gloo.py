@@ -66,6 +66,59 @@ def test_two_rank_gloo_allreduce_matches_full_batch():
     assert q.get() < 1e-5  # fp32 arena
 
 
+def _bpc_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+        from jpc_b200._bpc import _grad_arena
+        from jpc_b200._train import shard_rows
+        B, H, dims = 9, 2, (5, 8, 8, 3)  # 9 rows over 2 ranks: 5 + 4
+        td = O.make_mlp(0, dims[0], dims[1], H + 1, dims[3], "tanh", use_bias=True)
+        bu = O.make_mlp(1, dims[3], dims[1], H + 1, dims[0], "tanh", use_bias=True)[::-1]
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(B, dims[0], generator=g, dtype=torch.float64)
+        y = torch.randn(B, dims[3], generator=g, dtype=torch.float64)
+        acts = [a + 0.3 * torch.randn(a.shape, generator=g, dtype=torch.float64) for a in O.init_activities_with_ffwd(td, x)]
+        lo, hi = shard_rows(B, rank, world)
+        scale = (hi - lo) / B   # the oracle normalises by the rows it sees; the kernels by desc.batch_global
+        loc = [a[lo:hi] for a in acts]
+        tdg, bug = O.compute_bpc_param_grads(td, bu, loc, y[lo:hi], x=x[lo:hi])
+        E = O.bpc_energy_fn(td, bu, loc, y[lo:hi], x=x[lo:hi], record_layers=True)
+        net = SimpleNamespace(dims=list(dims), H=H, td_bias=True, bu_bias=True, dev=torch.device("cpu"))
+        flat, gW, gbW, gV, gbV, Ev = _grad_arena(net, True, zero=True)
+        for j in range(H + 1):
+            gW[j].copy_((tdg[j]["W"] * scale).float()); gbW[j].copy_((tdg[j]["b"] * scale).float())
+            gV[j].copy_((bug[j]["W"] * scale).float()); gbV[j].copy_((bug[j]["b"] * scale).float())
+        Ev.copy_((E * scale).float())
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)   # what _param_grads(exchange=True) does
+        if rank == 0:
+            ftd, fbu = O.compute_bpc_param_grads(td, bu, acts, y, x=x)
+            fE = O.bpc_energy_fn(td, bu, acts, y, x=x, record_layers=True)
+            err = O.max_rel_err(Ev, fE)
+            for j in range(H + 1):
+                err = max(err, O.max_rel_err(gW[j], ftd[j]["W"]), O.max_rel_err(gbW[j], ftd[j]["b"]),
+                          O.max_rel_err(gV[j], fbu[j]["W"]), O.max_rel_err(gbV[j], fbu[j]["b"]))
+            q.put(err)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bpc_gradient_exchange_matches_full_batch():
+    """bPC under data parallelism: the flat buffer `bpc_train_step` all-reduces (both models' gradients + energy pairs, each
+    rank's part normalised by the global batch) sums to the full-batch values; ragged 5 + 4 row split."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bpc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() < 1e-5  # fp32 buffer
+
+
 def test_shard_rows_cover_and_are_contiguous():
     from jpc_b200._train import shard_rows
     for n, w in ((10, 2), (10, 3), (4096, 8), (7, 8), (1, 1)):
