@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JPCB_VERSION 101
+#define JPCB_VERSION 102
 #define JPCB_MAX_LAYERS 256
 
 /* error codes */
@@ -325,6 +325,49 @@ int jpcb_plan_cache_configure(int max_plans /* 0: disable and drop all plans */,
 int jpcb_plan_cache_clear(void);
 void jpcb_plan_cache_stats(unsigned long long* replays, unsigned long long* captures,
                            unsigned long long* bypassed);
+
+/* ---- positional form of the compute entry points (csrc/call.cu) -----------------------------------------------------
+ * What an XLA custom call has in hand (jax.ffi -- the binding a jpc maintainer would add; the reference's
+ * functions are `eqx.filter_jit`ed, jpc/_train.py:35, so under JAX every call arrives this way): ONE flat list of operand
+ * buffers, ONE flat list of result buffers, the descriptor as an opaque byte attribute.  jpcb_call splits the lists into
+ * the pointer lists of the structured entry point `entry` and calls it; jpcb_call_counts says how many buffers the
+ * descriptor implies (host arithmetic only).  The LAST result is always the workspace (`workspace_bytes` long).  With
+ *   L = n_layers, [b] present iff has_bias, S = the state list (L entries; L + 1 when free_input), [x] absent iff free_input,
+ *   bPC: n = td.n_layers entries per list, [bW] iff td.has_bias, [bV] iff bu_has_bias:
+ *   PC_FFWD_INIT      args W [b] x y          rets A(L) loss ws
+ *   PC_ENERGY         args W [b] S [x] y      rets E_layers ws
+ *   PC_ACTIVITY_GRAD  args W [b] S [x] y      rets F gS ws
+ *   PC_INFER          args W [b] S [x] y      rets S' ws          (S' may be the S buffers themselves -- donated operands,
+ *                                                                 input_output_aliases -- else S is copied into S' first)
+ *   PC_PARAM_GRADS    args W [b] S [x] y      rets gW [gb] E_layers ws
+ *   PC_TRAIN_STEP     args W [b] x y          rets A(L) loss E_layers gW [gb] ws
+ *   HPC_PARAM_GRADS   args W [b] U(L) T(L)    rets gW [gb] E_layers ws
+ *   EPC_GRADS         args W [b] S [x] y      rets F gS gW [gb] ws
+ *   BPC_ENERGY        args W [bW] V [bV] A [x] y   rets E_pairs ws
+ *   BPC_ACTIVITY_GRAD args (same)                  rets F gA ws
+ *   BPC_INFER         args (same)                  rets A' ws
+ *   BPC_PARAM_GRADS   args (same)                  rets gW [gbW] gV [gbV] E_pairs ws
+ *   BPC_TRAIN_STEP    args (same)                  rets A' gW [gbW] gV [gbV] E_pairs ws
+ * `desc` is a jpcb_pc_desc (jpcb_bpc_desc for the BPC entries); desc_bytes must be its sizeof. */
+enum {
+  JPCB_CALL_PC_FFWD_INIT = 0,
+  JPCB_CALL_PC_ENERGY = 1,
+  JPCB_CALL_PC_ACTIVITY_GRAD = 2,
+  JPCB_CALL_PC_INFER = 3,
+  JPCB_CALL_PC_PARAM_GRADS = 4,
+  JPCB_CALL_PC_TRAIN_STEP = 5,
+  JPCB_CALL_HPC_PARAM_GRADS = 6,
+  JPCB_CALL_EPC_GRADS = 7,
+  JPCB_CALL_BPC_ENERGY = 8,
+  JPCB_CALL_BPC_ACTIVITY_GRAD = 9,
+  JPCB_CALL_BPC_INFER = 10,
+  JPCB_CALL_BPC_PARAM_GRADS = 11,
+  JPCB_CALL_BPC_TRAIN_STEP = 12,
+  JPCB_CALL_N_ENTRIES = 13
+};
+int jpcb_call_counts(int entry, const void* desc, size_t desc_bytes, int* n_args, int* n_rets);
+int jpcb_call(int entry, const void* desc, size_t desc_bytes, const void* const* args, int n_args,
+              void* const* rets, int n_rets, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

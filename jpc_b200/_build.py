@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjpc_b200.so")
-SOURCES = ["api.cu", "tc_gemm.cu", "bpc.cu", "optim.cu", "plan.cu", "reg.cu"]
+SOURCES = ["api.cu", "tc_gemm.cu", "bpc.cu", "optim.cu", "plan.cu", "reg.cu", "call.cu"]
 HEADERS = ["common.cuh", "simt_gemm.cuh", "tc_gemm.cuh", "tc_staged.cuh", "warp_gemm.cuh", "elementwise.cuh", "host.cuh", "chain_ffwd.cuh",
            os.path.join("..", "..", "include", "jpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -87,6 +87,8 @@ SIGNATURES = {
     "jpcb_plan_cache_configure": (C.c_int, [C.c_int, C.c_int]),
     "jpcb_plan_cache_clear": (C.c_int, []),
     "jpcb_plan_cache_stats": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "jpcb_call_counts": (C.c_int, [C.c_int, _P, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "jpcb_call": (C.c_int, [C.c_int, _P, C.c_size_t, _PP, C.c_int, _PP, C.c_int, C.c_size_t, _P]),
     "jpcb_optim_sgd": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), _PP, _PP, C.c_double, _PP, _P]),
     "jpcb_optim_adam": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), _PP, _PP, _PP, _PP, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int, _PP, _PP, _PP, _P]),
@@ -146,6 +148,25 @@ def ptr_array_from_ints(addrs) -> "C.Array":
 
 def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# entry ids of the positional form (include/jpc_b200.h: JPCB_CALL_*)
+CALL_ENTRIES = ("pc_ffwd_init", "pc_energy", "pc_activity_grad", "pc_infer", "pc_param_grads", "pc_train_step", "hpc_param_grads",
+                "epc_grads", "bpc_energy", "bpc_activity_grad", "bpc_infer", "bpc_param_grads", "bpc_train_step")
+
+
+def call_counts(entry: str, desc) -> tuple:
+    """(operands, results) the positional form of `entry` takes for `desc` (results include the trailing workspace)."""
+    na, nr = C.c_int(0), C.c_int(0)
+    check(lib.jpcb_call_counts(CALL_ENTRIES.index(entry), C.cast(C.pointer(desc), _P), C.sizeof(desc), C.byref(na), C.byref(nr)))
+    return na.value, nr.value
+
+
+def call(entry: str, desc, args, rets, stream) -> None:
+    """jpcb_call: the positional form an XLA custom call uses -- `args` / `rets` are flat lists of device tensors, the last
+    result is the workspace (a uint8 tensor)."""
+    check(lib.jpcb_call(CALL_ENTRIES.index(entry), C.cast(C.pointer(desc), _P), C.sizeof(desc), ptr_array(args), len(args),
+                        ptr_array(rets), len(rets), rets[-1].numel() * rets[-1].element_size(), stream))
 
 
 def plan_cache_configure(max_plans: int = 16, min_calls: int = 2) -> None:

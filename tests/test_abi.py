@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/jpc_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in jpc_b200/_lib.py"
-    assert _lib.lib.jpcb_version() == 101
+    assert _lib.lib.jpcb_version() == 102
 
 
 def _desc(dtype=0, dims=(10, 20, 20, 5), B=4):
@@ -86,3 +86,45 @@ def test_python_api_surface_matches_the_reference_names():
                  "compute_accuracy", "update_activities", "update_params", "bpc_energy_fn", "compute_bpc_activity_grad",
                  "compute_bpc_param_grads", "update_bpc_activities", "update_bpc_params"):
         assert callable(getattr(J, name)), name
+
+
+def test_positional_call_counts_follow_the_descriptor():
+    """jpcb_call_counts (host arithmetic): operands / results of the positional form for PC, free-input and bPC descriptors."""
+    from jpc_b200 import _lib
+    d = _desc()                      # L = 3, no bias
+    assert _lib.call_counts("pc_ffwd_init", d) == (3 + 2, 3 + 1 + 1)
+    assert _lib.call_counts("pc_energy", d) == (3 + 3 + 2, 2)
+    d.has_bias = 1
+    assert _lib.call_counts("pc_train_step", d) == (6 + 2, 3 + 2 + 6 + 1)
+    assert _lib.call_counts("pc_param_grads", d) == (6 + 3 + 2, 6 + 1 + 1)
+    assert _lib.call_counts("hpc_param_grads", d) == (6 + 6, 6 + 1 + 1)
+    assert _lib.call_counts("epc_grads", d) == (6 + 3 + 2, 1 + 3 + 6 + 1)
+    d.free_input = 1                 # the state list grows by z_0 and x disappears
+    assert _lib.call_counts("pc_infer", d) == (6 + 4 + 1, 4 + 1)
+    assert _lib.call_counts("pc_activity_grad", d) == (6 + 4 + 1, 1 + 4 + 1)
+    b = _lib.BpcDesc()
+    b.td = _desc()
+    b.td.has_bias, b.bu_has_bias = 1, 0
+    assert _lib.call_counts("bpc_energy", b) == (3 + 3 + 3 + 0 + 3 + 2, 2)
+    assert _lib.call_counts("bpc_train_step", b) == (14, 3 + (3 + 3 + 3 + 0) + 1 + 1)
+    b.td.free_input = 1
+    assert _lib.call_counts("bpc_infer", b) == (13, 3 + 1)
+    with pytest.raises(ValueError):  # a PC descriptor where a bPC one is expected
+        _lib.call_counts("bpc_infer", d)
+
+
+def test_xla_shim_registers_every_positional_entry():
+    """The shim cannot be compiled here (no jaxlib headers): keep it in step with the header by text -- one handler per
+    JPCB_CALL_* enumerator, and the enumerators in the order jpc_b200._lib.CALL_ENTRIES assumes."""
+    from jpc_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "jpc_b200.h")).read()
+    enum = re.findall(r"\b(JPCB_CALL_[A-Z_]+)\s*=\s*(\d+)", hdr)
+    names = [n for n, _ in enum if n != "JPCB_CALL_N_ENTRIES"]
+    assert [int(v) for n, v in enum if n != "JPCB_CALL_N_ENTRIES"] == list(range(len(names)))
+    assert dict(enum)["JPCB_CALL_N_ENTRIES"] == str(len(names))
+    assert [n[len("JPCB_CALL_"):].lower() for n in names] == list(_lib.CALL_ENTRIES)
+    shim = open(os.path.join(ROOT, "jpc_b200", "csrc", "xla_ffi_shim.cc")).read()
+    handlers = dict(re.findall(r"JPCB_XLA_HANDLER\((jpcb_xla_[a-z_]+),\s*(JPCB_CALL_[A-Z_]+)\)", shim))
+    assert sorted(handlers.values()) == sorted(names)
+    for sym, entry in handlers.items():
+        assert sym == "jpcb_xla_" + entry[len("JPCB_CALL_"):].lower()
