@@ -268,8 +268,17 @@ def run_bpc(args, w):
     ms = e0.elapsed_time(e1)
     launches = _lib.lib.jpcb_launch_count() - l0
     clocks = sampler.stop()
-    for _ in range(8):  # (the functional API's buffers cycle through a few address sets; the library's launch plans settle)
-        step(lab_p.to(dev, non_blocking=True), img_p.to(dev, non_blocking=True))
+    # End-to-end warm-up: the functional API's buffers cycle through a few address sets and the library captures a launch
+    # plan for each the second time it sees it (a one-off cost, like the reference's jit trace): run until four consecutive
+    # steps captured nothing (at least 8 steps, at most 40), and report what was still captured inside the timed region.
+    e2e_warm, quiet, caps = 0, 0, J.plan_cache_stats()["captures"]
+    while e2e_warm < 40 and (e2e_warm < 8 or quiet < 4):
+        gr = step(lab_p.to(dev, non_blocking=True), img_p.to(dev, non_blocking=True))
+        float(gr[0][0][1].weight[0, 0])
+        e2e_warm += 1
+        now = J.plan_cache_stats()["captures"]
+        quiet = quiet + 1 if now == caps else 0
+        caps = now
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -277,6 +286,7 @@ def run_bpc(args, w):
         float(gr[0][0][1].weight[0, 0])  # device -> host read of a result
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_caps = J.plan_cache_stats()["captures"] - caps
     dims = [w["d_in"]] + [w["width"]] * (w["depth"] - 1) + [w["d_out"]]
     gl = [2.0 * w["B"] * dims[l] * dims[l + 1] for l in range(w["depth"])]
     per_step = 4 * sum(gl) - 2 * gl[0] - 2 * gl[-1]            # 2 directions x (prediction + transposed) GEMMs, clamped ends hoisted
@@ -294,7 +304,7 @@ def run_bpc(args, w):
             "config": {"workload": w["desc"], "global_batch": w["B"], "inference_steps": T, "solver": "euler", "parallelism": "dp1",
                        "l2": "working set fits L2; no flush", "algorithmic_gflop_per_step": total / 1e9},
             "e2e": {"value": w["B"] * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * (img_p.numel() + lab_p.numel()),
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4, "warmup": e2e_warm, "plan_captures_in_timed_region": int(e2e_caps)},
             "gpu_launches": int(launches), "clocks": clocks, "launch_plans": J.plan_cache_stats(),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                          "kernel": {"bf16": "tc_grouped_gemm (bPC phases: errors / forward half / backward half + update), whole step",
