@@ -333,8 +333,8 @@ def run_bpc(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -492,15 +492,24 @@ def main():
         for b in bufs:
             b[3].record(torch.cuda.current_stream(dev))
         stage(0)
-        for i in range(E2E_WARM):
-            step_fn(i, blocking)
+        # warm-up: at least E2E_WARM steps; on one GPU, on until four consecutive steps captured no new launch plan (at most
+        # 40 steps) -- captures are a one-off cost like the reference's jit trace.  (Ranks of a data-parallel run must take
+        # the same number of steps -- every step holds a collective -- so there the count stays fixed.)
+        warm, quiet, caps = 0, 0, J.plan_cache_stats()["captures"]
+        while warm < E2E_WARM or (world == 1 and quiet < 4 and warm < 40):
+            step_fn(warm, blocking)
+            warm += 1
+            now = J.plan_cache_stats()["captures"]
+            quiet = quiet + 1 if now == caps else 0
+            caps = now
         sync_all()
         t0 = time.perf_counter()
-        for i in range(E2E_WARM, E2E_WARM + args.steps):
+        for i in range(warm, warm + args.steps):
             step_fn(i, blocking)
         sync_all()  # (drains the loss copies too)
         secs = time.perf_counter() - t0
-        if not bool(torch.isfinite(loss_pin[:min(256, E2E_WARM + args.steps)]).all()):
+        e2e_info["warmup"], e2e_info["plan_captures_in_timed_region"] = warm, int(J.plan_cache_stats()["captures"] - caps)
+        if not bool(torch.isfinite(loss_pin[:min(256, warm + args.steps)]).all()):
             raise SystemExit("bench.py: a non-finite loss came back from the end-to-end loop")
         if world > 1:
             t = torch.tensor([secs], device=dev)
@@ -509,7 +518,9 @@ def main():
         return secs
 
     loss_pin.zero_()
+    e2e_info = {}
     e2e_s = e2e_loop(e2e_step, False)
+    e2e_first = dict(e2e_info)
     e2e_val = B_global * args.steps / e2e_s
     e2e_blocking_val = B_global * args.steps / e2e_loop(e2e_step, True)
 
@@ -634,7 +645,8 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel() * 4,
                     "d2h_bytes_per_step": 4,
                     "d2h": "non-blocking copy of the step's loss into pinned host memory every step, drained at the end of the "
-                           "timed region", "warmup": E2E_WARM},
+                           "timed region", "warmup": e2e_first.get("warmup", E2E_WARM),
+                    "plan_captures_in_timed_region": e2e_first.get("plan_captures_in_timed_region")},
             "e2e_blocking_read": {"value": e2e_blocking_val, "unit": UNIT,
                                   "what": "the same loop with the host blocking on every step's loss (float(loss))"},
             "e2e_graph": e2e_graph,
