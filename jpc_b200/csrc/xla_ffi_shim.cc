@@ -8,9 +8,14 @@
 // jpcb_call_counts), where it IS built and tested (tests/test_gpu_call.py, tests/test_abi.py).  What is left here is one
 // generic handler: unpack XLA's buffers into two pointer arrays, pass the descriptor attribute through, enqueue on XLA's
 // stream.  One handler symbol per JPCB_CALL_* entry (tests/test_abi.py checks this list against the header's enum).
+// tests/test_xla_shim_mock.py compiles THIS file (-Wall -Wextra -Werror) against a mock of the FFI header that restates the
+// API surface used below and drives all 13 handlers with fake buffers and a recording jpcb_call: well-formed for that API
+// shape and marshalling verified, though never against the real header.
 // INTEGRATION.md shows the Python side (jax.ffi.register_ffi_target / jax.ffi.ffi_call) a jpc maintainer would add.
 #include <cstdint>
 #include <vector>
+
+#include <cuda_runtime_api.h>  // cudaStream_t
 
 #include "xla/ffi/api/ffi.h"
 
