@@ -66,6 +66,38 @@ def build(force: bool = False, verbose: bool = False, defines=()) -> str:
     return LIB
 
 
+XLA_LIB = os.path.join(HERE, "libjpc_b200_xla.so")
+
+
+def xla_ffi_include() -> str | None:
+    """Directory holding xla/ffi/api/ffi.h (shipped inside jaxlib), or None when jaxlib is not installed."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("jaxlib")
+    except (ImportError, ValueError):
+        spec = None
+    if spec is None or not spec.submodule_search_locations:
+        return None
+    inc = os.path.join(list(spec.submodule_search_locations)[0], "include")
+    return inc if os.path.exists(os.path.join(inc, "xla", "ffi", "api", "ffi.h")) else None
+
+
+def build_xla_shim(include_dir: str | None = None) -> str | None:
+    """Compiles csrc/xla_ffi_shim.cc (the jax.ffi handlers over jpcb_call) into libjpc_b200_xla.so next to the library.
+    Needs jaxlib's headers: returns None -- and builds nothing -- when they are absent (as in this image)."""
+    inc = include_dir or xla_ffi_include()
+    if inc is None:
+        return None
+    build()
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", inc, "-I", "/usr/local/cuda/include",
+           os.path.join(CSRC, "xla_ffi_shim.cc"), "-L", HERE, "-l:libjpc_b200.so", "-Wl,-rpath,$ORIGIN", "-o", XLA_LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building the XLA FFI shim failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return XLA_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
                 defines=[a[2:] for a in sys.argv if a.startswith("-D")]))
+    print(build_xla_shim() or "XLA FFI shim: jaxlib headers not found, not built")
