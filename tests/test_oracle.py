@@ -339,3 +339,28 @@ def test_weight_regularisers_apply_to_bare_linear_layers_only():
     mlp = O.make_mlp(0, 10, 12, 3, 5, "tanh")
     a2 = _perturb(O.init_activities_with_ffwd(mlp, x))
     assert float(O.pc_energy_fn(mlp, None, a2, y, x=x, weight_decay=wd, spectral_penalty=sp)) == float(O.pc_energy_fn(mlp, None, a2, y, x=x))
+
+
+def test_optimiser_restatements_match_torch_optim():
+    """optax is absent from the image, so `sgd_update` / `adam_update` restate its published rules.
+    torch.optim.SGD / Adam are independent implementations of the same published algorithms (Adam with bias correction, eps
+    added outside the square root): six steps on the same gradients must agree to rounding in fp64.  This pins the rule the
+    fused CUDA update is tested against (`test_fused_optimiser_matches_optax_protocol`) to something outside this repository."""
+    g = torch.Generator().manual_seed(5)
+    shapes = [(7, 5), (7,), (3, 7)]
+    p0 = [torch.randn(s, generator=g, dtype=torch.float64) for s in shapes]
+    grads = [[torch.randn(s, generator=g, dtype=torch.float64) * (10.0 ** (k % 3 - 1)) for s in shapes] for k in range(6)]
+    for name in ("sgd", "adam"):
+        tp = [p.clone().requires_grad_(True) for p in p0]
+        opt = torch.optim.SGD(tp, lr=0.05) if name == "sgd" else torch.optim.Adam(tp, lr=0.01, betas=(0.9, 0.999), eps=1e-8)
+        mine, state = [p.clone() for p in p0], None
+        for gs in grads:
+            for t, gr in zip(tp, gs):
+                t.grad = gr.clone()
+            opt.step()
+            if name == "sgd":
+                mine = O.sgd_update(mine, gs, 0.05)
+            else:
+                mine, state = O.adam_update(mine, gs, state, 0.01)
+            for a, b in zip(mine, tp):
+                assert float((a - b.detach()).abs().max()) <= 1e-13 * max(1.0, float(b.detach().abs().max()))
