@@ -364,3 +364,54 @@ def test_optimiser_restatements_match_torch_optim():
                 mine, state = O.adam_update(mine, gs, state, 0.01)
             for a, b in zip(mine, tp):
                 assert float((a - b.detach()).abs().max()) <= 1e-13 * max(1.0, float(b.detach().abs().max()))
+
+
+def test_integrators_converge_to_the_matrix_exponential_solution():
+    """diffrax is absent, so the Euler / Heun tableaux and the adaptive controller are restatements.
+    For a LINEAR network the inference ODE is dz/dt = -(H z - c), whose exact flow is z* + expm(-H t)(z_0 - z*)
+    (scipy.linalg.expm: independent of this repository).  Against it: Euler's error halves and Heun's quarters when the step
+    halves (orders 1 and 2 -- a wrong Heun tableau shows up as order 1), and the adaptive Heun + PID solve lands within its
+    tolerance."""
+    import numpy as np
+    from scipy.linalg import expm
+    model = O.make_mlp(0, 4, 5, 3, 3, "linear", use_bias=True)
+    x, y = _data(2, 4, 3, onehot_out=False)
+    acts = _perturb(O.init_activities_with_ffwd(model, x))
+    shapes = [a.shape for a in acts]
+    sizes = [a.numel() for a in acts]
+
+    def unflat(v):
+        out, o = [], 0
+        for s, n in zip(shapes, sizes):
+            out.append(v[o:o + n].reshape(s))
+            o += n
+        return out
+
+    def grad(v):
+        return torch.cat([g.reshape(-1) for g in O.compute_pc_activity_grad(model, None, unflat(v), y, x=x)[1]])
+
+    n = sum(sizes)
+    z0 = torch.cat([a.reshape(-1) for a in acts])
+    g0 = grad(torch.zeros(n, dtype=torch.float64))                       # = -c
+    H = torch.stack([grad(torch.eye(n, dtype=torch.float64)[i]) - g0 for i in range(n)], dim=1)
+    assert float((grad(z0) - (H @ z0 + g0)).abs().max()) < 1e-12          # the vector field is affine
+    live = [i for i in range(n) if float(H[i].abs().sum()) > 0]           # (the dummy output slot has no dynamics)
+    Hl, cl = H[live][:, live].numpy(), -(g0[live] + H[live][:, [i for i in range(n) if i not in live]] @ z0[[i for i in range(n) if i not in live]]).numpy()
+    t1 = 4.0
+    zstar = np.linalg.solve(Hl, cl)
+    exact = zstar + expm(-Hl * t1) @ (z0[live].numpy() - zstar)
+
+    def err(solver, dt):
+        sol, _ = O.solve_inference(model, None, acts, y, x=x, solver=solver, max_t1=t1, dt=dt, event_atol=0.0, event_rtol=0.0)
+        v = torch.cat([a.reshape(-1) for a in sol])[live].numpy()
+        return float(np.abs(v - exact).max())
+
+    e1, e2 = err("euler", 0.1), err("euler", 0.05)
+    h1, h2 = err("heun", 0.1), err("heun", 0.05)
+    assert 1.8 < e1 / e2 < 2.2, (e1, e2)        # first order
+    assert 3.6 < h1 / h2 < 4.4, (h1, h2)        # second order
+    assert h1 < 0.1 * e1
+    sol, stats = O.solve_inference_adaptive(model, None, acts, y, x=x, max_t1=t1)
+    v = torch.cat([a.reshape(-1) for a in sol])[live].numpy()
+    if not stats.get("event", False):          # ran to t1: within a few tolerances of the exact flow
+        assert float(np.abs(v - exact).max()) < 2e-2 * max(1.0, float(np.abs(exact).max()))
